@@ -1,0 +1,114 @@
+"""ctypes binding of libcrbe_b200.so (include/crbe_b200.h).
+
+The library is the product: there is no Python or CPU fallback.  If it has not
+been built (``python -m airpollution_b200.build``) importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libcrbe_b200.so")
+
+ABI_VERSION = 1
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_f64p = C.POINTER(C.c_double)
+vp = C.c_void_p   # device pointers are passed as plain addresses
+
+
+class SolveInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("restarts", C.c_int32), ("status", C.c_int32),
+                ("launches", C.c_int32), ("relres", C.c_double), ("true_relres", C.c_double),
+                ("bnorm", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+SOLVER_FUSED = 1
+SOLVER_VERIFY = 2
+SOLVER_GRAPH = 4
+
+# name -> (argtypes)   every function returns int unless listed in _RESTYPE
+_SIGNATURES = {
+    "crbe_abi_version": [],
+    "crbe_ctx_create": [C.c_int, C.POINTER(vp)],
+    "crbe_ctx_set_stream": [vp, vp],
+    "crbe_ctx_synchronize": [vp],
+    "crbe_ctx_destroy": [vp],
+    "crbe_memcpy_h2d": [vp, vp, vp, C.c_int64, C.c_int],
+    "crbe_memcpy_d2h": [vp, vp, vp, C.c_int64, C.c_int],
+    "crbe_topology_create": [vp, vp, C.c_int64, C.c_int64, C.POINTER(vp), c_i64p, c_i64p, c_i64p],
+    "crbe_topology_fill": [vp, vp, vp, vp, vp, vp, vp],
+    "crbe_topology_free": [vp],
+    "crbe_mesh_geometry": [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, vp, vp, c_f64p],
+    "crbe_csr_pattern_count": [vp, vp, vp, C.c_int64, vp, c_i64p],
+    "crbe_csr_pattern_fill": [vp, vp, vp, C.c_int64, C.c_int64, vp, vp, vp],
+    "crbe_colour_elements": [vp, vp, vp, C.c_int64, vp, vp, c_i64p, c_i32p],
+    "crbe_element_matrices": [vp, vp, vp, vp, C.c_int64, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp],
+    "crbe_assemble": [vp, vp, vp, vp, vp, vp, c_i64p, C.c_int32, C.c_int64, C.c_double, C.c_double, C.c_double,
+                      vp, vp, vp, vp],
+    "crbe_system_values": [vp, C.c_int64, vp, vp, vp, C.c_double, vp],
+    "crbe_spmv_csr": [vp, C.c_int64, vp, vp, vp, vp, vp],
+    "crbe_dot": [vp, C.c_int64, vp, vp, c_f64p],
+    "crbe_errors": [vp, C.c_int64, vp, vp, c_f64p],
+    "crbe_solver_create": [vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, C.POINTER(vp)],
+    "crbe_solver_set_system": [vp, vp, vp, vp],
+    "crbe_solver_set_options": [vp, C.c_double, C.c_int32, C.c_uint32],
+    "crbe_solver_step": [vp, vp, vp, C.c_double, C.POINTER(SolveInfo)],
+    "crbe_solver_solve": [vp, vp, vp, C.POINTER(SolveInfo)],
+    "crbe_solver_rhs": [vp, vp, vp, C.c_double, vp],
+    "crbe_solver_lift": [vp, vp, vp, vp],
+    "crbe_solver_destroy": [vp],
+}
+# test / debug hooks (not in the public header)
+_DEBUG_SIGNATURES = {
+    "crbe_test_exclusive_scan": [vp, vp, vp, C.c_int64, c_i64p],
+    "crbe_solver_debug_ell": [vp, c_i64p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
+}
+
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["crbe_last_error"])
+
+
+class CrbeError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libcrbe_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise if it is missing or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m airpollution_b200.build` "
+            "(the CRBE path has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.crbe_last_error.restype = C.c_char_p
+    lib.crbe_last_error.argtypes = []
+    for table in (_SIGNATURES, _DEBUG_SIGNATURES):
+        for name, args in table.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+    if lib.crbe_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.crbe_abi_version()} != {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise CrbeError(rc, load().crbe_last_error().decode("utf-8", "replace"))
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))

@@ -1,0 +1,567 @@
+"""Host-side mirror of the reference's ``crbe.py`` for the CRBE hot path.
+
+Same public names, constructor signatures, attributes and error behaviour as
+the reference (``create_mesh`` crbe.py:14-44, ``MeshData`` :47-164,
+``ElementCR`` :167-213, ``BESCRFEM`` :225-660), so ``crbe.py``-style drivers and
+``experiments/crbe_experiments.py`` run unchanged -- but every array the
+reference builds with Python loops, scipy.sparse and SuperLU is produced by
+libcrbe_b200.so (hand-written sm_100a CUDA, include/crbe_b200.h) through
+ctypes.  torch tensors serve as device buffers only.  No CPU fallback: without
+the library or without a CUDA device construction fails.
+
+Attributes documented as numpy arrays in the reference are numpy arrays here
+too; large ones are downloaded from the device the first time they are read.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from .common import AdDifProblem, Domain, Problem  # noqa: F401  (re-exported like crbe.py:12)
+from .runtime import Runtime, ptr, to_numpy
+
+try:  # the reference shows a tqdm bar over the time loop (crbe.py:419)
+    from tqdm import tqdm as _tqdm
+except Exception:  # pragma: no cover
+    _tqdm = None
+
+
+# --------------------------------------------------------------------------
+# mesh creation (crbe.py:14-44)
+# --------------------------------------------------------------------------
+def create_mesh(n_points_per_axis=20, domain_size=2.0, filename="square_mesh.msh"):
+    """Write a triangular mesh of ``[-domain_size, domain_size]^2`` with target
+    edge length ``2*domain_size/(n_points_per_axis-1)`` (crbe.py:32) to
+    ``filename`` and return the file name.  Uses gmsh exactly like the
+    reference when gmsh is importable, otherwise the bundled structured mesher
+    (airpollution_b200.compat) which writes the same MSH 2.2 container."""
+    from .compat import mesh_provider
+    return mesh_provider.create_mesh(n_points_per_axis, domain_size, filename)
+
+
+class _Lazy:
+    """numpy attribute backed by a device tensor, downloaded on first read."""
+
+    def __init__(self, key, post=None):
+        self.key, self.post = key, post
+
+    def __set_name__(self, owner, name):
+        self.name = "_np_" + name
+
+    def __get__(self, obj, objtype=None):
+        if obj is None:
+            return self
+        val = obj.__dict__.get(self.name)
+        if val is None:
+            val = to_numpy(obj._dev[self.key])
+            if self.post:
+                val = self.post(val)
+            obj.__dict__[self.name] = val
+        return val
+
+    def __set__(self, obj, value):
+        obj.__dict__[self.name] = value
+
+
+# --------------------------------------------------------------------------
+# MeshData (crbe.py:47-164)
+# --------------------------------------------------------------------------
+class MeshData:
+    """Mesh connectivity and geometry; the edge ("segment") numbering is the
+    DOF numbering of the solver.  Computed on the device by
+    ``crbe_topology_*`` / ``crbe_mesh_geometry`` and bit-identical to the
+    reference's arrays."""
+
+    segments = _Lazy("segments")                         # (N,2) int32 [min,max]       crbe.py:128
+    triangle_to_segments = _Lazy("t2s")                  # (Nt,3) int32                crbe.py:129
+    midpoints = _Lazy("midpoints")                       # (N,2) float64               crbe.py:71
+    segment_lengths = _Lazy("lengths")                   # (N,) float64                crbe.py:134-141
+    triangle_areas = _Lazy("areas")                      # (Nt,) float64               crbe.py:143-154
+    boundary_segments = _Lazy("bnd")                     # (Nb,) int32 sorted          crbe.py:78-80
+    boundary_triangles = _Lazy("bnd_tri")                # (Nbt,) int32                crbe.py:95
+
+    def __init__(self, mesh, domain, nt, device=None):
+        self.mesh = mesh
+        self.domain = domain
+        self.nt = nt
+        self.time_discr = np.linspace(0, domain.T, nt)                  # crbe.py:56
+        self.points = mesh.points[:, :2]                                # crbe.py:59
+        self.number_of_points = len(self.points)
+        self.triangles = mesh.cells_dict['triangle']                    # crbe.py:63
+        self.number_of_triangles = len(self.triangles)
+
+        rt = self._rt = Runtime.get(device)
+        nv, nt_tri = self.number_of_points, self.number_of_triangles
+        tri = np.asarray(self.triangles)
+        if tri.size and (tri.min() < 0 or tri.max() >= nv):
+            raise ValueError("triangle vertex ids out of range")
+        if 3 * nt_tri >= 2**31 or nv >= 2**31:
+            raise ValueError("mesh too large for int32 DOF ids")
+        d = self._dev = {}
+        d["points"] = rt.upload(self.points, np.float64)
+        d["tri"] = rt.upload(tri.reshape(-1, 3), np.int32)
+
+        topo = C.c_void_p()
+        n_seg, n_bnd, n_bnd_tri = C.c_int64(), C.c_int64(), C.c_int64()
+        rt.call("crbe_topology_create", rt.ctx, ptr(d["tri"]), nt_tri, nv, C.byref(topo),
+                C.byref(n_seg), C.byref(n_bnd), C.byref(n_bnd_tri))
+        try:
+            n = n_seg.value
+            d["t2s"] = rt.empty((nt_tri, 3), torch.int32)
+            d["segments"] = rt.empty((n, 2), torch.int32)
+            d["edge_slots"] = rt.empty((n, 2), torch.int32)
+            d["bnd"] = rt.empty((n_bnd.value,), torch.int32)
+            d["bnd_tri"] = rt.empty((n_bnd_tri.value,), torch.int32)
+            d["bnd_tri_seg"] = rt.empty((n_bnd_tri.value,), torch.int32)
+            rt.call("crbe_topology_fill", topo, ptr(d["t2s"]), ptr(d["segments"]), ptr(d["edge_slots"]),
+                    ptr(d["bnd"]), ptr(d["bnd_tri"]), ptr(d["bnd_tri_seg"]))
+        finally:
+            rt.call("crbe_topology_free", topo)
+        self.number_of_segments = n                                      # crbe.py:68
+
+        d["midpoints"] = rt.empty((n, 2), torch.float64)
+        d["lengths"] = rt.empty((n,), torch.float64)
+        d["areas"] = rt.empty((nt_tri,), torch.float64)
+        diam = C.c_double(0.0)
+        rt.call("crbe_mesh_geometry", rt.ctx, ptr(d["points"]), nv, ptr(d["tri"]), nt_tri, ptr(d["segments"]), n,
+                ptr(d["midpoints"]), ptr(d["lengths"]), ptr(d["areas"]), C.byref(diam))
+        self.diameter = diam.value if n else 0                           # crbe.py:98-106
+        self._bnd_tri_map = None
+
+    @property
+    def boundary_triangle_to_segments(self):
+        """{triangle: its first boundary edge}  (crbe.py:84-93)."""
+        if self._bnd_tri_map is None:
+            segs = to_numpy(self._dev["bnd_tri_seg"])
+            self._bnd_tri_map = {int(t): segs[k] for k, t in enumerate(self.boundary_triangles)}
+        return self._bnd_tri_map
+
+    def show(self):                                                      # crbe.py:156-164
+        import matplotlib.pyplot as plt
+        plt.figure(figsize=(10, 8))
+        plt.triplot(self.points[:, 0], self.points[:, 1], self.triangles)
+        plt.axis('equal')
+        plt.grid(False)
+        plt.savefig("mesh_visualition.pdf", dpi=300)
+        plt.title('2D Mesh Visualization')
+        plt.show()
+
+
+# --------------------------------------------------------------------------
+# ElementCR (crbe.py:167-213): reference-element constants
+# --------------------------------------------------------------------------
+class ElementCR:
+    def __init__(self):
+        self.points = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+        self.midpoints = np.array([[1 / 2, 1 / 2], [1 / 2, 0.0], [0.0, 1 / 2]])
+        self.segment_enumeration = np.array([[1, 2], [2, 0], [0, 1]])
+
+    def get_shape_functions(self, local_coords):
+        x, y = local_coords
+        return np.array([-1 + 2 * (x + y), 1 - 2 * x, 1 - 2 * y])
+
+    def get_jacobian(self):
+        pass
+
+    def get_shape_function_derivatives(self):
+        return np.array([[2.0, 2.0], [-2.0, 0.0], [0.0, -2.0]])
+
+    def get_stiffness_matrix(self):
+        return np.array([[4.0, -2.0, -2.0], [-2.0, 2.0, 0.0], [-2.0, 0.0, 2.0]])
+
+    def get_mass_matrix(self):
+        return np.eye(3) / 6.0
+
+
+_GRAD_REF = np.array([[2.0, 2.0], [-2.0, 0.0], [0.0, -2.0]])
+
+
+# --------------------------------------------------------------------------
+# BESCRFEM (crbe.py:225-660)
+# --------------------------------------------------------------------------
+class BESCRFEM:
+    """Backward-Euler (order 1) / Crank-Nicolson (order 2) time stepping of the
+    Crouzeix-Raviart discretisation, on the device.
+
+    Positional arguments are the reference's (crbe.py:228).  Keyword-only
+    additions keep the reference's behaviour at their defaults:
+
+    ``rtol``            BiCGStab stops at ||r|| <= rtol ||b|| (Jacobi-scaled, verified
+                        against the recomputed residual); 1e-13 keeps the solution
+                        within 1e-10 of the reference's direct solve.
+    ``max_iterations``  iteration limit per step (RuntimeError beyond it).
+    ``history``         ``"all"`` (reference: ``solutions`` is nt x N), ``"last"``
+                        (``solutions`` holds only the initial and final rows) or an
+                        int stride -- 1001 x 12.6 M doubles do not fit in host memory.
+    ``fused``           fuse the vector updates into the SpMV kernels.
+    ``progress``        tqdm bar like the reference (default: only for nt*N < 2e7).
+    """
+
+    def __init__(self, domain, problem, mesh_data, element, time_scheme_order=1, *, rtol=1e-13,
+                 max_iterations=10000, history="all", fused=True, verify=True, progress=None,
+                 velocity_field=None):
+        self.domain = domain
+        self.problem = problem
+        self.mesh_data = mesh_data
+        self.dt = domain.T / (mesh_data.nt - 1)                         # crbe.py:233
+        self.element = element
+        self._compute_reference_element_matrices()
+        self.time_scheme_order = time_scheme_order
+        self.rtol = rtol
+        self.max_iterations = max_iterations
+        self.history = history
+        self.fused = fused
+        self.verify = verify
+        self.progress = progress
+        self.velocity_field = velocity_field
+        self._rt = mesh_data._rt
+        self._dev = {}
+        self._solver = None
+        self._np = {}
+        self.step_info = []
+
+    def __del__(self):
+        try:
+            self._release_solver()
+        except Exception:
+            pass
+
+    def _release_solver(self):
+        if getattr(self, "_solver", None) is not None:
+            _lib.load().crbe_solver_destroy(self._solver)
+            self._solver = None
+
+    def _compute_reference_element_matrices(self):                      # crbe.py:238-247
+        self.reference_stiffness = self.element.get_stiffness_matrix()
+        self.reference_mass = self.element.get_mass_matrix()
+        self.triangle_grad_phis = self.element.get_shape_function_derivatives()
+        if not np.array_equal(np.asarray(self.triangle_grad_phis, dtype=np.float64), _GRAD_REF):
+            raise ValueError("the device kernels implement the Crouzeix-Raviart reference gradients "
+                             "of ElementCR (crbe.py:198-203); a different element is not supported")
+
+    # ---- element matrices (crbe.py:249-313) -------------------------------
+    def _velocity(self):
+        v = self.problem.v
+        return float(v[0]), float(v[1])
+
+    def _local(self, tri_idx):
+        md, rt = self.mesh_data, self._rt
+        rt.bind_stream()
+        nt = md.number_of_triangles
+        if not -nt <= tri_idx < nt:
+            raise IndexError("triangle index out of range")
+        t = tri_idx % nt
+        out = rt.empty((3, 9), torch.float64)
+        vx, vy = self._velocity()
+        d = md._dev
+        rt.call("crbe_element_matrices", rt.ctx, ptr(d["points"]), ptr(d["tri"][t:t + 1]), ptr(d["areas"][t:t + 1]), 1,
+                float(self.problem.D), vx, vy, ptr(None), ptr(out[0]), ptr(out[1]), ptr(out[2]))
+        return to_numpy(out).reshape(3, 3, 3)
+
+    def compute_stiffness_CR(self, tri_idx):
+        return self._local(tri_idx)[0]
+
+    def compute_mass_CR(self, tri_idx):
+        return self._local(tri_idx)[1]
+
+    def compute_advection_CR(self, tri_idx):
+        return self._local(tri_idx)[2]
+
+    # ---- global matrices (crbe.py:326-362) --------------------------------
+    def _coef(self):
+        if self.time_scheme_order == 1:
+            return self.dt
+        if self.time_scheme_order == 2:
+            return 0.5 * self.dt
+        raise ValueError(f"Order {self.time_scheme_order} numerical scheme not implemented")
+
+    def _build_pattern(self):
+        md, rt, d = self.mesh_data, self._rt, self._dev
+        if "indptr" in d:
+            return
+        m = md._dev
+        n, nt = md.number_of_segments, md.number_of_triangles
+        d["indptr"] = rt.empty((n + 1,), torch.int32)
+        nnz = C.c_int64()
+        rt.call("crbe_csr_pattern_count", rt.ctx, ptr(m["t2s"]), ptr(m["edge_slots"]), n, ptr(d["indptr"]), C.byref(nnz))
+        self._nnz = nnz.value
+        d["indices"] = rt.empty((self._nnz,), torch.int32)
+        d["scatter_pos"] = rt.empty((nt, 9), torch.int32)
+        rt.call("crbe_csr_pattern_fill", rt.ctx, ptr(m["t2s"]), ptr(m["edge_slots"]), n, nt, ptr(d["indptr"]),
+                ptr(d["indices"]), ptr(d["scatter_pos"]))
+        d["colour"] = rt.empty((nt,), torch.int32)
+        d["order"] = rt.empty((nt,), torch.int32)
+        offs = (C.c_int64 * 9)()
+        ncol = C.c_int32()
+        rt.call("crbe_colour_elements", rt.ctx, ptr(m["t2s"]), ptr(m["edge_slots"]), nt, ptr(d["colour"]), ptr(d["order"]),
+                offs, C.byref(ncol))
+        self._colour_offsets = offs
+        self.n_colours = ncol.value
+
+    def build_global_matrices(self):
+        """Assemble M, K, A on the structural CSR pattern and the system matrix
+        ``M + dt(K+A)`` (order 1) / ``M + dt/2 (K+A)`` (order 2)."""
+        coef = self._coef()                       # raises ValueError like crbe.py:362
+        md, rt, d = self.mesh_data, self._rt, self._dev
+        rt.bind_stream()
+        self._build_pattern()
+        m = md._dev
+        nnz = self._nnz
+        for k in ("m_val", "k_val", "a_val", "s_val"):
+            if k not in d:
+                d[k] = rt.empty((nnz,), torch.float64)
+        vx, vy = self._velocity()
+        v_elem = None
+        if self.velocity_field is not None:
+            v_elem = self._element_velocity(0.0)
+        rt.call("crbe_assemble", rt.ctx, ptr(m["points"]), ptr(m["tri"]), ptr(m["areas"]), ptr(d["scatter_pos"]),
+                ptr(d["order"]), self._colour_offsets, self.n_colours, nnz, float(self.problem.D), vx, vy, ptr(v_elem),
+                ptr(d["m_val"]), ptr(d["k_val"]), ptr(d["a_val"]))
+        rt.call("crbe_system_values", rt.ctx, nnz, ptr(d["m_val"]), ptr(d["k_val"]), ptr(d["a_val"]), coef, ptr(d["s_val"]))
+        if self.time_scheme_order == 2:
+            d["r_val"] = rt.empty((nnz,), torch.float64)
+            rt.call("crbe_system_values", rt.ctx, nnz, ptr(d["m_val"]), ptr(d["k_val"]), ptr(d["a_val"]), -coef, ptr(d["r_val"]))
+        self._np.clear()
+        self._assembled = True
+        self._load_solver()
+
+    def _element_velocity(self, t):
+        """Per-element velocity v(centroid, t) for the time-varying extension."""
+        md = self.mesh_data
+        if "centroids" not in self._dev:
+            p, tri = md._dev["points"], md._dev["tri"].long()
+            self._dev["centroids"] = (p[tri[:, 0]] + p[tri[:, 1]] + p[tri[:, 2]]) / 3.0
+        v = self.velocity_field(self._dev["centroids"], t)
+        return torch.as_tensor(v, dtype=torch.float64, device=self._rt.device).contiguous()
+
+    def _load_solver(self):
+        md, rt, d = self.mesh_data, self._rt, self._dev
+        if self._solver is None:
+            h = C.c_void_p()
+            rt.call("crbe_solver_create", rt.ctx, md.number_of_segments, ptr(d["indptr"]), ptr(d["indices"]), self._nnz,
+                    ptr(md._dev["bnd"]), md._dev["bnd"].numel(), C.byref(h))
+            self._solver = h
+        flags = (_lib.SOLVER_FUSED if self.fused else 0) | (_lib.SOLVER_VERIFY if self.verify else 0)
+        rt.call("crbe_solver_set_options", self._solver, float(self.rtol), int(self.max_iterations), flags)
+        rt.call("crbe_solver_set_system", self._solver, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
+
+    def _csr(self, key):
+        import scipy.sparse as sp
+        if key not in self._np:
+            d = self._dev
+            n = self.mesh_data.number_of_segments
+            if "indptr" not in self._np:
+                self._np["indptr"] = to_numpy(d["indptr"])
+                self._np["indices"] = to_numpy(d["indices"])
+            self._np[key] = sp.csr_matrix((to_numpy(d[key]), self._np["indices"], self._np["indptr"]), shape=(n, n))
+        return self._np[key]
+
+    @property
+    def global_mass(self):
+        return self._csr("m_val")
+
+    @property
+    def global_stiffness(self):
+        return self._csr("k_val")
+
+    @property
+    def global_advection(self):
+        return self._csr("a_val")
+
+    @property
+    def base_system(self):
+        """``M + c (K+A)`` with exact zeros dropped, as scipy's sparse add leaves it (crbe.py:358)."""
+        if "base" not in self._np:
+            s = self._csr("s_val").copy()
+            s.eliminate_zeros()
+            self._np["base"] = s
+        return self._np["base"]
+
+    # ---- time stepping (crbe.py:364-433) ---------------------------------
+    def set_initial_condition(self):
+        self.u_prev = self.problem.initial_condition_fn(self.mesh_data.midpoints)   # crbe.py:365
+
+    def _boundary_xyt(self, t):
+        md = self.mesh_data
+        bnd = md.boundary_segments
+        return np.hstack((md.midpoints[bnd], t * np.ones((bnd.shape[0], 1))))
+
+    def set_boundary_fn(self, t):                                        # crbe.py:367-379
+        md = self.mesh_data
+        bc = np.zeros(md.midpoints.shape[0])
+        bc[md.boundary_segments] = self.problem.boundary_fn(self._boundary_xyt(t))
+        return bc
+
+    def _source_on_device(self, t):
+        """dt-less source values f(midpoint, t) as a device vector, or None when
+        the problem keeps the stock zero source (common.py:72-76)."""
+        prob = self.problem
+        if getattr(type(prob), "source_term", None) is Problem.source_term:
+            return None
+        md, rt = self.mesh_data, self._rt
+        n = md.number_of_segments
+        if self._dev.get("xyt") is None:
+            buf = rt.empty((3, n), torch.float64)
+            buf[:2] = md._dev["midpoints"].t()
+            self._dev["xyt"] = buf
+            self._source_mode = "device"
+        if self._source_mode == "device":
+            buf = self._dev["xyt"]
+            buf[2].fill_(t)
+            try:
+                f = prob.source_term(buf.t())
+                if not isinstance(f, torch.Tensor):
+                    raise TypeError("source_term did not return a tensor")
+                return f.to(torch.float64).contiguous()
+            except Exception:
+                self._source_mode = "host"   # the user's callback only understands numpy
+        xyt = np.hstack((md.midpoints, t * np.ones((n, 1))))               # crbe.py:391-392
+        return rt.upload(np.asarray(prob.source_term(xyt), dtype=np.float64))
+
+    def set_source_term(self, t):
+        """(A, b) of the step at time ``t`` from ``self.u_prev`` (crbe.py:382-404): scipy CSR and numpy."""
+        if not getattr(self, "_assembled", False):
+            raise AttributeError("build_global_matrices() has not been called")
+        self._coef()
+        rt = self._rt
+        rt.bind_stream()
+        u = rt.upload(np.asarray(self.u_prev, dtype=np.float64))
+        b = rt.empty((self.mesh_data.number_of_segments,), torch.float64)
+        rt.call("crbe_solver_rhs", self._solver, ptr(u), ptr(self._source_on_device(t)), float(self.dt), ptr(b))
+        import scipy.sparse as sp
+        base = self.base_system
+        bnd = self.mesh_data.boundary_segments
+        n = base.shape[0]
+        isb = np.zeros(n, bool)
+        isb[bnd] = True
+        rows = np.repeat(np.arange(n), np.diff(base.indptr))
+        keep = ~isb[rows]
+        A = sp.csr_matrix((np.concatenate([base.data[keep], np.ones(len(bnd))]),
+                           (np.concatenate([rows[keep], bnd]), np.concatenate([base.indices[keep], bnd]))), shape=base.shape)
+        A.sort_indices()
+        return A, to_numpy(b)
+
+    def _history_rows(self, n_steps):
+        h = self.history
+        if h == "all":
+            return list(range(n_steps))
+        if h == "last":
+            return [0, n_steps - 1] if n_steps > 1 else [0]
+        stride = int(h)
+        rows = list(range(0, n_steps, stride))
+        if rows[-1] != n_steps - 1:
+            rows.append(n_steps - 1)
+        return rows
+
+    def solve(self):
+        md, rt = self.mesh_data, self._rt
+        rt.bind_stream()
+        # 1. initial condition and storage (crbe.py:408-412)
+        self.set_initial_condition()
+        n_steps = md.nt
+        n = md.number_of_segments
+        rows = self._history_rows(n_steps)
+        row_of = {s: k for k, s in enumerate(rows)}
+        try:
+            sol_t = torch.zeros((len(rows), n), dtype=torch.float64, pin_memory=True)
+        except RuntimeError:
+            sol_t = torch.zeros((len(rows), n), dtype=torch.float64)
+        self.solutions = sol_t.numpy()
+        self.solutions[0, :] = self.u_prev
+        u = rt.upload(np.asarray(self.u_prev, dtype=np.float64))
+        # 2. global matrices and the solver (crbe.py:415)
+        self.build_global_matrices()
+        # 3. time stepping (crbe.py:418-431)
+        stage = [rt.empty((n,), torch.float64), rt.empty((n,), torch.float64)]
+        stage_free = [None, None]
+        copy_stream = torch.cuda.Stream(device=rt.device)
+        main = torch.cuda.current_stream(rt.device)
+        info = _lib.SolveInfo()
+        self.step_info = []
+        show = self.progress if self.progress is not None else (n_steps * n < 2e7)
+        steps = range(1, n_steps)
+        if show and _tqdm is not None:
+            steps = _tqdm(steps, desc="Time-stepping")
+        dt = float(self.dt)
+        reassemble = self.velocity_field is not None
+        start = time.time()
+        k_out = 0
+        for step in steps:
+            t = step * self.dt                                               # crbe.py:420
+            if reassemble:
+                self._reassemble_advection(t)
+            src = self._source_on_device(t)
+            rt.call("crbe_solver_step", self._solver, ptr(u), ptr(src), dt, C.byref(info))
+            self.step_info.append((info.iterations, info.relres, info.true_relres, info.restarts))
+            if step in row_of:
+                # lifted copy of the step's solution (crbe.py:429), staged so the download overlaps the next step
+                bc = rt.upload(np.asarray(self.problem.boundary_fn(self._boundary_xyt(t)), dtype=np.float64))
+                sb = k_out & 1
+                if stage_free[sb] is not None:
+                    main.wait_event(stage_free[sb])
+                rt.call("crbe_solver_lift", self._solver, ptr(u), ptr(bc), ptr(stage[sb]))
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ready)
+                    sol_t[row_of[step]].copy_(stage[sb], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(copy_stream)
+                stage_free[sb] = done
+                self._last_stage = stage[sb]
+                k_out += 1
+        copy_stream.synchronize()
+        rt.synchronize()
+        self.solve_time = time.time() - start
+        self.u_prev = to_numpy(u)
+        self._dev["u"] = u
+        print(f"Solve completed in {self.solve_time:.2f}s")
+        return self.solutions
+
+    def _reassemble_advection(self, t):
+        md, rt, d = self.mesh_data, self._rt, self._dev
+        m = md._dev
+        v_elem = self._element_velocity(t)
+        rt.call("crbe_assemble", rt.ctx, ptr(m["points"]), ptr(m["tri"]), ptr(m["areas"]), ptr(d["scatter_pos"]),
+                ptr(d["order"]), self._colour_offsets, self.n_colours, self._nnz, float(self.problem.D), 0.0, 0.0,
+                ptr(v_elem), ptr(None), ptr(None), ptr(d["a_val"]))
+        coef = self._coef()
+        rt.call("crbe_system_values", rt.ctx, self._nnz, ptr(d["m_val"]), ptr(d["k_val"]), ptr(d["a_val"]), coef, ptr(d["s_val"]))
+        if self.time_scheme_order == 2:
+            rt.call("crbe_system_values", rt.ctx, self._nnz, ptr(d["m_val"]), ptr(d["k_val"]), ptr(d["a_val"]), -coef,
+                    ptr(d["r_val"]))
+        self._np.clear()
+        rt.call("crbe_solver_set_system", self._solver, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
+
+    # ---- errors (crbe.py:435-482) -----------------------------------------
+    def compute_errors(self, analytical_sol_fn):
+        """(rel_l2, l2, max) of the last stored solution against
+        ``analytical_sol_fn`` at ``t = domain.T`` at the edge midpoints
+        (unweighted discrete norms, crbe.py:447-453), reduced on the device."""
+        md, rt = self.mesh_data, self._rt
+        rt.bind_stream()
+        midpoints = md.midpoints
+        xyt = np.hstack([midpoints, np.full((midpoints.shape[0], 1), self.domain.T)])
+        u_exact = rt.upload(np.asarray(analytical_sol_fn(xyt), dtype=np.float64))
+        u_num = rt.upload(np.ascontiguousarray(self.solutions[-1, :]))
+        out = (C.c_double * 3)()
+        rt.call("crbe_errors", rt.ctx, md.number_of_segments, ptr(u_exact), ptr(u_num), out)
+        return np.float64(out[0]), np.float64(out[1]), np.float64(out[2])
+
+    # ---- plotting (crbe.py:485-660): host-side, needs matplotlib -----------
+    def plot_solution(self, analytical_sol_fn=None, time_index=None, save_dir="results"):
+        from .plotting import plot_solution
+        return plot_solution(self, analytical_sol_fn, time_index, save_dir)
+
+    def plot_error_evolution(self, errors, save_dir="results"):
+        from .plotting import plot_error_evolution
+        return plot_error_evolution(self, errors, save_dir)
+
+    def plot_interpolated_solution(self, analytical_sol_fn=None, time_index=None, save_dir="results", name=""):
+        from .plotting import plot_interpolated_solution
+        return plot_interpolated_solution(self, analytical_sol_fn, time_index, save_dir, name)

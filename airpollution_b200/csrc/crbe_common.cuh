@@ -1,0 +1,146 @@
+// Shared internals of libcrbe_b200: context, error plumbing, launch sizing,
+// warp/block reductions and the deterministic grid-wide reduction used by every
+// dot-product kernel.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/crbe_b200.h"
+
+void crbe_set_error(const char* fmt, ...);
+
+#define CRBE_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            crbe_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return CRBE_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+#define CRBE_CHECK(expr)                 \
+    do {                                 \
+        int rc_ = (expr);                \
+        if (rc_ != CRBE_OK) return rc_;  \
+    } while (0)
+
+#define CRBE_REQUIRE(cond, msg)                                            \
+    do {                                                                   \
+        if (!(cond)) {                                                     \
+            crbe_set_error("%s:%d: %s (%s)", __FILE__, __LINE__, msg, #cond); \
+            return CRBE_ERR_ARG;                                           \
+        }                                                                  \
+    } while (0)
+
+#define CRBE_KERNEL_CHECK() CRBE_CUDA(cudaGetLastError())
+
+constexpr int CRBE_BLOCK = 256;           // threads per CTA for the streaming kernels
+constexpr int CRBE_MAX_PARTIAL_BLOCKS = 4096;
+constexpr int CRBE_NSUMS = 16;            // slots of the device sums buffer
+
+struct crbe_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    // scratch for grid-wide reductions: partials[3][CRBE_MAX_PARTIAL_BLOCKS], arrival counter
+    double* partials = nullptr;
+    unsigned int* counter = nullptr;
+    double* dev_scalars = nullptr;   // small device buffer for results of utility reductions
+    double* host_scalars = nullptr;  // pinned
+    int64_t launches = 0;            // kernels launched through this context (for bench accounting)
+};
+
+// Persistent-style launch: enough CTAs to fill every SM at full occupancy, never more
+// than the work needs.  Rows are walked with a grid-stride loop.
+static inline int crbe_grid_for(const crbe_ctx* ctx, int64_t n, int block = CRBE_BLOCK, int ctas_per_sm = 8) {
+    int64_t need = (n + block - 1) / block;
+    int64_t cap = (int64_t)ctx->sm_count * ctas_per_sm;
+    if (cap > CRBE_MAX_PARTIAL_BLOCKS) cap = CRBE_MAX_PARTIAL_BLOCKS;
+    int64_t g = need < cap ? need : cap;
+    return g < 1 ? 1 : (int)g;
+}
+
+// Grid for a grid-stride kernel that must run as ONE resident wave: SMs x the CTAs of
+// this kernel that fit on an SM (register/shared-memory limited), capped by the work.
+template <class Kern>
+static inline int crbe_persistent_grid(const crbe_ctx* ctx, Kern kernel, int64_t n, int block = CRBE_BLOCK) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return crbe_grid_for(ctx, n, block, per_sm);
+}
+
+// core.cu
+int crbe_exclusive_scan_i32(crbe_ctx* ctx, const int32_t* in_d, int32_t* out_d, int64_t n, int64_t* total_h);
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, d));
+    return v;
+}
+
+// Sum of NV values over the CTA; result valid in thread 0.  Fixed shuffle tree: deterministic.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV]) {
+    __shared__ double sh[NV][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();  // protect sh against a previous use in the same kernel
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sh[k][w] = v[k];
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double t = lane < nw ? sh[k][lane] : 0.0;
+            v[k] = warp_sum(t);
+        }
+    }
+}
+
+// Grid-wide deterministic sum: every CTA stores its partial, the last CTA to
+// arrive adds the partials in index order and writes out[k].  No floating-point
+// atomics, so the result does not depend on CTA scheduling.  `counter` wraps
+// back to zero by itself (atomicInc), so the scratch is reusable by the next
+// kernel in the stream.
+template <int NV>
+__device__ __forceinline__ void grid_sum(double (&v)[NV], double* partials, unsigned int* counter,
+                                         double* const (&out)[NV]) {
+    block_sum<NV>(v);
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) partials[k * CRBE_MAX_PARTIAL_BLOCKS + blockIdx.x] = v[k];
+        __threadfence();
+        unsigned int t = atomicInc(counter, gridDim.x - 1);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        acc[k] = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+            acc[k] += __ldcg(&partials[k * CRBE_MAX_PARTIAL_BLOCKS + b]);
+    }
+    block_sum<NV>(acc);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) *out[k] = acc[k];
+    }
+}
+
+#endif  // __CUDACC__

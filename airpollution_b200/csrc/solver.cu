@@ -1,0 +1,812 @@
+// The per-step linear solve of BESCRFEM (crbe.py:382-429) on the device:
+// right-hand side, Dirichlet rows, and a Jacobi-preconditioned BiCGStab in
+// float64 in place of the reference's per-step SuperLU factorisation
+// (crbe.py:426).
+//
+// Data layout (HBM)
+//   A CR matrix row has the diagonal plus at most four off-diagonals (an edge
+//   belongs to <= 2 triangles with two other edges each).  The solver keeps
+//   the Dirichlet system row-scaled by its diagonal (Jacobi folded in, unit
+//   diagonal implicit) in a column-major 4-slot ELL layout:
+//       ell_val[k*ld + i], ell_col[k*ld + i]   k = 0..3,  ld = N rounded up to 32
+//   so a warp reads 32 consecutive doubles / ints per slot (fully coalesced,
+//   48 B per row instead of CSR's 64 B) and gathers x through L1/L2.  The CSR
+//   arrays stay the exchange format with the host (scipy) side.
+//
+// Kernels per BiCGStab iteration (FUSED):   bytes per row (fp64 vectors)
+//   k_pv : p = r + beta (p - omega v) recomputed at the neighbours, v = A p, (r^,v)   48 + 6*8
+//   k_st : s = r - alpha v recomputed at the neighbours,          t = A s, (t,s),(t,t) 48 + 4*8
+//   k_xr : x += alpha p + omega s, r = s - omega t, (r^,r), (r,r)                            7*8
+// Scalars (alpha, beta, omega) never visit the host: each kernel derives them
+// from a small device buffer of dot products written by the last CTA of the
+// producing kernel (deterministic two-stage reduction, no float atomics).
+// Kernels launched after convergence return at once, so the host enqueues a
+// predicted number of iterations and synchronises once per batch.
+#include <math.h>
+#include <string.h>
+
+#include "crbe_common.cuh"
+
+enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RRTRUE = 7, S_AUX0 = 8, S_AUX1 = 9 };
+enum { D_STATUS = 0, D_ITERS = 1 };
+
+struct crbe_solver {
+    crbe_ctx* ctx = nullptr;
+    int64_t n = 0, ld = 0, nnz = 0, nb = 0;
+    const int32_t* indptr = nullptr;   // caller-owned structural pattern
+    const int32_t* indices = nullptr;
+    int32_t* bnd = nullptr;            // Dirichlet row ids (copy)
+    unsigned char* is_bnd = nullptr;
+    int32_t* ell_col = nullptr;
+    double* ell_val = nullptr;
+    double *mdiag = nullptr, *mscale = nullptr, *dscale = nullptr;
+    double* rhs_val = nullptr;         // CN: values of M - c(K+A) on the structural pattern
+    double *b = nullptr, *r = nullptr, *rh = nullptr, *s = nullptr, *t = nullptr, *tmp = nullptr;
+    double* p[2] = {nullptr, nullptr};
+    double* v[2] = {nullptr, nullptr};
+    double* sums = nullptr;
+    int* dstate = nullptr;
+    double* sums_h = nullptr;  // pinned: CRBE_NSUMS doubles followed by 2 ints
+    double rtol = 1e-13;
+    int maxit = 10000;
+    unsigned flags = CRBE_SOLVER_FUSED | CRBE_SOLVER_VERIFY;
+    int last_iters = 8;
+    bool system_loaded = false;
+    // persistent grids: SMs x resident CTAs of each kernel (a grid-stride sweep must be one full wave)
+    int g_init = 1, g_pv = 1, g_st = 1, g_xr = 1, g_vec = 1, g_res = 1, g_spmv = 1;
+};
+
+// ---------------------------------------------------------------- helpers
+__device__ __forceinline__ bool solver_idle(const double* __restrict__ sums, const int* __restrict__ dstate, double rtol2) {
+    return dstate[D_STATUS] != 0 || !(sums[S_RR] > rtol2 * sums[S_BB]);
+}
+
+// y_i = x_i + sum_k val[k][i] * x[col[k][i]]   (unit diagonal implicit)
+template <class F>
+__device__ __forceinline__ double ell_row(const double* __restrict__ val, const int* __restrict__ col, int64_t ld, int64_t i,
+                                          double xi, F xat) {
+    double a[4];
+    int c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a[k] = __ldcs(val + k * ld + i);   // streamed once per sweep: keep L2 for the gathered vectors
+        c[k] = __ldcs(col + k * ld + i);
+    }
+    double acc = xi;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc = fma(a[k], xat(c[k]), acc);
+    return acc;
+}
+
+// grid_sum + "am I thread 0 of the last CTA" for bookkeeping writes
+template <int NV>
+__device__ __forceinline__ bool grid_sum_last(double (&v)[NV], double* partials, unsigned int* counter, double* const (&out)[NV]) {
+    block_sum<NV>(v);
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) partials[k * CRBE_MAX_PARTIAL_BLOCKS + blockIdx.x] = v[k];
+        __threadfence();
+        unsigned int tk = atomicInc(counter, gridDim.x - 1);
+        last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        acc[k] = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) acc[k] += __ldcg(&partials[k * CRBE_MAX_PARTIAL_BLOCKS + b]);
+    }
+    block_sum<NV>(acc);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) *out[k] = acc[k];
+        return true;
+    }
+    return false;
+}
+
+#define ROW_LOOP(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+// ---------------------------------------------------------------- set-up kernels
+__global__ void k_mark_boundary(const int* __restrict__ bnd, int64_t nb, unsigned char* __restrict__ is_bnd) {
+    ROW_LOOP(k, nb) is_bnd[bnd[k]] = 1;
+}
+
+// Dirichlet rows -> identity (crbe.py:399-401); other rows divided by their diagonal.
+__global__ void __launch_bounds__(CRBE_BLOCK) k_build_ell(int64_t n, int64_t ld, const int* __restrict__ indptr, const int* __restrict__ indices,
+                                                          const double* __restrict__ sval, const double* __restrict__ mval,
+                                                          const unsigned char* __restrict__ is_bnd, int* __restrict__ ecol,
+                                                          double* __restrict__ eval, double* __restrict__ mdiag, double* __restrict__ mscale,
+                                                          double* __restrict__ dscale, int* __restrict__ err) {
+    ROW_LOOP(i, n) {
+        const int p0 = indptr[i], p1 = indptr[i + 1];
+        double d = 0.0, m = 0.0;
+        bool have_diag = false;
+        for (int p = p0; p < p1; ++p)
+            if (indices[p] == (int)i) {
+                d = sval[p];
+                m = mval[p];
+                have_diag = true;
+            }
+        const bool bd = is_bnd[i] != 0;
+        if (!have_diag || p1 - p0 > 5 || (!bd && !(fabs(d) > 0.0))) atomicOr(err, !have_diag ? 1 : (p1 - p0 > 5 ? 2 : 4));
+        int k = 0;
+        if (!bd) {
+            for (int p = p0; p < p1 && k < 4; ++p) {
+                const int c = indices[p];
+                if (c == (int)i) continue;
+                ecol[k * ld + i] = c;
+                eval[k * ld + i] = sval[p] / d;
+                ++k;
+            }
+        }
+        for (; k < 4; ++k) {
+            ecol[k * ld + i] = (int)i;
+            eval[k * ld + i] = 0.0;
+        }
+        mdiag[i] = m;
+        mscale[i] = bd ? 0.0 : m / d;
+        dscale[i] = bd ? 0.0 : 1.0 / d;
+    }
+}
+
+__global__ void k_zero_rows(double* __restrict__ u, const int* __restrict__ bnd, int64_t nb) {
+    ROW_LOOP(k, nb) u[bnd[k]] = 0.0;
+}
+
+__global__ void k_lift(const double* __restrict__ bc, const int* __restrict__ bnd, int64_t nb, double* __restrict__ out) {
+    ROW_LOOP(k, nb) out[bnd[k]] += bc[k];
+}
+
+// ---------------------------------------------------------------- BiCGStab kernels
+// MODE 0: Backward Euler right-hand side  b = (M_ii u_i + dt f_i) / d_i     (crbe.py:384,394,402)
+// MODE 1: b = scale_i * (bin_i + dt f_i), scale_i = 1/d_i (0 on Dirichlet rows)           (CN, crbe.py:386)
+// MODE 2: b = bin_i / d_i, Dirichlet rows keep bin_i                                    (generic solve)
+// then r = r^ = b - A x and the norms (b,b), (r,r).
+template <int MODE>
+__global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, const double* __restrict__ eval, const int* __restrict__ ecol,
+                                                     const double* __restrict__ x, const double* __restrict__ bin,
+                                                     const double* __restrict__ src, double dt, const double* __restrict__ mscale,
+                                                     const double* __restrict__ dscale, const unsigned char* __restrict__ is_bnd,
+                                                     double* __restrict__ b, double* __restrict__ r, double* __restrict__ rh,
+                                                     double* sums, int* dstate, double* partials, unsigned int* counter) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        dstate[D_STATUS] = 0;
+        dstate[D_ITERS] = 0;
+    }
+    double acc[3] = {0.0, 0.0, 0.0};
+    ROW_LOOP(i, n) {
+        const double xi = x[i];
+        double bi;
+        if (MODE == 0) {
+            bi = mscale[i] * xi;
+            if (src) bi = fma(dscale[i] * dt, src[i], bi);
+        } else if (MODE == 1) {
+            double raw = bin[i];
+            if (src) raw = fma(dt, src[i], raw);
+            bi = dscale[i] * raw;
+        } else {
+            bi = is_bnd[i] ? bin[i] : dscale[i] * bin[i];
+        }
+        const double ax = ell_row(eval, ecol, ld, i, xi, [&](int j) { return __ldg(x + j); });
+        const double ri = bi - ax;
+        b[i] = bi;
+        r[i] = ri;
+        rh[i] = ri;
+        acc[0] = fma(bi, bi, acc[0]);
+        acc[1] = fma(ri, ri, acc[1]);
+    }
+    acc[2] = acc[1];
+    double* const out[3] = {sums + S_BB, sums + S_RR, sums + S_RHO0};
+    grid_sum_last<3>(acc, partials, counter, out);
+}
+
+struct IterScalars {
+    double alpha, omega, beta;
+    bool bad;
+};
+
+// beta_k and omega_{k-1} from the dot products of iteration k-1
+__device__ __forceinline__ IterScalars scalars_for_p(const double* __restrict__ sums, int k) {
+    IterScalars sc;
+    const double rho_new = sums[S_RHO0 + (k & 1)], rho_old = sums[S_RHO0 + ((k - 1) & 1)];
+    const double tt = sums[S_TT];
+    sc.alpha = rho_old / sums[S_RHV];
+    sc.omega = tt > 0.0 ? sums[S_TS] / tt : 0.0;
+    sc.beta = (rho_new / rho_old) * (sc.alpha / sc.omega);
+    sc.bad = !isfinite(sc.beta);
+    return sc;
+}
+
+__device__ __forceinline__ double p_update(double r, double p, double v, double beta, double omega) {
+    return fma(beta, fma(-omega, v, p), r);   // explicit fma: identical bits wherever it is recomputed
+}
+
+// unfused: p = r (k == 0) or p = r + beta (p - omega v)
+__global__ void __launch_bounds__(CRBE_BLOCK) k_p(int64_t n, int k, double rtol2, const double* __restrict__ r, const double* __restrict__ v,
+                                                  double* __restrict__ p, const double* sums, int* dstate) {
+    if (solver_idle(sums, dstate, rtol2)) return;
+    IterScalars sc = {0, 0, 0, false};
+    if (k > 0) {
+        sc = scalars_for_p(sums, k);
+        if (sc.bad) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
+            return;
+        }
+    }
+    ROW_LOOP(i, n) p[i] = k > 0 ? p_update(r[i], p[i], v[i], sc.beta, sc.omega) : r[i];
+}
+
+// v = A p, (r^, v).  FUSED: p is first advanced (here and at the gathered neighbours) from p_in, v_in.
+template <bool FUSED>
+__global__ void __launch_bounds__(CRBE_BLOCK) k_pv(int64_t n, int64_t ld, int k, double rtol2, const double* __restrict__ eval,
+                                                   const int* __restrict__ ecol, const double* __restrict__ r,
+                                                   const double* __restrict__ p_in, const double* __restrict__ v_in,
+                                                   double* __restrict__ p_out, double* __restrict__ v_out,
+                                                   const double* __restrict__ rh, double* sums, int* dstate, double* partials,
+                                                   unsigned int* counter) {
+    if (solver_idle(sums, dstate, rtol2)) return;
+    IterScalars sc = {0, 0, 0, false};
+    if (FUSED && k > 0) {
+        sc = scalars_for_p(sums, k);
+        if (sc.bad) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
+            return;
+        }
+    }
+    double acc[1] = {0.0};
+    ROW_LOOP(i, n) {
+        double pi, vi;
+        if (FUSED) {
+            const double beta = sc.beta, omega = sc.omega;
+            auto pnew = [&](int64_t j) {
+                return k > 0 ? p_update(__ldg(r + j), __ldg(p_in + j), __ldg(v_in + j), beta, omega) : __ldg(r + j);
+            };
+            pi = pnew(i);
+            p_out[i] = pi;
+            vi = ell_row(eval, ecol, ld, i, pi, [&](int j) { return pnew(j); });
+        } else {
+            pi = p_in[i];
+            vi = ell_row(eval, ecol, ld, i, pi, [&](int j) { return __ldg(p_in + j); });
+        }
+        v_out[i] = vi;
+        acc[0] = fma(rh[i], vi, acc[0]);
+    }
+    double* const out[1] = {sums + S_RHV};
+    grid_sum_last<1>(acc, partials, counter, out);
+}
+
+// unfused: s = r - alpha v
+__global__ void __launch_bounds__(CRBE_BLOCK) k_s(int64_t n, int k, double rtol2, const double* __restrict__ r, const double* __restrict__ v,
+                                                  double* __restrict__ s, const double* sums, int* dstate) {
+    if (solver_idle(sums, dstate, rtol2)) return;
+    const double alpha = sums[S_RHO0 + (k & 1)] / sums[S_RHV];
+    if (!isfinite(alpha)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
+        return;
+    }
+    ROW_LOOP(i, n) s[i] = fma(-alpha, v[i], r[i]);
+}
+
+// t = A s, (t,s), (t,t).  FUSED: s = r - alpha v is formed here (and at the gathered neighbours).
+template <bool FUSED>
+__global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, int k, double rtol2, const double* __restrict__ eval,
+                                                   const int* __restrict__ ecol, const double* __restrict__ r, const double* __restrict__ v,
+                                                   double* __restrict__ s, double* __restrict__ t, double* sums, int* dstate,
+                                                   double* partials, unsigned int* counter) {
+    if (solver_idle(sums, dstate, rtol2)) return;
+    double alpha = 0.0;
+    if (FUSED) {
+        alpha = sums[S_RHO0 + (k & 1)] / sums[S_RHV];
+        if (!isfinite(alpha)) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
+            return;
+        }
+    }
+    double acc[2] = {0.0, 0.0};
+    ROW_LOOP(i, n) {
+        double si, ti;
+        if (FUSED) {
+            auto snew = [&](int64_t j) { return fma(-alpha, __ldg(v + j), __ldg(r + j)); };
+            si = snew(i);
+            s[i] = si;
+            ti = ell_row(eval, ecol, ld, i, si, [&](int j) { return snew(j); });
+        } else {
+            si = s[i];
+            ti = ell_row(eval, ecol, ld, i, si, [&](int j) { return __ldg(s + j); });
+        }
+        t[i] = ti;
+        acc[0] = fma(ti, si, acc[0]);
+        acc[1] = fma(ti, ti, acc[1]);
+    }
+    double* const out[2] = {sums + S_TS, sums + S_TT};
+    grid_sum_last<2>(acc, partials, counter, out);
+}
+
+// x += alpha p + omega s;  r = s - omega t;  rho_{k+1} = (r^, r);  (r, r)
+__global__ void __launch_bounds__(CRBE_BLOCK) k_xr(int64_t n, int k, double rtol2, const double* __restrict__ p, const double* __restrict__ s,
+                                                   const double* __restrict__ t, const double* __restrict__ rh, double* __restrict__ x,
+                                                   double* __restrict__ r, double* sums, int* dstate, double* partials,
+                                                   unsigned int* counter) {
+    if (solver_idle(sums, dstate, rtol2)) return;
+    const double alpha = sums[S_RHO0 + (k & 1)] / sums[S_RHV];
+    const double tt = sums[S_TT];
+    const double omega = tt > 0.0 ? sums[S_TS] / tt : 0.0;
+    if (!isfinite(alpha) || !isfinite(omega)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
+        return;
+    }
+    double acc[2] = {0.0, 0.0};
+    ROW_LOOP(i, n) {
+        const double si = s[i];
+        x[i] = fma(alpha, p[i], fma(omega, si, x[i]));
+        const double ri = fma(-omega, t[i], si);
+        r[i] = ri;
+        acc[0] = fma(rh[i], ri, acc[0]);
+        acc[1] = fma(ri, ri, acc[1]);
+    }
+    double* const out[2] = {sums + S_RHO0 + ((k + 1) & 1), sums + S_RR};
+    if (grid_sum_last<2>(acc, partials, counter, out)) dstate[D_ITERS] += 1;
+}
+
+// true residual r = r^ = b - A x and its norm (restart / verification)
+__global__ void __launch_bounds__(CRBE_BLOCK) k_residual(int64_t n, int64_t ld, const double* __restrict__ eval, const int* __restrict__ ecol,
+                                                         const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
+                                                         double* __restrict__ rh, double* sums, double* partials, unsigned int* counter) {
+    double acc[1] = {0.0};
+    ROW_LOOP(i, n) {
+        const double ax = ell_row(eval, ecol, ld, i, x[i], [&](int j) { return __ldg(x + j); });
+        const double ri = b[i] - ax;
+        r[i] = ri;
+        rh[i] = ri;
+        acc[0] = fma(ri, ri, acc[0]);
+    }
+    double* const out[1] = {sums + S_RRTRUE};
+    grid_sum_last<1>(acc, partials, counter, out);
+}
+
+__global__ void k_restart(double* sums, int* dstate) {
+    sums[S_RR] = sums[S_RRTRUE];
+    sums[S_RHO0] = sums[S_RRTRUE];
+    dstate[D_STATUS] = 0;
+    dstate[D_ITERS] = 0;
+}
+
+// ---------------------------------------------------------------- general CSR SpMV
+// y = A x with the row sums accumulated in storage order without FMA -- the
+// arithmetic of scipy's csr_matvec, so results can be compared bit for bit.
+// A CTA owns 256 consecutive rows; their non-zeros form one contiguous span of
+// val/col which the CTA reads fully coalesced, multiplying on the fly into
+// shared memory; each thread then adds up its own row from shared memory.
+constexpr int SPMV_CAP = 2048;
+
+__global__ void __launch_bounds__(CRBE_BLOCK) k_spmv_csr(int64_t n, const int* __restrict__ indptr, const int* __restrict__ indices,
+                                                         const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y) {
+    __shared__ double prod[SPMV_CAP];
+    const int64_t nblk = (n + CRBE_BLOCK - 1) / CRBE_BLOCK;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int64_t row0 = blk * CRBE_BLOCK;
+        const int64_t row1 = row0 + CRBE_BLOCK < n ? row0 + CRBE_BLOCK : n;
+        const int p_begin = indptr[row0], p_end = indptr[row1];
+        const int cnt = p_end - p_begin;
+        const int64_t row = row0 + threadIdx.x;
+        if (cnt <= SPMV_CAP) {
+            for (int q = threadIdx.x; q < cnt; q += CRBE_BLOCK)
+                prod[q] = __dmul_rn(__ldcs(val + p_begin + q), __ldg(x + __ldcs(indices + p_begin + q)));
+            __syncthreads();
+            if (row < n) {
+                double sum = 0.0;
+                for (int q = indptr[row] - p_begin, e = indptr[row + 1] - p_begin; q < e; ++q) sum = __dadd_rn(sum, prod[q]);
+                y[row] = sum;
+            }
+            __syncthreads();
+        } else if (row < n) {
+            double sum = 0.0;
+            for (int q = indptr[row]; q < indptr[row + 1]; ++q) sum = __dadd_rn(sum, __dmul_rn(val[q], __ldg(x + indices[q])));
+            y[row] = sum;
+        }
+    }
+}
+
+extern "C" int crbe_spmv_csr(crbe_ctx* ctx, int64_t n, const int32_t* indptr_d, const int32_t* indices_d, const double* val_d,
+                             const double* x_d, double* y_d) {
+    CRBE_REQUIRE(ctx && (n == 0 || (indptr_d && indices_d && val_d && x_d && y_d)), "null argument");
+    if (n == 0) return CRBE_OK;
+    k_spmv_csr<<<crbe_grid_for(ctx, n), CRBE_BLOCK, 0, ctx->stream>>>(n, indptr_d, indices_d, val_d, x_d, y_d);
+    CRBE_KERNEL_CHECK();
+    ctx->launches += 1;
+    return CRBE_OK;
+}
+
+// ---------------------------------------------------------------- small reductions for the API
+__global__ void __launch_bounds__(CRBE_BLOCK) k_dot(int64_t n, const double* __restrict__ x, const double* __restrict__ y, double* out,
+                                                    double* partials, unsigned int* counter) {
+    double acc[1] = {0.0};
+    ROW_LOOP(i, n) acc[0] = fma(x[i], y[i], acc[0]);
+    double* const o[1] = {out};
+    grid_sum_last<1>(acc, partials, counter, o);
+}
+
+extern "C" int crbe_dot(crbe_ctx* ctx, int64_t n, const double* x_d, const double* y_d, double* out_h) {
+    CRBE_REQUIRE(ctx && out_h && (n == 0 || (x_d && y_d)), "null argument");
+    *out_h = 0.0;
+    if (n == 0) return CRBE_OK;
+    k_dot<<<crbe_grid_for(ctx, n), CRBE_BLOCK, 0, ctx->stream>>>(n, x_d, y_d, ctx->dev_scalars, ctx->partials, ctx->counter);
+    CRBE_KERNEL_CHECK();
+    ctx->launches += 1;
+    CRBE_CUDA(cudaMemcpyAsync(ctx->host_scalars, ctx->dev_scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out_h = ctx->host_scalars[0];
+    return CRBE_OK;
+}
+
+// crbe.py:447-453: error = |u_exact - u_num|; max; sqrt(sum error^2); sqrt(sum u_exact^2)
+__global__ void __launch_bounds__(CRBE_BLOCK) k_errors(int64_t n, const double* __restrict__ ue, const double* __restrict__ un, double* out,
+                                                       unsigned long long* max_bits, double* partials, unsigned int* counter) {
+    double acc[2] = {0.0, 0.0};
+    double emax = 0.0;
+    ROW_LOOP(i, n) {
+        const double e = fabs(ue[i] - un[i]);
+        emax = fmax(emax, e);
+        acc[0] = fma(e, e, acc[0]);
+        acc[1] = fma(ue[i], ue[i], acc[1]);
+    }
+    emax = warp_max(emax);
+    if ((threadIdx.x & 31) == 0) atomicMax(max_bits, (unsigned long long)__double_as_longlong(emax));
+    double* const o[2] = {out, out + 1};
+    grid_sum_last<2>(acc, partials, counter, o);
+}
+
+extern "C" int crbe_errors(crbe_ctx* ctx, int64_t n, const double* u_exact_d, const double* u_num_d, double* out3_h) {
+    CRBE_REQUIRE(ctx && out3_h && n > 0 && u_exact_d && u_num_d, "bad argument");
+    unsigned long long* max_bits = (unsigned long long*)(ctx->dev_scalars + 2);
+    CRBE_CUDA(cudaMemsetAsync(max_bits, 0, sizeof(unsigned long long), ctx->stream));
+    k_errors<<<crbe_grid_for(ctx, n), CRBE_BLOCK, 0, ctx->stream>>>(n, u_exact_d, u_num_d, ctx->dev_scalars, max_bits, ctx->partials,
+                                                                   ctx->counter);
+    CRBE_KERNEL_CHECK();
+    ctx->launches += 1;
+    CRBE_CUDA(cudaMemcpyAsync(ctx->host_scalars, ctx->dev_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double l2 = sqrt(ctx->host_scalars[0]);
+    out3_h[0] = l2 / sqrt(ctx->host_scalars[1]);
+    out3_h[1] = l2;
+    out3_h[2] = ctx->host_scalars[2];
+    return CRBE_OK;
+}
+
+// ---------------------------------------------------------------- solver object
+static int solver_release(crbe_solver* s) {
+    if (!s) return CRBE_OK;
+    cudaFree(s->bnd);
+    cudaFree(s->is_bnd);
+    cudaFree(s->ell_col);
+    cudaFree(s->ell_val);
+    cudaFree(s->mdiag);
+    cudaFree(s->mscale);
+    cudaFree(s->dscale);
+    cudaFree(s->rhs_val);
+    cudaFree(s->b);
+    cudaFree(s->r);
+    cudaFree(s->rh);
+    cudaFree(s->s);
+    cudaFree(s->t);
+    cudaFree(s->tmp);
+    cudaFree(s->p[0]);
+    cudaFree(s->p[1]);
+    cudaFree(s->v[0]);
+    cudaFree(s->v[1]);
+    cudaFree(s->sums);
+    cudaFree(s->dstate);
+    cudaFreeHost(s->sums_h);
+    delete s;
+    return CRBE_OK;
+}
+
+extern "C" int crbe_solver_create(crbe_ctx* ctx, int64_t n, const int32_t* indptr_d, const int32_t* indices_d, int64_t nnz,
+                                  const int32_t* bnd_seg_d, int64_t nb, crbe_solver** out) {
+    CRBE_REQUIRE(ctx && out && n > 0 && indptr_d && indices_d && nnz > 0 && nb >= 0 && (nb == 0 || bnd_seg_d), "bad argument");
+    crbe_solver* s = new crbe_solver();
+    s->ctx = ctx;
+    s->n = n;
+    s->ld = (n + 31) / 32 * 32;
+    s->nnz = nnz;
+    s->nb = nb;
+    s->indptr = indptr_d;
+    s->indices = indices_d;
+    *out = s;
+    const size_t vb = sizeof(double) * (size_t)n;
+    CRBE_CUDA(cudaMalloc(&s->is_bnd, (size_t)n));
+    CRBE_CUDA(cudaMemsetAsync(s->is_bnd, 0, (size_t)n, ctx->stream));
+    if (nb > 0) {
+        CRBE_CUDA(cudaMalloc(&s->bnd, sizeof(int32_t) * nb));
+        CRBE_CUDA(cudaMemcpyAsync(s->bnd, bnd_seg_d, sizeof(int32_t) * nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        k_mark_boundary<<<crbe_grid_for(ctx, nb), CRBE_BLOCK, 0, ctx->stream>>>(s->bnd, nb, s->is_bnd);
+        CRBE_KERNEL_CHECK();
+    }
+    CRBE_CUDA(cudaMalloc(&s->ell_col, sizeof(int32_t) * 4 * s->ld));
+    CRBE_CUDA(cudaMalloc(&s->ell_val, sizeof(double) * 4 * s->ld));
+    double** vecs[] = {&s->mdiag, &s->mscale, &s->dscale, &s->b, &s->r, &s->rh, &s->s, &s->t, &s->p[0], &s->v[0]};
+    for (double** vp : vecs) CRBE_CUDA(cudaMalloc(vp, vb));
+    CRBE_CUDA(cudaMalloc(&s->sums, sizeof(double) * CRBE_NSUMS));
+    CRBE_CUDA(cudaMemsetAsync(s->sums, 0, sizeof(double) * CRBE_NSUMS, ctx->stream));
+    CRBE_CUDA(cudaMalloc(&s->dstate, sizeof(int) * 4));
+    CRBE_CUDA(cudaMemsetAsync(s->dstate, 0, sizeof(int) * 4, ctx->stream));
+    CRBE_CUDA(cudaMallocHost(&s->sums_h, sizeof(double) * (CRBE_NSUMS + 2)));
+    {   // one resident wave per kernel; the fused and unfused variants share a grid (the smaller one)
+        const int a = crbe_persistent_grid(ctx, k_pv<true>, n), b = crbe_persistent_grid(ctx, k_pv<false>, n);
+        s->g_pv = a < b ? a : b;
+        const int c = crbe_persistent_grid(ctx, k_st<true>, n), d = crbe_persistent_grid(ctx, k_st<false>, n);
+        s->g_st = c < d ? c : d;
+        const int i0 = crbe_persistent_grid(ctx, k_init<0>, n), i1 = crbe_persistent_grid(ctx, k_init<1>, n),
+                  i2 = crbe_persistent_grid(ctx, k_init<2>, n);
+        s->g_init = i0 < i1 ? (i0 < i2 ? i0 : i2) : (i1 < i2 ? i1 : i2);
+        s->g_xr = crbe_persistent_grid(ctx, k_xr, n);
+        s->g_vec = crbe_persistent_grid(ctx, k_p, n);
+        s->g_res = crbe_persistent_grid(ctx, k_residual, n);
+        s->g_spmv = crbe_persistent_grid(ctx, k_spmv_csr, n);
+    }
+    CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CRBE_OK;
+}
+
+extern "C" int crbe_solver_destroy(crbe_solver* s) {
+    if (s) cudaStreamSynchronize(s->ctx->stream);
+    return solver_release(s);
+}
+
+extern "C" int crbe_solver_set_options(crbe_solver* s, double rtol, int32_t max_iterations, uint32_t flags) {
+    CRBE_REQUIRE(s && rtol > 0.0 && rtol < 1.0 && max_iterations > 0, "bad solver options");
+    s->rtol = rtol;
+    s->maxit = max_iterations;
+    s->flags = flags;
+    return CRBE_OK;
+}
+
+extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, const double* m_val_d, const double* rhs_val_d) {
+    CRBE_REQUIRE(s && s_val_d && m_val_d, "null argument");
+    crbe_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    int* err = s->dstate + 2;
+    CRBE_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+    k_build_ell<<<crbe_grid_for(ctx, s->n), CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->indptr, s->indices, s_val_d, m_val_d, s->is_bnd,
+                                                                 s->ell_col, s->ell_val, s->mdiag, s->mscale, s->dscale, err);
+    CRBE_KERNEL_CHECK();
+    ctx->launches += 1;
+    if (rhs_val_d) {
+        if (!s->rhs_val) CRBE_CUDA(cudaMalloc(&s->rhs_val, sizeof(double) * s->nnz));
+        if (!s->tmp) CRBE_CUDA(cudaMalloc(&s->tmp, sizeof(double) * s->n));
+        CRBE_CUDA(cudaMemcpyAsync(s->rhs_val, rhs_val_d, sizeof(double) * s->nnz, cudaMemcpyDeviceToDevice, st));
+    } else if (s->rhs_val) {
+        cudaFree(s->rhs_val);
+        s->rhs_val = nullptr;
+    }
+    int err_h = 0;
+    CRBE_CUDA(cudaMemcpyAsync(&err_h, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CRBE_CUDA(cudaStreamSynchronize(st));
+    if (err_h) {
+        crbe_set_error("system matrix unusable: %s%s%s", (err_h & 1) ? "row without diagonal; " : "",
+                       (err_h & 2) ? "row with more than 5 entries (not a CR pattern); " : "", (err_h & 4) ? "zero diagonal; " : "");
+        return CRBE_ERR_ARG;
+    }
+    s->system_loaded = true;
+    return CRBE_OK;
+}
+
+static inline void launch_iteration(crbe_solver* s, int k, double* x, int* launches) {
+    crbe_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const double rtol2 = s->rtol * s->rtol;
+    const bool fused = (s->flags & CRBE_SOLVER_FUSED) != 0;
+    double *p, *v;
+    if (fused) {
+        const int o = k & 1, in = (k - 1) & 1;
+        p = s->p[o];
+        v = s->v[o];
+        k_pv<true><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, s->p[in], s->v[in], p, v, s->rh,
+                                             s->sums, s->dstate, ctx->partials, ctx->counter);
+        k_st<true><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dstate,
+                                             ctx->partials, ctx->counter);
+        *launches += 2;
+    } else {
+        p = s->p[0];
+        v = s->v[0];
+        k_p<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, p, s->sums, s->dstate);
+        k_pv<false><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p, v, s->rh, s->sums,
+                                              s->dstate, ctx->partials, ctx->counter);
+        k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, s->s, s->sums, s->dstate);
+        k_st<false><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dstate,
+                                              ctx->partials, ctx->counter);
+        *launches += 4;
+    }
+    k_xr<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, p, s->s, s->t, s->rh, x, s->r, s->sums, s->dstate, ctx->partials, ctx->counter);
+    *launches += 1;
+}
+
+static int fetch_state(crbe_solver* s) {
+    cudaStream_t st = s->ctx->stream;
+    CRBE_CUDA(cudaMemcpyAsync(s->sums_h, s->sums, sizeof(double) * CRBE_NSUMS, cudaMemcpyDeviceToHost, st));
+    CRBE_CUDA(cudaMemcpyAsync(s->sums_h + CRBE_NSUMS, s->dstate, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    CRBE_CUDA(cudaStreamSynchronize(st));
+    return CRBE_OK;
+}
+
+// Iterate from the state left by k_init until converged.  b, r, r^ and the sums are on the device.
+static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* launches) {
+    crbe_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const double rtol2 = s->rtol * s->rtol;
+    const double accept2 = 100.0 * rtol2;   // the recomputed residual may sit up to 10x above rtol (rounding of b - A x)
+    const int* dst_h = (const int*)(s->sums_h + CRBE_NSUMS);
+    int total_iters = 0, restarts = 0, status = 0;
+    double true_rr = -1.0;
+    for (;;) {
+        int k = 0;
+        int target = s->last_iters + 1;
+        if (target > s->maxit - total_iters) target = s->maxit - total_iters;
+        if (target < 1) target = 1;
+        bool done = false;
+        for (;;) {
+            for (; k < target; ++k) launch_iteration(s, k, x, launches);
+            CRBE_KERNEL_CHECK();
+            CRBE_CHECK(fetch_state(s));
+            const double rr = s->sums_h[S_RR], bb = s->sums_h[S_BB];
+            status = dst_h[D_STATUS];
+            done = status != 0 || !(rr > rtol2 * bb) || !isfinite(rr);
+            if (!isfinite(rr)) status = 2;
+            if (done) break;
+            if (total_iters + k >= s->maxit) {
+                status = 1;
+                break;
+            }
+            target = k + 2;
+            if (target > s->maxit - total_iters) target = s->maxit - total_iters;
+        }
+        total_iters += dst_h[D_ITERS];
+        if (status == 1) break;
+        if (s->sums_h[S_BB] == 0.0) {   // b = 0: the Dirichlet system has the solution x = 0
+            CRBE_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * s->n, st));
+            s->sums_h[S_RR] = 0.0;
+            true_rr = 0.0;
+            status = 0;
+            break;
+        }
+        const bool verify = (s->flags & CRBE_SOLVER_VERIFY) != 0;
+        if (status == 0 && !verify) break;
+        k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->b, s->r, s->rh, s->sums, ctx->partials,
+                                             ctx->counter);
+        *launches += 1;
+        CRBE_KERNEL_CHECK();
+        CRBE_CHECK(fetch_state(s));
+        true_rr = s->sums_h[S_RRTRUE];
+        if (status == 0 && true_rr <= accept2 * s->sums_h[S_BB]) break;
+        if (!isfinite(true_rr) || restarts >= 5 || total_iters >= s->maxit) {
+            if (status == 0) status = 1;
+            break;
+        }
+        ++restarts;                      // breakdown, or recurrence and true residual have drifted apart
+        k_restart<<<1, 1, 0, st>>>(s->sums, s->dstate);
+        *launches += 1;
+        status = 0;
+    }
+    if (total_iters > 0) s->last_iters = total_iters;
+    const double bb = s->sums_h[S_BB];
+    info->iterations = total_iters;
+    info->restarts = restarts;
+    info->status = status;
+    info->bnorm = sqrt(bb);
+    info->relres = bb > 0.0 ? sqrt(s->sums_h[S_RR] / bb) : 0.0;
+    info->true_relres = true_rr >= 0.0 ? (bb > 0.0 ? sqrt(true_rr / bb) : 0.0) : -1.0;
+    if (status != 0) {
+        crbe_set_error("BiCGStab %s after %d iterations (%d restarts): ||r||/||b|| = %.3e", status == 1 ? "hit the iteration limit" : "broke down",
+                       total_iters, restarts, info->relres);
+        return CRBE_ERR_SOLVER;
+    }
+    return CRBE_OK;
+}
+
+static int ensure_pingpong(crbe_solver* s) {
+    if ((s->flags & CRBE_SOLVER_FUSED) && !s->p[1]) {
+        CRBE_CUDA(cudaMalloc(&s->p[1], sizeof(double) * s->n));
+        CRBE_CUDA(cudaMalloc(&s->v[1], sizeof(double) * s->n));
+    }
+    return CRBE_OK;
+}
+
+extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* source_d, double dt, crbe_solve_info* info_h) {
+    CRBE_REQUIRE(s && u_d && info_h, "null argument");
+    CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
+    crbe_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    CRBE_CHECK(ensure_pingpong(s));
+    memset(info_h, 0, sizeof(*info_h));
+    int launches = 0;
+    if (s->rhs_val) {   // Crank-Nicolson: (M - c(K+A)) u_prev with u_prev as given, boundary values included (crbe.py:386)
+        k_spmv_csr<<<s->g_spmv, CRBE_BLOCK, 0, st>>>(s->n, s->indptr, s->indices, s->rhs_val, u_d, s->tmp);
+        ++launches;
+    }
+    if (s->nb > 0) {    // the solution of the Dirichlet system is exactly 0 on its identity rows: start there
+        k_zero_rows<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, st>>>(u_d, s->bnd, s->nb);
+        ++launches;
+    }
+    if (s->rhs_val)
+        k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, s->tmp, source_d, dt, s->mscale, s->dscale,
+                                            s->is_bnd, s->b, s->r, s->rh, s->sums, s->dstate, ctx->partials, ctx->counter);
+    else
+        k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, nullptr, source_d, dt, s->mscale, s->dscale,
+                                            s->is_bnd, s->b, s->r, s->rh, s->sums, s->dstate, ctx->partials, ctx->counter);
+    ++launches;
+    CRBE_KERNEL_CHECK();
+    int rc = run_bicgstab(s, u_d, info_h, &launches);
+    info_h->launches = launches;
+    ctx->launches += launches;
+    return rc;
+}
+
+extern "C" int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d, crbe_solve_info* info_h) {
+    CRBE_REQUIRE(s && b_d && x_d && info_h, "null argument");
+    CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
+    crbe_ctx* ctx = s->ctx;
+    CRBE_CHECK(ensure_pingpong(s));
+    memset(info_h, 0, sizeof(*info_h));
+    int launches = 1;
+    k_init<2><<<s->g_init, CRBE_BLOCK, 0, ctx->stream>>>(s->n, s->ld, s->ell_val, s->ell_col, x_d, b_d, nullptr, 0.0,
+                                                                        s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums,
+                                                                        s->dstate, ctx->partials, ctx->counter);
+    CRBE_KERNEL_CHECK();
+    int rc = run_bicgstab(s, x_d, info_h, &launches);
+    info_h->launches = launches;
+    ctx->launches += launches;
+    return rc;
+}
+
+// b of crbe.py:384-402 (unscaled, Dirichlet rows zeroed)
+__global__ void __launch_bounds__(CRBE_BLOCK) k_rhs(int64_t n, const double* __restrict__ mdiag, const double* __restrict__ u,
+                                                    const double* __restrict__ ru, const double* __restrict__ src, double dt,
+                                                    const unsigned char* __restrict__ is_bnd, double* __restrict__ b) {
+    ROW_LOOP(i, n) {
+        double bi = ru ? ru[i] : __dmul_rn(mdiag[i], u[i]);
+        if (src) bi = __dadd_rn(bi, __dmul_rn(dt, src[i]));
+        b[i] = is_bnd[i] ? 0.0 : bi;
+    }
+}
+
+extern "C" int crbe_solver_rhs(crbe_solver* s, const double* u_d, const double* source_d, double dt, double* b_d) {
+    CRBE_REQUIRE(s && u_d && b_d, "null argument");
+    CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
+    crbe_ctx* ctx = s->ctx;
+    if (s->rhs_val) {
+        k_spmv_csr<<<s->g_spmv, CRBE_BLOCK, 0, ctx->stream>>>(s->n, s->indptr, s->indices, s->rhs_val, u_d, s->tmp);
+        ctx->launches += 1;
+    }
+    k_rhs<<<s->g_vec, CRBE_BLOCK, 0, ctx->stream>>>(s->n, s->mdiag, u_d, s->rhs_val ? s->tmp : nullptr, source_d, dt, s->is_bnd, b_d);
+    CRBE_KERNEL_CHECK();
+    ctx->launches += 1;
+    return CRBE_OK;
+}
+
+extern "C" int crbe_solver_lift(crbe_solver* s, const double* u_d, const double* bc_values_d, double* out_d) {
+    CRBE_REQUIRE(s && u_d && out_d && (s->nb == 0 || bc_values_d), "null argument");
+    crbe_ctx* ctx = s->ctx;
+    if (out_d != u_d) CRBE_CUDA(cudaMemcpyAsync(out_d, u_d, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (s->nb > 0) {
+        k_lift<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, ctx->stream>>>(bc_values_d, s->bnd, s->nb, out_d);
+        CRBE_KERNEL_CHECK();
+        ctx->launches += 1;
+    }
+    return CRBE_OK;
+}
+
+// test hook: copy out the scaled ELL rows (k-major) so the host can check them against scipy
+extern "C" int crbe_solver_debug_ell(crbe_solver* s, int64_t* ld_h, const int32_t** ell_col_d, const double** ell_val_d,
+                                     const double** mscale_d, const double** dscale_d) {
+    CRBE_REQUIRE(s != nullptr, "null solver");
+    if (ld_h) *ld_h = s->ld;
+    if (ell_col_d) *ell_col_d = s->ell_col;
+    if (ell_val_d) *ell_val_d = s->ell_val;
+    if (mscale_d) *mscale_d = s->mscale;
+    if (dscale_d) *dscale_d = s->dscale;
+    return CRBE_OK;
+}

@@ -1,0 +1,157 @@
+/*
+ * crbe_b200.h -- C ABI of libcrbe_b200.so, the sm_100a implementation of the
+ * CRBE hot path (Crouzeix-Raviart FEM + Backward Euler, ``BESCRFEM``) of
+ * clemsadand/AirPollution.
+ *
+ * The reference has no FFI: its boundary is the Python class API of crbe.py.
+ * Each entry point below replaces the arithmetic of the cited reference lines;
+ * the host mirror (airpollution_b200/crbe.py) binds them with ctypes and keeps
+ * the reference's class/attribute names.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (CRBE_ERR_*); the
+ *     message is available from crbe_last_error() (thread local).
+ *   - pointers named *_d are DEVICE pointers owned by the caller (the library
+ *     never frees them); pointers named *_h are HOST pointers.  Values are
+ *     IEEE float64, indices int32, sizes int64 -- as the reference produces.
+ *   - opaque handles own library-internal device memory and are released by
+ *     their *_destroy / *_free function.
+ *   - all work is enqueued on the context's stream; functions that return
+ *     host-side results synchronise that stream before returning.
+ *   - one host thread per context.
+ */
+#ifndef CRBE_B200_H
+#define CRBE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRBE_ABI_VERSION 1
+
+#define CRBE_OK 0
+#define CRBE_ERR_ARG (-1)      /* bad argument                                  */
+#define CRBE_ERR_CUDA (-2)     /* CUDA runtime error                            */
+#define CRBE_ERR_MESH (-3)     /* non-manifold / degenerate mesh                */
+#define CRBE_ERR_SOLVER (-4)   /* BiCGStab breakdown or iteration limit         */
+#define CRBE_ERR_COMM (-5)     /* NCCL / peer-access error                      */
+
+typedef struct crbe_ctx crbe_ctx;
+typedef struct crbe_topology crbe_topology;
+typedef struct crbe_solver crbe_solver;
+
+/* ---- errors / lifetime ------------------------------------------------- */
+int crbe_abi_version(void);
+const char* crbe_last_error(void);
+int crbe_ctx_create(int device, crbe_ctx** out);
+int crbe_ctx_set_stream(crbe_ctx* ctx, void* cuda_stream);   /* cudaStream_t; NULL = the default stream */
+int crbe_ctx_synchronize(crbe_ctx* ctx);
+int crbe_ctx_destroy(crbe_ctx* ctx);
+/* plain copies on the context stream (so non-torch hosts need nothing else) */
+int crbe_memcpy_h2d(crbe_ctx* ctx, void* dst_d, const void* src_h, int64_t bytes, int sync);
+int crbe_memcpy_d2h(crbe_ctx* ctx, void* dst_h, const void* src_d, int64_t bytes, int sync);
+
+/* ---- a-1 / a-2: DOF numbering and mesh geometry (crbe.py:50-154) -------- */
+/* Phase 1: first-seen edge numbering of the triangle list (crbe.py:109-131).
+ * tri_d: nt x 3 vertex ids.  Sizes are returned so the caller can allocate. */
+int crbe_topology_create(crbe_ctx* ctx, const int32_t* tri_d, int64_t nt, int64_t nv,
+                         crbe_topology** out, int64_t* n_segments, int64_t* n_boundary_segments,
+                         int64_t* n_boundary_triangles);
+/* Phase 2: write the arrays.
+ *   t2s_d       nt x 3   triangle_to_segments                    (crbe.py:129)
+ *   segments_d  N  x 2   [min,max] vertex ids in id order        (crbe.py:128)
+ *   edge_slots_d N x 2   the (<=2) slots 3*t+a holding each edge; second = -1 on the boundary
+ *   bnd_seg_d   Nb       sorted ids of edges seen once           (crbe.py:78-80)
+ *   bnd_tri_d   Nbt      triangles with a boundary edge          (crbe.py:83-95)
+ *   bnd_tri_seg_d Nbt    their first boundary edge in local order (crbe.py:92)        */
+int crbe_topology_fill(crbe_topology* topo, int32_t* t2s_d, int32_t* segments_d, int32_t* edge_slots_d,
+                       int32_t* bnd_seg_d, int32_t* bnd_tri_d, int32_t* bnd_tri_seg_d);
+int crbe_topology_free(crbe_topology* topo);
+/* midpoints (crbe.py:71), lengths (crbe.py:134-141), areas (crbe.py:143-154), diameter (crbe.py:98-106).
+ * points_d: nv x 2.  Any output may be NULL. */
+int crbe_mesh_geometry(crbe_ctx* ctx, const double* points_d, int64_t nv, const int32_t* tri_d, int64_t nt,
+                       const int32_t* segments_d, int64_t n_seg, double* midpoints_d, double* lengths_d,
+                       double* areas_d, double* diameter_h);
+
+/* ---- a-6 (structure): CSR pattern from edge connectivity (crbe.py:352-354) */
+/* indptr_d: N+1 (out).  The pattern equals scipy's canonical csr_matrix of the
+ * COO triplets (sorted columns, duplicates merged, explicit zeros kept). */
+int crbe_csr_pattern_count(crbe_ctx* ctx, const int32_t* t2s_d, const int32_t* edge_slots_d, int64_t n_seg,
+                           int32_t* indptr_d, int64_t* nnz_h);
+/* indices_d: nnz (out); scatter_pos_d: nt x 9 (out) CSR slot of local entry (a,b) of each triangle. */
+int crbe_csr_pattern_fill(crbe_ctx* ctx, const int32_t* t2s_d, const int32_t* edge_slots_d, int64_t n_seg,
+                          int64_t nt, const int32_t* indptr_d, int32_t* indices_d, int32_t* scatter_pos_d);
+/* Element colouring of the dual graph (no two triangles of one colour share an
+ * edge), deterministic.  colour_d: nt (out); order_d: nt (out) triangles grouped
+ * by colour, ascending inside a colour; colour_offsets_h: 9 entries (out). */
+int crbe_colour_elements(crbe_ctx* ctx, const int32_t* t2s_d, const int32_t* edge_slots_d, int64_t nt,
+                         int32_t* colour_d, int32_t* order_d, int64_t* colour_offsets_h, int32_t* n_colours_h);
+
+/* ---- a-3..a-6 (values): element matrices and global assembly ------------ */
+/* Local matrices of every triangle, for parity checks: k_loc_d, a_loc_d: nt x 9,
+ * m_loc_d: nt x 9 (crbe.py:249-313).  v_elem_d: NULL or nt x 2 per-element velocity. */
+int crbe_element_matrices(crbe_ctx* ctx, const double* points_d, const int32_t* tri_d, const double* areas_d,
+                          int64_t nt, double D, double vx, double vy, const double* v_elem_d,
+                          double* k_loc_d, double* m_loc_d, double* a_loc_d);
+/* One thread per element, colour by colour, no atomics (crbe.py:336-354).
+ * Any of m_val_d, k_val_d, a_val_d (nnz each, structural pattern) may be NULL. */
+int crbe_assemble(crbe_ctx* ctx, const double* points_d, const int32_t* tri_d, const double* areas_d,
+                  const int32_t* scatter_pos_d, const int32_t* order_d, const int64_t* colour_offsets_h,
+                  int32_t n_colours, int64_t nnz, double D, double vx, double vy, const double* v_elem_d,
+                  double* m_val_d, double* k_val_d, double* a_val_d);
+/* s = m + coef*(k + a) entry by entry in the reference's order (crbe.py:358,360,386). */
+int crbe_system_values(crbe_ctx* ctx, int64_t nnz, const double* m_val_d, const double* k_val_d,
+                       const double* a_val_d, double coef, double* s_val_d);
+
+/* ---- kernels exposed for unit tests and profiling ----------------------- */
+int crbe_spmv_csr(crbe_ctx* ctx, int64_t n, const int32_t* indptr_d, const int32_t* indices_d,
+                  const double* val_d, const double* x_d, double* y_d);
+int crbe_dot(crbe_ctx* ctx, int64_t n, const double* x_d, const double* y_d, double* out_h);
+/* (rel_l2, l2, max) of crbe.py:447-453 */
+int crbe_errors(crbe_ctx* ctx, int64_t n, const double* u_exact_d, const double* u_num_d, double* out3_h);
+
+/* ---- a-9..a-11: the per-step linear solve ------------------------------- */
+typedef struct crbe_solve_info {
+    int32_t iterations;      /* BiCGStab iterations of this solve                     */
+    int32_t restarts;        /* restarts from the true residual                       */
+    int32_t status;          /* 0 converged; 1 iteration limit; 2 breakdown           */
+    int32_t launches;        /* kernels launched by this call                         */
+    double relres;           /* recurrence residual  ||r|| / ||b||  (Jacobi-scaled)   */
+    double true_relres;      /* ||b - A x|| / ||b|| recomputed after convergence      */
+    double bnorm;            /* ||b|| (Jacobi-scaled)                                  */
+} crbe_solve_info;
+
+#define CRBE_SOLVER_FUSED 1u          /* fuse the p- and s-updates into the SpMV kernels       */
+#define CRBE_SOLVER_VERIFY 2u         /* recompute the true residual after convergence         */
+#define CRBE_SOLVER_GRAPH 4u          /* replay iterations from a CUDA graph                   */
+
+/* Build the solver for the pattern (indptr/indices, structural, N rows) with
+ * Dirichlet rows bnd_seg_d[0..nb) (crbe.py:397-402). */
+int crbe_solver_create(crbe_ctx* ctx, int64_t n, const int32_t* indptr_d, const int32_t* indices_d,
+                       int64_t nnz, const int32_t* bnd_seg_d, int64_t nb, crbe_solver** out);
+/* Load the system: s_val_d = M + c(K+A) on the structural pattern; m_val_d the
+ * mass matrix (its diagonal forms the BE right-hand side, crbe.py:384).
+ * rhs_val_d: NULL for Backward Euler, or the values of M - c(K+A) for
+ * Crank-Nicolson (crbe.py:386).  Applies the Dirichlet rows, folds the Jacobi
+ * preconditioner into the stored rows. */
+int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, const double* m_val_d,
+                           const double* rhs_val_d);
+int crbe_solver_set_options(crbe_solver* s, double rtol, int32_t max_iterations, uint32_t flags);
+/* One time step (crbe.py:419-426 without the lift): forms b from u_d (and
+ * dt*source_d if not NULL), solves the Dirichlet system, leaves the un-lifted
+ * solution in u_d. */
+int crbe_solver_step(crbe_solver* s, double* u_d, const double* source_d, double dt, crbe_solve_info* info_h);
+/* Solve  A x = b  for the loaded system (Dirichlet rows applied); x_d holds the initial guess. */
+int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d, crbe_solve_info* info_h);
+/* b of crbe.py:384-402 for inspection: b_d (out). */
+int crbe_solver_rhs(crbe_solver* s, const double* u_d, const double* source_d, double dt, double* b_d);
+/* out = u with out[bnd[k]] += bc[k]   (the lift of crbe.py:429) */
+int crbe_solver_lift(crbe_solver* s, const double* u_d, const double* bc_values_d, double* out_d);
+int crbe_solver_destroy(crbe_solver* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRBE_B200_H */

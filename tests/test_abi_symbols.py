@@ -1,0 +1,63 @@
+"""CPU checks of the drop-in boundary: the library builds, loads, and exports
+exactly the entry points include/crbe_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "crbe_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(crbe_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from airpollution_b200 import build
+    return build.build_library()
+
+
+def test_header_declares_the_path():
+    names = header_functions()
+    for required in ("crbe_topology_create", "crbe_csr_pattern_fill", "crbe_colour_elements", "crbe_assemble",
+                     "crbe_solver_step", "crbe_spmv_csr", "crbe_errors"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    missing = [n for n in header_functions() if not hasattr(lib, n)]
+    assert not missing, f"declared in crbe_b200.h but not exported: {missing}"
+    lib.crbe_abi_version.restype = ctypes.c_int
+    assert lib.crbe_abi_version() == 1
+
+
+def test_python_binding_covers_the_header(lib_path):
+    from airpollution_b200 import _lib
+    assert set(header_functions()) == set(_lib.EXPORTED_SYMBOLS)
+    _lib.load()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    from airpollution_b200 import crbe
+    from airpollution_b200.meshgen import structured_mesh
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        crbe.MeshData(structured_mesh(2), crbe.Domain(1, 1, 1), 3)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "airpollution_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "/root/reference" not in text, f
