@@ -63,6 +63,9 @@ _SIGNATURES = {
     "crbe_solver_rhs": [vp, vp, vp, C.c_double, vp],
     "crbe_solver_lift": [vp, vp, vp, vp],
     "crbe_solver_destroy": [vp],
+    "crbe_solver_profile": [vp, C.c_int],
+    "crbe_solver_profile_read": [vp, c_f64p, c_i64p],
+    "crbe_ctx_launch_count": [vp, c_i64p],
 }
 # test / debug hooks (not in the public header)
 _DEBUG_SIGNATURES = {

@@ -432,7 +432,8 @@ class BESCRFEM:
         rt.bind_stream()
         u = rt.upload(np.asarray(self.u_prev, dtype=np.float64))
         b = rt.empty((self.mesh_data.number_of_segments,), torch.float64)
-        rt.call("crbe_solver_rhs", self._solver, ptr(u), ptr(self._source_on_device(t)), float(self.dt), ptr(b))
+        src = self._source_on_device(t)
+        rt.call("crbe_solver_rhs", self._solver, ptr(u), ptr(src), float(self.dt), ptr(b))
         import scipy.sparse as sp
         base = self.base_system
         bnd = self.mesh_data.boundary_segments

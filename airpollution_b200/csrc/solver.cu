@@ -25,7 +25,25 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "crbe_common.cuh"
+
+enum { PK_INIT = 0, PK_PV, PK_ST, PK_XR, PK_P, PK_S, PK_RES, PK_COUNT };
+
+struct ProfRecord {
+    cudaEvent_t a, b;
+    int kind, iter;
+};
+
+struct crbe_profile {
+    bool on = false;
+    std::vector<ProfRecord> pending;
+    std::vector<cudaEvent_t> pool;
+    double ms[PK_COUNT] = {0};
+    long long count[PK_COUNT] = {0};
+};
+
 
 enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RRTRUE = 7, S_AUX0 = 8, S_AUX1 = 9 };
 enum { D_STATUS = 0, D_ITERS = 1 };
@@ -54,6 +72,7 @@ struct crbe_solver {
     bool system_loaded = false;
     // persistent grids: SMs x resident CTAs of each kernel (a grid-stride sweep must be one full wave)
     int g_init = 1, g_pv = 1, g_st = 1, g_xr = 1, g_vec = 1, g_res = 1, g_spmv = 1;
+    crbe_profile* prof = nullptr;
 };
 
 // ---------------------------------------------------------------- helpers
@@ -501,6 +520,14 @@ static int solver_release(crbe_solver* s) {
     cudaFree(s->sums);
     cudaFree(s->dstate);
     cudaFreeHost(s->sums_h);
+    if (s->prof) {
+        for (ProfRecord& r : s->prof->pending) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        for (cudaEvent_t e : s->prof->pool) cudaEventDestroy(e);
+        delete s->prof;
+    }
     delete s;
     return CRBE_OK;
 }
@@ -595,6 +622,49 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
     return CRBE_OK;
 }
 
+// ---- optional per-kernel timing (CUDA events on the launching stream) ----
+// Kinds: 0 init, 1 pv, 2 st, 3 xr, 4 p, 5 s, 6 residual.  Kernels of iterations that
+// turned out to be past convergence (they return at once) are not accounted.
+static cudaEvent_t prof_event(crbe_profile* pf) {
+    cudaEvent_t e;
+    if (!pf->pool.empty()) {
+        e = pf->pool.back();
+        pf->pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+
+#define PROF_LAUNCH(kind_, iter_, ...)                                   \
+    do {                                                                 \
+        if (s->prof && s->prof->on) {                                    \
+            ProfRecord pr_ = {prof_event(s->prof), prof_event(s->prof), kind_, iter_}; \
+            cudaEventRecord(pr_.a, st);                                  \
+            __VA_ARGS__;                                                 \
+            cudaEventRecord(pr_.b, st);                                  \
+            s->prof->pending.push_back(pr_);                             \
+        } else {                                                         \
+            __VA_ARGS__;                                                 \
+        }                                                                \
+    } while (0)
+
+// after a stream synchronisation: fold the finished records into the totals
+static void prof_collect(crbe_solver* s, int iterations_done) {
+    crbe_profile* pf = s->prof;
+    if (!pf) return;
+    for (const ProfRecord& r : pf->pending) {
+        float ms = 0.f;
+        if ((r.iter < 0 || r.iter < iterations_done) && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            pf->ms[r.kind] += ms;
+            pf->count[r.kind] += 1;
+        }
+        pf->pool.push_back(r.a);
+        pf->pool.push_back(r.b);
+    }
+    pf->pending.clear();
+}
+
 static inline void launch_iteration(crbe_solver* s, int k, double* x, int* launches) {
     crbe_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
@@ -605,23 +675,25 @@ static inline void launch_iteration(crbe_solver* s, int k, double* x, int* launc
         const int o = k & 1, in = (k - 1) & 1;
         p = s->p[o];
         v = s->v[o];
-        k_pv<true><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, s->p[in], s->v[in], p, v, s->rh,
-                                             s->sums, s->dstate, ctx->partials, ctx->counter);
-        k_st<true><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dstate,
-                                             ctx->partials, ctx->counter);
+        PROF_LAUNCH(PK_PV, k, (k_pv<true><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, s->p[in],
+                                                                       s->v[in], p, v, s->rh, s->sums, s->dstate, ctx->partials,
+                                                                       ctx->counter)));
+        PROF_LAUNCH(PK_ST, k, (k_st<true><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s,
+                                                                       s->t, s->sums, s->dstate, ctx->partials, ctx->counter)));
         *launches += 2;
     } else {
         p = s->p[0];
         v = s->v[0];
-        k_p<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, p, s->sums, s->dstate);
-        k_pv<false><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p, v, s->rh, s->sums,
-                                              s->dstate, ctx->partials, ctx->counter);
-        k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, s->s, s->sums, s->dstate);
-        k_st<false><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dstate,
-                                              ctx->partials, ctx->counter);
+        PROF_LAUNCH(PK_P, k, (k_p<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, p, s->sums, s->dstate)));
+        PROF_LAUNCH(PK_PV, k, (k_pv<false><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p, v,
+                                                                        s->rh, s->sums, s->dstate, ctx->partials, ctx->counter)));
+        PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, s->s, s->sums, s->dstate)));
+        PROF_LAUNCH(PK_ST, k, (k_st<false><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s,
+                                                                        s->t, s->sums, s->dstate, ctx->partials, ctx->counter)));
         *launches += 4;
     }
-    k_xr<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, p, s->s, s->t, s->rh, x, s->r, s->sums, s->dstate, ctx->partials, ctx->counter);
+    PROF_LAUNCH(PK_XR, k, (k_xr<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, p, s->s, s->t, s->rh, x, s->r, s->sums, s->dstate,
+                                                             ctx->partials, ctx->counter)));
     *launches += 1;
 }
 
@@ -652,6 +724,7 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
             for (; k < target; ++k) launch_iteration(s, k, x, launches);
             CRBE_KERNEL_CHECK();
             CRBE_CHECK(fetch_state(s));
+            prof_collect(s, dst_h[D_ITERS]);
             const double rr = s->sums_h[S_RR], bb = s->sums_h[S_BB];
             status = dst_h[D_STATUS];
             done = status != 0 || !(rr > rtol2 * bb) || !isfinite(rr);
@@ -675,11 +748,12 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
         }
         const bool verify = (s->flags & CRBE_SOLVER_VERIFY) != 0;
         if (status == 0 && !verify) break;
-        k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->b, s->r, s->rh, s->sums, ctx->partials,
-                                             ctx->counter);
+        PROF_LAUNCH(PK_RES, -1, (k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->b, s->r, s->rh,
+                                                                            s->sums, ctx->partials, ctx->counter)));
         *launches += 1;
         CRBE_KERNEL_CHECK();
         CRBE_CHECK(fetch_state(s));
+        prof_collect(s, 0);
         true_rr = s->sums_h[S_RRTRUE];
         if (status == 0 && true_rr <= accept2 * s->sums_h[S_BB]) break;
         if (!isfinite(true_rr) || restarts >= 5 || total_iters >= s->maxit) {
@@ -732,11 +806,13 @@ extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* sourc
         ++launches;
     }
     if (s->rhs_val)
-        k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, s->tmp, source_d, dt, s->mscale, s->dscale,
-                                            s->is_bnd, s->b, s->r, s->rh, s->sums, s->dstate, ctx->partials, ctx->counter);
+        PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, s->tmp, source_d, dt,
+                                                                             s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums,
+                                                                             s->dstate, ctx->partials, ctx->counter)));
     else
-        k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, nullptr, source_d, dt, s->mscale, s->dscale,
-                                            s->is_bnd, s->b, s->r, s->rh, s->sums, s->dstate, ctx->partials, ctx->counter);
+        PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, nullptr, source_d, dt,
+                                                                             s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums,
+                                                                             s->dstate, ctx->partials, ctx->counter)));
     ++launches;
     CRBE_KERNEL_CHECK();
     int rc = run_bicgstab(s, u_d, info_h, &launches);
@@ -808,5 +884,36 @@ extern "C" int crbe_solver_debug_ell(crbe_solver* s, int64_t* ld_h, const int32_
     if (ell_val_d) *ell_val_d = s->ell_val;
     if (mscale_d) *mscale_d = s->mscale;
     if (dscale_d) *dscale_d = s->dscale;
+    return CRBE_OK;
+}
+
+// Per-kernel timing of the solver kernels with CUDA events on the launching stream.
+// enable != 0 starts (and resets) the accumulation, enable == 0 stops it.
+extern "C" int crbe_solver_profile(crbe_solver* s, int enable) {
+    CRBE_REQUIRE(s != nullptr, "null solver");
+    if (!s->prof) s->prof = new crbe_profile();
+    s->prof->on = enable != 0;
+    if (enable) {
+        for (int k = 0; k < PK_COUNT; ++k) {
+            s->prof->ms[k] = 0.0;
+            s->prof->count[k] = 0;
+        }
+    }
+    return CRBE_OK;
+}
+
+// ms_h, count_h: 8 entries each: init, pv, st, xr, p, s, residual, (unused)
+extern "C" int crbe_solver_profile_read(crbe_solver* s, double* ms_h, int64_t* count_h) {
+    CRBE_REQUIRE(s && ms_h && count_h, "null argument");
+    for (int k = 0; k < 8; ++k) {
+        ms_h[k] = (s->prof && k < PK_COUNT) ? s->prof->ms[k] : 0.0;
+        count_h[k] = (s->prof && k < PK_COUNT) ? s->prof->count[k] : 0;
+    }
+    return CRBE_OK;
+}
+
+extern "C" int crbe_ctx_launch_count(crbe_ctx* ctx, int64_t* count_h) {
+    CRBE_REQUIRE(ctx && count_h, "null argument");
+    *count_h = ctx->launches;
     return CRBE_OK;
 }

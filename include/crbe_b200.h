@@ -151,6 +151,16 @@ int crbe_solver_rhs(crbe_solver* s, const double* u_d, const double* source_d, d
 int crbe_solver_lift(crbe_solver* s, const double* u_d, const double* bc_values_d, double* out_d);
 int crbe_solver_destroy(crbe_solver* s);
 
+/* ---- measurement -------------------------------------------------------- */
+/* Per-kernel device time of the solver kernels, CUDA events on the context stream.
+ * enable != 0 resets and starts the accumulation, 0 stops it.  crbe_solver_profile_read
+ * fills 8 entries: init, pv, st, xr, p, s, residual, (unused): total ms and launch counts
+ * (launches enqueued past convergence, which return at once, are not counted). */
+int crbe_solver_profile(crbe_solver* s, int enable);
+int crbe_solver_profile_read(crbe_solver* s, double* ms_h, int64_t* count_h);
+/* kernels launched through this context so far */
+int crbe_ctx_launch_count(crbe_ctx* ctx, int64_t* count_h);
+
 #ifdef __cplusplus
 }
 #endif

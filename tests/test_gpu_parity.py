@@ -214,8 +214,8 @@ def test_spmv_csr_bit_exact_vs_scipy(rt, n):
     A.sort_indices()
     x = rng.standard_normal(n)
     y = rt.empty((n,), torch.float64)
-    rt.call("crbe_spmv_csr", rt.ctx, n, ptr(rt.upload(A.indptr.astype(np.int32))), ptr(rt.upload(A.indices.astype(np.int32))),
-            ptr(rt.upload(A.data)), ptr(rt.upload(x)), ptr(y))
+    bufs = [rt.upload(A.indptr.astype(np.int32)), rt.upload(A.indices.astype(np.int32)), rt.upload(A.data), rt.upload(x)]
+    rt.call("crbe_spmv_csr", rt.ctx, n, ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]), ptr(bufs[3]), ptr(y))
     ref = A @ x
     got = y.cpu().numpy()
     assert np.abs(got - ref).max() <= 4 * np.spacing(np.abs(ref).max() + 1e-300)
@@ -229,14 +229,15 @@ def test_dot_and_errors(rt):
     rng = np.random.default_rng(0)
     for n in (1, 77, 100_003, 2_000_000):
         x, y = rng.standard_normal(n), rng.standard_normal(n)
+        xd, yd = rt.upload(x), rt.upload(y)
         out = C.c_double()
-        rt.call("crbe_dot", rt.ctx, n, ptr(rt.upload(x)), ptr(rt.upload(y)), C.byref(out))
+        rt.call("crbe_dot", rt.ctx, n, ptr(xd), ptr(yd), C.byref(out))
         assert abs(out.value - float(x @ y)) <= 1e-13 * float(np.abs(x) @ np.abs(y))
         out2 = C.c_double()
-        rt.call("crbe_dot", rt.ctx, n, ptr(rt.upload(x)), ptr(rt.upload(y)), C.byref(out2))
+        rt.call("crbe_dot", rt.ctx, n, ptr(xd), ptr(yd), C.byref(out2))
         assert out.value == out2.value          # deterministic reduction
         e3 = (C.c_double * 3)()
-        rt.call("crbe_errors", rt.ctx, n, ptr(rt.upload(x)), ptr(rt.upload(y)), e3)
+        rt.call("crbe_errors", rt.ctx, n, ptr(xd), ptr(yd), e3)
         np.testing.assert_allclose(list(e3), orc.errors(x, y), rtol=1e-13)
         assert e3[2] == np.max(np.abs(x - y))
 
@@ -257,7 +258,8 @@ def test_linear_solve_vs_superlu(rt, fused):
     b = rng.standard_normal(md.number_of_segments)
     x = rt.zeros((md.number_of_segments,), torch.float64)
     info = _lib.SolveInfo()
-    rt.call("crbe_solver_solve", s._solver, ptr(rt.upload(b)), ptr(x), C.byref(info))
+    bd = rt.upload(b)
+    rt.call("crbe_solver_solve", s._solver, ptr(bd), ptr(x), C.byref(info))
     ref = spla.spsolve(A.tocsc(), b)
     assert info.status == 0 and info.iterations > 0
     assert info.true_relres <= 1e-12
