@@ -31,6 +31,7 @@ class SolveInfo(C.Structure):
 SOLVER_FUSED = 1
 SOLVER_VERIFY = 2
 SOLVER_GRAPH = 4
+SOLVER_TMA = 8
 
 # name -> (argtypes)   every function returns int unless listed in _RESTYPE
 _SIGNATURES = {

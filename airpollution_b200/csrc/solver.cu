@@ -7,11 +7,12 @@
 //   A CR matrix row has the diagonal plus at most four off-diagonals (an edge
 //   belongs to <= 2 triangles with two other edges each).  The solver keeps
 //   the Dirichlet system row-scaled by its diagonal (Jacobi folded in, unit
-//   diagonal implicit) in a column-major 4-slot ELL layout:
-//       ell_val[k*ld + i], ell_col[k*ld + i]   k = 0..3,  ld = N rounded up to 32
+//   diagonal implicit) in a tile-major 4-slot ELL layout (slices of 256 rows):
+//       ell_val[tile*1024 + k*256 + i%256], same for ell_col,   k = 0..3
 //   so a warp reads 32 consecutive doubles / ints per slot (fully coalesced,
-//   48 B per row instead of CSR's 64 B) and gathers x through L1/L2.  The CSR
-//   arrays stay the exchange format with the host (scipy) side.
+//   48 B per row instead of CSR's 64 B), a whole tile is one contiguous burst
+//   for the bulk-copy pipeline (solver_tiles.cuh), and x is gathered through
+//   L1/L2.  The CSR arrays stay the exchange format with the host (scipy) side.
 //
 // Kernels per BiCGStab iteration (FUSED):   bytes per row (fp64 vectors)
 //   k_pv : p = r + beta (p - omega v) recomputed at the neighbours, v = A p, (r^,v)   48 + 6*8
@@ -67,15 +68,25 @@ struct crbe_solver {
     double* sums_h = nullptr;  // pinned: CRBE_NSUMS doubles followed by 2 ints
     double rtol = 1e-13;
     int maxit = 10000;
-    unsigned flags = CRBE_SOLVER_FUSED | CRBE_SOLVER_VERIFY;
+    unsigned flags = CRBE_SOLVER_TMA | CRBE_SOLVER_VERIFY;
     int last_iters = 8;
     bool system_loaded = false;
     // persistent grids: SMs x resident CTAs of each kernel (a grid-stride sweep must be one full wave)
     int g_init = 1, g_pv = 1, g_st = 1, g_xr = 1, g_vec = 1, g_res = 1, g_spmv = 1;
+    int gt_pv[2] = {1, 1}, gt_st[2] = {1, 1}, gt_init = 1, gt_res = 1;   // tile (bulk-copy) kernels: [unfused, fused]
+    int64_t ntiles = 0;
     crbe_profile* prof = nullptr;
 };
 
 // ---------------------------------------------------------------- helpers
+// Tile-major ("sliced") ELL: the 4 slots of the 256 rows of a tile are contiguous,
+//   slot k of row i at  (i / 256) * 1024 + k * 256 + (i % 256),
+// so a warp still reads 32 consecutive entries and a whole tile is one 8 KB + 4 KB burst.
+constexpr int CRBE_TILE = 256;
+__host__ __device__ __forceinline__ int64_t ell_at(int64_t i, int k) {
+    return (i / CRBE_TILE) * (4 * CRBE_TILE) + (int64_t)k * CRBE_TILE + (i % CRBE_TILE);
+}
+
 __device__ __forceinline__ bool solver_idle(const double* __restrict__ sums, const int* __restrict__ dstate, double rtol2) {
     return dstate[D_STATUS] != 0 || !(sums[S_RR] > rtol2 * sums[S_BB]);
 }
@@ -88,8 +99,8 @@ __device__ __forceinline__ double ell_row(const double* __restrict__ val, const 
     int c[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        a[k] = __ldcs(val + k * ld + i);   // streamed once per sweep: keep L2 for the gathered vectors
-        c[k] = __ldcs(col + k * ld + i);
+        a[k] = __ldcs(val + ell_at(i, k));   // streamed once per sweep: keep L2 for the gathered vectors
+        c[k] = __ldcs(col + ell_at(i, k));
     }
     double acc = xi;
 #pragma unroll
@@ -157,14 +168,14 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_build_ell(int64_t n, int64_t ld,
             for (int p = p0; p < p1 && k < 4; ++p) {
                 const int c = indices[p];
                 if (c == (int)i) continue;
-                ecol[k * ld + i] = c;
-                eval[k * ld + i] = sval[p] / d;
+                ecol[ell_at(i, k)] = c;
+                eval[ell_at(i, k)] = sval[p] / d;
                 ++k;
             }
         }
         for (; k < 4; ++k) {
-            ecol[k * ld + i] = (int)i;
-            eval[k * ld + i] = 0.0;
+            ecol[ell_at(i, k)] = (int)i;
+            eval[ell_at(i, k)] = 0.0;
         }
         mdiag[i] = m;
         mscale[i] = bd ? 0.0 : m / d;
@@ -394,6 +405,8 @@ __global__ void k_restart(double* sums, int* dstate) {
     dstate[D_ITERS] = 0;
 }
 
+#include "solver_tiles.cuh"
+
 // ---------------------------------------------------------------- general CSR SpMV
 // y = A x with the row sums accumulated in storage order without FMA -- the
 // arithmetic of scipy's csr_matvec, so results can be compared bit for bit.
@@ -497,6 +510,19 @@ extern "C" int crbe_errors(crbe_ctx* ctx, int64_t n, const double* u_exact_d, co
 }
 
 // ---------------------------------------------------------------- solver object
+template <class Kern>
+static int tile_grid(crbe_ctx* ctx, Kern kernel, int smem_bytes, int64_t ntiles, int* grid) {
+    CRBE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    int per_sm = 0;
+    CRBE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CRBE_TILE, smem_bytes));
+    if (per_sm < 1) per_sm = 1;
+    int64_t g = (int64_t)ctx->sm_count * per_sm;
+    if (g > CRBE_MAX_PARTIAL_BLOCKS) g = CRBE_MAX_PARTIAL_BLOCKS;
+    if (g > ntiles) g = ntiles;
+    *grid = g < 1 ? 1 : (int)g;
+    return CRBE_OK;
+}
+
 static int solver_release(crbe_solver* s) {
     if (!s) return CRBE_OK;
     cudaFree(s->bnd);
@@ -538,13 +564,13 @@ extern "C" int crbe_solver_create(crbe_ctx* ctx, int64_t n, const int32_t* indpt
     crbe_solver* s = new crbe_solver();
     s->ctx = ctx;
     s->n = n;
-    s->ld = (n + 31) / 32 * 32;
+    s->ld = (n + CRBE_TILE - 1) / CRBE_TILE * CRBE_TILE;   // rows padded to whole tiles
     s->nnz = nnz;
     s->nb = nb;
     s->indptr = indptr_d;
     s->indices = indices_d;
     *out = s;
-    const size_t vb = sizeof(double) * (size_t)n;
+    const size_t vb = sizeof(double) * (size_t)s->ld;   // internal vectors are padded to whole tiles, padding stays zero
     CRBE_CUDA(cudaMalloc(&s->is_bnd, (size_t)n));
     CRBE_CUDA(cudaMemsetAsync(s->is_bnd, 0, (size_t)n, ctx->stream));
     if (nb > 0) {
@@ -556,7 +582,12 @@ extern "C" int crbe_solver_create(crbe_ctx* ctx, int64_t n, const int32_t* indpt
     CRBE_CUDA(cudaMalloc(&s->ell_col, sizeof(int32_t) * 4 * s->ld));
     CRBE_CUDA(cudaMalloc(&s->ell_val, sizeof(double) * 4 * s->ld));
     double** vecs[] = {&s->mdiag, &s->mscale, &s->dscale, &s->b, &s->r, &s->rh, &s->s, &s->t, &s->p[0], &s->v[0]};
-    for (double** vp : vecs) CRBE_CUDA(cudaMalloc(vp, vb));
+    for (double** vp : vecs) {
+        CRBE_CUDA(cudaMalloc(vp, vb));
+        CRBE_CUDA(cudaMemsetAsync(*vp, 0, vb, ctx->stream));
+    }
+    CRBE_CUDA(cudaMemsetAsync(s->ell_col, 0, sizeof(int32_t) * 4 * s->ld, ctx->stream));
+    CRBE_CUDA(cudaMemsetAsync(s->ell_val, 0, sizeof(double) * 4 * s->ld, ctx->stream));
     CRBE_CUDA(cudaMalloc(&s->sums, sizeof(double) * CRBE_NSUMS));
     CRBE_CUDA(cudaMemsetAsync(s->sums, 0, sizeof(double) * CRBE_NSUMS, ctx->stream));
     CRBE_CUDA(cudaMalloc(&s->dstate, sizeof(int) * 4));
@@ -574,6 +605,14 @@ extern "C" int crbe_solver_create(crbe_ctx* ctx, int64_t n, const int32_t* indpt
         s->g_vec = crbe_persistent_grid(ctx, k_p, n);
         s->g_res = crbe_persistent_grid(ctx, k_residual, n);
         s->g_spmv = crbe_persistent_grid(ctx, k_spmv_csr, n);
+        // bulk-copy kernels: opt in to their dynamic shared memory, then size one resident wave over the tiles
+        s->ntiles = s->ld / CRBE_TILE;
+        CRBE_CHECK(tile_grid(ctx, t_pv<false>, TilePipe<2>::SMEM_BYTES, s->ntiles, &s->gt_pv[0]));
+        CRBE_CHECK(tile_grid(ctx, t_pv<true>, TilePipe<4>::SMEM_BYTES, s->ntiles, &s->gt_pv[1]));
+        CRBE_CHECK(tile_grid(ctx, t_st<false>, TilePipe<1>::SMEM_BYTES, s->ntiles, &s->gt_st[0]));
+        CRBE_CHECK(tile_grid(ctx, t_st<true>, TilePipe<2>::SMEM_BYTES, s->ntiles, &s->gt_st[1]));
+        CRBE_CHECK(tile_grid(ctx, t_init_be, TilePipe<1>::SMEM_BYTES, s->ntiles, &s->gt_init));
+        CRBE_CHECK(tile_grid(ctx, t_residual, TilePipe<1>::SMEM_BYTES, s->ntiles, &s->gt_res));
     }
     CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
     return CRBE_OK;
@@ -604,7 +643,7 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
     ctx->launches += 1;
     if (rhs_val_d) {
         if (!s->rhs_val) CRBE_CUDA(cudaMalloc(&s->rhs_val, sizeof(double) * s->nnz));
-        if (!s->tmp) CRBE_CUDA(cudaMalloc(&s->tmp, sizeof(double) * s->n));
+        if (!s->tmp) CRBE_CUDA(cudaMalloc(&s->tmp, sizeof(double) * s->ld));
         CRBE_CUDA(cudaMemcpyAsync(s->rhs_val, rhs_val_d, sizeof(double) * s->nnz, cudaMemcpyDeviceToDevice, st));
     } else if (s->rhs_val) {
         cudaFree(s->rhs_val);
@@ -670,26 +709,46 @@ static inline void launch_iteration(crbe_solver* s, int k, double* x, int* launc
     cudaStream_t st = ctx->stream;
     const double rtol2 = s->rtol * s->rtol;
     const bool fused = (s->flags & CRBE_SOLVER_FUSED) != 0;
+    const bool tma = (s->flags & CRBE_SOLVER_TMA) != 0;
     double *p, *v;
     if (fused) {
         const int o = k & 1, in = (k - 1) & 1;
         p = s->p[o];
         v = s->v[o];
-        PROF_LAUNCH(PK_PV, k, (k_pv<true><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, s->p[in],
-                                                                       s->v[in], p, v, s->rh, s->sums, s->dstate, ctx->partials,
-                                                                       ctx->counter)));
-        PROF_LAUNCH(PK_ST, k, (k_st<true><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s,
-                                                                       s->t, s->sums, s->dstate, ctx->partials, ctx->counter)));
+        if (tma) {
+            PROF_LAUNCH(PK_PV, k, (t_pv<true><<<s->gt_pv[1], CRBE_TILE, TilePipe<4>::SMEM_BYTES, st>>>(
+                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, s->p[in], s->v[in], p, v, s->rh, s->sums,
+                                      s->dstate, ctx->partials, ctx->counter)));
+            PROF_LAUNCH(PK_ST, k, (t_st<true><<<s->gt_st[1], CRBE_TILE, TilePipe<2>::SMEM_BYTES, st>>>(
+                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dstate,
+                                      ctx->partials, ctx->counter)));
+        } else {
+            PROF_LAUNCH(PK_PV, k, (k_pv<true><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, s->p[in],
+                                                                           s->v[in], p, v, s->rh, s->sums, s->dstate, ctx->partials,
+                                                                           ctx->counter)));
+            PROF_LAUNCH(PK_ST, k, (k_st<true><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s,
+                                                                           s->t, s->sums, s->dstate, ctx->partials, ctx->counter)));
+        }
         *launches += 2;
     } else {
         p = s->p[0];
         v = s->v[0];
         PROF_LAUNCH(PK_P, k, (k_p<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, p, s->sums, s->dstate)));
-        PROF_LAUNCH(PK_PV, k, (k_pv<false><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p, v,
-                                                                        s->rh, s->sums, s->dstate, ctx->partials, ctx->counter)));
+        if (tma)
+            PROF_LAUNCH(PK_PV, k, (t_pv<false><<<s->gt_pv[0], CRBE_TILE, TilePipe<2>::SMEM_BYTES, st>>>(
+                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p, v, s->rh, s->sums, s->dstate,
+                                      ctx->partials, ctx->counter)));
+        else
+            PROF_LAUNCH(PK_PV, k, (k_pv<false><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p,
+                                                                            v, s->rh, s->sums, s->dstate, ctx->partials, ctx->counter)));
         PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, s->s, s->sums, s->dstate)));
-        PROF_LAUNCH(PK_ST, k, (k_st<false><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s,
-                                                                        s->t, s->sums, s->dstate, ctx->partials, ctx->counter)));
+        if (tma)
+            PROF_LAUNCH(PK_ST, k, (t_st<false><<<s->gt_st[0], CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
+                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dstate,
+                                      ctx->partials, ctx->counter)));
+        else
+            PROF_LAUNCH(PK_ST, k, (k_st<false><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s,
+                                                                            s->t, s->sums, s->dstate, ctx->partials, ctx->counter)));
         *launches += 4;
     }
     PROF_LAUNCH(PK_XR, k, (k_xr<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, p, s->s, s->t, s->rh, x, s->r, s->sums, s->dstate,
@@ -748,8 +807,12 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
         }
         const bool verify = (s->flags & CRBE_SOLVER_VERIFY) != 0;
         if (status == 0 && !verify) break;
-        PROF_LAUNCH(PK_RES, -1, (k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->b, s->r, s->rh,
-                                                                            s->sums, ctx->partials, ctx->counter)));
+        if (s->flags & CRBE_SOLVER_TMA)
+            PROF_LAUNCH(PK_RES, -1, (t_residual<<<s->gt_res, CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
+                                        s->n, s->ntiles, s->ell_val, s->ell_col, x, s->b, s->r, s->rh, s->sums, ctx->partials, ctx->counter)));
+        else
+            PROF_LAUNCH(PK_RES, -1, (k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->b, s->r, s->rh,
+                                                                                s->sums, ctx->partials, ctx->counter)));
         *launches += 1;
         CRBE_KERNEL_CHECK();
         CRBE_CHECK(fetch_state(s));
@@ -783,8 +846,10 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
 
 static int ensure_pingpong(crbe_solver* s) {
     if ((s->flags & CRBE_SOLVER_FUSED) && !s->p[1]) {
-        CRBE_CUDA(cudaMalloc(&s->p[1], sizeof(double) * s->n));
-        CRBE_CUDA(cudaMalloc(&s->v[1], sizeof(double) * s->n));
+        CRBE_CUDA(cudaMalloc(&s->p[1], sizeof(double) * s->ld));
+        CRBE_CUDA(cudaMalloc(&s->v[1], sizeof(double) * s->ld));
+        CRBE_CUDA(cudaMemsetAsync(s->p[1], 0, sizeof(double) * s->ld, s->ctx->stream));
+        CRBE_CUDA(cudaMemsetAsync(s->v[1], 0, sizeof(double) * s->ld, s->ctx->stream));
     }
     return CRBE_OK;
 }
@@ -809,6 +874,10 @@ extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* sourc
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, s->tmp, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums,
                                                                              s->dstate, ctx->partials, ctx->counter)));
+    else if (s->flags & CRBE_SOLVER_TMA)
+        PROF_LAUNCH(PK_INIT, -1, (t_init_be<<<s->gt_init, CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
+                                     s->n, s->ntiles, s->ell_val, s->ell_col, u_d, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
+                                     s->sums, s->dstate, ctx->partials, ctx->counter)));
     else
         PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, nullptr, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums,

@@ -1,0 +1,314 @@
+// TMA-fed variants of the SpMV-type solver kernels.
+//
+// The classic kernels (solver.cu) issue every load from registers: one row per
+// thread, two dependent memory round trips (index -> gather), ~60 % occupancy;
+// ncu shows them latency bound (92 % long-scoreboard stalls at 53 % DRAM
+// utilisation).  Here the streaming operands of a 256-row tile -- 4 value
+// slots, 4 index slots and the row-aligned vectors -- are brought into shared
+// memory by bulk async copies (cp.async.bulk -> SASS UBLKCP) tracked by
+// mbarriers, STAGES tiles ahead, issued by one elected thread per CTA.  The
+// copies occupy no registers and no warp slots while in flight, so the memory
+// pipeline stays full independently of occupancy; the threads only perform the
+// gathers x[col] (L1/L2 hits for CR matrices) and the arithmetic.
+//
+// Included by solver.cu after the shared device helpers.
+#pragma once
+
+constexpr int TILE_STAGES = 3;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// One stage holds, for the 256 rows of a tile:  val[4][256] f64 | vec[NVEC][256] f64 | col[4][256] i32
+template <int NVEC>
+struct TilePipe {
+    static constexpr int VAL_BYTES = 4 * CRBE_TILE * 8;
+    static constexpr int VEC_BYTES = CRBE_TILE * 8;
+    static constexpr int COL_BYTES = 4 * CRBE_TILE * 4;
+    static constexpr int STAGE_BYTES = VAL_BYTES + NVEC * VEC_BYTES + COL_BYTES;
+    static constexpr int SMEM_BYTES = TILE_STAGES * STAGE_BYTES;
+
+    unsigned char* smem;
+    uint64_t* bars;
+    const double* eval;
+    const int* ecol;
+    const double* vec[NVEC > 0 ? NVEC : 1];
+    int64_t first, stride, count;   // tiles first, first+stride, ... (count of them) belong to this CTA
+
+    __device__ __forceinline__ int64_t tile_of(int64_t m) const { return first + m * stride; }
+
+    __device__ __forceinline__ void issue(int64_t m) {
+        const int st = (int)(m % TILE_STAGES);
+        unsigned char* base = smem + st * STAGE_BYTES;
+        const int64_t tile = tile_of(m);
+        mbar_expect_tx(&bars[st], STAGE_BYTES);
+        bulk_g2s(base, eval + tile * (4 * CRBE_TILE), VAL_BYTES, &bars[st]);
+#pragma unroll
+        for (int v = 0; v < NVEC; ++v) bulk_g2s(base + VAL_BYTES + v * VEC_BYTES, vec[v] + tile * CRBE_TILE, VEC_BYTES, &bars[st]);
+        bulk_g2s(base + VAL_BYTES + NVEC * VEC_BYTES, ecol + tile * (4 * CRBE_TILE), COL_BYTES, &bars[st]);
+    }
+
+    // all threads of the CTA; returns with the first TILE_STAGES tiles in flight
+    __device__ __forceinline__ void start(unsigned char* smem_, uint64_t* bars_, int64_t ntiles) {
+        smem = smem_;
+        bars = bars_;
+        first = blockIdx.x;
+        stride = gridDim.x;
+        count = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int s = 0; s < TILE_STAGES; ++s) mbar_init(&bars[s], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int64_t m = 0; m < TILE_STAGES && m < count; ++m) issue(m);
+    }
+
+    __device__ __forceinline__ void wait(int64_t m) const { mbar_wait(&bars[m % TILE_STAGES], (uint32_t)((m / TILE_STAGES) & 1)); }
+
+    // every thread has finished reading stage m: refill it with tile m + TILE_STAGES
+    __device__ __forceinline__ void release(int64_t m) {
+        __syncthreads();
+        if (threadIdx.x == 0 && m + TILE_STAGES < count) issue(m + TILE_STAGES);
+    }
+
+    __device__ __forceinline__ const double* sval(int64_t m) const { return (const double*)(smem + (m % TILE_STAGES) * STAGE_BYTES); }
+    __device__ __forceinline__ const double* svec(int64_t m, int v) const { return sval(m) + 4 * CRBE_TILE + v * CRBE_TILE; }
+    __device__ __forceinline__ const int* scol(int64_t m) const { return (const int*)(sval(m) + (4 + NVEC) * CRBE_TILE); }
+};
+
+// y = x_own + sum_k a_k * x(col_k) with the tile's values/indices read from shared memory
+template <class F>
+__device__ __forceinline__ double tile_row(const double* __restrict__ sval, const int* __restrict__ scol, int r, double xi, F xat) {
+    double a[4];
+    int c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a[k] = sval[k * CRBE_TILE + r];
+        c[k] = scol[k * CRBE_TILE + r];
+    }
+    double g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = xat(c[k]);
+    double acc = xi;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc = fma(a[k], g[k], acc);
+    return acc;
+}
+
+// ---- v = A p, (r^, v)   [FUSED: p advanced here and at the gathered neighbours] -------------------
+template <bool FUSED>
+__global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int k, double rtol2, const double* __restrict__ eval,
+                                                  const int* __restrict__ ecol, const double* __restrict__ r, const double* __restrict__ p_in,
+                                                  const double* __restrict__ v_in, double* __restrict__ p_out, double* __restrict__ v_out,
+                                                  const double* __restrict__ rh, double* sums, int* dstate, double* partials,
+                                                  unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ uint64_t bars[TILE_STAGES];
+    if (solver_idle(sums, dstate, rtol2)) return;
+    IterScalars sc = {0, 0, 0, false};
+    if (FUSED && k > 0) {
+        sc = scalars_for_p(sums, k);
+        if (sc.bad) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
+            return;
+        }
+    }
+    constexpr int NV = FUSED ? 4 : 2;
+    TilePipe<NV> pipe;
+    pipe.eval = eval;
+    pipe.ecol = ecol;
+    if (FUSED) {
+        pipe.vec[0] = r;
+        pipe.vec[1] = k > 0 ? p_in : r;   // unused when k == 0
+        pipe.vec[2] = k > 0 ? v_in : r;
+        pipe.vec[3] = rh;
+    } else {
+        pipe.vec[0] = p_in;
+        pipe.vec[1] = rh;
+    }
+    pipe.start(tile_smem, bars, ntiles);
+    const int tr = threadIdx.x;
+    double acc[1] = {0.0};
+    for (int64_t m = 0; m < pipe.count; ++m) {
+        pipe.wait(m);
+        const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
+        if (row < n) {
+            double pi, vi, rhi;
+            if (FUSED) {
+                const double beta = sc.beta, omega = sc.omega;
+                auto pnew = [&](int64_t j) {
+                    return k > 0 ? p_update(__ldg(r + j), __ldg(p_in + j), __ldg(v_in + j), beta, omega) : __ldg(r + j);
+                };
+                pi = k > 0 ? p_update(pipe.svec(m, 0)[tr], pipe.svec(m, 1)[tr], pipe.svec(m, 2)[tr], beta, omega) : pipe.svec(m, 0)[tr];
+                rhi = pipe.svec(m, 3)[tr];
+                p_out[row] = pi;
+                vi = tile_row(pipe.sval(m), pipe.scol(m), tr, pi, [&](int j) { return pnew(j); });
+            } else {
+                pi = pipe.svec(m, 0)[tr];
+                rhi = pipe.svec(m, 1)[tr];
+                vi = tile_row(pipe.sval(m), pipe.scol(m), tr, pi, [&](int j) { return __ldg(p_in + j); });
+            }
+            v_out[row] = vi;
+            acc[0] = fma(rhi, vi, acc[0]);
+        }
+        pipe.release(m);
+    }
+    double* const out[1] = {sums + S_RHV};
+    grid_sum_last<1>(acc, partials, counter, out);
+}
+
+// ---- t = A s, (t,s), (t,t)   [FUSED: s = r - alpha v formed here and at the gathered neighbours] ----
+template <bool FUSED>
+__global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int k, double rtol2, const double* __restrict__ eval,
+                                                  const int* __restrict__ ecol, const double* __restrict__ r, const double* __restrict__ v,
+                                                  double* __restrict__ s, double* __restrict__ t, double* sums, int* dstate, double* partials,
+                                                  unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ uint64_t bars[TILE_STAGES];
+    if (solver_idle(sums, dstate, rtol2)) return;
+    double alpha = 0.0;
+    if (FUSED) {
+        alpha = sums[S_RHO0 + (k & 1)] / sums[S_RHV];
+        if (!isfinite(alpha)) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
+            return;
+        }
+    }
+    constexpr int NV = FUSED ? 2 : 1;
+    TilePipe<NV> pipe;
+    pipe.eval = eval;
+    pipe.ecol = ecol;
+    if (FUSED) {
+        pipe.vec[0] = r;
+        pipe.vec[1] = v;
+    } else {
+        pipe.vec[0] = s;
+    }
+    pipe.start(tile_smem, bars, ntiles);
+    const int tr = threadIdx.x;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t m = 0; m < pipe.count; ++m) {
+        pipe.wait(m);
+        const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
+        if (row < n) {
+            double si, ti;
+            if (FUSED) {
+                si = fma(-alpha, pipe.svec(m, 1)[tr], pipe.svec(m, 0)[tr]);
+                s[row] = si;
+                ti = tile_row(pipe.sval(m), pipe.scol(m), tr, si, [&](int j) { return fma(-alpha, __ldg(v + j), __ldg(r + j)); });
+            } else {
+                si = pipe.svec(m, 0)[tr];
+                ti = tile_row(pipe.sval(m), pipe.scol(m), tr, si, [&](int j) { return __ldg(s + j); });
+            }
+            t[row] = ti;
+            acc[0] = fma(ti, si, acc[0]);
+            acc[1] = fma(ti, ti, acc[1]);
+        }
+        pipe.release(m);
+    }
+    double* const out[2] = {sums + S_TS, sums + S_TT};
+    grid_sum_last<2>(acc, partials, counter, out);
+}
+
+// ---- Backward-Euler step start: b = mscale*u (+ dscale*dt*f), r = r^ = b - A u, (b,b), (r,r) --------
+__global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles, const double* __restrict__ eval, const int* __restrict__ ecol,
+                                                       const double* __restrict__ x, const double* __restrict__ src, double dt,
+                                                       const double* __restrict__ mscale, const double* __restrict__ dscale,
+                                                       double* __restrict__ b, double* __restrict__ r, double* __restrict__ rh, double* sums,
+                                                       int* dstate, double* partials, unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ uint64_t bars[TILE_STAGES];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        dstate[D_STATUS] = 0;
+        dstate[D_ITERS] = 0;
+    }
+    TilePipe<1> pipe;
+    pipe.eval = eval;
+    pipe.ecol = ecol;
+    pipe.vec[0] = mscale;
+    pipe.start(tile_smem, bars, ntiles);
+    const int tr = threadIdx.x;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int64_t m = 0; m < pipe.count; ++m) {
+        const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
+        double xi = 0.0, extra = 0.0;
+        if (row < n) {                      // the caller-owned vectors are not padded: plain loads, issued before the wait
+            xi = x[row];
+            if (src) extra = dscale[row] * dt * src[row];
+        }
+        pipe.wait(m);
+        if (row < n) {
+            const double bi = fma(pipe.svec(m, 0)[tr], xi, extra);
+            const double ax = tile_row(pipe.sval(m), pipe.scol(m), tr, xi, [&](int j) { return __ldg(x + j); });
+            const double ri = bi - ax;
+            b[row] = bi;
+            r[row] = ri;
+            rh[row] = ri;
+            acc[0] = fma(bi, bi, acc[0]);
+            acc[1] = fma(ri, ri, acc[1]);
+        }
+        pipe.release(m);
+    }
+    acc[2] = acc[1];
+    double* const out[3] = {sums + S_BB, sums + S_RR, sums + S_RHO0};
+    grid_sum_last<3>(acc, partials, counter, out);
+}
+
+// ---- true residual r = r^ = b - A x and its norm -------------------------------------------------------
+__global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntiles, const double* __restrict__ eval, const int* __restrict__ ecol,
+                                                        const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
+                                                        double* __restrict__ rh, double* sums, double* partials, unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ uint64_t bars[TILE_STAGES];
+    TilePipe<1> pipe;
+    pipe.eval = eval;
+    pipe.ecol = ecol;
+    pipe.vec[0] = b;
+    pipe.start(tile_smem, bars, ntiles);
+    const int tr = threadIdx.x;
+    double acc[1] = {0.0};
+    for (int64_t m = 0; m < pipe.count; ++m) {
+        const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
+        const double xi = row < n ? x[row] : 0.0;
+        pipe.wait(m);
+        if (row < n) {
+            const double ax = tile_row(pipe.sval(m), pipe.scol(m), tr, xi, [&](int j) { return __ldg(x + j); });
+            const double ri = pipe.svec(m, 0)[tr] - ax;
+            r[row] = ri;
+            rh[row] = ri;
+            acc[0] = fma(ri, ri, acc[0]);
+        }
+        pipe.release(m);
+    }
+    double* const out[1] = {sums + S_RRTRUE};
+    grid_sum_last<1>(acc, partials, counter, out);
+}

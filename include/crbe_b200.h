@@ -126,6 +126,8 @@ typedef struct crbe_solve_info {
 #define CRBE_SOLVER_FUSED 1u          /* fuse the p- and s-updates into the SpMV kernels       */
 #define CRBE_SOLVER_VERIFY 2u         /* recompute the true residual after convergence         */
 #define CRBE_SOLVER_GRAPH 4u          /* replay iterations from a CUDA graph                   */
+#define CRBE_SOLVER_TMA 8u            /* SpMV-type kernels fed by bulk async copies (cp.async.bulk
+                                         + mbarrier pipeline through shared memory)               */
 
 /* Build the solver for the pattern (indptr/indices, structural, N rows) with
  * Dirichlet rows bnd_seg_d[0..nb) (crbe.py:397-402). */

@@ -242,8 +242,8 @@ def test_dot_and_errors(rt):
         assert e3[2] == np.max(np.abs(x - y))
 
 
-@pytest.mark.parametrize("fused", [True, False])
-def test_linear_solve_vs_superlu(rt, fused):
+@pytest.mark.parametrize("fused,tma", [(False, True), (True, True), (False, False), (True, False)])
+def test_linear_solve_vs_superlu(rt, fused, tma):
     """crbe_solver_solve on an assembled Dirichlet system against scipy's direct solve."""
     import torch
     from airpollution_b200 import _lib, crbe
@@ -251,7 +251,7 @@ def test_linear_solve_vs_superlu(rt, fused):
     from airpollution_b200.runtime import ptr
     dom = crbe.Domain(1, 1, T=0.5)
     md = crbe.MeshData(delaunay_mesh(4000, seed=4), dom, 6)
-    s = crbe.BESCRFEM(dom, crbe.Problem(v=[0.7, -0.3], D=0.05), md, crbe.ElementCR(), fused=fused)
+    s = crbe.BESCRFEM(dom, crbe.Problem(v=[0.7, -0.3], D=0.05), md, crbe.ElementCR(), fused=fused, tma=tma)
     s.build_global_matrices()
     A = orc.dirichlet_system_fast(s.base_system, md.boundary_segments)
     rng = np.random.default_rng(5)
@@ -268,12 +268,12 @@ def test_linear_solve_vs_superlu(rt, fused):
 
 # ------------------------------------------------------------------ a-7 .. a-12: the full path
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-@pytest.mark.parametrize("fused", [True, False])
-def test_solve_matches_reference_fixture(name, fused):
+@pytest.mark.parametrize("fused,tma", [(False, True), (True, True), (False, False), (True, False)])
+def test_solve_matches_reference_fixture(name, fused, tma):
     g = load_golden(name)
     crbe, dom, md = _product(g)
     prob = golden_problem(name, g)
-    s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), fused=fused, progress=False)
+    s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), fused=fused, tma=tma, progress=False)
     sol = s.solve()
     assert s.dt == float(g["dt"])
     assert sol.shape == (int(g["nt"]), len(g["segments"]))
@@ -360,9 +360,11 @@ def test_large_mesh_properties():
     s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), progress=False, history="last")
     sol = s.solve()
     assert s._nnz == nnz and s.n_colours <= 4
-    s2 = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), progress=False, history="last", fused=False)
-    sol2 = s2.solve()
-    assert rel_err(sol[-1], sol2[-1]) <= 1e-12
+    for fused, tma in ((True, True), (False, False), (True, False)):
+        s2 = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), progress=False, history="last", fused=fused, tma=tma)
+        sol2 = s2.solve()
+        assert rel_err(sol[-1], sol2[-1]) <= 1e-12
+        del s2
     # one more step by hand: the exported Dirichlet system reproduces the device step
     s.u_prev = s.u_prev.copy()
     A, b = s.set_source_term(nt * s.dt)
