@@ -67,11 +67,19 @@ _SIGNATURES = {
     "crbe_solver_profile": [vp, C.c_int],
     "crbe_solver_profile_read": [vp, c_f64p, c_i64p],
     "crbe_ctx_launch_count": [vp, c_i64p],
+    "crbe_comm_unique_id_bytes": [],
+    "crbe_comm_unique_id": [vp],
+    "crbe_comm_create": [vp, C.c_int, C.c_int, vp, C.POINTER(vp)],
+    "crbe_comm_destroy": [vp],
+    "crbe_solver_create_partitioned": [vp, vp, C.c_int64, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, C.c_int32,
+                                       c_i32p, c_i64p, vp, c_i64p, C.POINTER(vp)],
+    "crbe_solver_vector_length": [vp, c_i64p, c_i64p],
 }
 # test / debug hooks (not in the public header)
 _DEBUG_SIGNATURES = {
     "crbe_test_exclusive_scan": [vp, vp, vp, C.c_int64, c_i64p],
     "crbe_solver_debug_ell": [vp, c_i64p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
+    "crbe_comm_test_allreduce": [vp, vp, C.c_int],
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["crbe_last_error"])

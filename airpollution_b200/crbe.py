@@ -310,6 +310,10 @@ class BESCRFEM:
     def build_global_matrices(self):
         """Assemble M, K, A on the structural CSR pattern and the system matrix
         ``M + dt(K+A)`` (order 1) / ``M + dt/2 (K+A)`` (order 2)."""
+        self._assemble_values()
+        self._load_solver()
+
+    def _assemble_values(self):
         coef = self._coef()                       # raises ValueError like crbe.py:362
         md, rt, d = self.mesh_data, self._rt, self._dev
         rt.bind_stream()
@@ -332,7 +336,6 @@ class BESCRFEM:
             rt.call("crbe_system_values", rt.ctx, nnz, ptr(d["m_val"]), ptr(d["k_val"]), ptr(d["a_val"]), -coef, ptr(d["r_val"]))
         self._np.clear()
         self._assembled = True
-        self._load_solver()
 
     def _element_velocity(self, t):
         """Per-element velocity v(centroid, t) for the time-varying extension."""

@@ -70,6 +70,14 @@ static inline int crbe_persistent_grid(const crbe_ctx* ctx, Kern kernel, int64_t
     return crbe_grid_for(ctx, n, block, per_sm);
 }
 
+// dist.cu (NCCL is confined there)
+struct crbe_comm;
+int crbe_comm_rank(const crbe_comm* c);
+int crbe_comm_world(const crbe_comm* c);
+int crbe_comm_allreduce_sum(crbe_comm* c, double* buf_d, int count, cudaStream_t stream);
+int crbe_comm_exchange(crbe_comm* c, int n_neigh, const int* neigh, const double* sendbuf_d, const int64_t* send_off,
+                       double* recvbuf_d, const int64_t* recv_off, cudaStream_t stream);
+
 // core.cu
 int crbe_exclusive_scan_i32(crbe_ctx* ctx, const int32_t* in_d, int32_t* out_d, int64_t n, int64_t* total_h);
 

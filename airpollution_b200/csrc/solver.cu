@@ -75,6 +75,17 @@ struct crbe_solver {
     int g_init = 1, g_pv = 1, g_st = 1, g_xr = 1, g_vec = 1, g_res = 1, g_spmv = 1;
     int gt_pv[2] = {1, 1}, gt_st[2] = {1, 1}, gt_init = 1, gt_res = 1;   // tile (bulk-copy) kernels: [unfused, fused]
     int64_t ntiles = 0;
+    // row-block partition (world > 1): this solver holds the rows [0, n) of its rank; gathered vectors carry the
+    // halo entries (values owned by other ranks) behind the padded owned part, at [ld, ld + n_halo)
+    crbe_comm* comm = nullptr;
+    int world = 1;
+    int64_t n_halo = 0, veclen = 0;
+    std::vector<int> neigh;
+    std::vector<int64_t> send_off, recv_off;
+    int32_t* send_idx = nullptr;   // device: owned entries to pack for the neighbours, grouped by neighbour
+    double* sendbuf = nullptr;
+    double* red = nullptr;         // staging for the allreduce of the dot products (same slot layout as sums)
+    double* dots = nullptr;        // where the dot kernels write: sums (single GPU) or red
     crbe_profile* prof = nullptr;
 };
 
@@ -202,7 +213,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
                                                      const double* __restrict__ src, double dt, const double* __restrict__ mscale,
                                                      const double* __restrict__ dscale, const unsigned char* __restrict__ is_bnd,
                                                      double* __restrict__ b, double* __restrict__ r, double* __restrict__ rh,
-                                                     double* sums, int* dstate, double* partials, unsigned int* counter) {
+                                                     double* sums, double* dots, int* dstate, double* partials, unsigned int* counter) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         dstate[D_STATUS] = 0;
         dstate[D_ITERS] = 0;
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
         acc[1] = fma(ri, ri, acc[1]);
     }
     acc[2] = acc[1];
-    double* const out[3] = {sums + S_BB, sums + S_RR, sums + S_RHO0};
+    double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
     grid_sum_last<3>(acc, partials, counter, out);
 }
 
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_pv(int64_t n, int64_t ld, int k,
                                                    const int* __restrict__ ecol, const double* __restrict__ r,
                                                    const double* __restrict__ p_in, const double* __restrict__ v_in,
                                                    double* __restrict__ p_out, double* __restrict__ v_out,
-                                                   const double* __restrict__ rh, double* sums, int* dstate, double* partials,
+                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                    unsigned int* counter) {
     if (solver_idle(sums, dstate, rtol2)) return;
     IterScalars sc = {0, 0, 0, false};
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_pv(int64_t n, int64_t ld, int k,
         v_out[i] = vi;
         acc[0] = fma(rh[i], vi, acc[0]);
     }
-    double* const out[1] = {sums + S_RHV};
+    double* const out[1] = {dots + S_RHV};
     grid_sum_last<1>(acc, partials, counter, out);
 }
 
@@ -325,7 +336,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_s(int64_t n, int k, double rtol2
 template <bool FUSED>
 __global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, int k, double rtol2, const double* __restrict__ eval,
                                                    const int* __restrict__ ecol, const double* __restrict__ r, const double* __restrict__ v,
-                                                   double* __restrict__ s, double* __restrict__ t, double* sums, int* dstate,
+                                                   double* __restrict__ s, double* __restrict__ t, double* sums, double* dots, int* dstate,
                                                    double* partials, unsigned int* counter) {
     if (solver_idle(sums, dstate, rtol2)) return;
     double alpha = 0.0;
@@ -352,14 +363,14 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, int k,
         acc[0] = fma(ti, si, acc[0]);
         acc[1] = fma(ti, ti, acc[1]);
     }
-    double* const out[2] = {sums + S_TS, sums + S_TT};
+    double* const out[2] = {dots + S_TS, dots + S_TT};
     grid_sum_last<2>(acc, partials, counter, out);
 }
 
 // x += alpha p + omega s;  r = s - omega t;  rho_{k+1} = (r^, r);  (r, r)
 __global__ void __launch_bounds__(CRBE_BLOCK) k_xr(int64_t n, int k, double rtol2, const double* __restrict__ p, const double* __restrict__ s,
                                                    const double* __restrict__ t, const double* __restrict__ rh, double* __restrict__ x,
-                                                   double* __restrict__ r, double* sums, int* dstate, double* partials,
+                                                   double* __restrict__ r, double* sums, double* dots, int* dstate, double* partials,
                                                    unsigned int* counter) {
     if (solver_idle(sums, dstate, rtol2)) return;
     const double alpha = sums[S_RHO0 + (k & 1)] / sums[S_RHV];
@@ -378,14 +389,14 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_xr(int64_t n, int k, double rtol
         acc[0] = fma(rh[i], ri, acc[0]);
         acc[1] = fma(ri, ri, acc[1]);
     }
-    double* const out[2] = {sums + S_RHO0 + ((k + 1) & 1), sums + S_RR};
+    double* const out[2] = {dots + S_RHO0 + ((k + 1) & 1), dots + S_RR};
     if (grid_sum_last<2>(acc, partials, counter, out)) dstate[D_ITERS] += 1;
 }
 
 // true residual r = r^ = b - A x and its norm (restart / verification)
 __global__ void __launch_bounds__(CRBE_BLOCK) k_residual(int64_t n, int64_t ld, const double* __restrict__ eval, const int* __restrict__ ecol,
                                                          const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
-                                                         double* __restrict__ rh, double* sums, double* partials, unsigned int* counter) {
+                                                         double* __restrict__ rh, double* sums, double* dots, double* partials, unsigned int* counter) {
     double acc[1] = {0.0};
     ROW_LOOP(i, n) {
         const double ax = ell_row(eval, ecol, ld, i, x[i], [&](int j) { return __ldg(x + j); });
@@ -394,7 +405,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_residual(int64_t n, int64_t ld, 
         rh[i] = ri;
         acc[0] = fma(ri, ri, acc[0]);
     }
-    double* const out[1] = {sums + S_RRTRUE};
+    double* const out[1] = {dots + S_RRTRUE};
     grid_sum_last<1>(acc, partials, counter, out);
 }
 
@@ -544,6 +555,9 @@ static int solver_release(crbe_solver* s) {
     cudaFree(s->v[0]);
     cudaFree(s->v[1]);
     cudaFree(s->sums);
+    cudaFree(s->red);
+    cudaFree(s->send_idx);
+    cudaFree(s->sendbuf);
     cudaFree(s->dstate);
     cudaFreeHost(s->sums_h);
     if (s->prof) {
@@ -558,11 +572,15 @@ static int solver_release(crbe_solver* s) {
     return CRBE_OK;
 }
 
-extern "C" int crbe_solver_create(crbe_ctx* ctx, int64_t n, const int32_t* indptr_d, const int32_t* indices_d, int64_t nnz,
-                                  const int32_t* bnd_seg_d, int64_t nb, crbe_solver** out) {
-    CRBE_REQUIRE(ctx && out && n > 0 && indptr_d && indices_d && nnz > 0 && nb >= 0 && (nb == 0 || bnd_seg_d), "bad argument");
+static int solver_create_impl(crbe_ctx* ctx, crbe_comm* comm, int64_t n, int64_t n_halo, const int32_t* indptr_d,
+                              const int32_t* indices_d, int64_t nnz, const int32_t* bnd_seg_d, int64_t nb, crbe_solver** out) {
+    CRBE_REQUIRE(ctx && out && n > 0 && indptr_d && indices_d && nnz > 0 && nb >= 0 && (nb == 0 || bnd_seg_d) && n_halo >= 0,
+                 "bad argument");
     crbe_solver* s = new crbe_solver();
     s->ctx = ctx;
+    s->comm = comm;
+    s->world = crbe_comm_world(comm);
+    s->n_halo = n_halo;
     s->n = n;
     s->ld = (n + CRBE_TILE - 1) / CRBE_TILE * CRBE_TILE;   // rows padded to whole tiles
     s->nnz = nnz;
@@ -570,7 +588,9 @@ extern "C" int crbe_solver_create(crbe_ctx* ctx, int64_t n, const int32_t* indpt
     s->indptr = indptr_d;
     s->indices = indices_d;
     *out = s;
-    const size_t vb = sizeof(double) * (size_t)s->ld;   // internal vectors are padded to whole tiles, padding stays zero
+    // internal vectors: owned rows padded to whole tiles (padding stays zero), then the halo entries
+    s->veclen = s->ld + (n_halo + 31) / 32 * 32;
+    const size_t vb = sizeof(double) * (size_t)s->veclen;
     CRBE_CUDA(cudaMalloc(&s->is_bnd, (size_t)n));
     CRBE_CUDA(cudaMemsetAsync(s->is_bnd, 0, (size_t)n, ctx->stream));
     if (nb > 0) {
@@ -593,6 +613,13 @@ extern "C" int crbe_solver_create(crbe_ctx* ctx, int64_t n, const int32_t* indpt
     CRBE_CUDA(cudaMalloc(&s->dstate, sizeof(int) * 4));
     CRBE_CUDA(cudaMemsetAsync(s->dstate, 0, sizeof(int) * 4, ctx->stream));
     CRBE_CUDA(cudaMallocHost(&s->sums_h, sizeof(double) * (CRBE_NSUMS + 2)));
+    s->dots = s->sums;
+    if (s->world > 1) {
+        CRBE_CUDA(cudaMalloc(&s->red, sizeof(double) * CRBE_NSUMS));
+        CRBE_CUDA(cudaMemsetAsync(s->red, 0, sizeof(double) * CRBE_NSUMS, ctx->stream));
+        s->dots = s->red;
+        s->flags &= ~CRBE_SOLVER_FUSED;
+    }
     {   // one resident wave per kernel; the fused and unfused variants share a grid (the smaller one)
         const int a = crbe_persistent_grid(ctx, k_pv<true>, n), b = crbe_persistent_grid(ctx, k_pv<false>, n);
         s->g_pv = a < b ? a : b;
@@ -618,6 +645,49 @@ extern "C" int crbe_solver_create(crbe_ctx* ctx, int64_t n, const int32_t* indpt
     return CRBE_OK;
 }
 
+extern "C" int crbe_solver_create(crbe_ctx* ctx, int64_t n, const int32_t* indptr_d, const int32_t* indices_d, int64_t nnz,
+                                  const int32_t* bnd_seg_d, int64_t nb, crbe_solver** out) {
+    return solver_create_impl(ctx, nullptr, n, 0, indptr_d, indices_d, nnz, bnd_seg_d, nb, out);
+}
+
+// Row-block partitioned solver: this rank holds n_own rows; column indices are local: [0, n_own) owned,
+// ld + h (ld = n_own rounded up to 256) for halo entry h in [0, n_halo).  Neighbour q sends
+// send_counts[q] owned entries (their local indices listed, grouped by neighbour, in send_idx_d) and
+// delivers recv_counts[q] consecutive halo entries.
+extern "C" int crbe_solver_create_partitioned(crbe_ctx* ctx, crbe_comm* comm, int64_t n_own, int64_t n_halo, const int32_t* indptr_d,
+                                              const int32_t* indices_d, int64_t nnz, const int32_t* bnd_seg_d, int64_t nb,
+                                              int32_t n_neigh, const int32_t* neigh_ranks_h, const int64_t* send_counts_h,
+                                              const int32_t* send_idx_d, const int64_t* recv_counts_h, crbe_solver** out) {
+    CRBE_REQUIRE(comm != nullptr && n_neigh >= 0 && (n_neigh == 0 || (neigh_ranks_h && send_counts_h && recv_counts_h)), "bad partition");
+    CRBE_CHECK(solver_create_impl(ctx, comm, n_own, n_halo, indptr_d, indices_d, nnz, bnd_seg_d, nb, out));
+    crbe_solver* s = *out;
+    s->send_off.assign(1, 0);
+    s->recv_off.assign(1, 0);
+    for (int q = 0; q < n_neigh; ++q) {
+        s->neigh.push_back(neigh_ranks_h[q]);
+        s->send_off.push_back(s->send_off.back() + send_counts_h[q]);
+        s->recv_off.push_back(s->recv_off.back() + recv_counts_h[q]);
+    }
+    CRBE_REQUIRE(s->recv_off.back() == n_halo, "halo counts do not add up");
+    const int64_t ns = s->send_off.back();
+    if (ns > 0) {
+        CRBE_REQUIRE(send_idx_d != nullptr, "missing send indices");
+        CRBE_CUDA(cudaMalloc(&s->send_idx, sizeof(int32_t) * ns));
+        CRBE_CUDA(cudaMemcpyAsync(s->send_idx, send_idx_d, sizeof(int32_t) * ns, cudaMemcpyDeviceToDevice, ctx->stream));
+        CRBE_CUDA(cudaMalloc(&s->sendbuf, sizeof(double) * ns));
+    }
+    CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CRBE_OK;
+}
+
+// number of doubles a solution vector handed to crbe_solver_step / _solve must hold (owned rows, padding, halo)
+extern "C" int crbe_solver_vector_length(crbe_solver* s, int64_t* len_h, int64_t* halo_offset_h) {
+    CRBE_REQUIRE(s && len_h, "null argument");
+    *len_h = s->world > 1 ? s->veclen : s->n;
+    if (halo_offset_h) *halo_offset_h = s->ld;
+    return CRBE_OK;
+}
+
 extern "C" int crbe_solver_destroy(crbe_solver* s) {
     if (s) cudaStreamSynchronize(s->ctx->stream);
     return solver_release(s);
@@ -628,6 +698,7 @@ extern "C" int crbe_solver_set_options(crbe_solver* s, double rtol, int32_t max_
     s->rtol = rtol;
     s->maxit = max_iterations;
     s->flags = flags;
+    if (s->world > 1) s->flags &= ~CRBE_SOLVER_FUSED;   // the fused kernels would need the halos of r, p and v
     return CRBE_OK;
 }
 
@@ -643,7 +714,7 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
     ctx->launches += 1;
     if (rhs_val_d) {
         if (!s->rhs_val) CRBE_CUDA(cudaMalloc(&s->rhs_val, sizeof(double) * s->nnz));
-        if (!s->tmp) CRBE_CUDA(cudaMalloc(&s->tmp, sizeof(double) * s->ld));
+        if (!s->tmp) CRBE_CUDA(cudaMalloc(&s->tmp, sizeof(double) * s->veclen));
         CRBE_CUDA(cudaMemcpyAsync(s->rhs_val, rhs_val_d, sizeof(double) * s->nnz, cudaMemcpyDeviceToDevice, st));
     } else if (s->rhs_val) {
         cudaFree(s->rhs_val);
@@ -704,7 +775,42 @@ static void prof_collect(crbe_solver* s, int iterations_done) {
     pf->pending.clear();
 }
 
-static inline void launch_iteration(crbe_solver* s, int k, double* x, int* launches) {
+// ---- partitioned solve: halo exchange and allreduce of the dot products ----------------------------
+__global__ void k_pack(const double* __restrict__ vec, const int* __restrict__ idx, int64_t cnt, double* __restrict__ out) {
+    ROW_LOOP(q, cnt) out[q] = vec[idx[q]];
+}
+
+__global__ void k_commit(const double* __restrict__ red, double* __restrict__ sums, int a, int b, int c) {
+    if (a >= 0) sums[a] = red[a];
+    if (b >= 0) sums[b] = red[b];
+    if (c >= 0) sums[c] = red[c];
+}
+
+// refresh the halo entries of a gathered vector from their owners (no-op on a single GPU)
+static int halo_exchange(crbe_solver* s, double* vec, int* launches) {
+    if (s->world <= 1 || s->neigh.empty()) return CRBE_OK;
+    crbe_ctx* ctx = s->ctx;
+    const int64_t cnt = s->send_off.back();
+    if (cnt > 0) {
+        k_pack<<<crbe_grid_for(ctx, cnt), CRBE_BLOCK, 0, ctx->stream>>>(vec, s->send_idx, cnt, s->sendbuf);
+        CRBE_KERNEL_CHECK();
+        *launches += 1;
+    }
+    return crbe_comm_exchange(s->comm, (int)s->neigh.size(), s->neigh.data(), s->sendbuf, s->send_off.data(), vec + s->ld,
+                              s->recv_off.data(), ctx->stream);
+}
+
+// sum the freshly written dot products red[first .. first+count) over the ranks, then publish slots a, b, c
+static int reduce_dots(crbe_solver* s, int first, int count, int a, int b, int c, int* launches) {
+    if (s->world <= 1) return CRBE_OK;
+    CRBE_CHECK(crbe_comm_allreduce_sum(s->comm, s->red + first, count, s->ctx->stream));
+    k_commit<<<1, 1, 0, s->ctx->stream>>>(s->red, s->sums, a, b, c);
+    CRBE_KERNEL_CHECK();
+    *launches += 1;
+    return CRBE_OK;
+}
+
+static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launches) {
     crbe_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     const double rtol2 = s->rtol * s->rtol;
@@ -718,42 +824,48 @@ static inline void launch_iteration(crbe_solver* s, int k, double* x, int* launc
         if (tma) {
             PROF_LAUNCH(PK_PV, k, (t_pv<true><<<s->gt_pv[1], CRBE_TILE, TilePipe<4>::SMEM_BYTES, st>>>(
                                       s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, s->p[in], s->v[in], p, v, s->rh, s->sums,
-                                      s->dstate, ctx->partials, ctx->counter)));
+                                      s->dots, s->dstate, ctx->partials, ctx->counter)));
             PROF_LAUNCH(PK_ST, k, (t_st<true><<<s->gt_st[1], CRBE_TILE, TilePipe<2>::SMEM_BYTES, st>>>(
-                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dstate,
+                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dots, s->dstate,
                                       ctx->partials, ctx->counter)));
         } else {
             PROF_LAUNCH(PK_PV, k, (k_pv<true><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, s->p[in],
-                                                                           s->v[in], p, v, s->rh, s->sums, s->dstate, ctx->partials,
+                                                                           s->v[in], p, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
                                                                            ctx->counter)));
             PROF_LAUNCH(PK_ST, k, (k_st<true><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s,
-                                                                           s->t, s->sums, s->dstate, ctx->partials, ctx->counter)));
+                                                                           s->t, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter)));
         }
         *launches += 2;
     } else {
         p = s->p[0];
         v = s->v[0];
         PROF_LAUNCH(PK_P, k, (k_p<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, p, s->sums, s->dstate)));
+        CRBE_CHECK(halo_exchange(s, p, launches));
         if (tma)
             PROF_LAUNCH(PK_PV, k, (t_pv<false><<<s->gt_pv[0], CRBE_TILE, TilePipe<2>::SMEM_BYTES, st>>>(
-                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p, v, s->rh, s->sums, s->dstate,
+                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p, v, s->rh, s->sums, s->dots, s->dstate,
                                       ctx->partials, ctx->counter)));
         else
             PROF_LAUNCH(PK_PV, k, (k_pv<false><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p,
-                                                                            v, s->rh, s->sums, s->dstate, ctx->partials, ctx->counter)));
+                                                                            v, s->rh, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter)));
+        CRBE_CHECK(reduce_dots(s, S_RHV, 1, S_RHV, -1, -1, launches));
         PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, s->s, s->sums, s->dstate)));
+        CRBE_CHECK(halo_exchange(s, s->s, launches));
         if (tma)
             PROF_LAUNCH(PK_ST, k, (t_st<false><<<s->gt_st[0], CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
-                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dstate,
+                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dots, s->dstate,
                                       ctx->partials, ctx->counter)));
         else
             PROF_LAUNCH(PK_ST, k, (k_st<false><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s,
-                                                                            s->t, s->sums, s->dstate, ctx->partials, ctx->counter)));
+                                                                            s->t, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter)));
+        CRBE_CHECK(reduce_dots(s, S_TS, 2, S_TS, S_TT, -1, launches));
         *launches += 4;
     }
-    PROF_LAUNCH(PK_XR, k, (k_xr<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, p, s->s, s->t, s->rh, x, s->r, s->sums, s->dstate,
+    PROF_LAUNCH(PK_XR, k, (k_xr<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, p, s->s, s->t, s->rh, x, s->r, s->sums, s->dots, s->dstate,
                                                              ctx->partials, ctx->counter)));
     *launches += 1;
+    CRBE_CHECK(reduce_dots(s, S_RR, 3, S_RR, S_RHO0 + ((k + 1) & 1), -1, launches));
+    return CRBE_OK;
 }
 
 static int fetch_state(crbe_solver* s) {
@@ -780,7 +892,7 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
         if (target < 1) target = 1;
         bool done = false;
         for (;;) {
-            for (; k < target; ++k) launch_iteration(s, k, x, launches);
+            for (; k < target; ++k) CRBE_CHECK(launch_iteration(s, k, x, launches));
             CRBE_KERNEL_CHECK();
             CRBE_CHECK(fetch_state(s));
             prof_collect(s, dst_h[D_ITERS]);
@@ -807,14 +919,16 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
         }
         const bool verify = (s->flags & CRBE_SOLVER_VERIFY) != 0;
         if (status == 0 && !verify) break;
+        CRBE_CHECK(halo_exchange(s, x, launches));
         if (s->flags & CRBE_SOLVER_TMA)
             PROF_LAUNCH(PK_RES, -1, (t_residual<<<s->gt_res, CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
-                                        s->n, s->ntiles, s->ell_val, s->ell_col, x, s->b, s->r, s->rh, s->sums, ctx->partials, ctx->counter)));
+                                        s->n, s->ntiles, s->ell_val, s->ell_col, x, s->b, s->r, s->rh, s->sums, s->dots, ctx->partials, ctx->counter)));
         else
             PROF_LAUNCH(PK_RES, -1, (k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->b, s->r, s->rh,
-                                                                                s->sums, ctx->partials, ctx->counter)));
+                                                                                s->sums, s->dots, ctx->partials, ctx->counter)));
         *launches += 1;
         CRBE_KERNEL_CHECK();
+        CRBE_CHECK(reduce_dots(s, S_RRTRUE, 1, S_RRTRUE, -1, -1, launches));
         CRBE_CHECK(fetch_state(s));
         prof_collect(s, 0);
         true_rr = s->sums_h[S_RRTRUE];
@@ -846,10 +960,10 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
 
 static int ensure_pingpong(crbe_solver* s) {
     if ((s->flags & CRBE_SOLVER_FUSED) && !s->p[1]) {
-        CRBE_CUDA(cudaMalloc(&s->p[1], sizeof(double) * s->ld));
-        CRBE_CUDA(cudaMalloc(&s->v[1], sizeof(double) * s->ld));
-        CRBE_CUDA(cudaMemsetAsync(s->p[1], 0, sizeof(double) * s->ld, s->ctx->stream));
-        CRBE_CUDA(cudaMemsetAsync(s->v[1], 0, sizeof(double) * s->ld, s->ctx->stream));
+        CRBE_CUDA(cudaMalloc(&s->p[1], sizeof(double) * s->veclen));
+        CRBE_CUDA(cudaMalloc(&s->v[1], sizeof(double) * s->veclen));
+        CRBE_CUDA(cudaMemsetAsync(s->p[1], 0, sizeof(double) * s->veclen, s->ctx->stream));
+        CRBE_CUDA(cudaMemsetAsync(s->v[1], 0, sizeof(double) * s->veclen, s->ctx->stream));
     }
     return CRBE_OK;
 }
@@ -863,6 +977,7 @@ extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* sourc
     memset(info_h, 0, sizeof(*info_h));
     int launches = 0;
     if (s->rhs_val) {   // Crank-Nicolson: (M - c(K+A)) u_prev with u_prev as given, boundary values included (crbe.py:386)
+        CRBE_CHECK(halo_exchange(s, u_d, &launches));
         k_spmv_csr<<<s->g_spmv, CRBE_BLOCK, 0, st>>>(s->n, s->indptr, s->indices, s->rhs_val, u_d, s->tmp);
         ++launches;
     }
@@ -870,20 +985,22 @@ extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* sourc
         k_zero_rows<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, st>>>(u_d, s->bnd, s->nb);
         ++launches;
     }
+    CRBE_CHECK(halo_exchange(s, u_d, &launches));
     if (s->rhs_val)
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, s->tmp, source_d, dt,
-                                                                             s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums,
+                                                                             s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter)));
     else if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<<<s->gt_init, CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
                                      s->n, s->ntiles, s->ell_val, s->ell_col, u_d, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
-                                     s->sums, s->dstate, ctx->partials, ctx->counter)));
+                                     s->sums, s->dots, s->dstate, ctx->partials, ctx->counter)));
     else
         PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, nullptr, source_d, dt,
-                                                                             s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums,
+                                                                             s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter)));
     ++launches;
     CRBE_KERNEL_CHECK();
+    CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, &launches));
     int rc = run_bicgstab(s, u_d, info_h, &launches);
     info_h->launches = launches;
     ctx->launches += launches;
@@ -897,10 +1014,12 @@ extern "C" int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d,
     CRBE_CHECK(ensure_pingpong(s));
     memset(info_h, 0, sizeof(*info_h));
     int launches = 1;
+    CRBE_CHECK(halo_exchange(s, x_d, &launches));
     k_init<2><<<s->g_init, CRBE_BLOCK, 0, ctx->stream>>>(s->n, s->ld, s->ell_val, s->ell_col, x_d, b_d, nullptr, 0.0,
-                                                                        s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums,
+                                                                        s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums, s->dots,
                                                                         s->dstate, ctx->partials, ctx->counter);
     CRBE_KERNEL_CHECK();
+    CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, &launches));
     int rc = run_bicgstab(s, x_d, info_h, &launches);
     info_h->launches = launches;
     ctx->launches += launches;

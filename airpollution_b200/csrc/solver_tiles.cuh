@@ -129,7 +129,7 @@ template <bool FUSED>
 __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int k, double rtol2, const double* __restrict__ eval,
                                                   const int* __restrict__ ecol, const double* __restrict__ r, const double* __restrict__ p_in,
                                                   const double* __restrict__ v_in, double* __restrict__ p_out, double* __restrict__ v_out,
-                                                  const double* __restrict__ rh, double* sums, int* dstate, double* partials,
+                                                  const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int
         }
         pipe.release(m);
     }
-    double* const out[1] = {sums + S_RHV};
+    double* const out[1] = {dots + S_RHV};
     grid_sum_last<1>(acc, partials, counter, out);
 }
 
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int
 template <bool FUSED>
 __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int k, double rtol2, const double* __restrict__ eval,
                                                   const int* __restrict__ ecol, const double* __restrict__ r, const double* __restrict__ v,
-                                                  double* __restrict__ s, double* __restrict__ t, double* sums, int* dstate, double* partials,
+                                                  double* __restrict__ s, double* __restrict__ t, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int
         }
         pipe.release(m);
     }
-    double* const out[2] = {sums + S_TS, sums + S_TT};
+    double* const out[2] = {dots + S_TS, dots + S_TT};
     grid_sum_last<2>(acc, partials, counter, out);
 }
 
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
                                                        const double* __restrict__ x, const double* __restrict__ src, double dt,
                                                        const double* __restrict__ mscale, const double* __restrict__ dscale,
                                                        double* __restrict__ b, double* __restrict__ r, double* __restrict__ rh, double* sums,
-                                                       int* dstate, double* partials, unsigned int* counter) {
+                                                       double* dots, int* dstate, double* partials, unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -279,14 +279,14 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
         pipe.release(m);
     }
     acc[2] = acc[1];
-    double* const out[3] = {sums + S_BB, sums + S_RR, sums + S_RHO0};
+    double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
     grid_sum_last<3>(acc, partials, counter, out);
 }
 
 // ---- true residual r = r^ = b - A x and its norm -------------------------------------------------------
 __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntiles, const double* __restrict__ eval, const int* __restrict__ ecol,
                                                         const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
-                                                        double* __restrict__ rh, double* sums, double* partials, unsigned int* counter) {
+                                                        double* __restrict__ rh, double* sums, double* dots, double* partials, unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
     TilePipe<1> pipe;
@@ -309,6 +309,6 @@ __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntile
         }
         pipe.release(m);
     }
-    double* const out[1] = {sums + S_RRTRUE};
+    double* const out[1] = {dots + S_RRTRUE};
     grid_sum_last<1>(acc, partials, counter, out);
 }

@@ -1,0 +1,388 @@
+"""Row-block partitioned CRBE solve over the GPUs of one node.
+
+One process per GPU (torchrun).  Rank r owns a contiguous block of DOF rows of
+the global system -- for the structured benchmark meshes a horizontal strip of
+cell rows, because the reference's first-seen DOF numbering (crbe.py:109-131) is
+monotone in the cell row.  Each rank meshes and assembles only its strip plus
+one ghost cell row (every triangle touching an owned edge), with the
+single-GPU kernels; the local numbering is mapped to the reference's global
+numbering in closed form, the owned rows are re-indexed to
+``[owned | halo]`` local columns, and libcrbe_b200 runs the BiCGStab with NCCL
+halo exchange before each SpMV and an allreduce per group of dot products.
+
+The index logic here (offsets, global ids, halo plans) is plain torch/numpy on
+whatever device the tensors live on, so it is unit-tested on CPU with gloo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+TILE = 256
+
+
+# --------------------------------------------------------------------------
+# closed-form global numbering of the structured mesh
+# --------------------------------------------------------------------------
+def dof_row_start(nx, j):
+    """Global id of the first DOF created in cell row j (row 0 creates 4nx+1 ids, later rows 3nx+1)."""
+    j = np.asarray(j, dtype=np.int64)
+    return np.where(j == 0, 0, (4 * nx + 1) + (j - 1) * (3 * nx + 1))
+
+
+def structured_total_dofs(nx, ny):
+    return 3 * nx * ny + nx + ny
+
+
+def _cell_base(nx, i, j):
+    return torch.where(j == 0, 4 * i + (i > 0).long(), (4 * nx + 1) + (j - 1) * (3 * nx + 1) + 3 * i + (i > 0).long())
+
+
+def structured_global_dof(nx, seg, j0=0):
+    """Global DOF id of each edge of a strip mesh.
+
+    ``seg``: (N,2) [min,max] LOCAL vertex ids of a strip starting at global cell
+    row ``j0`` (vertex id = jj*(nx+1)+i).  Edges are the right/diagonal/top (and
+    bottom in row 0, left in column 0) edges of the cells, numbered in that
+    order cell by cell, row by row."""
+    seg = seg.long()
+    a, b = seg[:, 0], seg[:, 1]
+    row = nx + 1
+    ia = a % row
+    J = a // row + j0
+    diff = b - a
+    out = torch.empty_like(a)
+    # horizontal edge (ia,J)-(ia+1,J): bottom of cell (ia,J) in row 0, else top of cell (ia,J-1)
+    h = diff == 1
+    Jh = torch.clamp(J - 1, min=0)
+    base_h = _cell_base(nx, ia, Jh)
+    top_h = base_h + torch.where(Jh == 0, 3, 2)
+    out = torch.where(h, torch.where(J == 0, _cell_base(nx, ia, J) + 2, top_h), out)
+    # vertical edge (ia,J)-(ia,J+1): left of cell (0,J) in column 0, else right of cell (ia-1,J)
+    v = diff == row
+    base0 = _cell_base(nx, torch.zeros_like(ia), J)
+    left0 = base0 + torch.where(J == 0, 3, 2) + 1
+    right_prev = _cell_base(nx, torch.clamp(ia - 1, min=0), J)
+    out = torch.where(v, torch.where(ia == 0, left0, right_prev), out)
+    # diagonal of cell (ia,J)
+    d = diff == row + 1
+    out = torch.where(d, _cell_base(nx, ia, J) + 1, out)
+    if not bool((h | v | d).all()):
+        raise ValueError("not an edge of the structured triangulation")
+    return out
+
+
+def strip_rows(ny, world):
+    """Cell-row ranges [j0, j1) of the ranks (balanced)."""
+    cuts = [(ny * r) // world for r in range(world + 1)]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def strip_offsets(nx, ny, world):
+    """DOF offsets of the ranks: rank r owns the global ids [off[r], off[r+1])."""
+    rows = strip_rows(ny, world)
+    off = [int(dof_row_start(nx, j0)) for j0, _ in rows] + [structured_total_dofs(nx, ny)]
+    return off
+
+
+# --------------------------------------------------------------------------
+# localisation of the owned rows: global column ids -> [owned | halo]
+# --------------------------------------------------------------------------
+def localize_columns(cols_global, d0, d1):
+    """Return (local_cols int32, halo_ids sorted int64, ld).  Owned columns map
+    to ``col - d0``; a halo column maps to ``ld + position in halo_ids``."""
+    n_own = d1 - d0
+    ld = (n_own + TILE - 1) // TILE * TILE
+    owned = (cols_global >= d0) & (cols_global < d1)
+    halo_ids = torch.unique(cols_global[~owned])
+    pos = torch.searchsorted(halo_ids, cols_global)
+    local = torch.where(owned, cols_global - d0, ld + pos)
+    return local.to(torch.int32), halo_ids, ld
+
+
+def exchange_plan(halo_ids, offsets, rank, world, group=None):
+    """Who sends what.  Every rank publishes the halo ids it needs; rank r then
+    sends to q the ids of q's halo that r owns (in ascending order, which is the
+    order of q's halo segment).  Returns (neigh, send_ids per neighbour (global),
+    recv_counts per neighbour)."""
+    halo_np = halo_ids.cpu().numpy().astype(np.int64)
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, halo_np, group=group)
+    else:
+        gathered = [halo_np]
+    d0, d1 = offsets[rank], offsets[rank + 1]
+    off = np.asarray(offsets, dtype=np.int64)
+    owner = np.searchsorted(off, halo_np, side="right") - 1
+    neigh, send_ids, recv_counts = [], [], []
+    for q in range(world):
+        if q == rank:
+            continue
+        want = gathered[q]
+        mine = want[(want >= d0) & (want < d1)]
+        nrecv = int(np.count_nonzero(owner == q))
+        if len(mine) or nrecv:
+            neigh.append(q)
+            send_ids.append(mine)
+            recv_counts.append(nrecv)
+    # the halo region is ordered by global id = by owner rank: segments arrive in neighbour order
+    assert sum(recv_counts) == len(halo_np)
+    return neigh, send_ids, recv_counts
+
+
+# --------------------------------------------------------------------------
+# communicator
+# --------------------------------------------------------------------------
+class Comm:
+    """NCCL communicator of libcrbe_b200 (separate from torch's process group,
+    which only ships the 128-byte unique id and set-up metadata)."""
+
+    def __init__(self, rt, rank, world):
+        from . import _lib
+        lib = _lib.load()
+        nbytes = lib.crbe_comm_unique_id_bytes()
+        buf = C.create_string_buffer(nbytes)
+        if rank == 0:
+            _lib.call("crbe_comm_unique_id", buf)
+        box = [bytes(buf.raw) if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        self.rank, self.world = rank, world
+        self.handle = C.c_void_p()
+        uid = C.create_string_buffer(box[0], nbytes)
+        _lib.call("crbe_comm_create", rt.ctx, rank, world, uid, C.byref(self.handle))
+
+    def destroy(self):
+        from . import _lib
+        if self.handle:
+            _lib.load().crbe_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+# --------------------------------------------------------------------------
+# the partitioned problem
+# --------------------------------------------------------------------------
+class PartitionedCRBE:
+    """Backward-Euler / Crank-Nicolson stepping of a structured ``Workload``
+    (``airpollution_b200.workloads``) split into strips of cell rows, or of an
+    arbitrary mesh (``mesh=``) with the global system assembled redundantly and
+    split into equal blocks of rows."""
+
+    def __init__(self, workload=None, *, mesh=None, domain=None, problem=None, nt=None, order=1, rank=None, world=None,
+                 device=None, comm=None, rtol=1e-13, max_iterations=10000, tma=True, verify=True):
+        from . import _lib, crbe
+        from .runtime import Runtime, ptr
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        rt = self.rt = Runtime.get(device)
+        self.comm = comm if comm is not None else Comm(rt, self.rank, self.world)
+        self._own_comm = comm is None
+        if workload is not None:
+            domain, problem, nt = workload.domain(), workload.problem(), workload.nt
+            nx, ny = workload.nx, workload.ny
+            rows = strip_rows(ny, self.world)
+            self.offsets = strip_offsets(nx, ny, self.world)
+            j0, j1 = rows[self.rank]
+            j1g = min(j1 + 1, ny)                      # one ghost cell row above completes the owned rows
+            ly = 0.5 * ny / nx
+            from .meshgen import structured_mesh
+            local_mesh = structured_mesh(nx, ny, lo=(-0.5, -ly), hi=(0.5, ly), strip=(j0, j1g))
+            md = crbe.MeshData(local_mesh, domain, nt, device=rt.device)
+            gid = structured_global_dof(nx, md._dev["segments"], j0)
+            self.n_global = structured_total_dofs(nx, ny)
+        else:
+            md = crbe.MeshData(mesh, domain, nt, device=rt.device)
+            n = md.number_of_segments
+            self.offsets = [(n * r) // self.world for r in range(self.world + 1)]
+            gid = torch.arange(n, device=rt.device, dtype=torch.int64)
+            self.n_global = n
+        self.domain, self.problem, self.nt, self.order = domain, problem, nt, order
+        self.dt = domain.T / (nt - 1)
+        d0, d1 = self.offsets[self.rank], self.offsets[self.rank + 1]
+        self.d0, self.d1, self.n_own = d0, d1, d1 - d0
+
+        # local assembly with the single-GPU kernels (set-up, not timed)
+        loc = crbe.BESCRFEM(domain, problem, md, crbe.ElementCR(), order, rtol=rtol, progress=False)
+        loc._coef()
+        loc._build_pattern()
+        loc._assemble_values()
+        ld_ = loc._dev
+        indptr_l, indices_l = ld_["indptr"].long(), ld_["indices"].long()
+        owned_mask = (gid >= d0) & (gid < d1)
+        own_local = torch.nonzero(owned_mask).squeeze(1)
+        order_ = torch.argsort(gid[own_local])
+        lrow = own_local[order_]                           # local edge id of global row d0 + k
+        if lrow.numel() != self.n_own or not bool((gid[lrow] == torch.arange(d0, d1, device=gid.device)).all()):
+            raise RuntimeError("strip does not contain every owned DOF")
+        counts = indptr_l[lrow + 1] - indptr_l[lrow]
+        indptr = torch.zeros(self.n_own + 1, dtype=torch.int64, device=gid.device)
+        indptr[1:] = torch.cumsum(counts, 0)
+        total = int(indptr[-1])
+        src = torch.repeat_interleave(indptr_l[lrow] - indptr[:-1], counts) + torch.arange(total, device=gid.device)
+        cols_g = gid[indices_l[src]]
+        local_cols, halo_ids, self.ld = localize_columns(cols_g, d0, d1)
+        self.halo_ids = halo_ids
+        self.n_halo = int(halo_ids.numel())
+        neigh, send_ids, recv_counts = exchange_plan(halo_ids, self.offsets, self.rank, self.world)
+        send_idx = np.concatenate([s - d0 for s in send_ids]).astype(np.int32) if send_ids else np.zeros(0, np.int32)
+        d = self._dev = {}
+        d["indptr"] = indptr.to(torch.int32)
+        d["indices"] = local_cols.contiguous()
+        d["s_val"] = ld_["s_val"][src].contiguous()
+        d["m_val"] = ld_["m_val"][src].contiguous()
+        if order == 2:
+            d["r_val"] = ld_["r_val"][src].contiguous()
+        isb = torch.zeros(md.number_of_segments, dtype=torch.bool, device=gid.device)
+        isb[md._dev["bnd"].long()] = True
+        d["bnd"] = torch.nonzero(isb[lrow]).squeeze(1).to(torch.int32)
+        d["send_idx"] = rt.upload(send_idx)
+        self.midpoints = md._dev["midpoints"][lrow].contiguous()     # owned rows, global order
+        self.bnd_global = (d["bnd"].long() + d0).cpu().numpy()
+        nb = int(d["bnd"].numel())
+        nn = len(neigh)
+        self.neigh = neigh
+        h = C.c_void_p()
+        rt.call("crbe_solver_create_partitioned", rt.ctx, self.comm.handle, self.n_own, self.n_halo, ptr(d["indptr"]),
+                ptr(d["indices"]), total, ptr(d["bnd"]), nb, nn, (C.c_int32 * max(nn, 1))(*neigh),
+                (C.c_int64 * max(nn, 1))(*[len(s) for s in send_ids]), ptr(d["send_idx"]),
+                (C.c_int64 * max(nn, 1))(*recv_counts), C.byref(h))
+        self._solver = h
+        flags = (_lib.SOLVER_VERIFY if verify else 0) | (_lib.SOLVER_TMA if tma else 0)
+        rt.call("crbe_solver_set_options", h, float(rtol), int(max_iterations), flags)
+        rt.call("crbe_solver_set_system", h, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
+        vlen = C.c_int64()
+        rt.call("crbe_solver_vector_length", h, C.byref(vlen), None)
+        self.u = rt.zeros((vlen.value,), torch.float64)
+        # initial condition at the owned midpoints (crbe.py:364-365), evaluated on the host like the reference
+        u0 = problem.initial_condition_fn(self.midpoints.cpu().numpy())
+        self.u[:self.n_own] = rt.upload(np.asarray(u0, dtype=np.float64))
+        self.info = _lib.SolveInfo()
+        self.step_index = 0
+        self.step_info = []
+        del loc, md
+        torch.cuda.empty_cache()
+
+    def step(self, source=None):
+        from .runtime import ptr
+        self.step_index += 1
+        self.rt.call("crbe_solver_step", self._solver, ptr(self.u), ptr(source), float(self.dt), C.byref(self.info))
+        self.step_info.append((self.info.iterations, self.info.relres, self.info.true_relres, self.info.restarts))
+        return self.info.iterations
+
+    def owned_solution(self, lifted=True):
+        """Owned block of the current solution (global rows d0..d1), lifted by the boundary data (crbe.py:429)."""
+        x = self.u[:self.n_own].cpu().numpy().copy()
+        if lifted and self.step_index > 0 and len(self.bnd_global):
+            t = self.step_index * self.dt
+            loc = self.bnd_global - self.d0
+            mid = self.midpoints.cpu().numpy()[loc]
+            x[loc] += self.problem.boundary_fn(np.hstack((mid, t * np.ones((len(loc), 1)))))
+        return x
+
+    def gather_solution(self, lifted=True):
+        """Full solution in the reference's global numbering on every rank."""
+        mine = self.owned_solution(lifted)
+        if self.world == 1:
+            return mine
+        parts = [None] * self.world
+        dist.all_gather_object(parts, mine)
+        return np.concatenate(parts)
+
+    def close(self):
+        from . import _lib
+        if self._solver:
+            _lib.load().crbe_solver_destroy(self._solver)
+            self._solver = None
+        if self._own_comm:
+            self.comm.destroy()
+
+
+# --------------------------------------------------------------------------
+# bench.py --gpus N
+# --------------------------------------------------------------------------
+def bench_partitioned(args, K, W, device):
+    import bench as B
+    from . import workloads
+    from .runtime import Runtime
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rt = Runtime.get(device)
+    if args.strong:
+        wl = workloads.unit_square(args.n, steps=K + W, regime=args.regime)
+        scaling = "strong"
+    else:
+        wl = workloads.unit_square(args.n, steps=K + W, regime=args.regime, ny=args.n * world)
+        scaling = "weak"
+    t0 = time.time()
+    part = PartitionedCRBE(wl, device=device, tma=not args.classic)
+    setup_s = time.time() - t0
+    for _ in range(W):
+        part.step()
+    sampler = B.ClockSampler(device.index)
+    sampler.start()
+    rt.call("crbe_solver_profile", part._solver, 1)
+    l0, l1 = C.c_int64(), C.c_int64()
+    rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l0))
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    iters = [part.step() for _ in range(K)]
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = float(ms_t.item())
+    rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l1))
+    rt.call("crbe_solver_profile", part._solver, 0)
+    clocks = sampler.stop()
+    pms, pcnt = (C.c_double * 8)(), (C.c_int64 * 8)()
+    rt.call("crbe_solver_profile_read", part._solver, pms, pcnt)
+    n_own = part.n_own
+    rb = dict(B.ROW_BYTES)
+    rb["pv"], rb["st"] = 48 + 3 * 8, 48 + 2 * 8
+    kern = {B.KINDS[k]: {"launches": int(pcnt[k]), "ms_per_launch": pms[k] / pcnt[k],
+                         "GBps": rb[B.KINDS[k]] * n_own / (pms[k] / pcnt[k] * 1e-3) / 1e9} for k in range(7) if pcnt[k] > 0}
+    steps_per_s = K / (ms * 1e-3)
+    counts = wl.counts()
+    units = world if scaling == "weak" else 1
+    # e2e: every step the owned block of the solution is downloaded into pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        E = max(2, min(args.e2e_steps, K))
+        host = torch.zeros((2, n_own), dtype=torch.float64, pin_memory=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        for k in range(E):
+            part.step()
+            host[k & 1].copy_(part.u[:n_own], non_blocking=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        el = torch.tensor([time.time() - t1], device=device, dtype=torch.float64)
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e = {"value": units * E / float(el.item()), "unit": B.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * n_own,
+               "steps": E, "api": "PartitionedCRBE.step() + download of the owned solution block per rank"}
+    result = {
+        "metric": B.METRIC, "value": units * steps_per_s, "unit": B.UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": wl.name + f", {world} strips of cell rows", **counts, "regime": wl.regime, "dt": wl.dt,
+                   "rtol": 1e-13, "dofs_per_gpu": n_own, "halo_dofs_rank0": part.n_halo,
+                   "value_definition": ("n_gpus x steps/s of the partitioned mesh: every GPU advances a 12.6M-DOF strip per step"
+                                        if scaling == "weak" else "steps/s of the fixed mesh"),
+                   "solver": "Jacobi-BiCGStab 5-kernel, NCCL halo exchange + allreduce",
+                   "iters_per_step": float(np.mean(iters)), "l2": "inputs larger than L2", "setup_s": setup_s},
+        "dof_updates_per_s": steps_per_s * counts["dofs"],
+        "clocks": clocks, "gpu_launches": int(l1.value - l0.value), "kernels": kern,
+        "roofline": {"bound": "hbm", "kernel": "pv: ELL SpMV v = A p + dot (r^,v), rank 0", "achieved": kern["pv"]["GBps"],
+                     "unit": "GB/s", "bytes_per_launch": rb["pv"] * n_own, "traffic": None},
+    }
+    if e2e:
+        result["e2e"] = e2e
+    part.close()
+    return result

@@ -29,7 +29,7 @@ class TriMesh:
 
 
 def structured_mesh(nx, ny=None, lo=(-0.5, -0.5), hi=(0.5, 0.5), index_dtype=np.int64,
-                    row_range=None):
+                    row_range=None, strip=None):
     """Row-major structured triangulation of ``[lo,hi]`` with ``nx*ny`` cells.
 
     Vertices ``vid = j*(nx+1)+i``; cell (i,j) with ``a=vid(i,j), b=a+1,
@@ -41,6 +41,12 @@ def structured_mesh(nx, ny=None, lo=(-0.5, -0.5), hi=(0.5, 0.5), index_dtype=np.
     ny = nx if ny is None else ny
     xs = np.linspace(lo[0], hi[0], nx + 1)
     ys = np.linspace(lo[1], hi[1], ny + 1)
+    if strip is not None:
+        # stand-alone mesh of the cell rows [s0, s1) with LOCAL vertex ids; the coordinates are slices of
+        # the global linspace so that every vertex has bit-identical coordinates in every strip
+        s0, s1 = strip
+        ys = ys[s0:s1 + 1]
+        ny = s1 - s0
     X, Y = np.meshgrid(xs, ys)
     points = np.stack([X.reshape(-1), Y.reshape(-1), np.zeros(X.size)], axis=1)
     j0, j1 = (0, ny) if row_range is None else row_range

@@ -153,6 +153,27 @@ int crbe_solver_rhs(crbe_solver* s, const double* u_d, const double* source_d, d
 int crbe_solver_lift(crbe_solver* s, const double* u_d, const double* bc_values_d, double* out_d);
 int crbe_solver_destroy(crbe_solver* s);
 
+/* ---- row-block partitioned solve over several GPUs (one process per GPU) -- */
+/* The reference is single-process; this is the multi-GPU extension of the same
+ * solve.  Rank r owns a contiguous block of DOF rows; NCCL
+ * carries the halo DOFs before each SpMV and the allreduce of the dot products. */
+typedef struct crbe_comm crbe_comm;
+int crbe_comm_unique_id_bytes(void);
+int crbe_comm_unique_id(void* id_out_h);                       /* rank 0 creates it, the host broadcasts it */
+int crbe_comm_create(crbe_ctx* ctx, int rank, int world, const void* unique_id_h, crbe_comm** out);
+int crbe_comm_destroy(crbe_comm* comm);
+/* Local rows only.  Column indices are local: [0, n_own) owned, ld + h for halo entry h
+ * (ld = n_own rounded up to 256, see crbe_solver_vector_length).  Neighbour q receives the
+ * owned entries send_idx_d[send_off[q] .. send_off[q+1]) and delivers recv_counts_h[q]
+ * consecutive halo entries.  Vectors passed to crbe_solver_step must have
+ * crbe_solver_vector_length doubles. */
+int crbe_solver_create_partitioned(crbe_ctx* ctx, crbe_comm* comm, int64_t n_own, int64_t n_halo,
+                                   const int32_t* indptr_d, const int32_t* indices_d, int64_t nnz,
+                                   const int32_t* bnd_seg_d, int64_t nb, int32_t n_neigh,
+                                   const int32_t* neigh_ranks_h, const int64_t* send_counts_h,
+                                   const int32_t* send_idx_d, const int64_t* recv_counts_h, crbe_solver** out);
+int crbe_solver_vector_length(crbe_solver* s, int64_t* len_h, int64_t* halo_offset_h);
+
 /* ---- measurement -------------------------------------------------------- */
 /* Per-kernel device time of the solver kernels, CUDA events on the context stream.
  * enable != 0 resets and starts the accumulation, 0 stops it.  crbe_solver_profile_read

@@ -1,0 +1,78 @@
+"""Row-block partitioned solve on 2 (or more) GPUs against the single-GPU solve and
+the CPU oracle.  Needs >= 2 CUDA devices; one process per GPU over NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, case, out_q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from airpollution_b200 import crbe, workloads
+        from airpollution_b200.distributed import PartitionedCRBE
+        from airpollution_b200.meshgen import delaunay_mesh
+        steps = 6
+        if case == "strips":
+            wl = workloads.unit_square(48, steps=steps, regime="P-T10", ny=96)
+            part = PartitionedCRBE(wl, device=dev)
+            mesh, dom, prob, nt, order = wl.mesh(), wl.domain(), wl.problem(), wl.nt, 1
+        else:
+            mesh = delaunay_mesh(3000, seed=7, lo=(-2.0, -2.0), hi=(2.0, 2.0))
+            order = 2 if case == "unstructured_cn" else 1
+            dom, prob, nt = crbe.Domain(2.0, 2.0, T=0.3), crbe.Problem(v=[1.0, 0.5], D=0.1, sigma=0.5), steps + 1
+            part = PartitionedCRBE(mesh=mesh, domain=dom, problem=prob, nt=nt, order=order, device=dev)
+        its = [part.step() for _ in range(steps)]
+        sol = part.gather_solution()
+        n_halo, neigh = part.n_halo, part.neigh
+        part.close()
+        res = None
+        if rank == 0:
+            md = crbe.MeshData(mesh, dom, nt, device=dev)
+            s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), order, progress=False)
+            ref = s.solve()[-1]
+            res = (float(np.linalg.norm(sol - ref) / np.linalg.norm(ref)), its, [i[0] for i in s.step_info])
+        out_q.put((rank, res, n_halo, neigh))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["strips", "unstructured", "unstructured_cn"])
+def test_partitioned_solve_matches_single_gpu(case):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rel, its, its_ref = results[0][1]
+    assert rel <= 1e-11, rel            # partitioned == single GPU up to the order of the dot-product sums
+    assert max(abs(a - b) for a, b in zip(its, its_ref)) <= 2
+    for rank, _, n_halo, neigh in results:
+        assert n_halo > 0 and len(neigh) >= 1
+        if case == "strips":
+            assert neigh == [r for r in (rank - 1, rank + 1) if 0 <= r < world]

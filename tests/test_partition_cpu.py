@@ -1,0 +1,123 @@
+"""CPU tests of the host logic of the row-block partition: closed-form
+global numbering of strips, localisation of the owned rows, and the halo plan run
+between two gloo ranks.  No GPU, no NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from airpollution_b200 import distributed as D
+from airpollution_b200.meshgen import structured_mesh
+from oracle import crbe_oracle as orc
+
+
+@pytest.mark.parametrize("nx,ny", [(1, 1), (3, 2), (5, 7), (16, 16), (9, 40)])
+def test_structured_global_dof_is_the_reference_numbering(nx, ny):
+    mesh = structured_mesh(nx, ny)
+    seg, _ = orc.enumerate_segments(mesh.triangles)
+    gid = D.structured_global_dof(nx, torch.from_numpy(seg))
+    np.testing.assert_array_equal(gid.numpy(), np.arange(len(seg)))
+    assert D.structured_total_dofs(nx, ny) == len(seg)
+
+
+@pytest.mark.parametrize("nx,ny,world", [(4, 8, 2), (5, 9, 3), (7, 16, 4), (3, 8, 8)])
+def test_strips_tile_the_global_numbering(nx, ny, world):
+    gmesh = structured_mesh(nx, ny, lo=(-0.5, -1.0), hi=(0.5, 1.0))
+    gm = orc.OracleMesh(gmesh.points, gmesh.triangles, 1.0, 3)
+    offsets = D.strip_offsets(nx, ny, world)
+    assert offsets[0] == 0 and offsets[-1] == gm.number_of_segments
+    seen = np.zeros(gm.number_of_segments, dtype=int)
+    for r, (j0, j1) in enumerate(D.strip_rows(ny, world)):
+        j1g = min(j1 + 1, ny)
+        lmesh = structured_mesh(nx, ny, lo=(-0.5, -1.0), hi=(0.5, 1.0), strip=(j0, j1g))
+        lm = orc.OracleMesh(lmesh.points, lmesh.triangles, 1.0, 3)
+        gid = D.structured_global_dof(nx, torch.from_numpy(lm.segments), j0).numpy()
+        # same physical edge: identical midpoints, bit for bit
+        np.testing.assert_array_equal(lm.midpoints, gm.midpoints[gid])
+        own = (gid >= offsets[r]) & (gid < offsets[r + 1])
+        assert own.sum() == offsets[r + 1] - offsets[r]
+        seen[gid[own]] += 1
+        # every triangle touching an owned edge is in the strip: owned rows of the local matrix are complete
+        cnt_l = np.bincount(lm.triangle_to_segments.reshape(-1), minlength=lm.number_of_segments)
+        cnt_g = np.bincount(gm.triangle_to_segments.reshape(-1), minlength=gm.number_of_segments)
+        np.testing.assert_array_equal(cnt_l[own], cnt_g[gid[own]])
+    assert (seen == 1).all()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, nx, ny, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gmesh = structured_mesh(nx, ny)
+        gm = orc.OracleMesh(gmesh.points, gmesh.triangles, 1.0, 3)
+        M, K, A = orc.assemble_global(gm.points, gm.triangles, gm.triangle_to_segments, gm.triangle_areas, 0.1, (1.0, 0.5),
+                                      gm.number_of_segments)
+        S = (M + 0.01 * (K + A)).tocsr()
+        offsets = D.strip_offsets(nx, ny, world)
+        d0, d1 = offsets[rank], offsets[rank + 1]
+        rows = S[d0:d1]
+        cols = torch.from_numpy(rows.indices.astype(np.int64))
+        local_cols, halo_ids, ld = D.localize_columns(cols, d0, d1)
+        neigh, send_ids, recv_counts = D.exchange_plan(halo_ids, offsets, rank, world)
+        # a vector whose entries are recognisable: x[g] = g + 0.5
+        x_loc = np.zeros(ld + len(halo_ids))
+        x_loc[:d1 - d0] = np.arange(d0, d1) + 0.5
+        reqs, bufs = [], []
+        pos = 0
+        for q, sids, nr in zip(neigh, send_ids, recv_counts):
+            send = torch.from_numpy(x_loc[sids - d0].copy())
+            recv = torch.zeros(nr, dtype=torch.float64)
+            reqs.append(dist.isend(send, q))
+            reqs.append(dist.irecv(recv, q))
+            bufs.append((pos, recv, send))
+            pos += nr
+        for r in reqs:
+            r.wait()
+        for p, recv, _ in bufs:
+            x_loc[ld + p: ld + p + len(recv)] = recv.numpy()
+        ok_halo = np.array_equal(x_loc[ld:], halo_ids.numpy() + 0.5)
+        # local SpMV over the owned rows == the global SpMV restricted to them
+        lc = local_cols.numpy()
+        y_loc = np.add.reduceat(rows.data * x_loc[lc], rows.indptr[:-1])
+        y_ref = (S @ (np.arange(S.shape[0]) + 0.5))[d0:d1]
+        out_q.put((rank, ok_halo, float(np.abs(y_loc - y_ref).max()), neigh, [len(s) for s in send_ids], recv_counts))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_plan_between_gloo_ranks(world):
+    nx, ny = 6, 12
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, ny, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    results.sort()
+    for rank, ok_halo, err, neigh, ns, nr in results:
+        assert ok_halo
+        assert err < 1e-12
+        assert neigh == [r for r in (rank - 1, rank + 1) if 0 <= r < world]   # strips only talk to their neighbours
+    # what r sends to q is what q expects from r
+    by_rank = {r[0]: r for r in results}
+    for rank, _, _, neigh, ns, nr in results:
+        for k, qq in enumerate(neigh):
+            other = by_rank[qq]
+            assert ns[k] == other[5][other[3].index(rank)]
