@@ -49,6 +49,17 @@ struct crbe_profile {
 enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RRTRUE = 7, S_AUX0 = 8, S_AUX1 = 9 };
 enum { D_STATUS = 0, D_ITERS = 1 };
 
+constexpr int CRBE_MAX_RANKS = 8;
+constexpr size_t P2P_HEADER_BYTES = 8192;
+// mailbox at the start of every rank's window.  Flags carry monotonically increasing epochs (never reset).
+struct P2PHeader {
+    unsigned int halo_flag[4][CRBE_MAX_RANKS];                 // [x, p, s][source rank]
+    unsigned int dot_flag[8][CRBE_MAX_RANKS];                  // [reduction kind][source rank]
+    double inbox[2][CRBE_NSUMS][CRBE_MAX_RANKS];               // [epoch parity][slot][source rank]
+    int error;
+};
+static_assert(sizeof(P2PHeader) <= P2P_HEADER_BYTES, "mailbox does not fit its header");
+
 struct crbe_solver {
     crbe_ctx* ctx = nullptr;
     int64_t n = 0, ld = 0, nnz = 0, nb = 0;
@@ -86,6 +97,20 @@ struct crbe_solver {
     double* sendbuf = nullptr;
     double* red = nullptr;         // staging for the allreduce of the dot products (same slot layout as sums)
     double* dots = nullptr;        // where the dot kernels write: sums (single GPU) or red
+    // peer-memory transport: the gathered vectors x, p, s and a small mailbox live in one CUDA-IPC window per rank;
+    // neighbours store halo values straight into it over NVLink and raise epoch flags (replaces the NCCL calls)
+    bool p2p = false;
+    int rank = 0;
+    unsigned char* window = nullptr;
+    void* peer_base[CRBE_MAX_RANKS] = {nullptr};
+    P2PHeader** d_peer_hdr = nullptr;          // device array [world]
+    double** d_halo_dst = nullptr;             // device array [3][n_neigh]: my segment inside neighbour q's halo of x, p, s
+    int* d_neigh = nullptr;
+    long long* d_send_off = nullptr;
+    unsigned epoch_halo[3] = {0, 0, 0};
+    unsigned epoch_dot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double* saved_p0 = nullptr;                // the stand-alone p, s allocations replaced by window storage
+    double* saved_s = nullptr;
     crbe_profile* prof = nullptr;
 };
 
@@ -396,13 +421,18 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_xr(int64_t n, int k, double rtol
 // true residual r = r^ = b - A x and its norm (restart / verification)
 __global__ void __launch_bounds__(CRBE_BLOCK) k_residual(int64_t n, int64_t ld, const double* __restrict__ eval, const int* __restrict__ ecol,
                                                          const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
-                                                         double* __restrict__ rh, double* sums, double* dots, double* partials, unsigned int* counter) {
+                                                         double* __restrict__ rh, double* sums, double* dots, double* partials, unsigned int* counter,
+                                                         const int* dstate, int guard, double rtol2) {
+    // guard: verification enqueued speculatively behind the iterations -- runs only once they have converged, writes nothing but the norm
+    if (guard && (dstate[D_STATUS] != 0 || sums[S_RR] > rtol2 * sums[S_BB])) return;
     double acc[1] = {0.0};
     ROW_LOOP(i, n) {
         const double ax = ell_row(eval, ecol, ld, i, x[i], [&](int j) { return __ldg(x + j); });
         const double ri = b[i] - ax;
-        r[i] = ri;
-        rh[i] = ri;
+        if (!guard) {
+            r[i] = ri;
+            rh[i] = ri;
+        }
         acc[0] = fma(ri, ri, acc[0]);
     }
     double* const out[1] = {dots + S_RRTRUE};
@@ -536,6 +566,10 @@ static int tile_grid(crbe_ctx* ctx, Kern kernel, int smem_bytes, int64_t ntiles,
 
 static int solver_release(crbe_solver* s) {
     if (!s) return CRBE_OK;
+    if (s->window) {               // p and s live in the window: free the stand-alone allocations they replaced
+        s->p[0] = s->saved_p0;
+        s->s = s->saved_s;
+    }
     cudaFree(s->bnd);
     cudaFree(s->is_bnd);
     cudaFree(s->ell_col);
@@ -556,6 +590,15 @@ static int solver_release(crbe_solver* s) {
     cudaFree(s->v[1]);
     cudaFree(s->sums);
     cudaFree(s->red);
+    if (s->window) {
+        for (int r = 0; r < s->world; ++r)
+            if (s->peer_base[r] && s->peer_base[r] != s->window) cudaIpcCloseMemHandle(s->peer_base[r]);
+        cudaFree(s->window);
+        cudaFree(s->d_peer_hdr);
+        cudaFree(s->d_halo_dst);
+        cudaFree(s->d_neigh);
+        cudaFree(s->d_send_off);
+    }
     cudaFree(s->send_idx);
     cudaFree(s->sendbuf);
     cudaFree(s->dstate);
@@ -688,6 +731,85 @@ extern "C" int crbe_solver_vector_length(crbe_solver* s, int64_t* len_h, int64_t
     return CRBE_OK;
 }
 
+// ---- peer-memory transport set-up -------------------------------------------------------------------------
+// Step 1 (every rank): move x, p, s into one IPC-exportable window and hand out its handle.
+extern "C" int crbe_solver_p2p_export(crbe_solver* s, void* ipc_handle_out, int64_t* meta_out) {
+    CRBE_REQUIRE(s && ipc_handle_out && meta_out && s->world > 1 && s->world <= CRBE_MAX_RANKS, "bad argument");
+    crbe_ctx* ctx = s->ctx;
+    if (!s->window) {
+        const size_t bytes = P2P_HEADER_BYTES + 3 * sizeof(double) * (size_t)s->veclen;
+        CRBE_CUDA(cudaMalloc(&s->window, bytes));
+        CRBE_CUDA(cudaMemsetAsync(s->window, 0, bytes, ctx->stream));
+        CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
+        double* base = (double*)(s->window + P2P_HEADER_BYTES);
+        s->saved_p0 = s->p[0];
+        s->saved_s = s->s;
+        s->p[0] = base + s->veclen;
+        s->s = base + 2 * s->veclen;
+    }
+    cudaIpcMemHandle_t h;
+    CRBE_CUDA(cudaIpcGetMemHandle(&h, s->window));
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    meta_out[0] = s->ld;
+    meta_out[1] = s->veclen;
+    return CRBE_OK;
+}
+
+// Step 2: handles_h = world x 64 bytes (rank order), ld_all/veclen_all = every rank's meta, halo_seg_off[q] = element
+// offset of MY segment inside neighbour q's halo region (its recv offset for me).
+extern "C" int crbe_solver_p2p_connect(crbe_solver* s, int rank, const void* handles_h, const int64_t* ld_all, const int64_t* veclen_all,
+                                       const int64_t* halo_seg_off) {
+    CRBE_REQUIRE(s && s->window && handles_h && ld_all && veclen_all && rank >= 0 && rank < s->world, "bad argument");
+    crbe_ctx* ctx = s->ctx;
+    s->rank = rank;
+    P2PHeader* hdrs[CRBE_MAX_RANKS] = {nullptr};
+    for (int r = 0; r < s->world; ++r) {
+        if (r == rank) {
+            s->peer_base[r] = s->window;
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const unsigned char*)handles_h + 64 * r, sizeof(h));
+            CRBE_CUDA(cudaIpcOpenMemHandle(&s->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        hdrs[r] = (P2PHeader*)s->peer_base[r];
+    }
+    const int nn = (int)s->neigh.size();
+    std::vector<double*> dst(3 * (nn > 0 ? nn : 1), nullptr);
+    for (int kind = 0; kind < 3; ++kind)
+        for (int q = 0; q < nn; ++q) {
+            const int r = s->neigh[q];
+            CRBE_REQUIRE(halo_seg_off != nullptr, "missing halo offsets");
+            double* vbase = (double*)((unsigned char*)s->peer_base[r] + P2P_HEADER_BYTES) + (size_t)kind * veclen_all[r];
+            dst[kind * nn + q] = vbase + ld_all[r] + halo_seg_off[q];
+        }
+    std::vector<long long> soff(s->send_off.begin(), s->send_off.end());
+    CRBE_CUDA(cudaMalloc(&s->d_peer_hdr, sizeof(P2PHeader*) * CRBE_MAX_RANKS));
+    CRBE_CUDA(cudaMemcpy(s->d_peer_hdr, hdrs, sizeof(P2PHeader*) * CRBE_MAX_RANKS, cudaMemcpyHostToDevice));
+    CRBE_CUDA(cudaMalloc(&s->d_halo_dst, sizeof(double*) * dst.size()));
+    CRBE_CUDA(cudaMemcpy(s->d_halo_dst, dst.data(), sizeof(double*) * dst.size(), cudaMemcpyHostToDevice));
+    CRBE_CUDA(cudaMalloc(&s->d_neigh, sizeof(int) * (nn > 0 ? nn : 1)));
+    if (nn > 0) CRBE_CUDA(cudaMemcpy(s->d_neigh, s->neigh.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
+    CRBE_CUDA(cudaMalloc(&s->d_send_off, sizeof(long long) * soff.size()));
+    CRBE_CUDA(cudaMemcpy(s->d_send_off, soff.data(), sizeof(long long) * soff.size(), cudaMemcpyHostToDevice));
+    CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->p2p = true;
+    return CRBE_OK;
+}
+
+// device pointer of the solver-owned solution vector (peer-memory transport: x must live in the window)
+extern "C" int crbe_solver_x(crbe_solver* s, void** x_out) {
+    CRBE_REQUIRE(s && x_out && s->window, "no window: call crbe_solver_p2p_export first");
+    *x_out = s->window + P2P_HEADER_BYTES;
+    return CRBE_OK;
+}
+
+extern "C" int crbe_solver_p2p_error(crbe_solver* s, int* err_h) {
+    CRBE_REQUIRE(s && err_h, "null argument");
+    *err_h = 0;
+    if (s->window) CRBE_CUDA(cudaMemcpy(err_h, &((P2PHeader*)s->window)->error, sizeof(int), cudaMemcpyDeviceToHost));
+    return CRBE_OK;
+}
+
 extern "C" int crbe_solver_destroy(crbe_solver* s) {
     if (s) cudaStreamSynchronize(s->ctx->stream);
     return solver_release(s);
@@ -760,12 +882,13 @@ static cudaEvent_t prof_event(crbe_profile* pf) {
     } while (0)
 
 // after a stream synchronisation: fold the finished records into the totals
-static void prof_collect(crbe_solver* s, int iterations_done) {
+static void prof_collect(crbe_solver* s, int iterations_done, bool converged) {
     crbe_profile* pf = s->prof;
     if (!pf) return;
     for (const ProfRecord& r : pf->pending) {
         float ms = 0.f;
-        if ((r.iter < 0 || r.iter < iterations_done) && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+        const bool ran = r.iter == -1 || (r.iter == -2 && converged) || (r.iter >= 0 && r.iter < iterations_done);
+        if (ran && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
             pf->ms[r.kind] += ms;
             pf->count[r.kind] += 1;
         }
@@ -786,10 +909,85 @@ __global__ void k_commit(const double* __restrict__ red, double* __restrict__ su
     if (c >= 0) sums[c] = red[c];
 }
 
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *flag has reached `epoch` (wrap-safe); gives up after ~20 s so a dead peer cannot wedge the GPU
+__device__ __forceinline__ bool wait_epoch(const unsigned int* flag, unsigned int epoch) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+        if (clock64() - t0 > (1LL << 35)) return false;
+        __nanosleep(64);
+    }
+    return true;
+}
+
+// Halo push over NVLink + arrival wait, one CTA.  Every neighbour q receives my boundary entries directly in
+// the halo segment of its own vector (dst[q]); a release store of the epoch tells it they are there; then the
+// CTA waits for the neighbours' epochs, so the kernel that follows in the stream sees a complete halo.
+__global__ void __launch_bounds__(1024) k_p2p_halo(const double* __restrict__ vec, const int* __restrict__ send_idx,
+                                                   const long long* __restrict__ send_off, double* const* __restrict__ dst,
+                                                   const int* __restrict__ neigh, int n_neigh, P2PHeader* self,
+                                                   P2PHeader* const* __restrict__ peers, int kind, unsigned int epoch, int rank) {
+    for (int q = 0; q < n_neigh; ++q) {
+        double* d = dst[q];
+        const long long o = send_off[q], cnt = send_off[q + 1] - o;
+        for (long long k = threadIdx.x; k < cnt; k += blockDim.x) d[k] = vec[send_idx[o + k]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < n_neigh) {
+        st_release_sys(&peers[neigh[threadIdx.x]]->halo_flag[kind][rank], epoch);
+        if (!wait_epoch(&self->halo_flag[kind][neigh[threadIdx.x]], epoch)) self->error = 1;
+    }
+    __syncthreads();
+}
+
+// Allreduce of `count` doubles red[first..] through the peers' mailboxes, one CTA: every rank deposits its
+// partial sums in everybody's inbox, waits for all deposits and adds them in rank order -- the same bits on
+// every rank, no NCCL call, no separate commit.  Slots a, b, c are then published in `sums`.
+__global__ void __launch_bounds__(32) k_p2p_allreduce(const double* __restrict__ red, double* __restrict__ sums, int first, int count,
+                                                      int a, int b, int c, P2PHeader* self, P2PHeader* const* __restrict__ peers,
+                                                      int kind, unsigned int epoch, int rank, int world) {
+    const int t = threadIdx.x, par = epoch & 1;
+    if (t < world) {
+        P2PHeader* d = peers[t];
+        for (int sl = first; sl < first + count; ++sl) d->inbox[par][sl][rank] = red[sl];
+        __threadfence_system();
+        st_release_sys(&d->dot_flag[kind][rank], epoch);
+        if (!wait_epoch(&self->dot_flag[kind][t], epoch)) self->error = 2;
+    }
+    __syncwarp();
+    if (t < 3) {
+        const int sl = t == 0 ? a : (t == 1 ? b : c);
+        if (sl >= 0) {
+            double acc = 0.0;
+            for (int r = 0; r < world; ++r) acc += __ldcv(&self->inbox[par][sl][r]);
+            sums[sl] = acc;
+        }
+    }
+}
+
 // refresh the halo entries of a gathered vector from their owners (no-op on a single GPU)
 static int halo_exchange(crbe_solver* s, double* vec, int* launches) {
     if (s->world <= 1 || s->neigh.empty()) return CRBE_OK;
     crbe_ctx* ctx = s->ctx;
+    if (s->p2p) {
+        const int kind = vec == (double*)(s->window + P2P_HEADER_BYTES) ? 0 : (vec == s->p[0] ? 1 : (vec == s->s ? 2 : -1));
+        CRBE_REQUIRE(kind >= 0, "peer-memory transport: the vector is not one of the window vectors (use crbe_solver_x)");
+        const unsigned epoch = ++s->epoch_halo[kind];
+        const int nn = (int)s->neigh.size();
+        k_p2p_halo<<<1, 1024, 0, ctx->stream>>>(vec, s->send_idx, s->d_send_off, s->d_halo_dst + kind * nn, s->d_neigh, nn,
+                                                (P2PHeader*)s->window, s->d_peer_hdr, kind, epoch, s->rank);
+        CRBE_KERNEL_CHECK();
+        *launches += 1;
+        return CRBE_OK;
+    }
     const int64_t cnt = s->send_off.back();
     if (cnt > 0) {
         k_pack<<<crbe_grid_for(ctx, cnt), CRBE_BLOCK, 0, ctx->stream>>>(vec, s->send_idx, cnt, s->sendbuf);
@@ -803,6 +1001,15 @@ static int halo_exchange(crbe_solver* s, double* vec, int* launches) {
 // sum the freshly written dot products red[first .. first+count) over the ranks, then publish slots a, b, c
 static int reduce_dots(crbe_solver* s, int first, int count, int a, int b, int c, int* launches) {
     if (s->world <= 1) return CRBE_OK;
+    if (s->p2p) {
+        const int kind = first == S_BB ? 0 : (first == S_RHV ? 1 : (first == S_TS ? 2 : (first == S_RR ? 3 : 4)));
+        const unsigned epoch = ++s->epoch_dot[kind];
+        k_p2p_allreduce<<<1, 32, 0, s->ctx->stream>>>(s->red, s->sums, first, count, a, b, c, (P2PHeader*)s->window, s->d_peer_hdr, kind,
+                                                      epoch, s->rank, s->world);
+        CRBE_KERNEL_CHECK();
+        *launches += 1;
+        return CRBE_OK;
+    }
     CRBE_CHECK(crbe_comm_allreduce_sum(s->comm, s->red + first, count, s->ctx->stream));
     k_commit<<<1, 1, 0, s->ctx->stream>>>(s->red, s->sums, a, b, c);
     CRBE_KERNEL_CHECK();
@@ -876,6 +1083,25 @@ static int fetch_state(crbe_solver* s) {
     return CRBE_OK;
 }
 
+// true residual ||b - A x||^2 -> S_RRTRUE.  guard = 1: speculative verification (see the kernels)
+static int launch_residual(crbe_solver* s, double* x, int guard, int* launches) {
+    crbe_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const double rtol2 = s->rtol * s->rtol;
+    CRBE_CHECK(halo_exchange(s, x, launches));
+    if (s->flags & CRBE_SOLVER_TMA)
+        PROF_LAUNCH(PK_RES, guard ? -2 : -1, (t_residual<<<s->gt_res, CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
+                                                 s->n, s->ntiles, s->ell_val, s->ell_col, x, s->b, s->r, s->rh, s->sums, s->dots, ctx->partials,
+                                                 ctx->counter, s->dstate, guard, rtol2)));
+    else
+        PROF_LAUNCH(PK_RES, guard ? -2 : -1, (k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->b, s->r,
+                                                                                         s->rh, s->sums, s->dots, ctx->partials, ctx->counter,
+                                                                                         s->dstate, guard, rtol2)));
+    *launches += 1;
+    CRBE_KERNEL_CHECK();
+    return reduce_dots(s, S_RRTRUE, 1, S_RRTRUE, -1, -1, launches);
+}
+
 // Iterate from the state left by k_init until converged.  b, r, r^ and the sums are on the device.
 static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* launches) {
     crbe_ctx* ctx = s->ctx;
@@ -885,6 +1111,7 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
     const int* dst_h = (const int*)(s->sums_h + CRBE_NSUMS);
     int total_iters = 0, restarts = 0, status = 0;
     double true_rr = -1.0;
+    const bool verify = (s->flags & CRBE_SOLVER_VERIFY) != 0;
     for (;;) {
         int k = 0;
         int target = s->last_iters + 1;
@@ -893,12 +1120,14 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
         bool done = false;
         for (;;) {
             for (; k < target; ++k) CRBE_CHECK(launch_iteration(s, k, x, launches));
+            // the verification rides behind the batch (it returns at once unless the batch converged): one sync per step
+            if (verify) CRBE_CHECK(launch_residual(s, x, 1, launches));
             CRBE_KERNEL_CHECK();
             CRBE_CHECK(fetch_state(s));
-            prof_collect(s, dst_h[D_ITERS]);
             const double rr = s->sums_h[S_RR], bb = s->sums_h[S_BB];
             status = dst_h[D_STATUS];
             done = status != 0 || !(rr > rtol2 * bb) || !isfinite(rr);
+            prof_collect(s, dst_h[D_ITERS], done && status == 0 && isfinite(rr));
             if (!isfinite(rr)) status = 2;
             if (done) break;
             if (total_iters + k >= s->maxit) {
@@ -917,27 +1146,30 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
             status = 0;
             break;
         }
-        const bool verify = (s->flags & CRBE_SOLVER_VERIFY) != 0;
         if (status == 0 && !verify) break;
-        CRBE_CHECK(halo_exchange(s, x, launches));
-        if (s->flags & CRBE_SOLVER_TMA)
-            PROF_LAUNCH(PK_RES, -1, (t_residual<<<s->gt_res, CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
-                                        s->n, s->ntiles, s->ell_val, s->ell_col, x, s->b, s->r, s->rh, s->sums, s->dots, ctx->partials, ctx->counter)));
-        else
-            PROF_LAUNCH(PK_RES, -1, (k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->b, s->r, s->rh,
-                                                                                s->sums, s->dots, ctx->partials, ctx->counter)));
-        *launches += 1;
-        CRBE_KERNEL_CHECK();
-        CRBE_CHECK(reduce_dots(s, S_RRTRUE, 1, S_RRTRUE, -1, -1, launches));
-        CRBE_CHECK(fetch_state(s));
-        prof_collect(s, 0);
-        true_rr = s->sums_h[S_RRTRUE];
-        if (status == 0 && true_rr <= accept2 * s->sums_h[S_BB]) break;
-        if (!isfinite(true_rr) || restarts >= 5 || total_iters >= s->maxit) {
+        if (status == 0) {
+            true_rr = s->sums_h[S_RRTRUE];
+            if (true_rr <= accept2 * s->sums_h[S_BB]) break;
+        }
+        if (restarts >= 5 || total_iters >= s->maxit) {
             if (status == 0) status = 1;
             break;
         }
-        ++restarts;                      // breakdown, or recurrence and true residual have drifted apart
+        // breakdown, or recurrence and true residual have drifted apart: restart from the true residual
+        CRBE_CHECK(launch_residual(s, x, 0, launches));
+        CRBE_CHECK(fetch_state(s));
+        prof_collect(s, 0, true);
+        true_rr = s->sums_h[S_RRTRUE];
+        if (!isfinite(true_rr)) {
+            status = 2;
+            break;
+        }
+        if (true_rr <= rtol2 * s->sums_h[S_BB]) {   // the iterate is already good enough
+            s->sums_h[S_RR] = true_rr;
+            status = 0;
+            break;
+        }
+        ++restarts;
         k_restart<<<1, 1, 0, st>>>(s->sums, s->dstate);
         *launches += 1;
         status = 0;

@@ -165,14 +165,20 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int
             double pi, vi, rhi;
             if (FUSED) {
                 const double beta = sc.beta, omega = sc.omega;
-                auto pnew = [&](int64_t j) {
+                const double *sr = pipe.svec(m, 0), *sp = pipe.svec(m, 1), *sv = pipe.svec(m, 2);
+                const int row0 = (int)(row - tr);
+                // neighbours inside the tile (3 of 4 for a CR row) come from the staged copies in shared memory
+                auto pnew = [&](int j) {
+                    const unsigned q = (unsigned)(j - row0);
+                    if (q < (unsigned)CRBE_TILE) return k > 0 ? p_update(sr[q], sp[q], sv[q], beta, omega) : sr[q];
                     return k > 0 ? p_update(__ldg(r + j), __ldg(p_in + j), __ldg(v_in + j), beta, omega) : __ldg(r + j);
                 };
-                pi = k > 0 ? p_update(pipe.svec(m, 0)[tr], pipe.svec(m, 1)[tr], pipe.svec(m, 2)[tr], beta, omega) : pipe.svec(m, 0)[tr];
+                pi = pnew((int)row);
                 rhi = pipe.svec(m, 3)[tr];
                 p_out[row] = pi;
-                vi = tile_row(pipe.sval(m), pipe.scol(m), tr, pi, [&](int j) { return pnew(j); });
+                vi = tile_row(pipe.sval(m), pipe.scol(m), tr, pi, pnew);
             } else {
+                // (serving the in-tile neighbours from the staged copy was measured slower than L1 hits here)
                 pi = pipe.svec(m, 0)[tr];
                 rhi = pipe.svec(m, 1)[tr];
                 vi = tile_row(pipe.sval(m), pipe.scol(m), tr, pi, [&](int j) { return __ldg(p_in + j); });
@@ -286,9 +292,12 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
 // ---- true residual r = r^ = b - A x and its norm -------------------------------------------------------
 __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntiles, const double* __restrict__ eval, const int* __restrict__ ecol,
                                                         const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
-                                                        double* __restrict__ rh, double* sums, double* dots, double* partials, unsigned int* counter) {
+                                                        double* __restrict__ rh, double* sums, double* dots, double* partials, unsigned int* counter,
+                                                        const int* dstate, int guard, double rtol2) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
+    // guard: verification enqueued speculatively behind the iterations -- runs only once they have converged, writes nothing but the norm
+    if (guard && (dstate[D_STATUS] != 0 || sums[S_RR] > rtol2 * sums[S_BB])) return;
     TilePipe<1> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
@@ -303,8 +312,10 @@ __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntile
         if (row < n) {
             const double ax = tile_row(pipe.sval(m), pipe.scol(m), tr, xi, [&](int j) { return __ldg(x + j); });
             const double ri = pipe.svec(m, 0)[tr] - ax;
-            r[row] = ri;
-            rh[row] = ri;
+            if (!guard) {
+                r[row] = ri;
+                rh[row] = ri;
+            }
             acc[0] = fma(ri, ri, acc[0]);
         }
         pipe.release(m);

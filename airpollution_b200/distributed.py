@@ -173,11 +173,14 @@ class PartitionedCRBE:
     split into equal blocks of rows."""
 
     def __init__(self, workload=None, *, mesh=None, domain=None, problem=None, nt=None, order=1, rank=None, world=None,
-                 device=None, comm=None, rtol=1e-13, max_iterations=10000, tma=True, verify=True):
+                 device=None, comm=None, rtol=1e-13, max_iterations=10000, tma=True, verify=True, p2p=None):
         from . import _lib, crbe
         from .runtime import Runtime, ptr
+        import os
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
+        if p2p is None:
+            p2p = os.environ.get("CRBE_P2P", "1") != "0"
         rt = self.rt = Runtime.get(device)
         self.comm = comm if comm is not None else Comm(rt, self.rank, self.world)
         self._own_comm = comm is None
@@ -256,7 +259,12 @@ class PartitionedCRBE:
         rt.call("crbe_solver_set_system", h, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
         vlen = C.c_int64()
         rt.call("crbe_solver_vector_length", h, C.byref(vlen), None)
-        self.u = rt.zeros((vlen.value,), torch.float64)
+        self.transport = "nccl"
+        if self.world > 1 and p2p:
+            self.u = self._connect_peers(rt, h, neigh, recv_counts, vlen.value)
+            self.transport = "peer-memory (CUDA IPC over NVLink)"
+        else:
+            self.u = rt.zeros((vlen.value,), torch.float64)
         # initial condition at the owned midpoints (crbe.py:364-365), evaluated on the host like the reference
         u0 = problem.initial_condition_fn(self.midpoints.cpu().numpy())
         self.u[:self.n_own] = rt.upload(np.asarray(u0, dtype=np.float64))
@@ -265,6 +273,33 @@ class PartitionedCRBE:
         self.step_info = []
         del loc, md
         torch.cuda.empty_cache()
+
+    def _connect_peers(self, rt, h, neigh, recv_counts, veclen):
+        """Peer-memory transport: gather every rank's IPC handle and layout, connect, and return the
+        solver-owned solution vector (it lives in the IPC window so that neighbours can write its halo)."""
+        handle = C.create_string_buffer(64)
+        meta = (C.c_int64 * 2)()
+        rt.call("crbe_solver_p2p_export", h, handle, meta)
+        mine = {"handle": bytes(handle.raw), "ld": int(meta[0]), "veclen": int(meta[1]), "neigh": list(neigh),
+                "recv_counts": list(recv_counts)}
+        allm = [None] * self.world
+        dist.all_gather_object(allm, mine)
+        seg = []
+        for q in neigh:           # where my values land inside q's halo region: q's receive offset for me
+            k = allm[q]["neigh"].index(self.rank)
+            seg.append(sum(allm[q]["recv_counts"][:k]))
+        handles = b"".join(m["handle"] for m in allm)
+        nn = max(len(neigh), 1)
+        rt.call("crbe_solver_p2p_connect", h, self.rank, C.create_string_buffer(handles, len(handles)),
+                (C.c_int64 * self.world)(*[m["ld"] for m in allm]), (C.c_int64 * self.world)(*[m["veclen"] for m in allm]),
+                (C.c_int64 * nn)(*(seg or [0])))
+        xp = C.c_void_p()
+        rt.call("crbe_solver_x", h, C.byref(xp))
+        dist.barrier()            # every window is mapped before anybody starts pushing into it
+
+        class _Window:
+            __cuda_array_interface__ = {"shape": (veclen,), "typestr": "<f8", "data": (xp.value, False), "version": 3}
+        return torch.as_tensor(_Window(), device=rt.device)
 
     def step(self, source=None):
         from .runtime import ptr
@@ -294,6 +329,10 @@ class PartitionedCRBE:
 
     def close(self):
         from . import _lib
+        self.u = None             # aliases library memory
+        if self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()        # nobody unmaps a window a neighbour may still write to
         if self._solver:
             _lib.load().crbe_solver_destroy(self._solver)
             self._solver = None
@@ -375,7 +414,7 @@ def bench_partitioned(args, K, W, device):
                    "rtol": 1e-13, "dofs_per_gpu": n_own, "halo_dofs_rank0": part.n_halo,
                    "value_definition": ("n_gpus x steps/s of the partitioned mesh: every GPU advances a 12.6M-DOF strip per step"
                                         if scaling == "weak" else "steps/s of the fixed mesh"),
-                   "solver": "Jacobi-BiCGStab 5-kernel, NCCL halo exchange + allreduce",
+                   "solver": "Jacobi-BiCGStab 5-kernel, halo exchange + allreduce over " + part.transport,
                    "iters_per_step": float(np.mean(iters)), "l2": "inputs larger than L2", "setup_s": setup_s},
         "dof_updates_per_s": steps_per_s * counts["dofs"],
         "clocks": clocks, "gpu_launches": int(l1.value - l0.value), "kernels": kern,

@@ -228,7 +228,6 @@ def main():
         step()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    rt.call("crbe_solver_profile", solver._solver, 1)
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l0))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -239,6 +238,17 @@ def main():
     ms = e0.elapsed_time(e1)
     l1 = C.c_int64()
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l1))
+    # same region once more with a CUDA event pair around every kernel launch: per-kernel durations for the roofline
+    KP = min(K, 40)
+    rt.call("crbe_solver_profile", solver._solver, 1)
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(KP):
+        step()
+    p1.record()
+    torch.cuda.synchronize()
+    ms_prof = p0.elapsed_time(p1)
     rt.call("crbe_solver_profile", solver._solver, 0)
     clocks = sampler.stop()
     pms = (C.c_double * 8)()
@@ -271,6 +281,7 @@ def main():
                    "iters_per_step": it_mean, "l2": "inputs larger than L2 (1.9 GB touched per iteration vs 126 MB L2)",
                    "setup_s": t_setup},
         "dof_updates_per_s": steps_per_s * n,
+        "steps_per_s_with_kernel_events": KP / (ms_prof * 1e-3),
         "clocks": clocks,
         "gpu_launches": int(l1.value - l0.value),
         "kernels": kern,

@@ -173,6 +173,18 @@ int crbe_solver_create_partitioned(crbe_ctx* ctx, crbe_comm* comm, int64_t n_own
                                    const int32_t* neigh_ranks_h, const int64_t* send_counts_h,
                                    const int32_t* send_idx_d, const int64_t* recv_counts_h, crbe_solver** out);
 int crbe_solver_vector_length(crbe_solver* s, int64_t* len_h, int64_t* halo_offset_h);
+/* Peer-memory transport (optional, replaces the NCCL calls of the partitioned solver): the gathered
+ * vectors x, p, s and a mailbox live in one CUDA-IPC window per rank; neighbours store halo values
+ * straight into it over NVLink and raise epoch flags, dot products are all-reduced through the mailboxes
+ * by one-CTA kernels.  Step 1, every rank: export (64-byte IPC handle; meta_h[2] = {ld, veclen}).
+ * The host gathers handles and metas of all ranks.  Step 2: connect (handles_h = world x 64 bytes in rank
+ * order; halo_seg_off_h[q] = offset of this rank's segment inside neighbour q's halo region).
+ * Afterwards crbe_solver_step must be given the window vector returned by crbe_solver_x. */
+int crbe_solver_p2p_export(crbe_solver* s, void* ipc_handle_out_h, int64_t* meta_h);
+int crbe_solver_p2p_connect(crbe_solver* s, int rank, const void* handles_h, const int64_t* ld_all_h,
+                            const int64_t* veclen_all_h, const int64_t* halo_seg_off_h);
+int crbe_solver_x(crbe_solver* s, void** x_d_out);
+int crbe_solver_p2p_error(crbe_solver* s, int* err_h);       /* non-zero: a peer never signalled (timeout) */
 
 /* ---- measurement -------------------------------------------------------- */
 /* Per-kernel device time of the solver kernels, CUDA events on the context stream.

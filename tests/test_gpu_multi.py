@@ -16,8 +16,9 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case, out_q):
+def _worker(rank, world, port, case, p2p, out_q):
     import torch.distributed as dist
+    os.environ["CRBE_P2P"] = "1" if p2p else "0"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -40,6 +41,7 @@ def _worker(rank, world, port, case, out_q):
         its = [part.step() for _ in range(steps)]
         sol = part.gather_solution()
         n_halo, neigh = part.n_halo, part.neigh
+        assert ("peer-memory" in part.transport) == bool(p2p)
         part.close()
         res = None
         if rank == 0:
@@ -53,8 +55,9 @@ def _worker(rank, world, port, case, out_q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [True, False], ids=["peer-memory", "nccl"])
 @pytest.mark.parametrize("case", ["strips", "strips_stiff", "unstructured", "unstructured_cn"])
-def test_partitioned_solve_matches_single_gpu(case):
+def test_partitioned_solve_matches_single_gpu(case, p2p):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -62,7 +65,7 @@ def test_partitioned_solve_matches_single_gpu(case):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, p2p, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = sorted(q.get(timeout=600) for _ in range(world))

@@ -382,3 +382,30 @@ def test_large_mesh_properties():
     assert np.linalg.norm(x - x_prev) > 0
     # mass is transported, not created: total stays within the O(dt) boundary flux
     assert abs(x.sum() / x_prev.sum() - 1.0) < 1e-3
+
+
+def test_callers_run_through_the_drop_in_module(tmp_path, monkeypatch):
+    """The reference's drivers: `import crbe; import meshio; crbe.create_mesh -> meshio.read -> MeshData ->
+    BESCRFEM.solve -> compute_errors` (crbe.py:675-695, experiments/crbe_experiments.py:43-83)."""
+    import importlib
+    import sys
+    monkeypatch.setenv("CRBE_SWEEP_SIZES", "4,8,16")
+    monkeypatch.setenv("CRBE_SWEEP_NT", "128")
+    monkeypatch.setenv("CRBE_SWEEP_DIR", str(tmp_path))
+    sys.modules.pop("experiments.crbe_experiments", None)
+    mod = importlib.import_module("experiments.crbe_experiments")
+    df = mod.run_sweep()
+    assert list(df["n_dofs"]) == [33, 161, 705]          # n_points_per_axis 4, 8, 16 -> 3, 7, 15 cells per axis
+    for col in ("mesh_size", "n_dofs", "n_boundary_dofs", "l2_error", "rel_l2_error", "max_error", "train_time",
+                "gpu_memory_usage_MB", "cpu_memory_usage_MB", "number_of_collocation_points"):
+        assert col in df.columns
+    assert (tmp_path / "df_crbe_training_results.csv").exists()
+    # same meshes through the oracle: identical error table
+    import crbe
+    import meshio
+    for ms, rel in zip((4, 8, 16), df["rel_l2_error"]):
+        mesh = meshio.read(crbe.create_mesh(ms, domain_size=20.0, filename=str(tmp_path / "m.msh")))
+        om = orc.OracleMesh(mesh.points, mesh.cells_dict["triangle"], 10, 128)
+        o = orc.OracleSolver(10, crbe.Problem(sigma=1.0), om)
+        o.solve()
+        assert abs(o.compute_errors(crbe.Problem(sigma=1.0).analytical_solution)[0] - rel) <= 1e-10 * rel
