@@ -73,7 +73,7 @@ def build_library(force=False, verbose=False):
             if p.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {cmd[-3]}")
     if force or jobs or _stale(LIB, objs):
-        libs = ["-lnccl"] if "dist.cu" in sources else []
+        libs = ["-ldl"]   # NCCL is bound with dlopen at run time (dist.cu), never at link time
         cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + libs
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:

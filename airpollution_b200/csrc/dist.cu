@@ -3,10 +3,61 @@
 // (SURVEY.md section 8e): the halo-DOF exchange before each SpMV (grouped
 // ncclSend/ncclRecv with the one or two strip neighbours) and the allreduce of
 // the 1-3 BiCGStab dot products.  NCCL is confined to this translation unit.
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is bound at run time (see nccl_api below)
 #include <string.h>
 
 #include "crbe_common.cuh"
+
+// libnccl is dlopen'ed on first use instead of being a link-time dependency: a process that has already
+// loaded a (newer) libnccl.so.2 -- PyTorch bundles its own -- must keep using that one, and hosts that never
+// go multi-GPU do not need NCCL at all.
+struct nccl_api {
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+};
+
+static nccl_api* nccl() {
+    static nccl_api api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+#define CRBE_BIND(name) api.name = (decltype(api.name))dlsym(h, "nccl" #name)
+            CRBE_BIND(GetUniqueId);
+            CRBE_BIND(CommInitRank);
+            CRBE_BIND(CommDestroy);
+            CRBE_BIND(AllReduce);
+            CRBE_BIND(Send);
+            CRBE_BIND(Recv);
+            CRBE_BIND(GroupStart);
+            CRBE_BIND(GroupEnd);
+            CRBE_BIND(GetErrorString);
+#undef CRBE_BIND
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Send && api.Recv &&
+                     api.GroupStart && api.GroupEnd && api.GetErrorString;
+        }
+    }
+    return &api;
+}
+
+#define CRBE_NEED_NCCL()                                                                  \
+    do {                                                                                  \
+        if (!nccl()->ok) {                                                                \
+            crbe_set_error("libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbols"); \
+            return CRBE_ERR_COMM;                                                         \
+        }                                                                                 \
+    } while (0)
 
 struct crbe_comm {
     ncclComm_t nccl = nullptr;
@@ -18,7 +69,7 @@ struct crbe_comm {
     do {                                                                                         \
         ncclResult_t r_ = (call);                                                                \
         if (r_ != ncclSuccess) {                                                                 \
-            crbe_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+            crbe_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, nccl()->GetErrorString(r_)); \
             return CRBE_ERR_COMM;                                                                \
         }                                                                                        \
     } while (0)
@@ -28,13 +79,15 @@ extern "C" int crbe_comm_unique_id_bytes(void) { return (int)sizeof(ncclUniqueId
 extern "C" int crbe_comm_unique_id(void* id_out) {
     CRBE_REQUIRE(id_out != nullptr, "null argument");
     ncclUniqueId id;
-    CRBE_NCCL(ncclGetUniqueId(&id));
+    CRBE_NEED_NCCL();
+    CRBE_NCCL(nccl()->GetUniqueId(&id));
     memcpy(id_out, &id, sizeof(id));
     return CRBE_OK;
 }
 
 extern "C" int crbe_comm_create(crbe_ctx* ctx, int rank, int world, const void* unique_id, crbe_comm** out) {
     CRBE_REQUIRE(ctx && out && unique_id && world >= 1 && rank >= 0 && rank < world, "bad argument");
+    CRBE_NEED_NCCL();
     CRBE_CUDA(cudaSetDevice(ctx->device));
     crbe_comm* c = new crbe_comm();
     c->rank = rank;
@@ -42,9 +95,9 @@ extern "C" int crbe_comm_create(crbe_ctx* ctx, int rank, int world, const void* 
     c->ctx = ctx;
     ncclUniqueId id;
     memcpy(&id, unique_id, sizeof(id));
-    ncclResult_t r = ncclCommInitRank(&c->nccl, world, id, rank);
+    ncclResult_t r = nccl()->CommInitRank(&c->nccl, world, id, rank);
     if (r != ncclSuccess) {
-        crbe_set_error("ncclCommInitRank failed: %s", ncclGetErrorString(r));
+        crbe_set_error("ncclCommInitRank failed: %s", nccl()->GetErrorString(r));
         delete c;
         return CRBE_ERR_COMM;
     }
@@ -54,7 +107,7 @@ extern "C" int crbe_comm_create(crbe_ctx* ctx, int rank, int world, const void* 
 
 extern "C" int crbe_comm_destroy(crbe_comm* c) {
     if (!c) return CRBE_OK;
-    if (c->nccl) ncclCommDestroy(c->nccl);
+    if (c->nccl) nccl()->CommDestroy(c->nccl);
     delete c;
     return CRBE_OK;
 }
@@ -64,7 +117,7 @@ int crbe_comm_world(const crbe_comm* c) { return c ? c->world : 1; }
 
 // in-place sum of `count` doubles over all ranks, enqueued on `stream`
 int crbe_comm_allreduce_sum(crbe_comm* c, double* buf_d, int count, cudaStream_t stream) {
-    CRBE_NCCL(ncclAllReduce(buf_d, buf_d, (size_t)count, ncclDouble, ncclSum, c->nccl, stream));
+    CRBE_NCCL(nccl()->AllReduce(buf_d, buf_d, (size_t)count, ncclDouble, ncclSum, c->nccl, stream));
     return CRBE_OK;
 }
 
@@ -72,13 +125,13 @@ int crbe_comm_allreduce_sum(crbe_comm* c, double* buf_d, int count, cudaStream_t
 // recv_off[q+1]-recv_off[q] doubles from it into recvbuf + recv_off[q].
 int crbe_comm_exchange(crbe_comm* c, int n_neigh, const int* neigh, const double* sendbuf_d, const int64_t* send_off,
                        double* recvbuf_d, const int64_t* recv_off, cudaStream_t stream) {
-    CRBE_NCCL(ncclGroupStart());
+    CRBE_NCCL(nccl()->GroupStart());
     for (int q = 0; q < n_neigh; ++q) {
         const int64_t ns = send_off[q + 1] - send_off[q], nr = recv_off[q + 1] - recv_off[q];
-        if (ns > 0) CRBE_NCCL(ncclSend(sendbuf_d + send_off[q], (size_t)ns, ncclDouble, neigh[q], c->nccl, stream));
-        if (nr > 0) CRBE_NCCL(ncclRecv(recvbuf_d + recv_off[q], (size_t)nr, ncclDouble, neigh[q], c->nccl, stream));
+        if (ns > 0) CRBE_NCCL(nccl()->Send(sendbuf_d + send_off[q], (size_t)ns, ncclDouble, neigh[q], c->nccl, stream));
+        if (nr > 0) CRBE_NCCL(nccl()->Recv(recvbuf_d + recv_off[q], (size_t)nr, ncclDouble, neigh[q], c->nccl, stream));
     }
-    CRBE_NCCL(ncclGroupEnd());
+    CRBE_NCCL(nccl()->GroupEnd());
     return CRBE_OK;
 }
 
