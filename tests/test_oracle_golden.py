@@ -180,3 +180,20 @@ def test_structured_closed_form_numbering(nx, ny):
 def test_empty_mesh():
     seg, t2s = orc.enumerate_segments(np.zeros((0, 3), np.int64))
     assert seg.shape == (0, 2) and t2s.shape == (0, 3)
+
+
+def test_openmp_leg_matches_numpy_oracle():
+    """oracle/crbe_oracle_omp.c (the multi-threaded cpu_baseline leg) against the numpy oracle and, through it,
+    the reference fixture."""
+    from oracle import omp
+    g = load_golden("struct_n16_o1")
+    m = _mesh(g)
+    prob = golden_problem("struct_n16_o1", g)
+    s = orc.OracleSolver(float(g["T"]), prob, m, order=1, linear_solver="bicgstab")
+    s.solve()
+    omp.load().crbe_omp_set_threads(2)
+    A = orc.dirichlet_system_fast(s.base_system, m.boundary_segments)
+    u, its = omp.be_steps(A, s.global_mass.diagonal(), m.boundary_segments, prob.initial_condition_fn(m.midpoints), int(g["nt"]) - 1)
+    assert rel_err(u, g["u_prev_final"]) <= 1e-10
+    assert rel_err(u, s.u_prev) <= 1e-12
+    assert its == s.iterations
