@@ -49,16 +49,8 @@ struct crbe_profile {
 enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RRTRUE = 7, S_AUX0 = 8, S_AUX1 = 9 };
 enum { D_STATUS = 0, D_ITERS = 1 };
 
-constexpr int CRBE_MAX_RANKS = 8;
-constexpr size_t P2P_HEADER_BYTES = 8192;
-// mailbox at the start of every rank's window.  Flags carry monotonically increasing epochs (never reset).
-struct P2PHeader {
-    unsigned int halo_flag[4][CRBE_MAX_RANKS];                 // [x, p, s][source rank]
-    unsigned int dot_flag[8][CRBE_MAX_RANKS];                  // [reduction kind][source rank]
-    double inbox[2][CRBE_NSUMS][CRBE_MAX_RANKS];               // [epoch parity][slot][source rank]
-    int error;
-};
-static_assert(sizeof(P2PHeader) <= P2P_HEADER_BYTES, "mailbox does not fit its header");
+struct P2PHeader;
+struct CommArgs;
 
 struct crbe_solver {
     crbe_ctx* ctx = nullptr;
@@ -102,13 +94,8 @@ struct crbe_solver {
     bool p2p = false;
     int rank = 0;
     unsigned char* window = nullptr;
-    void* peer_base[CRBE_MAX_RANKS] = {nullptr};
-    P2PHeader** d_peer_hdr = nullptr;          // device array [world]
-    double** d_halo_dst = nullptr;             // device array [3][n_neigh]: my segment inside neighbour q's halo of x, p, s
-    int* d_neigh = nullptr;
-    long long* d_send_off = nullptr;
-    unsigned epoch_halo[3] = {0, 0, 0};
-    unsigned epoch_dot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* peer_base[8] = {nullptr};
+    CommArgs* d_comm = nullptr;                // device copy of the peer table handed to the kernels (nullptr: not connected)
     double* saved_p0 = nullptr;                // the stand-alone p, s allocations replaced by window storage
     double* saved_s = nullptr;
     crbe_profile* prof = nullptr;
@@ -145,8 +132,63 @@ __device__ __forceinline__ double ell_row(const double* __restrict__ val, const 
 }
 
 // grid_sum + "am I thread 0 of the last CTA" for bookkeeping writes
+// ---- peer-memory transport (partitioned solve) ---------------------------------------------------------
+constexpr int CRBE_MAX_RANKS = 8;
+constexpr size_t P2P_HEADER_BYTES = 8192;
+// Mailbox at the start of every rank's CUDA-IPC window.  Flags carry monotonically increasing epochs (never
+// reset); every rank counts its own epochs on the device, in lock step with the others because all ranks take
+// identical control decisions from identical reduced sums.
+struct P2PHeader {
+    unsigned int halo_flag[4][CRBE_MAX_RANKS];                 // [x, p, s][source rank]
+    unsigned int dot_flag[8][CRBE_MAX_RANKS];                  // [reduction kind][source rank]
+    double inbox[2][CRBE_NSUMS][CRBE_MAX_RANKS];               // [epoch parity][slot][source rank]
+    unsigned int my_halo_epoch[4];
+    unsigned int my_dot_epoch[8];
+    unsigned int ticket[4];
+    int error;
+};
+static_assert(sizeof(P2PHeader) <= P2P_HEADER_BYTES, "mailbox does not fit its header");
+
+// what the kernels need to talk to the peers (lives in device memory, one per partitioned solver)
+struct CommArgs {
+    P2PHeader* self;
+    P2PHeader* peers[CRBE_MAX_RANKS];
+    int world, rank, n_neigh;
+    int neigh[2 * CRBE_MAX_RANKS];
+    long long send_off[2 * CRBE_MAX_RANKS + 1];
+    double* dst[3][2 * CRBE_MAX_RANKS];     // my segment inside neighbour q's halo of x, p, s
+    const int* send_idx;
+    double* sums;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *flag has reached `epoch` (wrap-safe); gives up after ~20 s so a dead peer cannot wedge the GPU
+__device__ __forceinline__ bool wait_epoch(const unsigned int* flag, unsigned int epoch) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+        if (clock64() - t0 > (1LL << 35)) return false;
+    }
+    return true;
+}
+__device__ __forceinline__ int dot_kind_of(int first_slot) {
+    return first_slot == S_BB ? 0 : (first_slot == S_RHV ? 1 : (first_slot == S_TS ? 2 : (first_slot == S_RR ? 3 : 4)));
+}
+
+// Grid-wide deterministic sum (warp shuffles -> CTA partial -> the last CTA to arrive adds the partials in index
+// order), returning true in thread 0 of that last CTA.  In the partitioned solve (ca != nullptr) the same CTA
+// finishes the job across GPUs before the kernel ends: it deposits the local sums in every peer's mailbox over
+// NVLink, waits for all deposits of this epoch and publishes the totals (added in rank order, so every rank
+// holds the same bits) -- the allreduce is fused into the tail of the kernel that produced the partial sums.
 template <int NV>
-__device__ __forceinline__ bool grid_sum_last(double (&v)[NV], double* partials, unsigned int* counter, double* const (&out)[NV]) {
+__device__ __forceinline__ bool grid_sum_last(double (&v)[NV], double* partials, unsigned int* counter, double* const (&out)[NV],
+                                              const CommArgs* __restrict__ ca) {
     block_sum<NV>(v);
     __shared__ bool last;
     if (threadIdx.x == 0) {
@@ -166,12 +208,76 @@ __device__ __forceinline__ bool grid_sum_last(double (&v)[NV], double* partials,
         for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) acc[k] += __ldcg(&partials[k * CRBE_MAX_PARTIAL_BLOCKS + b]);
     }
     block_sum<NV>(acc);
+    if (ca == nullptr || ca->world <= 1) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) *out[k] = acc[k];
+            return true;
+        }
+        return false;
+    }
+    __shared__ double loc[NV];
+    __shared__ unsigned int ep;
+    const int kind = dot_kind_of((int)(out[0] - ca->sums));
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < NV; ++k) *out[k] = acc[k];
+        for (int k = 0; k < NV; ++k) loc[k] = acc[k];
+        ep = ++ca->self->my_dot_epoch[kind];
+    }
+    __syncthreads();
+    const unsigned int epoch = ep;
+    const int par = epoch & 1;
+    if ((int)threadIdx.x < ca->world) {
+        P2PHeader* d = ca->peers[threadIdx.x];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) d->inbox[par][(int)(out[k] - ca->sums)][ca->rank] = loc[k];
+        __threadfence_system();
+        st_release_sys(&d->dot_flag[kind][ca->rank], epoch);
+        if (!wait_epoch(&ca->self->dot_flag[kind][threadIdx.x], epoch)) ca->self->error = 2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int sl = (int)(out[k] - ca->sums);
+            double a = 0.0;
+            for (int r = 0; r < ca->world; ++r) a += __ldcv(&ca->self->inbox[par][sl][r]);
+            *out[k] = a;
+        }
         return true;
     }
     return false;
+}
+
+// Tail of the kernels that produce a gathered vector (p, s) in the partitioned solve: the last CTA to finish
+// stores this rank's boundary entries straight into the neighbours' halo segments over NVLink, raises their
+// epoch flags and waits for its own halo to arrive -- the halo exchange is part of the producing kernel.
+__device__ __forceinline__ void halo_push_tail(const double* vec, int kind, const CommArgs* __restrict__ ca) {
+    if (ca == nullptr || ca->world <= 1 || ca->n_neigh == 0) return;
+    __shared__ bool last_h;
+    __shared__ unsigned int ep_h;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tk = atomicInc(&ca->self->ticket[kind], gridDim.x - 1);
+        last_h = (tk == gridDim.x - 1);
+        if (last_h) ep_h = ++ca->self->my_halo_epoch[kind];
+    }
+    __syncthreads();
+    if (!last_h) return;
+    __threadfence();
+    for (int q = 0; q < ca->n_neigh; ++q) {
+        double* d = ca->dst[kind][q];
+        const long long o = ca->send_off[q], cnt = ca->send_off[q + 1] - o;
+        for (long long k = threadIdx.x; k < cnt; k += blockDim.x) d[k] = __ldcg(vec + ca->send_idx[o + k]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < ca->n_neigh) {
+        st_release_sys(&ca->peers[ca->neigh[threadIdx.x]]->halo_flag[kind][ca->rank], ep_h);
+        if (!wait_epoch(&ca->self->halo_flag[kind][ca->neigh[threadIdx.x]], ep_h)) ca->self->error = 1;
+    }
+    __syncthreads();
 }
 
 #define ROW_LOOP(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
@@ -238,7 +344,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
                                                      const double* __restrict__ src, double dt, const double* __restrict__ mscale,
                                                      const double* __restrict__ dscale, const unsigned char* __restrict__ is_bnd,
                                                      double* __restrict__ b, double* __restrict__ r, double* __restrict__ rh,
-                                                     double* sums, double* dots, int* dstate, double* partials, unsigned int* counter) {
+                                                     double* sums, double* dots, int* dstate, double* partials, unsigned int* counter, const CommArgs* __restrict__ ca) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         dstate[D_STATUS] = 0;
         dstate[D_ITERS] = 0;
@@ -267,7 +373,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
     }
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
-    grid_sum_last<3>(acc, partials, counter, out);
+    grid_sum_last<3>(acc, partials, counter, out, ca);
 }
 
 struct IterScalars {
@@ -293,7 +399,7 @@ __device__ __forceinline__ double p_update(double r, double p, double v, double 
 
 // unfused: p = r (k == 0) or p = r + beta (p - omega v)
 __global__ void __launch_bounds__(CRBE_BLOCK) k_p(int64_t n, int k, double rtol2, const double* __restrict__ r, const double* __restrict__ v,
-                                                  double* __restrict__ p, const double* sums, int* dstate) {
+                                                  double* __restrict__ p, const double* sums, int* dstate, const CommArgs* __restrict__ ca) {
     if (solver_idle(sums, dstate, rtol2)) return;
     IterScalars sc = {0, 0, 0, false};
     if (k > 0) {
@@ -304,6 +410,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_p(int64_t n, int k, double rtol2
         }
     }
     ROW_LOOP(i, n) p[i] = k > 0 ? p_update(r[i], p[i], v[i], sc.beta, sc.omega) : r[i];
+    halo_push_tail(p, 1, ca);
 }
 
 // v = A p, (r^, v).  FUSED: p is first advanced (here and at the gathered neighbours) from p_in, v_in.
@@ -313,7 +420,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_pv(int64_t n, int64_t ld, int k,
                                                    const double* __restrict__ p_in, const double* __restrict__ v_in,
                                                    double* __restrict__ p_out, double* __restrict__ v_out,
                                                    const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
-                                                   unsigned int* counter) {
+                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
     if (solver_idle(sums, dstate, rtol2)) return;
     IterScalars sc = {0, 0, 0, false};
     if (FUSED && k > 0) {
@@ -342,12 +449,12 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_pv(int64_t n, int64_t ld, int k,
         acc[0] = fma(rh[i], vi, acc[0]);
     }
     double* const out[1] = {dots + S_RHV};
-    grid_sum_last<1>(acc, partials, counter, out);
+    grid_sum_last<1>(acc, partials, counter, out, ca);
 }
 
 // unfused: s = r - alpha v
 __global__ void __launch_bounds__(CRBE_BLOCK) k_s(int64_t n, int k, double rtol2, const double* __restrict__ r, const double* __restrict__ v,
-                                                  double* __restrict__ s, const double* sums, int* dstate) {
+                                                  double* __restrict__ s, const double* sums, int* dstate, const CommArgs* __restrict__ ca) {
     if (solver_idle(sums, dstate, rtol2)) return;
     const double alpha = sums[S_RHO0 + (k & 1)] / sums[S_RHV];
     if (!isfinite(alpha)) {
@@ -355,6 +462,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_s(int64_t n, int k, double rtol2
         return;
     }
     ROW_LOOP(i, n) s[i] = fma(-alpha, v[i], r[i]);
+    halo_push_tail(s, 2, ca);
 }
 
 // t = A s, (t,s), (t,t).  FUSED: s = r - alpha v is formed here (and at the gathered neighbours).
@@ -362,7 +470,7 @@ template <bool FUSED>
 __global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, int k, double rtol2, const double* __restrict__ eval,
                                                    const int* __restrict__ ecol, const double* __restrict__ r, const double* __restrict__ v,
                                                    double* __restrict__ s, double* __restrict__ t, double* sums, double* dots, int* dstate,
-                                                   double* partials, unsigned int* counter) {
+                                                   double* partials, unsigned int* counter, const CommArgs* __restrict__ ca) {
     if (solver_idle(sums, dstate, rtol2)) return;
     double alpha = 0.0;
     if (FUSED) {
@@ -389,14 +497,14 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, int k,
         acc[1] = fma(ti, ti, acc[1]);
     }
     double* const out[2] = {dots + S_TS, dots + S_TT};
-    grid_sum_last<2>(acc, partials, counter, out);
+    grid_sum_last<2>(acc, partials, counter, out, ca);
 }
 
 // x += alpha p + omega s;  r = s - omega t;  rho_{k+1} = (r^, r);  (r, r)
 __global__ void __launch_bounds__(CRBE_BLOCK) k_xr(int64_t n, int k, double rtol2, const double* __restrict__ p, const double* __restrict__ s,
                                                    const double* __restrict__ t, const double* __restrict__ rh, double* __restrict__ x,
                                                    double* __restrict__ r, double* sums, double* dots, int* dstate, double* partials,
-                                                   unsigned int* counter) {
+                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
     if (solver_idle(sums, dstate, rtol2)) return;
     const double alpha = sums[S_RHO0 + (k & 1)] / sums[S_RHV];
     const double tt = sums[S_TT];
@@ -415,14 +523,14 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_xr(int64_t n, int k, double rtol
         acc[1] = fma(ri, ri, acc[1]);
     }
     double* const out[2] = {dots + S_RHO0 + ((k + 1) & 1), dots + S_RR};
-    if (grid_sum_last<2>(acc, partials, counter, out)) dstate[D_ITERS] += 1;
+    if (grid_sum_last<2>(acc, partials, counter, out, ca)) dstate[D_ITERS] += 1;
 }
 
 // true residual r = r^ = b - A x and its norm (restart / verification)
 __global__ void __launch_bounds__(CRBE_BLOCK) k_residual(int64_t n, int64_t ld, const double* __restrict__ eval, const int* __restrict__ ecol,
                                                          const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
                                                          double* __restrict__ rh, double* sums, double* dots, double* partials, unsigned int* counter,
-                                                         const int* dstate, int guard, double rtol2) {
+                                                         const CommArgs* __restrict__ ca, const int* dstate, int guard, double rtol2) {
     // guard: verification enqueued speculatively behind the iterations -- runs only once they have converged, writes nothing but the norm
     if (guard && (dstate[D_STATUS] != 0 || sums[S_RR] > rtol2 * sums[S_BB])) return;
     double acc[1] = {0.0};
@@ -436,7 +544,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_residual(int64_t n, int64_t ld, 
         acc[0] = fma(ri, ri, acc[0]);
     }
     double* const out[1] = {dots + S_RRTRUE};
-    grid_sum_last<1>(acc, partials, counter, out);
+    grid_sum_last<1>(acc, partials, counter, out, ca);
 }
 
 __global__ void k_restart(double* sums, int* dstate) {
@@ -496,18 +604,18 @@ extern "C" int crbe_spmv_csr(crbe_ctx* ctx, int64_t n, const int32_t* indptr_d, 
 
 // ---------------------------------------------------------------- small reductions for the API
 __global__ void __launch_bounds__(CRBE_BLOCK) k_dot(int64_t n, const double* __restrict__ x, const double* __restrict__ y, double* out,
-                                                    double* partials, unsigned int* counter) {
+                                                    double* partials, unsigned int* counter, const CommArgs* __restrict__ ca) {
     double acc[1] = {0.0};
     ROW_LOOP(i, n) acc[0] = fma(x[i], y[i], acc[0]);
     double* const o[1] = {out};
-    grid_sum_last<1>(acc, partials, counter, o);
+    grid_sum_last<1>(acc, partials, counter, o, ca);
 }
 
 extern "C" int crbe_dot(crbe_ctx* ctx, int64_t n, const double* x_d, const double* y_d, double* out_h) {
     CRBE_REQUIRE(ctx && out_h && (n == 0 || (x_d && y_d)), "null argument");
     *out_h = 0.0;
     if (n == 0) return CRBE_OK;
-    k_dot<<<crbe_grid_for(ctx, n), CRBE_BLOCK, 0, ctx->stream>>>(n, x_d, y_d, ctx->dev_scalars, ctx->partials, ctx->counter);
+    k_dot<<<crbe_grid_for(ctx, n), CRBE_BLOCK, 0, ctx->stream>>>(n, x_d, y_d, ctx->dev_scalars, ctx->partials, ctx->counter, nullptr);
     CRBE_KERNEL_CHECK();
     ctx->launches += 1;
     CRBE_CUDA(cudaMemcpyAsync(ctx->host_scalars, ctx->dev_scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -518,7 +626,7 @@ extern "C" int crbe_dot(crbe_ctx* ctx, int64_t n, const double* x_d, const doubl
 
 // crbe.py:447-453: error = |u_exact - u_num|; max; sqrt(sum error^2); sqrt(sum u_exact^2)
 __global__ void __launch_bounds__(CRBE_BLOCK) k_errors(int64_t n, const double* __restrict__ ue, const double* __restrict__ un, double* out,
-                                                       unsigned long long* max_bits, double* partials, unsigned int* counter) {
+                                                       unsigned long long* max_bits, double* partials, unsigned int* counter, const CommArgs* __restrict__ ca) {
     double acc[2] = {0.0, 0.0};
     double emax = 0.0;
     ROW_LOOP(i, n) {
@@ -530,7 +638,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_errors(int64_t n, const double* 
     emax = warp_max(emax);
     if ((threadIdx.x & 31) == 0) atomicMax(max_bits, (unsigned long long)__double_as_longlong(emax));
     double* const o[2] = {out, out + 1};
-    grid_sum_last<2>(acc, partials, counter, o);
+    grid_sum_last<2>(acc, partials, counter, o, ca);
 }
 
 extern "C" int crbe_errors(crbe_ctx* ctx, int64_t n, const double* u_exact_d, const double* u_num_d, double* out3_h) {
@@ -538,7 +646,7 @@ extern "C" int crbe_errors(crbe_ctx* ctx, int64_t n, const double* u_exact_d, co
     unsigned long long* max_bits = (unsigned long long*)(ctx->dev_scalars + 2);
     CRBE_CUDA(cudaMemsetAsync(max_bits, 0, sizeof(unsigned long long), ctx->stream));
     k_errors<<<crbe_grid_for(ctx, n), CRBE_BLOCK, 0, ctx->stream>>>(n, u_exact_d, u_num_d, ctx->dev_scalars, max_bits, ctx->partials,
-                                                                   ctx->counter);
+                                                                   ctx->counter, nullptr);
     CRBE_KERNEL_CHECK();
     ctx->launches += 1;
     CRBE_CUDA(cudaMemcpyAsync(ctx->host_scalars, ctx->dev_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -594,10 +702,7 @@ static int solver_release(crbe_solver* s) {
         for (int r = 0; r < s->world; ++r)
             if (s->peer_base[r] && s->peer_base[r] != s->window) cudaIpcCloseMemHandle(s->peer_base[r]);
         cudaFree(s->window);
-        cudaFree(s->d_peer_hdr);
-        cudaFree(s->d_halo_dst);
-        cudaFree(s->d_neigh);
-        cudaFree(s->d_send_off);
+        cudaFree(s->d_comm);
     }
     cudaFree(s->send_idx);
     cudaFree(s->sendbuf);
@@ -762,7 +867,10 @@ extern "C" int crbe_solver_p2p_connect(crbe_solver* s, int rank, const void* han
     CRBE_REQUIRE(s && s->window && handles_h && ld_all && veclen_all && rank >= 0 && rank < s->world, "bad argument");
     crbe_ctx* ctx = s->ctx;
     s->rank = rank;
-    P2PHeader* hdrs[CRBE_MAX_RANKS] = {nullptr};
+    const int nn = (int)s->neigh.size();
+    CRBE_REQUIRE(nn <= 2 * CRBE_MAX_RANKS && s->world <= CRBE_MAX_RANKS, "too many ranks / neighbours for the peer-memory transport");
+    CommArgs ca;
+    memset(&ca, 0, sizeof(ca));
     for (int r = 0; r < s->world; ++r) {
         if (r == rank) {
             s->peer_base[r] = s->window;
@@ -771,27 +879,28 @@ extern "C" int crbe_solver_p2p_connect(crbe_solver* s, int rank, const void* han
             memcpy(&h, (const unsigned char*)handles_h + 64 * r, sizeof(h));
             CRBE_CUDA(cudaIpcOpenMemHandle(&s->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
         }
-        hdrs[r] = (P2PHeader*)s->peer_base[r];
+        ca.peers[r] = (P2PHeader*)s->peer_base[r];
     }
-    const int nn = (int)s->neigh.size();
-    std::vector<double*> dst(3 * (nn > 0 ? nn : 1), nullptr);
-    for (int kind = 0; kind < 3; ++kind)
-        for (int q = 0; q < nn; ++q) {
-            const int r = s->neigh[q];
-            CRBE_REQUIRE(halo_seg_off != nullptr, "missing halo offsets");
+    ca.self = (P2PHeader*)s->window;
+    ca.world = s->world;
+    ca.rank = rank;
+    ca.n_neigh = nn;
+    ca.send_idx = s->send_idx;
+    ca.sums = s->sums;
+    for (int q = 0; q <= nn; ++q) ca.send_off[q] = s->send_off[q];
+    for (int q = 0; q < nn; ++q) {
+        const int r = s->neigh[q];
+        CRBE_REQUIRE(halo_seg_off != nullptr, "missing halo offsets");
+        ca.neigh[q] = r;
+        for (int kind = 0; kind < 3; ++kind) {
             double* vbase = (double*)((unsigned char*)s->peer_base[r] + P2P_HEADER_BYTES) + (size_t)kind * veclen_all[r];
-            dst[kind * nn + q] = vbase + ld_all[r] + halo_seg_off[q];
+            ca.dst[kind][q] = vbase + ld_all[r] + halo_seg_off[q];
         }
-    std::vector<long long> soff(s->send_off.begin(), s->send_off.end());
-    CRBE_CUDA(cudaMalloc(&s->d_peer_hdr, sizeof(P2PHeader*) * CRBE_MAX_RANKS));
-    CRBE_CUDA(cudaMemcpy(s->d_peer_hdr, hdrs, sizeof(P2PHeader*) * CRBE_MAX_RANKS, cudaMemcpyHostToDevice));
-    CRBE_CUDA(cudaMalloc(&s->d_halo_dst, sizeof(double*) * dst.size()));
-    CRBE_CUDA(cudaMemcpy(s->d_halo_dst, dst.data(), sizeof(double*) * dst.size(), cudaMemcpyHostToDevice));
-    CRBE_CUDA(cudaMalloc(&s->d_neigh, sizeof(int) * (nn > 0 ? nn : 1)));
-    if (nn > 0) CRBE_CUDA(cudaMemcpy(s->d_neigh, s->neigh.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
-    CRBE_CUDA(cudaMalloc(&s->d_send_off, sizeof(long long) * soff.size()));
-    CRBE_CUDA(cudaMemcpy(s->d_send_off, soff.data(), sizeof(long long) * soff.size(), cudaMemcpyHostToDevice));
+    }
+    CRBE_CUDA(cudaMalloc(&s->d_comm, sizeof(CommArgs)));
+    CRBE_CUDA(cudaMemcpy(s->d_comm, &ca, sizeof(CommArgs), cudaMemcpyHostToDevice));
     CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->dots = s->sums;          // the totals are published by the producing kernel itself: no staging buffer
     s->p2p = true;
     return CRBE_OK;
 }
@@ -909,68 +1018,9 @@ __global__ void k_commit(const double* __restrict__ red, double* __restrict__ su
     if (c >= 0) sums[c] = red[c];
 }
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// spin until *flag has reached `epoch` (wrap-safe); gives up after ~20 s so a dead peer cannot wedge the GPU
-__device__ __forceinline__ bool wait_epoch(const unsigned int* flag, unsigned int epoch) {
-    const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
-        if (clock64() - t0 > (1LL << 35)) return false;
-        __nanosleep(64);
-    }
-    return true;
-}
-
-// Halo push over NVLink + arrival wait, one CTA.  Every neighbour q receives my boundary entries directly in
-// the halo segment of its own vector (dst[q]); a release store of the epoch tells it they are there; then the
-// CTA waits for the neighbours' epochs, so the kernel that follows in the stream sees a complete halo.
-__global__ void __launch_bounds__(1024) k_p2p_halo(const double* __restrict__ vec, const int* __restrict__ send_idx,
-                                                   const long long* __restrict__ send_off, double* const* __restrict__ dst,
-                                                   const int* __restrict__ neigh, int n_neigh, P2PHeader* self,
-                                                   P2PHeader* const* __restrict__ peers, int kind, unsigned int epoch, int rank) {
-    for (int q = 0; q < n_neigh; ++q) {
-        double* d = dst[q];
-        const long long o = send_off[q], cnt = send_off[q + 1] - o;
-        for (long long k = threadIdx.x; k < cnt; k += blockDim.x) d[k] = vec[send_idx[o + k]];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < n_neigh) {
-        st_release_sys(&peers[neigh[threadIdx.x]]->halo_flag[kind][rank], epoch);
-        if (!wait_epoch(&self->halo_flag[kind][neigh[threadIdx.x]], epoch)) self->error = 1;
-    }
-    __syncthreads();
-}
-
-// Allreduce of `count` doubles red[first..] through the peers' mailboxes, one CTA: every rank deposits its
-// partial sums in everybody's inbox, waits for all deposits and adds them in rank order -- the same bits on
-// every rank, no NCCL call, no separate commit.  Slots a, b, c are then published in `sums`.
-__global__ void __launch_bounds__(32) k_p2p_allreduce(const double* __restrict__ red, double* __restrict__ sums, int first, int count,
-                                                      int a, int b, int c, P2PHeader* self, P2PHeader* const* __restrict__ peers,
-                                                      int kind, unsigned int epoch, int rank, int world) {
-    const int t = threadIdx.x, par = epoch & 1;
-    if (t < world) {
-        P2PHeader* d = peers[t];
-        for (int sl = first; sl < first + count; ++sl) d->inbox[par][sl][rank] = red[sl];
-        __threadfence_system();
-        st_release_sys(&d->dot_flag[kind][rank], epoch);
-        if (!wait_epoch(&self->dot_flag[kind][t], epoch)) self->error = 2;
-    }
-    __syncwarp();
-    if (t < 3) {
-        const int sl = t == 0 ? a : (t == 1 ? b : c);
-        if (sl >= 0) {
-            double acc = 0.0;
-            for (int r = 0; r < world; ++r) acc += __ldcv(&self->inbox[par][sl][r]);
-            sums[sl] = acc;
-        }
-    }
+// x halo (step start, verification): a one-CTA kernel with the same push-and-wait as halo_push_tail
+__global__ void __launch_bounds__(1024) k_p2p_halo(const double* __restrict__ vec, int kind, const CommArgs* __restrict__ ca) {
+    halo_push_tail(vec, kind, ca);
 }
 
 // refresh the halo entries of a gathered vector from their owners (no-op on a single GPU)
@@ -978,12 +1028,11 @@ static int halo_exchange(crbe_solver* s, double* vec, int* launches) {
     if (s->world <= 1 || s->neigh.empty()) return CRBE_OK;
     crbe_ctx* ctx = s->ctx;
     if (s->p2p) {
-        const int kind = vec == (double*)(s->window + P2P_HEADER_BYTES) ? 0 : (vec == s->p[0] ? 1 : (vec == s->s ? 2 : -1));
-        CRBE_REQUIRE(kind >= 0, "peer-memory transport: the vector is not one of the window vectors (use crbe_solver_x)");
-        const unsigned epoch = ++s->epoch_halo[kind];
-        const int nn = (int)s->neigh.size();
-        k_p2p_halo<<<1, 1024, 0, ctx->stream>>>(vec, s->send_idx, s->d_send_off, s->d_halo_dst + kind * nn, s->d_neigh, nn,
-                                                (P2PHeader*)s->window, s->d_peer_hdr, kind, epoch, s->rank);
+        // p and s are pushed to the neighbours by the tail of the kernel that produced them (halo_push_tail)
+        if (vec == s->p[0] || vec == s->s) return CRBE_OK;
+        CRBE_REQUIRE(vec == (double*)(s->window + P2P_HEADER_BYTES),
+                     "peer-memory transport: the solution vector must be the window vector (crbe_solver_x)");
+        k_p2p_halo<<<1, 1024, 0, ctx->stream>>>(vec, 0, s->d_comm);
         CRBE_KERNEL_CHECK();
         *launches += 1;
         return CRBE_OK;
@@ -1000,16 +1049,7 @@ static int halo_exchange(crbe_solver* s, double* vec, int* launches) {
 
 // sum the freshly written dot products red[first .. first+count) over the ranks, then publish slots a, b, c
 static int reduce_dots(crbe_solver* s, int first, int count, int a, int b, int c, int* launches) {
-    if (s->world <= 1) return CRBE_OK;
-    if (s->p2p) {
-        const int kind = first == S_BB ? 0 : (first == S_RHV ? 1 : (first == S_TS ? 2 : (first == S_RR ? 3 : 4)));
-        const unsigned epoch = ++s->epoch_dot[kind];
-        k_p2p_allreduce<<<1, 32, 0, s->ctx->stream>>>(s->red, s->sums, first, count, a, b, c, (P2PHeader*)s->window, s->d_peer_hdr, kind,
-                                                      epoch, s->rank, s->world);
-        CRBE_KERNEL_CHECK();
-        *launches += 1;
-        return CRBE_OK;
-    }
+    if (s->world <= 1 || s->p2p) return CRBE_OK;   // peer-memory transport: done in the tail of the dot kernel (grid_sum_last)
     CRBE_CHECK(crbe_comm_allreduce_sum(s->comm, s->red + first, count, s->ctx->stream));
     k_commit<<<1, 1, 0, s->ctx->stream>>>(s->red, s->sums, a, b, c);
     CRBE_KERNEL_CHECK();
@@ -1031,45 +1071,45 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
         if (tma) {
             PROF_LAUNCH(PK_PV, k, (t_pv<true><<<s->gt_pv[1], CRBE_TILE, TilePipe<4>::SMEM_BYTES, st>>>(
                                       s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, s->p[in], s->v[in], p, v, s->rh, s->sums,
-                                      s->dots, s->dstate, ctx->partials, ctx->counter)));
+                                      s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
             PROF_LAUNCH(PK_ST, k, (t_st<true><<<s->gt_st[1], CRBE_TILE, TilePipe<2>::SMEM_BYTES, st>>>(
                                       s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dots, s->dstate,
-                                      ctx->partials, ctx->counter)));
+                                      ctx->partials, ctx->counter, s->d_comm)));
         } else {
             PROF_LAUNCH(PK_PV, k, (k_pv<true><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, s->p[in],
                                                                            s->v[in], p, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
-                                                                           ctx->counter)));
+                                                                           ctx->counter, s->d_comm)));
             PROF_LAUNCH(PK_ST, k, (k_st<true><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s,
-                                                                           s->t, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter)));
+                                                                           s->t, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
         }
         *launches += 2;
     } else {
         p = s->p[0];
         v = s->v[0];
-        PROF_LAUNCH(PK_P, k, (k_p<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, p, s->sums, s->dstate)));
+        PROF_LAUNCH(PK_P, k, (k_p<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, p, s->sums, s->dstate, s->d_comm)));
         CRBE_CHECK(halo_exchange(s, p, launches));
         if (tma)
             PROF_LAUNCH(PK_PV, k, (t_pv<false><<<s->gt_pv[0], CRBE_TILE, TilePipe<2>::SMEM_BYTES, st>>>(
                                       s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p, v, s->rh, s->sums, s->dots, s->dstate,
-                                      ctx->partials, ctx->counter)));
+                                      ctx->partials, ctx->counter, s->d_comm)));
         else
             PROF_LAUNCH(PK_PV, k, (k_pv<false><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p,
-                                                                            v, s->rh, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter)));
+                                                                            v, s->rh, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
         CRBE_CHECK(reduce_dots(s, S_RHV, 1, S_RHV, -1, -1, launches));
-        PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, s->s, s->sums, s->dstate)));
+        PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, s->s, s->sums, s->dstate, s->d_comm)));
         CRBE_CHECK(halo_exchange(s, s->s, launches));
         if (tma)
             PROF_LAUNCH(PK_ST, k, (t_st<false><<<s->gt_st[0], CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
                                       s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dots, s->dstate,
-                                      ctx->partials, ctx->counter)));
+                                      ctx->partials, ctx->counter, s->d_comm)));
         else
             PROF_LAUNCH(PK_ST, k, (k_st<false><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s,
-                                                                            s->t, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter)));
+                                                                            s->t, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
         CRBE_CHECK(reduce_dots(s, S_TS, 2, S_TS, S_TT, -1, launches));
         *launches += 4;
     }
     PROF_LAUNCH(PK_XR, k, (k_xr<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, p, s->s, s->t, s->rh, x, s->r, s->sums, s->dots, s->dstate,
-                                                             ctx->partials, ctx->counter)));
+                                                             ctx->partials, ctx->counter, s->d_comm)));
     *launches += 1;
     CRBE_CHECK(reduce_dots(s, S_RR, 3, S_RR, S_RHO0 + ((k + 1) & 1), -1, launches));
     return CRBE_OK;
@@ -1092,11 +1132,11 @@ static int launch_residual(crbe_solver* s, double* x, int guard, int* launches) 
     if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_RES, guard ? -2 : -1, (t_residual<<<s->gt_res, CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
                                                  s->n, s->ntiles, s->ell_val, s->ell_col, x, s->b, s->r, s->rh, s->sums, s->dots, ctx->partials,
-                                                 ctx->counter, s->dstate, guard, rtol2)));
+                                                 ctx->counter, s->d_comm, s->dstate, guard, rtol2)));
     else
         PROF_LAUNCH(PK_RES, guard ? -2 : -1, (k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->b, s->r,
                                                                                          s->rh, s->sums, s->dots, ctx->partials, ctx->counter,
-                                                                                         s->dstate, guard, rtol2)));
+                                                                                         s->d_comm, s->dstate, guard, rtol2)));
     *launches += 1;
     CRBE_KERNEL_CHECK();
     return reduce_dots(s, S_RRTRUE, 1, S_RRTRUE, -1, -1, launches);
@@ -1221,15 +1261,15 @@ extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* sourc
     if (s->rhs_val)
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, s->tmp, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums, s->dots,
-                                                                             s->dstate, ctx->partials, ctx->counter)));
+                                                                             s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<<<s->gt_init, CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
                                      s->n, s->ntiles, s->ell_val, s->ell_col, u_d, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
-                                     s->sums, s->dots, s->dstate, ctx->partials, ctx->counter)));
+                                     s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else
         PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, nullptr, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums, s->dots,
-                                                                             s->dstate, ctx->partials, ctx->counter)));
+                                                                             s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     ++launches;
     CRBE_KERNEL_CHECK();
     CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, &launches));
@@ -1249,7 +1289,7 @@ extern "C" int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d,
     CRBE_CHECK(halo_exchange(s, x_d, &launches));
     k_init<2><<<s->g_init, CRBE_BLOCK, 0, ctx->stream>>>(s->n, s->ld, s->ell_val, s->ell_col, x_d, b_d, nullptr, 0.0,
                                                                         s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums, s->dots,
-                                                                        s->dstate, ctx->partials, ctx->counter);
+                                                                        s->dstate, ctx->partials, ctx->counter, s->d_comm);
     CRBE_KERNEL_CHECK();
     CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, &launches));
     int rc = run_bicgstab(s, x_d, info_h, &launches);

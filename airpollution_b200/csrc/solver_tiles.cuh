@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int
                                                   const int* __restrict__ ecol, const double* __restrict__ r, const double* __restrict__ p_in,
                                                   const double* __restrict__ v_in, double* __restrict__ p_out, double* __restrict__ v_out,
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
-                                                  unsigned int* counter) {
+                                                  unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
     if (solver_idle(sums, dstate, rtol2)) return;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int
         pipe.release(m);
     }
     double* const out[1] = {dots + S_RHV};
-    grid_sum_last<1>(acc, partials, counter, out);
+    grid_sum_last<1>(acc, partials, counter, out, ca);
 }
 
 // ---- t = A s, (t,s), (t,t)   [FUSED: s = r - alpha v formed here and at the gathered neighbours] ----
@@ -197,7 +197,7 @@ template <bool FUSED>
 __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int k, double rtol2, const double* __restrict__ eval,
                                                   const int* __restrict__ ecol, const double* __restrict__ r, const double* __restrict__ v,
                                                   double* __restrict__ s, double* __restrict__ t, double* sums, double* dots, int* dstate, double* partials,
-                                                  unsigned int* counter) {
+                                                  unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
     if (solver_idle(sums, dstate, rtol2)) return;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int
         pipe.release(m);
     }
     double* const out[2] = {dots + S_TS, dots + S_TT};
-    grid_sum_last<2>(acc, partials, counter, out);
+    grid_sum_last<2>(acc, partials, counter, out, ca);
 }
 
 // ---- Backward-Euler step start: b = mscale*u (+ dscale*dt*f), r = r^ = b - A u, (b,b), (r,r) --------
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
                                                        const double* __restrict__ x, const double* __restrict__ src, double dt,
                                                        const double* __restrict__ mscale, const double* __restrict__ dscale,
                                                        double* __restrict__ b, double* __restrict__ r, double* __restrict__ rh, double* sums,
-                                                       double* dots, int* dstate, double* partials, unsigned int* counter) {
+                                                       double* dots, int* dstate, double* partials, unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -286,14 +286,14 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
     }
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
-    grid_sum_last<3>(acc, partials, counter, out);
+    grid_sum_last<3>(acc, partials, counter, out, ca);
 }
 
 // ---- true residual r = r^ = b - A x and its norm -------------------------------------------------------
 __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntiles, const double* __restrict__ eval, const int* __restrict__ ecol,
                                                         const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
                                                         double* __restrict__ rh, double* sums, double* dots, double* partials, unsigned int* counter,
-                                                        const int* dstate, int guard, double rtol2) {
+                                                        const CommArgs* __restrict__ ca, const int* dstate, int guard, double rtol2) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
     // guard: verification enqueued speculatively behind the iterations -- runs only once they have converged, writes nothing but the norm
@@ -321,5 +321,5 @@ __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntile
         pipe.release(m);
     }
     double* const out[1] = {dots + S_RRTRUE};
-    grid_sum_last<1>(acc, partials, counter, out);
+    grid_sum_last<1>(acc, partials, counter, out, ca);
 }

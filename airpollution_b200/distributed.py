@@ -362,7 +362,6 @@ def bench_partitioned(args, K, W, device):
         part.step()
     sampler = B.ClockSampler(device.index)
     sampler.start()
-    rt.call("crbe_solver_profile", part._solver, 1)
     l0, l1 = C.c_int64(), C.c_int64()
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l0))
     dist.barrier()
@@ -377,6 +376,11 @@ def bench_partitioned(args, K, W, device):
     dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms = float(ms_t.item())
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l1))
+    # the same steps once more with a CUDA event pair around every kernel launch (per-kernel durations)
+    rt.call("crbe_solver_profile", part._solver, 1)
+    for _ in range(min(K, 30)):
+        part.step()
+    torch.cuda.synchronize()
     rt.call("crbe_solver_profile", part._solver, 0)
     clocks = sampler.stop()
     pms, pcnt = (C.c_double * 8)(), (C.c_int64 * 8)()
