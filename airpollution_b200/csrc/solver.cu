@@ -250,8 +250,8 @@ __device__ __forceinline__ bool grid_sum_last(double (&v)[NV], double* partials,
 }
 
 // Tail of the kernels that produce a gathered vector (p, s) in the partitioned solve: the last CTA to finish
-// stores this rank's boundary entries straight into the neighbours' halo segments over NVLink, raises their
-// epoch flags and waits for its own halo to arrive -- the halo exchange is part of the producing kernel.
+// stores this rank's boundary entries straight into the neighbours' halo segments over NVLink and raises their
+// epoch flags -- the halo exchange is part of the producing kernel; the consuming kernel waits (halo_wait).
 __device__ __forceinline__ void halo_push_tail(const double* vec, int kind, const CommArgs* __restrict__ ca) {
     if (ca == nullptr || ca->world <= 1 || ca->n_neigh == 0) return;
     __shared__ bool last_h;
@@ -268,14 +268,32 @@ __device__ __forceinline__ void halo_push_tail(const double* vec, int kind, cons
     __threadfence();
     for (int q = 0; q < ca->n_neigh; ++q) {
         double* d = ca->dst[kind][q];
-        const long long o = ca->send_off[q], cnt = ca->send_off[q + 1] - o;
-        for (long long k = threadIdx.x; k < cnt; k += blockDim.x) d[k] = __ldcg(vec + ca->send_idx[o + k]);
+        const int* idx = ca->send_idx + ca->send_off[q];
+        const long long cnt = ca->send_off[q + 1] - ca->send_off[q];
+        const int nt = blockDim.x;
+        long long k = threadIdx.x;
+        for (; k + 3 * nt < cnt; k += 4 * nt) {      // four independent gather->remote-store chains in flight per thread
+            const int i0 = __ldg(idx + k), i1 = __ldg(idx + k + nt), i2 = __ldg(idx + k + 2 * nt), i3 = __ldg(idx + k + 3 * nt);
+            const double v0 = __ldcg(vec + i0), v1 = __ldcg(vec + i1), v2 = __ldcg(vec + i2), v3 = __ldcg(vec + i3);
+            d[k] = v0;
+            d[k + nt] = v1;
+            d[k + 2 * nt] = v2;
+            d[k + 3 * nt] = v3;
+        }
+        for (; k < cnt; k += nt) d[k] = __ldcg(vec + __ldg(idx + k));
     }
     __threadfence_system();
     __syncthreads();
+    if ((int)threadIdx.x < ca->n_neigh) st_release_sys(&ca->peers[ca->neigh[threadIdx.x]]->halo_flag[kind][ca->rank], ep_h);
+}
+
+// Consumer side of the halo exchange: before gathering, wait until every neighbour's push of the current epoch
+// has landed (the epoch is the one this rank's own producer tail just counted; all ranks count in lock step).
+__device__ __forceinline__ void halo_wait(int kind, const CommArgs* __restrict__ ca) {
+    if (ca == nullptr || ca->world <= 1 || ca->n_neigh == 0) return;
     if ((int)threadIdx.x < ca->n_neigh) {
-        st_release_sys(&ca->peers[ca->neigh[threadIdx.x]]->halo_flag[kind][ca->rank], ep_h);
-        if (!wait_epoch(&ca->self->halo_flag[kind][ca->neigh[threadIdx.x]], ep_h)) ca->self->error = 1;
+        const unsigned int epoch = *(volatile unsigned int*)&ca->self->my_halo_epoch[kind];
+        if (!wait_epoch(&ca->self->halo_flag[kind][ca->neigh[threadIdx.x]], epoch)) ca->self->error = 1;
     }
     __syncthreads();
 }
@@ -349,6 +367,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
         dstate[D_STATUS] = 0;
         dstate[D_ITERS] = 0;
     }
+    halo_wait(0, ca);
     double acc[3] = {0.0, 0.0, 0.0};
     ROW_LOOP(i, n) {
         const double xi = x[i];
@@ -430,6 +449,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_pv(int64_t n, int64_t ld, int k,
             return;
         }
     }
+    halo_wait(1, ca);
     double acc[1] = {0.0};
     ROW_LOOP(i, n) {
         double pi, vi;
@@ -480,6 +500,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, int k,
             return;
         }
     }
+    halo_wait(2, ca);
     double acc[2] = {0.0, 0.0};
     ROW_LOOP(i, n) {
         double si, ti;
@@ -533,6 +554,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_residual(int64_t n, int64_t ld, 
                                                          const CommArgs* __restrict__ ca, const int* dstate, int guard, double rtol2) {
     // guard: verification enqueued speculatively behind the iterations -- runs only once they have converged, writes nothing but the norm
     if (guard && (dstate[D_STATUS] != 0 || sums[S_RR] > rtol2 * sums[S_BB])) return;
+    halo_wait(0, ca);
     double acc[1] = {0.0};
     ROW_LOOP(i, n) {
         const double ax = ell_row(eval, ecol, ld, i, x[i], [&](int j) { return __ldg(x + j); });
@@ -1018,7 +1040,9 @@ __global__ void k_commit(const double* __restrict__ red, double* __restrict__ su
     if (c >= 0) sums[c] = red[c];
 }
 
-// x halo (step start, verification): a one-CTA kernel with the same push-and-wait as halo_push_tail
+__global__ void k_p2p_wait(int kind, const CommArgs* __restrict__ ca) { halo_wait(kind, ca); }
+
+// x halo (step start, verification): a one-CTA kernel running the same push as halo_push_tail
 __global__ void __launch_bounds__(1024) k_p2p_halo(const double* __restrict__ vec, int kind, const CommArgs* __restrict__ ca) {
     halo_push_tail(vec, kind, ca);
 }
@@ -1250,6 +1274,7 @@ extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* sourc
     int launches = 0;
     if (s->rhs_val) {   // Crank-Nicolson: (M - c(K+A)) u_prev with u_prev as given, boundary values included (crbe.py:386)
         CRBE_CHECK(halo_exchange(s, u_d, &launches));
+        if (s->p2p) k_p2p_wait<<<1, 32, 0, st>>>(0, s->d_comm);
         k_spmv_csr<<<s->g_spmv, CRBE_BLOCK, 0, st>>>(s->n, s->indptr, s->indices, s->rhs_val, u_d, s->tmp);
         ++launches;
     }

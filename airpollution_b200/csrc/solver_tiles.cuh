@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int
         pipe.vec[1] = rh;
     }
     pipe.start(tile_smem, bars, ntiles);
+    halo_wait(1, ca);   // the bulk copies are already in flight
     const int tr = threadIdx.x;
     double acc[1] = {0.0};
     for (int64_t m = 0; m < pipe.count; ++m) {
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int
         pipe.vec[0] = s;
     }
     pipe.start(tile_smem, bars, ntiles);
+    halo_wait(2, ca);
     const int tr = threadIdx.x;
     double acc[2] = {0.0, 0.0};
     for (int64_t m = 0; m < pipe.count; ++m) {
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
     pipe.ecol = ecol;
     pipe.vec[0] = mscale;
     pipe.start(tile_smem, bars, ntiles);
+    halo_wait(0, ca);
     const int tr = threadIdx.x;
     double acc[3] = {0.0, 0.0, 0.0};
     for (int64_t m = 0; m < pipe.count; ++m) {
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntile
     pipe.ecol = ecol;
     pipe.vec[0] = b;
     pipe.start(tile_smem, bars, ntiles);
+    halo_wait(0, ca);
     const int tr = threadIdx.x;
     double acc[1] = {0.0};
     for (int64_t m = 0; m < pipe.count; ++m) {
