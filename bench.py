@@ -69,6 +69,18 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, args, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json); only valid for the configuration it was taken on."""
+    if args.classic or args.n != 2048:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clock/throttle samples during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -336,7 +348,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "pv fused: p-update + ELL SpMV + dot" if args.fused else "pv: ELL SpMV v = A p + dot (r^,v)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "frac_of_8TBps_nominal": achieved / 8000.0, "peak_source": peak_src,
-                     "bytes_per_launch": ROW_BYTES[dom_k] * n, "traffic": None},
+                     "bytes_per_launch": ROW_BYTES[dom_k] * n, "traffic": ncu_traffic("t_pv<1>" if args.fused else "t_pv<0>", args, n)},
     }
 
     # ---- e2e: the public API with host buffers ---------------------------------
