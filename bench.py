@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("CRBE_BENCH_N", 2048)), help="cells per axis (per GPU strip)")
+    ap.add_argument("--cells", "--n", dest="n", type=int, default=int(os.environ.get("CRBE_BENCH_N", 2048)), help="cells per axis (per GPU strip)")
     ap.add_argument("--regime", default="P-ref", choices=["P-ref", "P-T10", "P-stiff"])
     ap.add_argument("--fused", action="store_true", help="fuse the p/s updates into the SpMV kernels (3-kernel iteration)")
     ap.add_argument("--classic", action="store_true", help="register-load kernels instead of the bulk-copy (TMA) pipeline")
