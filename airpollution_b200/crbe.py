@@ -203,6 +203,9 @@ class BESCRFEM:
     ``tma``             feed the SpMV-type kernels through the bulk-copy/mbarrier shared-memory
                         pipeline (default) instead of per-thread register loads.
     ``progress``        tqdm bar like the reference (default: only for nt*N < 2e7).
+    ``velocity_field``  ``f(centroids[Nt,2], t) -> v[Nt,2]`` (torch tensors on the device): a velocity that varies in
+                        space and time, one value per triangle, re-assembled every step (BASELINE config 5).  The
+                        reference's constant ``problem.v`` (crbe.py:309) is the default.
     """
 
     def __init__(self, domain, problem, mesh_data, element, time_scheme_order=1, *, rtol=1e-13,
@@ -503,7 +506,7 @@ class BESCRFEM:
         for step in steps:
             t = step * self.dt                                               # crbe.py:420
             if reassemble:
-                self._reassemble_advection(t)
+                self._reassemble_advection(t, export=(step == n_steps - 1))
             src = self._source_on_device(t)
             rt.call("crbe_solver_step", self._solver, ptr(u), ptr(src), dt, C.byref(info))
             self.step_info.append((info.iterations, info.relres, info.true_relres, info.restarts))
@@ -532,20 +535,18 @@ class BESCRFEM:
         print(f"Solve completed in {self.solve_time:.2f}s")
         return self.solutions
 
-    def _reassemble_advection(self, t):
+    def _reassemble_advection(self, t, export=False):
+        """Time-varying velocity (config 5): v_T = velocity_field(centroid_T, t) per triangle, A(v) and the solver's
+        system rows rebuilt in one fused pass (``crbe_solver_update_advection``)."""
         md, rt, d = self.mesh_data, self._rt, self._dev
         m = md._dev
         v_elem = self._element_velocity(t)
-        rt.call("crbe_assemble", rt.ctx, ptr(m["points"]), ptr(m["tri"]), ptr(m["areas"]), ptr(d["scatter_pos"]),
-                ptr(d["order"]), self._colour_offsets, self.n_colours, self._nnz, float(self.problem.D), 0.0, 0.0,
-                ptr(v_elem), ptr(None), ptr(None), ptr(d["a_val"]))
-        coef = self._coef()
-        rt.call("crbe_system_values", rt.ctx, self._nnz, ptr(d["m_val"]), ptr(d["k_val"]), ptr(d["a_val"]), coef, ptr(d["s_val"]))
-        if self.time_scheme_order == 2:
-            rt.call("crbe_system_values", rt.ctx, self._nnz, ptr(d["m_val"]), ptr(d["k_val"]), ptr(d["a_val"]), -coef,
-                    ptr(d["r_val"]))
-        self._np.clear()
-        rt.call("crbe_solver_set_system", self._solver, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
+        rt.call("crbe_solver_update_advection", self._solver, ptr(m["points"]), ptr(m["tri"]), ptr(m["areas"]),
+                ptr(m["edge_slots"]), ptr(d["scatter_pos"]), ptr(d["m_val"]), ptr(d["k_val"]), ptr(v_elem), 0.0, 0.0,
+                float(self._coef()), ptr(d["a_val"] if export else None), ptr(d["s_val"] if export else None))
+        self._v_elem = v_elem          # keep alive until the kernel has run
+        if export:
+            self._np.clear()
 
     # ---- errors (crbe.py:435-482) -----------------------------------------
     def compute_errors(self, analytical_sol_fn):

@@ -113,3 +113,92 @@ extern "C" int crbe_system_values(crbe_ctx* ctx, int64_t nnz, const double* m_va
     ctx->launches += 1;
     return CRBE_OK;
 }
+
+// --------------------------------------------------------------------------
+// Time-varying velocity (BASELINE config 5): A changes every step, M and K do not.  One thread per ROW gathers the
+// advection contributions of the (<= 2) triangles on its edge, forms  s = m + c (k + a)  entry by entry in the
+// reference's order (crbe.py:358) and writes the solver's rows directly -- Dirichlet identity rows, division by the
+// diagonal, tile-major ELL slots, mass/diagonal scalings -- without materialising A or S and without the element
+// colouring: every output is written once, coalesced, by its own thread.  Values are bit-identical to
+// crbe_assemble + crbe_system_values + crbe_solver_set_system (two-term sums commute).
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(CRBE_BLOCK) k_update_system_rows(
+    int64_t n, const int* __restrict__ indptr, const int* __restrict__ indices, const unsigned char* __restrict__ is_bnd,
+    const double* __restrict__ pts, const int* __restrict__ tri, const double* __restrict__ areas, const int* __restrict__ edge_slots,
+    const int* __restrict__ pos, const double* __restrict__ mval, const double* __restrict__ kval, const double* __restrict__ v_elem,
+    double vx0, double vy0, double coef, double* __restrict__ ell_val, double* __restrict__ mdiag, double* __restrict__ mscale,
+    double* __restrict__ dscale, double* __restrict__ rhs_val, double* __restrict__ a_out, double* __restrict__ s_out, int* __restrict__ err) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p0 = indptr[i], p1 = indptr[i + 1];
+        double a_loc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (p1 - p0 > 5) {
+            atomicOr(err, 2);
+            continue;
+        }
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int slot = edge_slots[2 * i + side];
+            if (slot < 0) continue;
+            const int64_t t = slot / 3;
+            const int a = slot - 3 * (int)t;
+            const int i0 = tri[3 * t], i1 = tri[3 * t + 1], i2 = tri[3 * t + 2];
+            double vx = vx0, vy = vy0;
+            if (v_elem) {
+                vx = v_elem[2 * t];
+                vy = v_elem[2 * t + 1];
+            }
+            double arow[3];
+            crbe_element_advection(pts[2 * (int64_t)i0], pts[2 * (int64_t)i0 + 1], pts[2 * (int64_t)i1], pts[2 * (int64_t)i1 + 1],
+                                   pts[2 * (int64_t)i2], pts[2 * (int64_t)i2 + 1], areas[t], vx, vy, arow);
+#pragma unroll
+            for (int b = 0; b < 3; ++b) a_loc[pos[9 * t + 3 * a + b] - p0] += arow[b];   // A_loc[a][b] = arow[b] for every a
+        }
+        double sv[5];
+        double d = 0.0, m = 0.0;
+        int diag = -1;
+        for (int p = p0; p < p1; ++p) {
+            const double av = a_loc[p - p0];
+            const double s = mval[p] + coef * (kval[p] + av);        // (K+A) first, times c, plus M     crbe.py:358
+            sv[p - p0] = s;
+            if (a_out) a_out[p] = av;
+            if (s_out) s_out[p] = s;
+            if (rhs_val) rhs_val[p] = mval[p] + (-coef) * (kval[p] + av);   // M - c (K+A)                crbe.py:386
+            if (indices[p] == (int)i) {
+                diag = p - p0;
+                d = s;
+                m = mval[p];
+            }
+        }
+        const bool bd = is_bnd[i] != 0;
+        if (diag < 0 || (!bd && !(fabs(d) > 0.0))) atomicOr(err, diag < 0 ? 1 : 4);
+        int k = 0;
+        if (!bd)
+            for (int p = p0; p < p1 && k < 4; ++p) {
+                if (p - p0 == diag) continue;
+                ell_val[ell_at(i, k)] = sv[p - p0] / d;
+                ++k;
+            }
+        for (; k < 4; ++k) ell_val[ell_at(i, k)] = 0.0;
+        mdiag[i] = m;
+        mscale[i] = bd ? 0.0 : m / d;
+        dscale[i] = bd ? 0.0 : 1.0 / d;
+    }
+}
+
+extern "C" int crbe_solver_update_advection(crbe_solver* solver, const double* points_d, const int32_t* tri_d, const double* areas_d,
+                                            const int32_t* edge_slots_d, const int32_t* scatter_pos_d, const double* m_val_d,
+                                            const double* k_val_d, const double* v_elem_d, double vx, double vy, double coef,
+                                            double* a_val_out_d, double* s_val_out_d) {
+    CRBE_REQUIRE(solver && points_d && tri_d && areas_d && edge_slots_d && scatter_pos_d && m_val_d && k_val_d, "null argument");
+    crbe_solver_arrays ar;
+    CRBE_CHECK(crbe_solver_get_arrays(solver, &ar));
+    crbe_ctx* ctx = ar.ctx;
+    int* err = (int*)(ctx->dev_scalars + 48);
+    CRBE_CUDA(cudaMemsetAsync(err, 0, sizeof(int), ctx->stream));
+    k_update_system_rows<<<crbe_grid_for(ctx, ar.n), CRBE_BLOCK, 0, ctx->stream>>>(
+        ar.n, ar.indptr, ar.indices, ar.is_bnd, points_d, tri_d, areas_d, edge_slots_d, scatter_pos_d, m_val_d, k_val_d, v_elem_d, vx, vy,
+        coef, ar.ell_val, ar.mdiag, ar.mscale, ar.dscale, ar.rhs_val, a_val_out_d, s_val_out_d, err);
+    CRBE_KERNEL_CHECK();
+    ctx->launches += 1;
+    return CRBE_OK;
+}

@@ -70,6 +70,27 @@ static inline int crbe_persistent_grid(const crbe_ctx* ctx, Kern kernel, int64_t
     return crbe_grid_for(ctx, n, block, per_sm);
 }
 
+// Tile-major ("sliced") ELL of the solver: the 4 slots of the 256 rows of a tile are contiguous,
+//   slot k of row i at  (i / 256) * 1024 + k * 256 + (i % 256),
+// so a warp still reads 32 consecutive entries and a whole tile is one 8 KB + 4 KB burst.
+constexpr int CRBE_TILE = 256;
+#ifdef __CUDACC__
+__host__ __device__ __forceinline__ int64_t ell_at(int64_t i, int k) {
+    return (i / CRBE_TILE) * (4 * CRBE_TILE) + (int64_t)k * CRBE_TILE + (i % CRBE_TILE);
+}
+#endif
+
+// solver.cu: the arrays of a solver that the fused re-assembly kernel (assembly.cu) writes
+struct crbe_solver_arrays {
+    crbe_ctx* ctx;
+    int64_t n, nnz;
+    const int32_t* indptr;
+    const int32_t* indices;
+    const unsigned char* is_bnd;
+    double *ell_val, *mdiag, *mscale, *dscale, *rhs_val;
+};
+int crbe_solver_get_arrays(crbe_solver* s, crbe_solver_arrays* out);
+
 // dist.cu (NCCL is confined there)
 struct crbe_comm;
 int crbe_comm_rank(const crbe_comm* c);

@@ -66,3 +66,20 @@ CRBE_HD void crbe_element_eval(double x0, double y0, double x1, double y1, doubl
 CRBE_HD double crbe_triangle_area(double x1, double y1, double x2, double y2, double x3, double y3) {
     return 0.5 * fabs((x2 - x1) * (y3 - y1) - (x3 - x1) * (y2 - y1));
 }
+
+// Advection row only (crbe.py:284-313), same operation order as crbe_element_eval: used when the velocity
+// changes every step and A is rebuilt while K and M stay.
+CRBE_HD void crbe_element_advection(double x0, double y0, double x1, double y1, double x2, double y2, double area, double vx,
+                                    double vy, double (&arow)[3]) {
+    const double j00 = x1 - x0, j10 = y1 - y0, j01 = x2 - x0, j11 = y2 - y0;
+    const double det = fabs(j00 * j11 - j01 * j10);
+    const double b00 = j11 / det, b01 = (-j01) / det;
+    const double b10 = (-j10) / det, b11 = j00 / det;
+    const double phi_int = area / 6.0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const double gx = b00 * CRBE_G(b, 0) + b10 * CRBE_G(b, 1);
+        const double gy = b01 * CRBE_G(b, 0) + b11 * CRBE_G(b, 1);
+        arow[b] = 2 * (phi_int * (gx * vx + gy * vy));
+    }
+}

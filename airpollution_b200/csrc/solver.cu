@@ -102,14 +102,6 @@ struct crbe_solver {
 };
 
 // ---------------------------------------------------------------- helpers
-// Tile-major ("sliced") ELL: the 4 slots of the 256 rows of a tile are contiguous,
-//   slot k of row i at  (i / 256) * 1024 + k * 256 + (i % 256),
-// so a warp still reads 32 consecutive entries and a whole tile is one 8 KB + 4 KB burst.
-constexpr int CRBE_TILE = 256;
-__host__ __device__ __forceinline__ int64_t ell_at(int64_t i, int k) {
-    return (i / CRBE_TILE) * (4 * CRBE_TILE) + (int64_t)k * CRBE_TILE + (i % CRBE_TILE);
-}
-
 __device__ __forceinline__ bool solver_idle(const double* __restrict__ sums, const int* __restrict__ dstate, double rtol2) {
     return dstate[D_STATUS] != 0 || !(sums[S_RR] > rtol2 * sums[S_BB]);
 }
@@ -938,6 +930,23 @@ extern "C" int crbe_solver_p2p_error(crbe_solver* s, int* err_h) {
     CRBE_REQUIRE(s && err_h, "null argument");
     *err_h = 0;
     if (s->window) CRBE_CUDA(cudaMemcpy(err_h, &((P2PHeader*)s->window)->error, sizeof(int), cudaMemcpyDeviceToHost));
+    return CRBE_OK;
+}
+
+int crbe_solver_get_arrays(crbe_solver* s, crbe_solver_arrays* out) {
+    CRBE_REQUIRE(s && out, "null argument");
+    out->ctx = s->ctx;
+    out->n = s->n;
+    out->nnz = s->nnz;
+    out->indptr = s->indptr;
+    out->indices = s->indices;
+    out->is_bnd = s->is_bnd;
+    out->ell_val = s->ell_val;
+    out->mdiag = s->mdiag;
+    out->mscale = s->mscale;
+    out->dscale = s->dscale;
+    out->rhs_val = s->rhs_val;
+    s->system_loaded = true;
     return CRBE_OK;
 }
 

@@ -281,7 +281,7 @@ class OracleSolver:
     """
 
     def __init__(self, T, problem, mesh: OracleMesh, order=1, linear_solver="splu",
-                 v_elem=None, rtol=1e-13):
+                 v_elem=None, rtol=1e-13, velocity_fn=None):
         self.T = T
         self.problem = problem
         self.mesh = mesh
@@ -289,6 +289,7 @@ class OracleSolver:
         self.order = order
         self.linear_solver = linear_solver
         self.v_elem = v_elem
+        self.velocity_fn = velocity_fn      # config-5 extension: v_T(t) = velocity_fn(centroids, t), rebuilt every step
         self.rtol = rtol
         self.iterations = []
 
@@ -344,6 +345,15 @@ class OracleSolver:
         start = time.time()
         for step in range(1, nsteps):
             t = step * self.dt                                          # :420
+            if self.velocity_fn is not None:
+                p, tr = m.points, m.triangles
+                cent = (p[tr[:, 0]] + p[tr[:, 1]] + p[tr[:, 2]]) / 3.0
+                self.v_elem = np.asarray(self.velocity_fn(cent, t), dtype=np.float64)
+                self.build_global_matrices()
+                A = dirichlet_system_fast(self.base_system, m.boundary_segments)
+                self.system = A
+                lu = spla.splu(A.tocsc()) if self.linear_solver == "splu" else None
+                dinv = 1.0 / A.diagonal()
             b = self.rhs(t, u_prev)
             if self.linear_solver == "spsolve":
                 u_prev = spla.spsolve(A, b)                             # :426

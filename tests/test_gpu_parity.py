@@ -409,3 +409,53 @@ def test_callers_run_through_the_drop_in_module(tmp_path, monkeypatch):
         o = orc.OracleSolver(10, crbe.Problem(sigma=1.0), om)
         o.solve()
         assert abs(o.compute_errors(crbe.Problem(sigma=1.0).analytical_solution)[0] - rel) <= 1e-10 * rel
+
+
+def _rotating_field(omega0, T):
+    """v(x, t) = omega(t) * (-y, x), omega(t) = omega0 cos(2 pi t / T): works on numpy arrays and torch tensors."""
+    import math
+
+    def field(c, t):
+        w = omega0 * math.cos(2.0 * math.pi * t / T)
+        if isinstance(c, np.ndarray):
+            return np.stack([-w * c[:, 1], w * c[:, 0]], axis=1)
+        import torch
+        return torch.stack([-w * c[:, 1], w * c[:, 0]], dim=1)
+    return field
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("kind", ["structured", "delaunay"])
+def test_time_varying_velocity_matches_oracle(kind, order):
+    """BASELINE config 5: advection re-assembled every step from a per-element velocity (fused row kernel)."""
+    from airpollution_b200 import crbe
+    from airpollution_b200.meshgen import delaunay_mesh, structured_mesh
+    mesh = structured_mesh(24, lo=(-2.0, -2.0), hi=(2.0, 2.0)) if kind == "structured" else \
+        delaunay_mesh(600, seed=13, lo=(-2.0, -2.0), hi=(2.0, 2.0), flip_fraction=0.2)
+    T, nt = 1.0, 17
+    dom, prob = crbe.Domain(2.0, 2.0, T), crbe.Problem(v=[0.0, 0.0], D=0.05, sigma=0.5)
+    field = _rotating_field(1.5, T)
+    md = crbe.MeshData(mesh, dom, nt)
+    s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), order, progress=False, velocity_field=field)
+    sol = s.solve()
+    o = orc.OracleSolver(T, prob, orc.OracleMesh(mesh.points, mesh.triangles, T, nt), order=order, velocity_fn=field)
+    ref = o.solve()
+    assert max(rel_err(sol[k], ref[k]) for k in range(1, nt)) <= SOLUTION_RTOL
+    # the matrices exported after the last step are those of the last velocity, bit for bit
+    np.testing.assert_array_equal(s.global_advection.data, o.global_advection.data)
+    np.testing.assert_array_equal(s.base_system.data, o.base_system.data)
+
+
+def test_constant_velocity_field_reduces_to_reference_path():
+    """A velocity_field that returns problem.v everywhere must reproduce the constant-v solve exactly."""
+    import torch
+    from airpollution_b200 import crbe
+    g = load_golden("delaunay40_o1")
+    crbe_, dom, md = _product(g)
+    prob = golden_problem("delaunay40_o1", g)
+    a = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), progress=False).solve()
+    vx, vy = float(prob.v[0]), float(prob.v[1])
+    const = lambda c, t: torch.stack([torch.full_like(c[:, 0], vx), torch.full_like(c[:, 0], vy)], dim=1)  # noqa: E731
+    b = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), progress=False, velocity_field=const).solve()
+    np.testing.assert_array_equal(a, b)
+    assert rel_err(b[-1], g["final"]) <= SOLUTION_RTOL
