@@ -501,32 +501,61 @@ class BESCRFEM:
             steps = _tqdm(steps, desc="Time-stepping")
         dt = float(self.dt)
         reassemble = self.velocity_field is not None
+        # The boundary data of the lift (crbe.py:367-379) is the user's numpy callback on the Nb boundary midpoints.
+        # It is evaluated and uploaded one stored step ahead by a helper thread while the GPU solves the current
+        # step (the C call releases the GIL), so the host work is off the critical path.
+        nb = md.boundary_segments.shape[0]
+        mid_b = md.midpoints[md.boundary_segments] if nb else np.zeros((0, 2))
+        bc_host = [torch.zeros((max(nb, 1),), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        bc_dev = [rt.empty((max(nb, 1),), torch.float64) for _ in range(2)]
+        bc_ready = [None, None]
+
+        def prepare_bc(slot, t_out):
+            vals = self.problem.boundary_fn(np.hstack((mid_b, t_out * np.ones((nb, 1))))) if nb else np.zeros(0)
+            if bc_ready[slot] is not None:
+                bc_ready[slot].synchronize()       # the previous upload from this pinned slot has left the host
+            bc_host[slot][:nb].copy_(torch.from_numpy(np.ascontiguousarray(vals, dtype=np.float64)))
+            with torch.cuda.device(rt.device), torch.cuda.stream(copy_stream):
+                bc_dev[slot].copy_(bc_host[slot], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            bc_ready[slot] = ev
+
+        from concurrent.futures import ThreadPoolExecutor
+        stored = [st for st in range(1, n_steps) if st in row_of]
+        pool = ThreadPoolExecutor(max_workers=1)
+        pending = pool.submit(prepare_bc, 0, stored[0] * self.dt) if stored else None
         start = time.time()
         k_out = 0
-        for step in steps:
-            t = step * self.dt                                               # crbe.py:420
-            if reassemble:
-                self._reassemble_advection(t, export=(step == n_steps - 1))
-            src = self._source_on_device(t)
-            rt.call("crbe_solver_step", self._solver, ptr(u), ptr(src), dt, C.byref(info))
-            self.step_info.append((info.iterations, info.relres, info.true_relres, info.restarts))
-            if step in row_of:
-                # lifted copy of the step's solution (crbe.py:429), staged so the download overlaps the next step
-                bc = rt.upload(np.asarray(self.problem.boundary_fn(self._boundary_xyt(t)), dtype=np.float64))
-                sb = k_out & 1
-                if stage_free[sb] is not None:
-                    main.wait_event(stage_free[sb])
-                rt.call("crbe_solver_lift", self._solver, ptr(u), ptr(bc), ptr(stage[sb]))
-                ready = torch.cuda.Event()
-                ready.record(main)
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(ready)
-                    sol_t[row_of[step]].copy_(stage[sb], non_blocking=True)
-                    done = torch.cuda.Event()
-                    done.record(copy_stream)
-                stage_free[sb] = done
-                self._last_stage = stage[sb]
-                k_out += 1
+        try:
+            for step in steps:
+                t = step * self.dt                                               # crbe.py:420
+                if reassemble:
+                    self._reassemble_advection(t, export=(step == n_steps - 1))
+                src = self._source_on_device(t)
+                rt.call("crbe_solver_step", self._solver, ptr(u), ptr(src), dt, C.byref(info))
+                self.step_info.append((info.iterations, info.relres, info.true_relres, info.restarts))
+                if step in row_of:
+                    # lifted copy of the step's solution (crbe.py:429), staged so the download overlaps the next step
+                    sb = k_out & 1
+                    pending.result()
+                    if k_out + 1 < len(stored):
+                        pending = pool.submit(prepare_bc, sb ^ 1, stored[k_out + 1] * self.dt)
+                    main.wait_event(bc_ready[sb])
+                    if stage_free[sb] is not None:
+                        main.wait_event(stage_free[sb])
+                    rt.call("crbe_solver_lift", self._solver, ptr(u), ptr(bc_dev[sb]), ptr(stage[sb]))
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(ready)
+                        sol_t[row_of[step]].copy_(stage[sb], non_blocking=True)
+                        done = torch.cuda.Event()
+                        done.record(copy_stream)
+                    stage_free[sb] = done
+                    k_out += 1
+        finally:
+            pool.shutdown(wait=True)
         copy_stream.synchronize()
         rt.synchronize()
         self.solve_time = time.time() - start
