@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcrbe_b200.so")
+LIB_PATH = os.environ.get("CRBE_LIB_PATH") or os.path.join(_PKG, "libcrbe_b200.so")   # env: experimental builds only
 
 ABI_VERSION = 1
 
@@ -32,6 +32,7 @@ SOLVER_FUSED = 1
 SOLVER_VERIFY = 2
 SOLVER_GRAPH = 4
 SOLVER_TMA = 8
+SOLVER_EXTRAPOLATE = 16
 
 # name -> (argtypes)   every function returns int unless listed in _RESTYPE
 _SIGNATURES = {

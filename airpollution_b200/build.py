@@ -46,7 +46,21 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, defines=(), lib=None, obj=None):
+    """``defines``/``lib``/``obj`` build an experimental variant (e.g. -DCRBE_TILE_STAGES=4) next to the default one."""
+    global OBJ, LIB
+    saved = (OBJ, LIB)
+    if lib:
+        LIB = lib
+        OBJ = obj or (lib + ".obj")
+        force = True
+    try:
+        return _build(force, verbose, list(defines))
+    finally:
+        OBJ, LIB = saved
+
+
+def _build(force, verbose, defines):
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
@@ -58,7 +72,7 @@ def build_library(force=False, verbose=False):
         opath = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(opath)
         if force or _stale(opath, [spath, __file__] + hdrs):
-            cmd = [nvcc] + ARCH + COMMON + (["-fmad=false"] if src in NO_FMAD else []) + \
+            cmd = [nvcc] + ARCH + COMMON + defines + (["-fmad=false"] if src in NO_FMAD else []) + \
                   (["-Xptxas", "-v"] if verbose else []) + ["-c", spath, "-o", opath]
             jobs.append(cmd)
 

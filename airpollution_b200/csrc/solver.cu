@@ -64,6 +64,8 @@ struct crbe_solver {
     double *mdiag = nullptr, *mscale = nullptr, *dscale = nullptr;
     double* rhs_val = nullptr;         // CN: values of M - c(K+A) on the structural pattern
     double *b = nullptr, *r = nullptr, *rh = nullptr, *s = nullptr, *t = nullptr, *tmp = nullptr;
+    double* hist = nullptr;            // u^n of the running time loop (right-hand side / extrapolation of the initial guess)
+    bool hist_valid = false;
     double* p[2] = {nullptr, nullptr};
     double* v[2] = {nullptr, nullptr};
     double* sums = nullptr;
@@ -339,6 +341,15 @@ __global__ void k_zero_rows(double* __restrict__ u, const int* __restrict__ bnd,
     ROW_LOOP(k, nb) u[bnd[k]] = 0.0;
 }
 
+// u holds u^n, hist holds u^(n-1):  hist <- u^n,  u <- 2 u^n - u^(n-1)  (initial guess of the next solve)
+__global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate(int64_t n, double* __restrict__ u, double* __restrict__ hist) {
+    ROW_LOOP(i, n) {
+        const double un = u[i], uo = hist[i];
+        hist[i] = un;
+        u[i] = fma(2.0, un, -uo);
+    }
+}
+
 __global__ void k_lift(const double* __restrict__ bc, const int* __restrict__ bnd, int64_t nb, double* __restrict__ out) {
     ROW_LOOP(k, nb) out[bnd[k]] += bc[k];
 }
@@ -365,7 +376,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
         const double xi = x[i];
         double bi;
         if (MODE == 0) {
-            bi = mscale[i] * xi;
+            bi = mscale[i] * bin[i];      // bin = u^n (x may hold an extrapolated initial guess)
             if (src) bi = fma(dscale[i] * dt, src[i], bi);
         } else if (MODE == 1) {
             double raw = bin[i];
@@ -706,6 +717,7 @@ static int solver_release(crbe_solver* s) {
     cudaFree(s->s);
     cudaFree(s->t);
     cudaFree(s->tmp);
+    cudaFree(s->hist);
     cudaFree(s->p[0]);
     cudaFree(s->p[1]);
     cudaFree(s->v[0]);
@@ -763,7 +775,7 @@ static int solver_create_impl(crbe_ctx* ctx, crbe_comm* comm, int64_t n, int64_t
     }
     CRBE_CUDA(cudaMalloc(&s->ell_col, sizeof(int32_t) * 4 * s->ld));
     CRBE_CUDA(cudaMalloc(&s->ell_val, sizeof(double) * 4 * s->ld));
-    double** vecs[] = {&s->mdiag, &s->mscale, &s->dscale, &s->b, &s->r, &s->rh, &s->s, &s->t, &s->p[0], &s->v[0]};
+    double** vecs[] = {&s->mdiag, &s->mscale, &s->dscale, &s->b, &s->r, &s->rh, &s->s, &s->t, &s->p[0], &s->v[0], &s->hist};
     for (double** vp : vecs) {
         CRBE_CUDA(cudaMalloc(vp, vb));
         CRBE_CUDA(cudaMemsetAsync(*vp, 0, vb, ctx->stream));
@@ -796,11 +808,11 @@ static int solver_create_impl(crbe_ctx* ctx, crbe_comm* comm, int64_t n, int64_t
         s->g_spmv = crbe_persistent_grid(ctx, k_spmv_csr, n);
         // bulk-copy kernels: opt in to their dynamic shared memory, then size one resident wave over the tiles
         s->ntiles = s->ld / CRBE_TILE;
-        CRBE_CHECK(tile_grid(ctx, t_pv<false>, TilePipe<2>::SMEM_BYTES, s->ntiles, &s->gt_pv[0]));
+        CRBE_CHECK(tile_grid(ctx, t_pv<false>, TilePipe<2, SPMV_STAGES>::SMEM_BYTES, s->ntiles, &s->gt_pv[0]));
         CRBE_CHECK(tile_grid(ctx, t_pv<true>, TilePipe<4>::SMEM_BYTES, s->ntiles, &s->gt_pv[1]));
-        CRBE_CHECK(tile_grid(ctx, t_st<false>, TilePipe<1>::SMEM_BYTES, s->ntiles, &s->gt_st[0]));
+        CRBE_CHECK(tile_grid(ctx, t_st<false>, TilePipe<1, SPMV_STAGES>::SMEM_BYTES, s->ntiles, &s->gt_st[0]));
         CRBE_CHECK(tile_grid(ctx, t_st<true>, TilePipe<2>::SMEM_BYTES, s->ntiles, &s->gt_st[1]));
-        CRBE_CHECK(tile_grid(ctx, t_init_be, TilePipe<1>::SMEM_BYTES, s->ntiles, &s->gt_init));
+        CRBE_CHECK(tile_grid(ctx, t_init_be, TilePipe<2>::SMEM_BYTES, s->ntiles, &s->gt_init));
         CRBE_CHECK(tile_grid(ctx, t_residual, TilePipe<1>::SMEM_BYTES, s->ntiles, &s->gt_res));
     }
     CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -991,6 +1003,7 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
         return CRBE_ERR_ARG;
     }
     s->system_loaded = true;
+    s->hist_valid = false;      // a new system starts a new time loop
     return CRBE_OK;
 }
 
@@ -1122,7 +1135,7 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
         PROF_LAUNCH(PK_P, k, (k_p<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, p, s->sums, s->dstate, s->d_comm)));
         CRBE_CHECK(halo_exchange(s, p, launches));
         if (tma)
-            PROF_LAUNCH(PK_PV, k, (t_pv<false><<<s->gt_pv[0], CRBE_TILE, TilePipe<2>::SMEM_BYTES, st>>>(
+            PROF_LAUNCH(PK_PV, k, (t_pv<false><<<s->gt_pv[0], CRBE_TILE, TilePipe<2, SPMV_STAGES>::SMEM_BYTES, st>>>(
                                       s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p, v, s->rh, s->sums, s->dots, s->dstate,
                                       ctx->partials, ctx->counter, s->d_comm)));
         else
@@ -1132,7 +1145,7 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
         PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, s->s, s->sums, s->dstate, s->d_comm)));
         CRBE_CHECK(halo_exchange(s, s->s, launches));
         if (tma)
-            PROF_LAUNCH(PK_ST, k, (t_st<false><<<s->gt_st[0], CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
+            PROF_LAUNCH(PK_ST, k, (t_st<false><<<s->gt_st[0], CRBE_TILE, TilePipe<1, SPMV_STAGES>::SMEM_BYTES, st>>>(
                                       s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dots, s->dstate,
                                       ctx->partials, ctx->counter, s->d_comm)));
         else
@@ -1291,17 +1304,28 @@ extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* sourc
         k_zero_rows<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, st>>>(u_d, s->bnd, s->nb);
         ++launches;
     }
+    // hist <- u^n for the right-hand side; with one step of history the initial guess is extrapolated linearly in time
+    // (2 u^n - u^(n-1)): the first residual drops by 2-3 orders of magnitude, which saves about one iteration per step
+    if (!s->rhs_val) {
+        if (s->hist_valid && (s->flags & CRBE_SOLVER_EXTRAPOLATE)) {
+            k_extrapolate<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, u_d, s->hist);
+            ++launches;
+        } else {
+            CRBE_CUDA(cudaMemcpyAsync(s->hist, u_d, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
+        }
+        s->hist_valid = true;
+    }
     CRBE_CHECK(halo_exchange(s, u_d, &launches));
     if (s->rhs_val)
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, s->tmp, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if (s->flags & CRBE_SOLVER_TMA)
-        PROF_LAUNCH(PK_INIT, -1, (t_init_be<<<s->gt_init, CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->ell_val, s->ell_col, u_d, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
+        PROF_LAUNCH(PK_INIT, -1, (t_init_be<<<s->gt_init, CRBE_TILE, TilePipe<2>::SMEM_BYTES, st>>>(
+                                     s->n, s->ntiles, s->ell_val, s->ell_col, u_d, s->hist, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
                                      s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else
-        PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, nullptr, source_d, dt,
+        PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, s->hist, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     ++launches;

@@ -14,7 +14,19 @@
 // Included by solver.cu after the shared device helpers.
 #pragma once
 
-constexpr int TILE_STAGES = 3;
+#ifndef CRBE_TILE_STAGES
+#define CRBE_TILE_STAGES 3
+#endif
+#ifndef CRBE_GATHER_PREFETCH
+#define CRBE_GATHER_PREFETCH 1
+#endif
+#ifndef CRBE_SPMV_STAGES
+#define CRBE_SPMV_STAGES 2
+#endif
+constexpr int TILE_STAGES = CRBE_TILE_STAGES;     // init / residual / fused kernels
+// The unfused SpMV kernels prefetch their gathers one tile ahead; two bulk-copy stages then suffice and the smaller
+// shared-memory footprint lets 6 CTAs share an SM (measured best of {2,3,4} stages x {prefetch on, off}).
+constexpr int SPMV_STAGES = CRBE_SPMV_STAGES;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -47,13 +59,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // One stage holds, for the 256 rows of a tile:  val[4][256] f64 | vec[NVEC][256] f64 | col[4][256] i32
-template <int NVEC>
+template <int NVEC, int STAGES = TILE_STAGES>
 struct TilePipe {
     static constexpr int VAL_BYTES = 4 * CRBE_TILE * 8;
     static constexpr int VEC_BYTES = CRBE_TILE * 8;
     static constexpr int COL_BYTES = 4 * CRBE_TILE * 4;
     static constexpr int STAGE_BYTES = VAL_BYTES + NVEC * VEC_BYTES + COL_BYTES;
-    static constexpr int SMEM_BYTES = TILE_STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES;
 
     unsigned char* smem;
     uint64_t* bars;
@@ -65,7 +77,7 @@ struct TilePipe {
     __device__ __forceinline__ int64_t tile_of(int64_t m) const { return first + m * stride; }
 
     __device__ __forceinline__ void issue(int64_t m) {
-        const int st = (int)(m % TILE_STAGES);
+        const int st = (int)(m % STAGES);
         unsigned char* base = smem + st * STAGE_BYTES;
         const int64_t tile = tile_of(m);
         mbar_expect_tx(&bars[st], STAGE_BYTES);
@@ -75,7 +87,7 @@ struct TilePipe {
         bulk_g2s(base + VAL_BYTES + NVEC * VEC_BYTES, ecol + tile * (4 * CRBE_TILE), COL_BYTES, &bars[st]);
     }
 
-    // all threads of the CTA; returns with the first TILE_STAGES tiles in flight
+    // all threads of the CTA; returns with the first STAGES tiles in flight
     __device__ __forceinline__ void start(unsigned char* smem_, uint64_t* bars_, int64_t ntiles) {
         smem = smem_;
         bars = bars_;
@@ -84,23 +96,23 @@ struct TilePipe {
         count = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int s = 0; s < TILE_STAGES; ++s) mbar_init(&bars[s], 1);
+            for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
             mbar_fence_init();
         }
         __syncthreads();
         if (threadIdx.x == 0)
-            for (int64_t m = 0; m < TILE_STAGES && m < count; ++m) issue(m);
+            for (int64_t m = 0; m < STAGES && m < count; ++m) issue(m);
     }
 
-    __device__ __forceinline__ void wait(int64_t m) const { mbar_wait(&bars[m % TILE_STAGES], (uint32_t)((m / TILE_STAGES) & 1)); }
+    __device__ __forceinline__ void wait(int64_t m) const { mbar_wait(&bars[m % STAGES], (uint32_t)((m / STAGES) & 1)); }
 
-    // every thread has finished reading stage m: refill it with tile m + TILE_STAGES
+    // every thread has finished reading stage m: refill it with tile m + STAGES
     __device__ __forceinline__ void release(int64_t m) {
         __syncthreads();
-        if (threadIdx.x == 0 && m + TILE_STAGES < count) issue(m + TILE_STAGES);
+        if (threadIdx.x == 0 && m + STAGES < count) issue(m + STAGES);
     }
 
-    __device__ __forceinline__ const double* sval(int64_t m) const { return (const double*)(smem + (m % TILE_STAGES) * STAGE_BYTES); }
+    __device__ __forceinline__ const double* sval(int64_t m) const { return (const double*)(smem + (m % STAGES) * STAGE_BYTES); }
     __device__ __forceinline__ const double* svec(int64_t m, int v) const { return sval(m) + 4 * CRBE_TILE + v * CRBE_TILE; }
     __device__ __forceinline__ const int* scol(int64_t m) const { return (const int*)(sval(m) + (4 + NVEC) * CRBE_TILE); }
 };
@@ -124,6 +136,42 @@ __device__ __forceinline__ double tile_row(const double* __restrict__ sval, cons
     return acc;
 }
 
+// Unfused SpMV over the tiles of this CTA with the gathers software-pipelined one tile ahead: the x[col] loads of
+// tile m+1 are issued before tile m is finished, so gather latency overlaps arithmetic, stores and the barrier.
+// body(row, r, own, y) consumes the row result y = own + sum a_k x[col_k]; own = staged vector 0.
+template <int NV, int ST, class Body>
+__device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST>& pipe, const double* __restrict__ x, int64_t n, Body body) {
+    const int tr = threadIdx.x;
+    double g[4], gn[4];
+    auto gather = [&](int64_t m, double (&dst)[4]) {
+        const int* sc = pipe.scol(m);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[k] = __ldg(x + sc[k * CRBE_TILE + tr]);
+    };
+    if (pipe.count > 0) {
+        pipe.wait(0);
+        gather(0, g);
+    }
+    for (int64_t m = 0; m < pipe.count; ++m) {
+        if (m + 1 < pipe.count) {
+            pipe.wait(m + 1);
+            gather(m + 1, gn);
+        }
+        const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
+        if (row < n) {
+            const double* sv = pipe.sval(m);
+            const double own = pipe.svec(m, 0)[tr];
+            double y = own;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) y = fma(sv[k * CRBE_TILE + tr], g[k], y);
+            body(m, row, tr, own, y);
+        }
+        pipe.release(m);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g[k] = gn[k];
+    }
+}
+
 // ---- v = A p, (r^, v)   [FUSED: p advanced here and at the gathered neighbours] -------------------
 template <bool FUSED>
 __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int k, double rtol2, const double* __restrict__ eval,
@@ -132,7 +180,8 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
-    __shared__ uint64_t bars[TILE_STAGES];
+    constexpr int ST = FUSED ? TILE_STAGES : SPMV_STAGES;
+    __shared__ uint64_t bars[ST];
     if (solver_idle(sums, dstate, rtol2)) return;
     IterScalars sc = {0, 0, 0, false};
     if (FUSED && k > 0) {
@@ -143,7 +192,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int
         }
     }
     constexpr int NV = FUSED ? 4 : 2;
-    TilePipe<NV> pipe;
+    TilePipe<NV, ST> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
     if (FUSED) {
@@ -159,6 +208,17 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int
     halo_wait(1, ca);   // the bulk copies are already in flight
     const int tr = threadIdx.x;
     double acc[1] = {0.0};
+#if CRBE_GATHER_PREFETCH
+    if (!FUSED) {
+        tile_spmv_prefetch(pipe, p_in, n, [&](int64_t m, int64_t row, int t_, double, double vi) {
+            v_out[row] = vi;
+            acc[0] = fma(pipe.svec(m, 1)[t_], vi, acc[0]);
+        });
+        double* const out_p[1] = {dots + S_RHV};
+        grid_sum_last<1>(acc, partials, counter, out_p, ca);
+        return;
+    }
+#endif
     for (int64_t m = 0; m < pipe.count; ++m) {
         pipe.wait(m);
         const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
@@ -200,7 +260,8 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int
                                                   double* __restrict__ s, double* __restrict__ t, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
-    __shared__ uint64_t bars[TILE_STAGES];
+    constexpr int ST = FUSED ? TILE_STAGES : SPMV_STAGES;
+    __shared__ uint64_t bars[ST];
     if (solver_idle(sums, dstate, rtol2)) return;
     double alpha = 0.0;
     if (FUSED) {
@@ -211,7 +272,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int
         }
     }
     constexpr int NV = FUSED ? 2 : 1;
-    TilePipe<NV> pipe;
+    TilePipe<NV, ST> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
     if (FUSED) {
@@ -224,6 +285,18 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int
     halo_wait(2, ca);
     const int tr = threadIdx.x;
     double acc[2] = {0.0, 0.0};
+#if CRBE_GATHER_PREFETCH
+    if (!FUSED) {
+        tile_spmv_prefetch(pipe, s, n, [&](int64_t, int64_t row, int, double si, double ti) {
+            t[row] = ti;
+            acc[0] = fma(ti, si, acc[0]);
+            acc[1] = fma(ti, ti, acc[1]);
+        });
+        double* const out_p[2] = {dots + S_TS, dots + S_TT};
+        grid_sum_last<2>(acc, partials, counter, out_p, ca);
+        return;
+    }
+#endif
     for (int64_t m = 0; m < pipe.count; ++m) {
         pipe.wait(m);
         const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
@@ -247,9 +320,10 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int
     grid_sum_last<2>(acc, partials, counter, out, ca);
 }
 
-// ---- Backward-Euler step start: b = mscale*u (+ dscale*dt*f), r = r^ = b - A u, (b,b), (r,r) --------
+// ---- Backward-Euler step start: b = mscale*u^n (+ dscale*dt*f), r = r^ = b - A x0, (b,b), (r,r) --------
 __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles, const double* __restrict__ eval, const int* __restrict__ ecol,
-                                                       const double* __restrict__ x, const double* __restrict__ src, double dt,
+                                                       const double* __restrict__ x, const double* __restrict__ xb,
+                                                       const double* __restrict__ src, double dt,
                                                        const double* __restrict__ mscale, const double* __restrict__ dscale,
                                                        double* __restrict__ b, double* __restrict__ r, double* __restrict__ rh, double* sums,
                                                        double* dots, int* dstate, double* partials, unsigned int* counter, const CommArgs* __restrict__ ca) {
@@ -259,10 +333,11 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
         dstate[D_STATUS] = 0;
         dstate[D_ITERS] = 0;
     }
-    TilePipe<1> pipe;
+    TilePipe<2> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
     pipe.vec[0] = mscale;
+    pipe.vec[1] = xb;     // previous solution u^n (right-hand side); x is the initial guess, possibly extrapolated
     pipe.start(tile_smem, bars, ntiles);
     halo_wait(0, ca);
     const int tr = threadIdx.x;
@@ -276,7 +351,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
         }
         pipe.wait(m);
         if (row < n) {
-            const double bi = fma(pipe.svec(m, 0)[tr], xi, extra);
+            const double bi = fma(pipe.svec(m, 0)[tr], pipe.svec(m, 1)[tr], extra);
             const double ax = tile_row(pipe.sval(m), pipe.scol(m), tr, xi, [&](int j) { return __ldg(x + j); });
             const double ri = bi - ax;
             b[row] = bi;

@@ -173,7 +173,8 @@ class PartitionedCRBE:
     split into equal blocks of rows."""
 
     def __init__(self, workload=None, *, mesh=None, domain=None, problem=None, nt=None, order=1, rank=None, world=None,
-                 device=None, comm=None, rtol=1e-13, max_iterations=10000, tma=True, verify=True, p2p=None):
+                 device=None, comm=None, rtol=1e-13, max_iterations=10000, tma=True, verify=True, p2p=None,
+                 extrapolate=True):
         from . import _lib, crbe
         from .runtime import Runtime, ptr
         import os
@@ -254,7 +255,8 @@ class PartitionedCRBE:
                 (C.c_int64 * max(nn, 1))(*[len(s) for s in send_ids]), ptr(d["send_idx"]),
                 (C.c_int64 * max(nn, 1))(*recv_counts), C.byref(h))
         self._solver = h
-        flags = (_lib.SOLVER_VERIFY if verify else 0) | (_lib.SOLVER_TMA if tma else 0)
+        flags = (_lib.SOLVER_VERIFY if verify else 0) | (_lib.SOLVER_TMA if tma else 0) | \
+                (_lib.SOLVER_EXTRAPOLATE if extrapolate else 0)
         rt.call("crbe_solver_set_options", h, float(rtol), int(max_iterations), flags)
         rt.call("crbe_solver_set_system", h, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
         vlen = C.c_int64()
@@ -356,7 +358,7 @@ def bench_partitioned(args, K, W, device):
         wl = workloads.unit_square(args.n, steps=K + W, regime=args.regime, ny=args.n * world)
         scaling = "weak"
     t0 = time.time()
-    part = PartitionedCRBE(wl, device=device, tma=not args.classic)
+    part = PartitionedCRBE(wl, device=device, tma=not args.classic, extrapolate=not args.no_extrapolate)
     setup_s = time.time() - t0
     for _ in range(W):
         part.step()

@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--cells", "--n", dest="n", type=int, default=int(os.environ.get("CRBE_BENCH_N", 2048)), help="cells per axis (per GPU strip)")
     ap.add_argument("--regime", default="P-ref", choices=["P-ref", "P-T10", "P-stiff"])
     ap.add_argument("--fused", action="store_true", help="fuse the p/s updates into the SpMV kernels (3-kernel iteration)")
+    ap.add_argument("--no-extrapolate", action="store_true", help="start every solve from u^n instead of 2u^n - u^(n-1)")
     ap.add_argument("--classic", action="store_true", help="register-load kernels instead of the bulk-copy (TMA) pipeline")
     ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--cpu-steps", type=int, default=2)
@@ -325,7 +326,7 @@ def main():
     mesh = wl.mesh()
     dom, prob = wl.domain(), wl.problem()
     md = crbe.MeshData(mesh, dom, wl.nt)
-    solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", fused=args.fused, tma=not args.classic, progress=False)
+    solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", fused=args.fused, tma=not args.classic, extrapolate=not args.no_extrapolate, progress=False)
     rt = Runtime.get(device)
     solver.set_initial_condition()
     u = rt.upload(np.asarray(solver.u_prev, dtype=np.float64))
@@ -417,7 +418,7 @@ def main():
         E = max(2, min(args.e2e_steps, K))
         wl_e = workloads.unit_square(args.n, steps=E, regime=args.regime)
         md_e = crbe.MeshData(mesh, wl_e.domain(), wl_e.nt)
-        s_e = crbe.BESCRFEM(wl_e.domain(), prob, md_e, crbe.ElementCR(), 1, history="all", fused=args.fused, tma=not args.classic, progress=False)
+        s_e = crbe.BESCRFEM(wl_e.domain(), prob, md_e, crbe.ElementCR(), 1, history="all", fused=args.fused, tma=not args.classic, extrapolate=not args.no_extrapolate, progress=False)
         import contextlib
         import io
         with contextlib.redirect_stdout(io.StringIO()):
