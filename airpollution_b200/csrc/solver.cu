@@ -30,7 +30,7 @@
 
 #include "crbe_common.cuh"
 
-enum { PK_INIT = 0, PK_PV, PK_ST, PK_XR, PK_P, PK_S, PK_RES, PK_COUNT };
+enum { PK_INIT = 0, PK_PV, PK_ST, PK_XR, PK_P, PK_S, PK_RES, PK_EXTRAP, PK_COUNT };
 
 struct ProfRecord {
     cudaEvent_t a, b;
@@ -1008,7 +1008,7 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
 }
 
 // ---- optional per-kernel timing (CUDA events on the launching stream) ----
-// Kinds: 0 init, 1 pv, 2 st, 3 xr, 4 p, 5 s, 6 residual.  Kernels of iterations that
+// Kinds: 0 init, 1 pv, 2 st, 3 xr, 4 p, 5 s, 6 residual, 7 extrapolation of the initial guess.  Kernels of iterations that
 // turned out to be past convergence (they return at once) are not accounted.
 static cudaEvent_t prof_event(crbe_profile* pf) {
     cudaEvent_t e;
@@ -1308,7 +1308,7 @@ extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* sourc
     // (2 u^n - u^(n-1)): the first residual drops by 2-3 orders of magnitude, which saves about one iteration per step
     if (!s->rhs_val) {
         if (s->hist_valid && (s->flags & CRBE_SOLVER_EXTRAPOLATE)) {
-            k_extrapolate<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, u_d, s->hist);
+            PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, u_d, s->hist)));
             ++launches;
         } else {
             CRBE_CUDA(cudaMemcpyAsync(s->hist, u_d, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
@@ -1420,7 +1420,7 @@ extern "C" int crbe_solver_profile(crbe_solver* s, int enable) {
     return CRBE_OK;
 }
 
-// ms_h, count_h: 8 entries each: init, pv, st, xr, p, s, residual, (unused)
+// ms_h, count_h: 8 entries each: init, pv, st, xr, p, s, residual, extrapolate
 extern "C" int crbe_solver_profile_read(crbe_solver* s, double* ms_h, int64_t* count_h) {
     CRBE_REQUIRE(s && ms_h && count_h, "null argument");
     for (int k = 0; k < 8; ++k) {

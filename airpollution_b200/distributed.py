@@ -391,7 +391,7 @@ def bench_partitioned(args, K, W, device):
     rb = dict(B.ROW_BYTES)
     rb["pv"], rb["st"] = 48 + 3 * 8, 48 + 2 * 8
     kern = {B.KINDS[k]: {"launches": int(pcnt[k]), "ms_per_launch": pms[k] / pcnt[k],
-                         "GBps": rb[B.KINDS[k]] * n_own / (pms[k] / pcnt[k] * 1e-3) / 1e9} for k in range(7) if pcnt[k] > 0}
+                         "GBps": rb[B.KINDS[k]] * n_own / (pms[k] / pcnt[k] * 1e-3) / 1e9} for k in range(8) if pcnt[k] > 0}
     steps_per_s = K / (ms * 1e-3)
     counts = wl.counts()
     units = world if scaling == "weak" else 1

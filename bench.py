@@ -39,8 +39,9 @@ sys.path.insert(0, ROOT)
 METRIC = "Backward-Euler steps/s at 12.6M CR DOFs"
 UNIT = "steps/s"
 # bytes per matrix row moved by each solver kernel in the ELL-4/unit-diagonal layout
-ROW_BYTES = {"init": 48 + 5 * 8, "pv": 48 + 6 * 8, "st": 48 + 4 * 8, "xr": 7 * 8, "p": 4 * 8, "s": 3 * 8, "residual": 48 + 4 * 8}
-KINDS = ["init", "pv", "st", "xr", "p", "s", "residual", "unused"]
+ROW_BYTES = {"init": 48 + 6 * 8, "pv": 48 + 6 * 8, "st": 48 + 4 * 8, "xr": 7 * 8, "p": 4 * 8, "s": 3 * 8, "residual": 48 + 2 * 8,
+             "extrapolate": 4 * 8}
+KINDS = ["init", "pv", "st", "xr", "p", "s", "residual", "extrapolate"]
 
 
 def parse_args():
@@ -376,7 +377,7 @@ def main():
     rt.call("crbe_solver_profile_read", solver._solver, pms, pcnt)
     kern = {KINDS[k]: {"launches": int(pcnt[k]), "ms_per_launch": pms[k] / pcnt[k],
                        "GBps": ROW_BYTES[KINDS[k]] * n / (pms[k] / pcnt[k] * 1e-3) / 1e9}
-            for k in range(7) if pcnt[k] > 0}
+            for k in range(8) if pcnt[k] > 0}
     steps_per_s = K / (ms * 1e-3)
     it_mean = float(np.mean(iters))
     if not args.fused:   # unfused SpMV kernels move fewer vectors: p,rh in / v out and s in / t out
@@ -387,7 +388,8 @@ def main():
     achieved = kern[dom_k]["GBps"]
     # whole-step traffic in this layout: per iteration pv+st+xr (unfused: +p+s), per step init + residual
     per_it = ROW_BYTES["pv"] + ROW_BYTES["st"] + ROW_BYTES["xr"] + (0 if args.fused else ROW_BYTES["p"] + ROW_BYTES["s"] - 3 * 8)
-    step_bytes = (it_mean * per_it + ROW_BYTES["init"] + ROW_BYTES["residual"]) * n
+    step_bytes = (it_mean * per_it + ROW_BYTES["init"] + ROW_BYTES["residual"]
+                  + (0 if args.no_extrapolate else ROW_BYTES["extrapolate"])) * n
     # SURVEY 8(d) CSR accounting of the same work, for comparison
     csr_spmv = 12 * counts["nnz_sys"] + 4 * (n + 1)
     csr_iter = 2 * csr_spmv + 19 * 8 * n

@@ -202,7 +202,7 @@ int crbe_solver_p2p_error(crbe_solver* s, int* err_h);       /* non-zero: a peer
 /* ---- measurement -------------------------------------------------------- */
 /* Per-kernel device time of the solver kernels, CUDA events on the context stream.
  * enable != 0 resets and starts the accumulation, 0 stops it.  crbe_solver_profile_read
- * fills 8 entries: init, pv, st, xr, p, s, residual, (unused): total ms and launch counts
+ * fills 8 entries: init, pv, st, xr, p, s, residual, extrapolate: total ms and launch counts
  * (launches enqueued past convergence, which return at once, are not counted). */
 int crbe_solver_profile(crbe_solver* s, int enable);
 int crbe_solver_profile_read(crbe_solver* s, double* ms_h, int64_t* count_h);
