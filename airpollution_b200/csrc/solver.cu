@@ -46,7 +46,7 @@ struct crbe_profile {
 };
 
 
-enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RRTRUE = 7, S_AUX0 = 8, S_AUX1 = 9 };
+enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RS = 7, S_RT = 8, S_RRTRUE = 10 };
 enum { D_STATUS = 0, D_ITERS = 1 };
 
 struct P2PHeader;
@@ -73,12 +73,12 @@ struct crbe_solver {
     double* sums_h = nullptr;  // pinned: CRBE_NSUMS doubles followed by 2 ints
     double rtol = 1e-13;
     int maxit = 10000;
-    unsigned flags = CRBE_SOLVER_TMA | CRBE_SOLVER_VERIFY;
+    unsigned flags = CRBE_SOLVER_TMA | CRBE_SOLVER_VERIFY | CRBE_SOLVER_EXTRAPOLATE;
     int last_iters = 8;
     bool system_loaded = false;
     // persistent grids: SMs x resident CTAs of each kernel (a grid-stride sweep must be one full wave)
     int g_init = 1, g_pv = 1, g_st = 1, g_xr = 1, g_vec = 1, g_res = 1, g_spmv = 1;
-    int gt_pv[2] = {1, 1}, gt_st[2] = {1, 1}, gt_init = 1, gt_res = 1;   // tile (bulk-copy) kernels: [unfused, fused]
+    int gt_pv = 1, gt_st = 1, gt_init = 1, gt_res = 1;   // tile (bulk-copy) kernels
     int64_t ntiles = 0;
     // row-block partition (world > 1): this solver holds the rows [0, n) of its rank; gathered vectors carry the
     // halo entries (values owned by other ranks) behind the padded owned part, at [ld, ld + n_halo)
@@ -355,17 +355,26 @@ __global__ void k_lift(const double* __restrict__ bc, const int* __restrict__ bn
 }
 
 // ---------------------------------------------------------------- BiCGStab kernels
-// MODE 0: Backward Euler right-hand side  b = (M_ii u_i + dt f_i) / d_i     (crbe.py:384,394,402)
+// The iteration is the merged-reduction form of BiCGStab (Yang & Brent): (r^,s) and (r^,t) are taken together with
+// (t,s), (t,t), so rho_{k+1} = (r^,s) - omega (r^,t) and beta are known when x and r are updated and the p-update
+// joins that kernel.  Four kernels and 232 B per row and iteration (bulk-copy layout):
+//   pv : v = A p, (r^,v)                                              48 + 3*8
+//   s  : s = r - alpha v                                              3*8
+//   st : t = A s, (t,s), (t,t), (r^,s), (r^,t)                        48 + 3*8
+//   xrp: x += alpha p + omega s; r = s - omega t; p = r + beta (p - omega v); (r,r)      8*8
+//
+// MODE 0: Backward Euler right-hand side  b = (M_ii u^n_i + dt f_i) / d_i   (crbe.py:384,394,402); bin = u^n
 // MODE 1: b = scale_i * (bin_i + dt f_i), scale_i = 1/d_i (0 on Dirichlet rows)           (CN, crbe.py:386)
 // MODE 2: b = bin_i / d_i, Dirichlet rows keep bin_i                                    (generic solve)
-// then r = r^ = b - A x and the norms (b,b), (r,r).
+// then r = r^ = p = b - A x and the norms (b,b), (r,r).
 template <int MODE>
 __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, const double* __restrict__ eval, const int* __restrict__ ecol,
                                                      const double* __restrict__ x, const double* __restrict__ bin,
                                                      const double* __restrict__ src, double dt, const double* __restrict__ mscale,
                                                      const double* __restrict__ dscale, const unsigned char* __restrict__ is_bnd,
                                                      double* __restrict__ b, double* __restrict__ r, double* __restrict__ rh,
-                                                     double* sums, double* dots, int* dstate, double* partials, unsigned int* counter, const CommArgs* __restrict__ ca) {
+                                                     double* __restrict__ p, double* sums, double* dots, int* dstate, double* partials,
+                                                     unsigned int* counter, const CommArgs* __restrict__ ca) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         dstate[D_STATUS] = 0;
         dstate[D_ITERS] = 0;
@@ -390,92 +399,34 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
         b[i] = bi;
         r[i] = ri;
         rh[i] = ri;
+        p[i] = ri;
         acc[0] = fma(bi, bi, acc[0]);
         acc[1] = fma(ri, ri, acc[1]);
     }
+    halo_push_tail(p, 1, ca);
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
     grid_sum_last<3>(acc, partials, counter, out, ca);
 }
 
-struct IterScalars {
-    double alpha, omega, beta;
-    bool bad;
-};
-
-// beta_k and omega_{k-1} from the dot products of iteration k-1
-__device__ __forceinline__ IterScalars scalars_for_p(const double* __restrict__ sums, int k) {
-    IterScalars sc;
-    const double rho_new = sums[S_RHO0 + (k & 1)], rho_old = sums[S_RHO0 + ((k - 1) & 1)];
-    const double tt = sums[S_TT];
-    sc.alpha = rho_old / sums[S_RHV];
-    sc.omega = tt > 0.0 ? sums[S_TS] / tt : 0.0;
-    sc.beta = (rho_new / rho_old) * (sc.alpha / sc.omega);
-    sc.bad = !isfinite(sc.beta);
-    return sc;
-}
-
-__device__ __forceinline__ double p_update(double r, double p, double v, double beta, double omega) {
-    return fma(beta, fma(-omega, v, p), r);   // explicit fma: identical bits wherever it is recomputed
-}
-
-// unfused: p = r (k == 0) or p = r + beta (p - omega v)
-__global__ void __launch_bounds__(CRBE_BLOCK) k_p(int64_t n, int k, double rtol2, const double* __restrict__ r, const double* __restrict__ v,
-                                                  double* __restrict__ p, const double* sums, int* dstate, const CommArgs* __restrict__ ca) {
-    if (solver_idle(sums, dstate, rtol2)) return;
-    IterScalars sc = {0, 0, 0, false};
-    if (k > 0) {
-        sc = scalars_for_p(sums, k);
-        if (sc.bad) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
-            return;
-        }
-    }
-    ROW_LOOP(i, n) p[i] = k > 0 ? p_update(r[i], p[i], v[i], sc.beta, sc.omega) : r[i];
-    halo_push_tail(p, 1, ca);
-}
-
-// v = A p, (r^, v).  FUSED: p is first advanced (here and at the gathered neighbours) from p_in, v_in.
-template <bool FUSED>
-__global__ void __launch_bounds__(CRBE_BLOCK) k_pv(int64_t n, int64_t ld, int k, double rtol2, const double* __restrict__ eval,
-                                                   const int* __restrict__ ecol, const double* __restrict__ r,
-                                                   const double* __restrict__ p_in, const double* __restrict__ v_in,
-                                                   double* __restrict__ p_out, double* __restrict__ v_out,
+// v = A p, (r^, v)
+__global__ void __launch_bounds__(CRBE_BLOCK) k_pv(int64_t n, int64_t ld, double rtol2, const double* __restrict__ eval,
+                                                   const int* __restrict__ ecol, const double* __restrict__ p, double* __restrict__ v,
                                                    const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                    unsigned int* counter, const CommArgs* __restrict__ ca) {
     if (solver_idle(sums, dstate, rtol2)) return;
-    IterScalars sc = {0, 0, 0, false};
-    if (FUSED && k > 0) {
-        sc = scalars_for_p(sums, k);
-        if (sc.bad) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
-            return;
-        }
-    }
     halo_wait(1, ca);
     double acc[1] = {0.0};
     ROW_LOOP(i, n) {
-        double pi, vi;
-        if (FUSED) {
-            const double beta = sc.beta, omega = sc.omega;
-            auto pnew = [&](int64_t j) {
-                return k > 0 ? p_update(__ldg(r + j), __ldg(p_in + j), __ldg(v_in + j), beta, omega) : __ldg(r + j);
-            };
-            pi = pnew(i);
-            p_out[i] = pi;
-            vi = ell_row(eval, ecol, ld, i, pi, [&](int j) { return pnew(j); });
-        } else {
-            pi = p_in[i];
-            vi = ell_row(eval, ecol, ld, i, pi, [&](int j) { return __ldg(p_in + j); });
-        }
-        v_out[i] = vi;
+        const double vi = ell_row(eval, ecol, ld, i, p[i], [&](int j) { return __ldg(p + j); });
+        v[i] = vi;
         acc[0] = fma(rh[i], vi, acc[0]);
     }
     double* const out[1] = {dots + S_RHV};
     grid_sum_last<1>(acc, partials, counter, out, ca);
 }
 
-// unfused: s = r - alpha v
+// s = r - alpha v
 __global__ void __launch_bounds__(CRBE_BLOCK) k_s(int64_t n, int k, double rtol2, const double* __restrict__ r, const double* __restrict__ v,
                                                   double* __restrict__ s, const double* sums, int* dstate, const CommArgs* __restrict__ ca) {
     if (solver_idle(sums, dstate, rtol2)) return;
@@ -488,74 +439,71 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_s(int64_t n, int k, double rtol2
     halo_push_tail(s, 2, ca);
 }
 
-// t = A s, (t,s), (t,t).  FUSED: s = r - alpha v is formed here (and at the gathered neighbours).
-template <bool FUSED>
-__global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, int k, double rtol2, const double* __restrict__ eval,
-                                                   const int* __restrict__ ecol, const double* __restrict__ r, const double* __restrict__ v,
-                                                   double* __restrict__ s, double* __restrict__ t, double* sums, double* dots, int* dstate,
-                                                   double* partials, unsigned int* counter, const CommArgs* __restrict__ ca) {
+// t = A s, (t,s), (t,t), (r^,s), (r^,t)
+__global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, double rtol2, const double* __restrict__ eval,
+                                                   const int* __restrict__ ecol, const double* __restrict__ s, double* __restrict__ t,
+                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
+                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
     if (solver_idle(sums, dstate, rtol2)) return;
-    double alpha = 0.0;
-    if (FUSED) {
-        alpha = sums[S_RHO0 + (k & 1)] / sums[S_RHV];
-        if (!isfinite(alpha)) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
-            return;
-        }
-    }
     halo_wait(2, ca);
-    double acc[2] = {0.0, 0.0};
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     ROW_LOOP(i, n) {
-        double si, ti;
-        if (FUSED) {
-            auto snew = [&](int64_t j) { return fma(-alpha, __ldg(v + j), __ldg(r + j)); };
-            si = snew(i);
-            s[i] = si;
-            ti = ell_row(eval, ecol, ld, i, si, [&](int j) { return snew(j); });
-        } else {
-            si = s[i];
-            ti = ell_row(eval, ecol, ld, i, si, [&](int j) { return __ldg(s + j); });
-        }
+        const double si = s[i];
+        const double ti = ell_row(eval, ecol, ld, i, si, [&](int j) { return __ldg(s + j); });
+        const double rhi = rh[i];
         t[i] = ti;
         acc[0] = fma(ti, si, acc[0]);
         acc[1] = fma(ti, ti, acc[1]);
+        acc[2] = fma(rhi, si, acc[2]);
+        acc[3] = fma(rhi, ti, acc[3]);
     }
-    double* const out[2] = {dots + S_TS, dots + S_TT};
-    grid_sum_last<2>(acc, partials, counter, out, ca);
+    double* const out[4] = {dots + S_TS, dots + S_TT, dots + S_RS, dots + S_RT};
+    grid_sum_last<4>(acc, partials, counter, out, ca);
 }
 
-// x += alpha p + omega s;  r = s - omega t;  rho_{k+1} = (r^, r);  (r, r)
-__global__ void __launch_bounds__(CRBE_BLOCK) k_xr(int64_t n, int k, double rtol2, const double* __restrict__ p, const double* __restrict__ s,
-                                                   const double* __restrict__ t, const double* __restrict__ rh, double* __restrict__ x,
-                                                   double* __restrict__ r, double* sums, double* dots, int* dstate, double* partials,
-                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
+// x += alpha p + omega s;  r = s - omega t;  p = r + beta (p - omega v);  (r, r);
+// rho_{k+1} = (r^,s) - omega (r^,t) is published by the last CTA (every rank computes the same value).
+__global__ void __launch_bounds__(CRBE_BLOCK) k_xrp(int64_t n, int k, double rtol2, const double* __restrict__ s, const double* __restrict__ t,
+                                                    const double* __restrict__ v, double* __restrict__ x, double* __restrict__ r,
+                                                    double* __restrict__ p, double* sums, double* dots, int* dstate, double* partials,
+                                                    unsigned int* counter, const CommArgs* __restrict__ ca) {
     if (solver_idle(sums, dstate, rtol2)) return;
-    const double alpha = sums[S_RHO0 + (k & 1)] / sums[S_RHV];
+    const double rho = sums[S_RHO0 + (k & 1)];
+    const double alpha = rho / sums[S_RHV];
     const double tt = sums[S_TT];
     const double omega = tt > 0.0 ? sums[S_TS] / tt : 0.0;
     if (!isfinite(alpha) || !isfinite(omega)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
         return;
     }
-    double acc[2] = {0.0, 0.0};
+    const double rho_next = fma(-omega, sums[S_RT], sums[S_RS]);
+    const double beta = (rho_next / rho) * (alpha / omega);
+    const double thr = rtol2 * sums[S_BB];
+    double acc[1] = {0.0};
     ROW_LOOP(i, n) {
-        const double si = s[i];
-        x[i] = fma(alpha, p[i], fma(omega, si, x[i]));
+        const double si = s[i], pi = p[i];
+        x[i] = fma(alpha, pi, fma(omega, si, x[i]));
         const double ri = fma(-omega, t[i], si);
         r[i] = ri;
-        acc[0] = fma(rh[i], ri, acc[0]);
-        acc[1] = fma(ri, ri, acc[1]);
+        p[i] = fma(beta, fma(-omega, v[i], pi), ri);
+        acc[0] = fma(ri, ri, acc[0]);
     }
-    double* const out[2] = {dots + S_RHO0 + ((k + 1) & 1), dots + S_RR};
-    if (grid_sum_last<2>(acc, partials, counter, out, ca)) dstate[D_ITERS] += 1;
+    halo_push_tail(p, 1, ca);
+    double* const out[1] = {dots + S_RR};
+    if (grid_sum_last<1>(acc, partials, counter, out, ca)) {
+        dstate[D_ITERS] += 1;
+        sums[S_RHO0 + ((k + 1) & 1)] = rho_next;
+        if (!isfinite(beta) && (ca == nullptr || ca->world <= 1 || dots == sums) && *out[0] > thr) dstate[D_STATUS] = 2;
+    }
 }
 
-// true residual r = r^ = b - A x and its norm (restart / verification)
+// true residual b - A x and its norm.  guard = 1: verification enqueued speculatively behind the iterations -- runs
+// only once they have converged, writes nothing but the norm.  guard = 0: restart -- r = r^ = p = b - A x.
 __global__ void __launch_bounds__(CRBE_BLOCK) k_residual(int64_t n, int64_t ld, const double* __restrict__ eval, const int* __restrict__ ecol,
                                                          const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
-                                                         double* __restrict__ rh, double* sums, double* dots, double* partials, unsigned int* counter,
-                                                         const CommArgs* __restrict__ ca, const int* dstate, int guard, double rtol2) {
-    // guard: verification enqueued speculatively behind the iterations -- runs only once they have converged, writes nothing but the norm
+                                                         double* __restrict__ rh, double* __restrict__ p, double* sums, double* dots,
+                                                         double* partials, unsigned int* counter, const CommArgs* __restrict__ ca,
+                                                         const int* dstate, int guard, double rtol2) {
     if (guard && (dstate[D_STATUS] != 0 || sums[S_RR] > rtol2 * sums[S_BB])) return;
     halo_wait(0, ca);
     double acc[1] = {0.0};
@@ -565,9 +513,11 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_residual(int64_t n, int64_t ld, 
         if (!guard) {
             r[i] = ri;
             rh[i] = ri;
+            p[i] = ri;
         }
         acc[0] = fma(ri, ri, acc[0]);
     }
+    if (!guard) halo_push_tail(p, 1, ca);
     double* const out[1] = {dots + S_RRTRUE};
     grid_sum_last<1>(acc, partials, counter, out, ca);
 }
@@ -792,26 +742,21 @@ static int solver_create_impl(crbe_ctx* ctx, crbe_comm* comm, int64_t n, int64_t
         CRBE_CUDA(cudaMalloc(&s->red, sizeof(double) * CRBE_NSUMS));
         CRBE_CUDA(cudaMemsetAsync(s->red, 0, sizeof(double) * CRBE_NSUMS, ctx->stream));
         s->dots = s->red;
-        s->flags &= ~CRBE_SOLVER_FUSED;
     }
-    {   // one resident wave per kernel; the fused and unfused variants share a grid (the smaller one)
-        const int a = crbe_persistent_grid(ctx, k_pv<true>, n), b = crbe_persistent_grid(ctx, k_pv<false>, n);
-        s->g_pv = a < b ? a : b;
-        const int c = crbe_persistent_grid(ctx, k_st<true>, n), d = crbe_persistent_grid(ctx, k_st<false>, n);
-        s->g_st = c < d ? c : d;
+    {   // one resident wave per kernel (a grid-stride sweep must not spill into a second, partial wave)
+        s->g_pv = crbe_persistent_grid(ctx, k_pv, n);
+        s->g_st = crbe_persistent_grid(ctx, k_st, n);
         const int i0 = crbe_persistent_grid(ctx, k_init<0>, n), i1 = crbe_persistent_grid(ctx, k_init<1>, n),
                   i2 = crbe_persistent_grid(ctx, k_init<2>, n);
         s->g_init = i0 < i1 ? (i0 < i2 ? i0 : i2) : (i1 < i2 ? i1 : i2);
-        s->g_xr = crbe_persistent_grid(ctx, k_xr, n);
-        s->g_vec = crbe_persistent_grid(ctx, k_p, n);
+        s->g_xr = crbe_persistent_grid(ctx, k_xrp, n);
+        s->g_vec = crbe_persistent_grid(ctx, k_s, n);
         s->g_res = crbe_persistent_grid(ctx, k_residual, n);
         s->g_spmv = crbe_persistent_grid(ctx, k_spmv_csr, n);
         // bulk-copy kernels: opt in to their dynamic shared memory, then size one resident wave over the tiles
         s->ntiles = s->ld / CRBE_TILE;
-        CRBE_CHECK(tile_grid(ctx, t_pv<false>, TilePipe<2, SPMV_STAGES>::SMEM_BYTES, s->ntiles, &s->gt_pv[0]));
-        CRBE_CHECK(tile_grid(ctx, t_pv<true>, TilePipe<4>::SMEM_BYTES, s->ntiles, &s->gt_pv[1]));
-        CRBE_CHECK(tile_grid(ctx, t_st<false>, TilePipe<1, SPMV_STAGES>::SMEM_BYTES, s->ntiles, &s->gt_st[0]));
-        CRBE_CHECK(tile_grid(ctx, t_st<true>, TilePipe<2>::SMEM_BYTES, s->ntiles, &s->gt_st[1]));
+        CRBE_CHECK(tile_grid(ctx, t_pv, TilePipe<2, SPMV_STAGES>::SMEM_BYTES, s->ntiles, &s->gt_pv));
+        CRBE_CHECK(tile_grid(ctx, t_st, TilePipe<2, SPMV_STAGES>::SMEM_BYTES, s->ntiles, &s->gt_st));
         CRBE_CHECK(tile_grid(ctx, t_init_be, TilePipe<2>::SMEM_BYTES, s->ntiles, &s->gt_init));
         CRBE_CHECK(tile_grid(ctx, t_residual, TilePipe<1>::SMEM_BYTES, s->ntiles, &s->gt_res));
     }
@@ -972,7 +917,6 @@ extern "C" int crbe_solver_set_options(crbe_solver* s, double rtol, int32_t max_
     s->rtol = rtol;
     s->maxit = max_iterations;
     s->flags = flags;
-    if (s->world > 1) s->flags &= ~CRBE_SOLVER_FUSED;   // the fused kernels would need the halos of r, p and v
     return CRBE_OK;
 }
 
@@ -1056,10 +1000,11 @@ __global__ void k_pack(const double* __restrict__ vec, const int* __restrict__ i
     ROW_LOOP(q, cnt) out[q] = vec[idx[q]];
 }
 
-__global__ void k_commit(const double* __restrict__ red, double* __restrict__ sums, int a, int b, int c) {
+__global__ void k_commit(const double* __restrict__ red, double* __restrict__ sums, int a, int b, int c, int d) {
     if (a >= 0) sums[a] = red[a];
     if (b >= 0) sums[b] = red[b];
     if (c >= 0) sums[c] = red[c];
+    if (d >= 0) sums[d] = red[d];
 }
 
 __global__ void k_p2p_wait(int kind, const CommArgs* __restrict__ ca) { halo_wait(kind, ca); }
@@ -1093,11 +1038,11 @@ static int halo_exchange(crbe_solver* s, double* vec, int* launches) {
                               s->recv_off.data(), ctx->stream);
 }
 
-// sum the freshly written dot products red[first .. first+count) over the ranks, then publish slots a, b, c
-static int reduce_dots(crbe_solver* s, int first, int count, int a, int b, int c, int* launches) {
+// sum the freshly written dot products red[first .. first+count) over the ranks, then publish slots a, b, c, d
+static int reduce_dots(crbe_solver* s, int first, int count, int a, int b, int c, int d, int* launches) {
     if (s->world <= 1 || s->p2p) return CRBE_OK;   // peer-memory transport: done in the tail of the dot kernel (grid_sum_last)
     CRBE_CHECK(crbe_comm_allreduce_sum(s->comm, s->red + first, count, s->ctx->stream));
-    k_commit<<<1, 1, 0, s->ctx->stream>>>(s->red, s->sums, a, b, c);
+    k_commit<<<1, 1, 0, s->ctx->stream>>>(s->red, s->sums, a, b, c, d);
     CRBE_KERNEL_CHECK();
     *launches += 1;
     return CRBE_OK;
@@ -1107,57 +1052,32 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
     crbe_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     const double rtol2 = s->rtol * s->rtol;
-    const bool fused = (s->flags & CRBE_SOLVER_FUSED) != 0;
     const bool tma = (s->flags & CRBE_SOLVER_TMA) != 0;
-    double *p, *v;
-    if (fused) {
-        const int o = k & 1, in = (k - 1) & 1;
-        p = s->p[o];
-        v = s->v[o];
-        if (tma) {
-            PROF_LAUNCH(PK_PV, k, (t_pv<true><<<s->gt_pv[1], CRBE_TILE, TilePipe<4>::SMEM_BYTES, st>>>(
-                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, s->p[in], s->v[in], p, v, s->rh, s->sums,
-                                      s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
-            PROF_LAUNCH(PK_ST, k, (t_st<true><<<s->gt_st[1], CRBE_TILE, TilePipe<2>::SMEM_BYTES, st>>>(
-                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dots, s->dstate,
-                                      ctx->partials, ctx->counter, s->d_comm)));
-        } else {
-            PROF_LAUNCH(PK_PV, k, (k_pv<true><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, s->p[in],
-                                                                           s->v[in], p, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
-                                                                           ctx->counter, s->d_comm)));
-            PROF_LAUNCH(PK_ST, k, (k_st<true><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s,
-                                                                           s->t, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
-        }
-        *launches += 2;
-    } else {
-        p = s->p[0];
-        v = s->v[0];
-        PROF_LAUNCH(PK_P, k, (k_p<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, p, s->sums, s->dstate, s->d_comm)));
-        CRBE_CHECK(halo_exchange(s, p, launches));
-        if (tma)
-            PROF_LAUNCH(PK_PV, k, (t_pv<false><<<s->gt_pv[0], CRBE_TILE, TilePipe<2, SPMV_STAGES>::SMEM_BYTES, st>>>(
-                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p, v, s->rh, s->sums, s->dots, s->dstate,
-                                      ctx->partials, ctx->counter, s->d_comm)));
-        else
-            PROF_LAUNCH(PK_PV, k, (k_pv<false><<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, p, v, p,
-                                                                            v, s->rh, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
-        CRBE_CHECK(reduce_dots(s, S_RHV, 1, S_RHV, -1, -1, launches));
-        PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, s->s, s->sums, s->dstate, s->d_comm)));
-        CRBE_CHECK(halo_exchange(s, s->s, launches));
-        if (tma)
-            PROF_LAUNCH(PK_ST, k, (t_st<false><<<s->gt_st[0], CRBE_TILE, TilePipe<1, SPMV_STAGES>::SMEM_BYTES, st>>>(
-                                      s->n, s->ntiles, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s, s->t, s->sums, s->dots, s->dstate,
-                                      ctx->partials, ctx->counter, s->d_comm)));
-        else
-            PROF_LAUNCH(PK_ST, k, (k_st<false><<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, k, rtol2, s->ell_val, s->ell_col, s->r, v, s->s,
-                                                                            s->t, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
-        CRBE_CHECK(reduce_dots(s, S_TS, 2, S_TS, S_TT, -1, launches));
-        *launches += 4;
-    }
-    PROF_LAUNCH(PK_XR, k, (k_xr<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, p, s->s, s->t, s->rh, x, s->r, s->sums, s->dots, s->dstate,
-                                                             ctx->partials, ctx->counter, s->d_comm)));
-    *launches += 1;
-    CRBE_CHECK(reduce_dots(s, S_RR, 3, S_RR, S_RHO0 + ((k + 1) & 1), -1, launches));
+    double *p = s->p[0], *v = s->v[0];
+    // p is up to date (written by the init / restart kernel at k = 0, by k_xrp afterwards), its halo refreshed
+    CRBE_CHECK(halo_exchange(s, p, launches));
+    if (tma)
+        PROF_LAUNCH(PK_PV, k, (t_pv<<<s->gt_pv, CRBE_TILE, TilePipe<2, SPMV_STAGES>::SMEM_BYTES, st>>>(
+                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, p, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
+                                  ctx->counter, s->d_comm)));
+    else
+        PROF_LAUNCH(PK_PV, k, (k_pv<<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, rtol2, s->ell_val, s->ell_col, p, v, s->rh, s->sums, s->dots,
+                                                                 s->dstate, ctx->partials, ctx->counter, s->d_comm)));
+    CRBE_CHECK(reduce_dots(s, S_RHV, 1, S_RHV, -1, -1, -1, launches));
+    PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, s->s, s->sums, s->dstate, s->d_comm)));
+    CRBE_CHECK(halo_exchange(s, s->s, launches));
+    if (tma)
+        PROF_LAUNCH(PK_ST, k, (t_st<<<s->gt_st, CRBE_TILE, TilePipe<2, SPMV_STAGES>::SMEM_BYTES, st>>>(
+                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, s->s, s->t, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
+                                  ctx->counter, s->d_comm)));
+    else
+        PROF_LAUNCH(PK_ST, k, (k_st<<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, rtol2, s->ell_val, s->ell_col, s->s, s->t, s->rh, s->sums,
+                                                                 s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
+    CRBE_CHECK(reduce_dots(s, S_TS, 4, S_TS, S_TT, S_RS, S_RT, launches));
+    PROF_LAUNCH(PK_XR, k, (k_xrp<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->s, s->t, v, x, s->r, p, s->sums, s->dots, s->dstate,
+                                                              ctx->partials, ctx->counter, s->d_comm)));
+    *launches += 4;
+    CRBE_CHECK(reduce_dots(s, S_RR, 1, S_RR, -1, -1, -1, launches));
     return CRBE_OK;
 }
 
@@ -1177,15 +1097,15 @@ static int launch_residual(crbe_solver* s, double* x, int guard, int* launches) 
     CRBE_CHECK(halo_exchange(s, x, launches));
     if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_RES, guard ? -2 : -1, (t_residual<<<s->gt_res, CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
-                                                 s->n, s->ntiles, s->ell_val, s->ell_col, x, s->b, s->r, s->rh, s->sums, s->dots, ctx->partials,
-                                                 ctx->counter, s->d_comm, s->dstate, guard, rtol2)));
+                                                 s->n, s->ntiles, s->ell_val, s->ell_col, x, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
+                                                 ctx->partials, ctx->counter, s->d_comm, s->dstate, guard, rtol2)));
     else
         PROF_LAUNCH(PK_RES, guard ? -2 : -1, (k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->b, s->r,
-                                                                                         s->rh, s->sums, s->dots, ctx->partials, ctx->counter,
-                                                                                         s->d_comm, s->dstate, guard, rtol2)));
+                                                                                         s->rh, s->p[0], s->sums, s->dots, ctx->partials,
+                                                                                         ctx->counter, s->d_comm, s->dstate, guard, rtol2)));
     *launches += 1;
     CRBE_KERNEL_CHECK();
-    return reduce_dots(s, S_RRTRUE, 1, S_RRTRUE, -1, -1, launches);
+    return reduce_dots(s, S_RRTRUE, 1, S_RRTRUE, -1, -1, -1, launches);
 }
 
 // Iterate from the state left by k_init until converged.  b, r, r^ and the sums are on the device.
@@ -1276,22 +1196,11 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
     return CRBE_OK;
 }
 
-static int ensure_pingpong(crbe_solver* s) {
-    if ((s->flags & CRBE_SOLVER_FUSED) && !s->p[1]) {
-        CRBE_CUDA(cudaMalloc(&s->p[1], sizeof(double) * s->veclen));
-        CRBE_CUDA(cudaMalloc(&s->v[1], sizeof(double) * s->veclen));
-        CRBE_CUDA(cudaMemsetAsync(s->p[1], 0, sizeof(double) * s->veclen, s->ctx->stream));
-        CRBE_CUDA(cudaMemsetAsync(s->v[1], 0, sizeof(double) * s->veclen, s->ctx->stream));
-    }
-    return CRBE_OK;
-}
-
 extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* source_d, double dt, crbe_solve_info* info_h) {
     CRBE_REQUIRE(s && u_d && info_h, "null argument");
     CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
     crbe_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    CRBE_CHECK(ensure_pingpong(s));
     memset(info_h, 0, sizeof(*info_h));
     int launches = 0;
     if (s->rhs_val) {   // Crank-Nicolson: (M - c(K+A)) u_prev with u_prev as given, boundary values included (crbe.py:386)
@@ -1318,19 +1227,19 @@ extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* sourc
     CRBE_CHECK(halo_exchange(s, u_d, &launches));
     if (s->rhs_val)
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, s->tmp, source_d, dt,
-                                                                             s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums, s->dots,
+                                                                             s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<<<s->gt_init, CRBE_TILE, TilePipe<2>::SMEM_BYTES, st>>>(
                                      s->n, s->ntiles, s->ell_val, s->ell_col, u_d, s->hist, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
-                                     s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
+                                     s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else
         PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, s->hist, source_d, dt,
-                                                                             s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums, s->dots,
+                                                                             s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     ++launches;
     CRBE_KERNEL_CHECK();
-    CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, &launches));
+    CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, -1, &launches));
     int rc = run_bicgstab(s, u_d, info_h, &launches);
     info_h->launches = launches;
     ctx->launches += launches;
@@ -1341,15 +1250,14 @@ extern "C" int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d,
     CRBE_REQUIRE(s && b_d && x_d && info_h, "null argument");
     CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
     crbe_ctx* ctx = s->ctx;
-    CRBE_CHECK(ensure_pingpong(s));
     memset(info_h, 0, sizeof(*info_h));
     int launches = 1;
     CRBE_CHECK(halo_exchange(s, x_d, &launches));
     k_init<2><<<s->g_init, CRBE_BLOCK, 0, ctx->stream>>>(s->n, s->ld, s->ell_val, s->ell_col, x_d, b_d, nullptr, 0.0,
-                                                                        s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->sums, s->dots,
+                                                                        s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                                         s->dstate, ctx->partials, ctx->counter, s->d_comm);
     CRBE_KERNEL_CHECK();
-    CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, &launches));
+    CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, -1, &launches));
     int rc = run_bicgstab(s, x_d, info_h, &launches);
     info_h->launches = launches;
     ctx->launches += launches;

@@ -23,9 +23,9 @@
 #ifndef CRBE_SPMV_STAGES
 #define CRBE_SPMV_STAGES 2
 #endif
-constexpr int TILE_STAGES = CRBE_TILE_STAGES;     // init / residual / fused kernels
-// The unfused SpMV kernels prefetch their gathers one tile ahead; two bulk-copy stages then suffice and the smaller
-// shared-memory footprint lets 6 CTAs share an SM (measured best of {2,3,4} stages x {prefetch on, off}).
+constexpr int TILE_STAGES = CRBE_TILE_STAGES;     // init / residual kernels
+// The SpMV kernels of the iteration prefetch their gathers one tile ahead; two bulk-copy stages then suffice and the
+// smaller shared-memory footprint lets more CTAs share an SM (measured best of {2,3,4} stages x {prefetch on, off}).
 constexpr int SPMV_STAGES = CRBE_SPMV_STAGES;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -136,9 +136,9 @@ __device__ __forceinline__ double tile_row(const double* __restrict__ sval, cons
     return acc;
 }
 
-// Unfused SpMV over the tiles of this CTA with the gathers software-pipelined one tile ahead: the x[col] loads of
-// tile m+1 are issued before tile m is finished, so gather latency overlaps arithmetic, stores and the barrier.
-// body(row, r, own, y) consumes the row result y = own + sum a_k x[col_k]; own = staged vector 0.
+// SpMV over the tiles of this CTA with the gathers software-pipelined one tile ahead: the x[col] loads of tile m+1
+// are issued before tile m is finished, so gather latency overlaps arithmetic, stores and the barrier.
+// body(m, row, tr, own, y) consumes the row result y = own + sum a_k x[col_k]; own = staged vector 0.
 template <int NV, int ST, class Body>
 __device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST>& pipe, const double* __restrict__ x, int64_t n, Body body) {
     const int tr = threadIdx.x;
@@ -172,161 +172,66 @@ __device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST>& pipe, const
     }
 }
 
-// ---- v = A p, (r^, v)   [FUSED: p advanced here and at the gathered neighbours] -------------------
-template <bool FUSED>
-__global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int k, double rtol2, const double* __restrict__ eval,
-                                                  const int* __restrict__ ecol, const double* __restrict__ r, const double* __restrict__ p_in,
-                                                  const double* __restrict__ v_in, double* __restrict__ p_out, double* __restrict__ v_out,
+// ---- v = A p, (r^, v) ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, double rtol2, const double* __restrict__ eval,
+                                                  const int* __restrict__ ecol, const double* __restrict__ p, double* __restrict__ v,
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
-    constexpr int ST = FUSED ? TILE_STAGES : SPMV_STAGES;
-    __shared__ uint64_t bars[ST];
+    __shared__ uint64_t bars[SPMV_STAGES];
     if (solver_idle(sums, dstate, rtol2)) return;
-    IterScalars sc = {0, 0, 0, false};
-    if (FUSED && k > 0) {
-        sc = scalars_for_p(sums, k);
-        if (sc.bad) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
-            return;
-        }
-    }
-    constexpr int NV = FUSED ? 4 : 2;
-    TilePipe<NV, ST> pipe;
+    TilePipe<2, SPMV_STAGES> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
-    if (FUSED) {
-        pipe.vec[0] = r;
-        pipe.vec[1] = k > 0 ? p_in : r;   // unused when k == 0
-        pipe.vec[2] = k > 0 ? v_in : r;
-        pipe.vec[3] = rh;
-    } else {
-        pipe.vec[0] = p_in;
-        pipe.vec[1] = rh;
-    }
+    pipe.vec[0] = p;
+    pipe.vec[1] = rh;
     pipe.start(tile_smem, bars, ntiles);
     halo_wait(1, ca);   // the bulk copies are already in flight
-    const int tr = threadIdx.x;
     double acc[1] = {0.0};
-#if CRBE_GATHER_PREFETCH
-    if (!FUSED) {
-        tile_spmv_prefetch(pipe, p_in, n, [&](int64_t m, int64_t row, int t_, double, double vi) {
-            v_out[row] = vi;
-            acc[0] = fma(pipe.svec(m, 1)[t_], vi, acc[0]);
-        });
-        double* const out_p[1] = {dots + S_RHV};
-        grid_sum_last<1>(acc, partials, counter, out_p, ca);
-        return;
-    }
-#endif
-    for (int64_t m = 0; m < pipe.count; ++m) {
-        pipe.wait(m);
-        const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
-        if (row < n) {
-            double pi, vi, rhi;
-            if (FUSED) {
-                const double beta = sc.beta, omega = sc.omega;
-                const double *sr = pipe.svec(m, 0), *sp = pipe.svec(m, 1), *sv = pipe.svec(m, 2);
-                const int row0 = (int)(row - tr);
-                // neighbours inside the tile (3 of 4 for a CR row) come from the staged copies in shared memory
-                auto pnew = [&](int j) {
-                    const unsigned q = (unsigned)(j - row0);
-                    if (q < (unsigned)CRBE_TILE) return k > 0 ? p_update(sr[q], sp[q], sv[q], beta, omega) : sr[q];
-                    return k > 0 ? p_update(__ldg(r + j), __ldg(p_in + j), __ldg(v_in + j), beta, omega) : __ldg(r + j);
-                };
-                pi = pnew((int)row);
-                rhi = pipe.svec(m, 3)[tr];
-                p_out[row] = pi;
-                vi = tile_row(pipe.sval(m), pipe.scol(m), tr, pi, pnew);
-            } else {
-                // (serving the in-tile neighbours from the staged copy was measured slower than L1 hits here)
-                pi = pipe.svec(m, 0)[tr];
-                rhi = pipe.svec(m, 1)[tr];
-                vi = tile_row(pipe.sval(m), pipe.scol(m), tr, pi, [&](int j) { return __ldg(p_in + j); });
-            }
-            v_out[row] = vi;
-            acc[0] = fma(rhi, vi, acc[0]);
-        }
-        pipe.release(m);
-    }
+    tile_spmv_prefetch(pipe, p, n, [&](int64_t m, int64_t row, int tr, double, double vi) {
+        v[row] = vi;
+        acc[0] = fma(pipe.svec(m, 1)[tr], vi, acc[0]);
+    });
     double* const out[1] = {dots + S_RHV};
     grid_sum_last<1>(acc, partials, counter, out, ca);
 }
 
-// ---- t = A s, (t,s), (t,t)   [FUSED: s = r - alpha v formed here and at the gathered neighbours] ----
-template <bool FUSED>
-__global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int k, double rtol2, const double* __restrict__ eval,
-                                                  const int* __restrict__ ecol, const double* __restrict__ r, const double* __restrict__ v,
-                                                  double* __restrict__ s, double* __restrict__ t, double* sums, double* dots, int* dstate, double* partials,
+// ---- t = A s, (t,s), (t,t), (r^,s), (r^,t) -----------------------------------------------------------------
+__global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, double rtol2, const double* __restrict__ eval,
+                                                  const int* __restrict__ ecol, const double* __restrict__ s, double* __restrict__ t,
+                                                  const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
-    constexpr int ST = FUSED ? TILE_STAGES : SPMV_STAGES;
-    __shared__ uint64_t bars[ST];
+    __shared__ uint64_t bars[SPMV_STAGES];
     if (solver_idle(sums, dstate, rtol2)) return;
-    double alpha = 0.0;
-    if (FUSED) {
-        alpha = sums[S_RHO0 + (k & 1)] / sums[S_RHV];
-        if (!isfinite(alpha)) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
-            return;
-        }
-    }
-    constexpr int NV = FUSED ? 2 : 1;
-    TilePipe<NV, ST> pipe;
+    TilePipe<2, SPMV_STAGES> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
-    if (FUSED) {
-        pipe.vec[0] = r;
-        pipe.vec[1] = v;
-    } else {
-        pipe.vec[0] = s;
-    }
+    pipe.vec[0] = s;
+    pipe.vec[1] = rh;
     pipe.start(tile_smem, bars, ntiles);
     halo_wait(2, ca);
-    const int tr = threadIdx.x;
-    double acc[2] = {0.0, 0.0};
-#if CRBE_GATHER_PREFETCH
-    if (!FUSED) {
-        tile_spmv_prefetch(pipe, s, n, [&](int64_t, int64_t row, int, double si, double ti) {
-            t[row] = ti;
-            acc[0] = fma(ti, si, acc[0]);
-            acc[1] = fma(ti, ti, acc[1]);
-        });
-        double* const out_p[2] = {dots + S_TS, dots + S_TT};
-        grid_sum_last<2>(acc, partials, counter, out_p, ca);
-        return;
-    }
-#endif
-    for (int64_t m = 0; m < pipe.count; ++m) {
-        pipe.wait(m);
-        const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
-        if (row < n) {
-            double si, ti;
-            if (FUSED) {
-                si = fma(-alpha, pipe.svec(m, 1)[tr], pipe.svec(m, 0)[tr]);
-                s[row] = si;
-                ti = tile_row(pipe.sval(m), pipe.scol(m), tr, si, [&](int j) { return fma(-alpha, __ldg(v + j), __ldg(r + j)); });
-            } else {
-                si = pipe.svec(m, 0)[tr];
-                ti = tile_row(pipe.sval(m), pipe.scol(m), tr, si, [&](int j) { return __ldg(s + j); });
-            }
-            t[row] = ti;
-            acc[0] = fma(ti, si, acc[0]);
-            acc[1] = fma(ti, ti, acc[1]);
-        }
-        pipe.release(m);
-    }
-    double* const out[2] = {dots + S_TS, dots + S_TT};
-    grid_sum_last<2>(acc, partials, counter, out, ca);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    tile_spmv_prefetch(pipe, s, n, [&](int64_t m, int64_t row, int tr, double si, double ti) {
+        const double rhi = pipe.svec(m, 1)[tr];
+        t[row] = ti;
+        acc[0] = fma(ti, si, acc[0]);
+        acc[1] = fma(ti, ti, acc[1]);
+        acc[2] = fma(rhi, si, acc[2]);
+        acc[3] = fma(rhi, ti, acc[3]);
+    });
+    double* const out[4] = {dots + S_TS, dots + S_TT, dots + S_RS, dots + S_RT};
+    grid_sum_last<4>(acc, partials, counter, out, ca);
 }
 
-// ---- Backward-Euler step start: b = mscale*u^n (+ dscale*dt*f), r = r^ = b - A x0, (b,b), (r,r) --------
+// ---- Backward-Euler step start: b = mscale*u^n (+ dscale*dt*f), r = r^ = p = b - A x0, (b,b), (r,r) --------
 __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles, const double* __restrict__ eval, const int* __restrict__ ecol,
                                                        const double* __restrict__ x, const double* __restrict__ xb,
                                                        const double* __restrict__ src, double dt,
                                                        const double* __restrict__ mscale, const double* __restrict__ dscale,
-                                                       double* __restrict__ b, double* __restrict__ r, double* __restrict__ rh, double* sums,
-                                                       double* dots, int* dstate, double* partials, unsigned int* counter, const CommArgs* __restrict__ ca) {
+                                                       double* __restrict__ b, double* __restrict__ r, double* __restrict__ rh,
+                                                       double* __restrict__ p, double* sums, double* dots, int* dstate, double* partials,
+                                                       unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -357,24 +262,26 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
             b[row] = bi;
             r[row] = ri;
             rh[row] = ri;
+            p[row] = ri;
             acc[0] = fma(bi, bi, acc[0]);
             acc[1] = fma(ri, ri, acc[1]);
         }
         pipe.release(m);
     }
+    halo_push_tail(p, 1, ca);
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
     grid_sum_last<3>(acc, partials, counter, out, ca);
 }
 
-// ---- true residual r = r^ = b - A x and its norm -------------------------------------------------------
+// ---- true residual b - A x and its norm (guard = 1: verification, norm only; guard = 0: restart, r = r^ = p) ----
 __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntiles, const double* __restrict__ eval, const int* __restrict__ ecol,
                                                         const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
-                                                        double* __restrict__ rh, double* sums, double* dots, double* partials, unsigned int* counter,
-                                                        const CommArgs* __restrict__ ca, const int* dstate, int guard, double rtol2) {
+                                                        double* __restrict__ rh, double* __restrict__ p, double* sums, double* dots,
+                                                        double* partials, unsigned int* counter, const CommArgs* __restrict__ ca,
+                                                        const int* dstate, int guard, double rtol2) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
-    // guard: verification enqueued speculatively behind the iterations -- runs only once they have converged, writes nothing but the norm
     if (guard && (dstate[D_STATUS] != 0 || sums[S_RR] > rtol2 * sums[S_BB])) return;
     TilePipe<1> pipe;
     pipe.eval = eval;
@@ -394,11 +301,13 @@ __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntile
             if (!guard) {
                 r[row] = ri;
                 rh[row] = ri;
+                p[row] = ri;
             }
             acc[0] = fma(ri, ri, acc[0]);
         }
         pipe.release(m);
     }
+    if (!guard) halo_push_tail(p, 1, ca);
     double* const out[1] = {dots + S_RRTRUE};
     grid_sum_last<1>(acc, partials, counter, out, ca);
 }

@@ -17,8 +17,8 @@ Timed regions
   e2e     the same metric through the public API ``BESCRFEM.solve()`` with host
           buffers: per step the boundary data goes host->device and the lifted
           solution row comes back device->host into ``solutions`` (pinned).
-  roofline  per-launch duration of the dominant kernel (k_pv: fused p-update +
-          SpMV + dot) from CUDA events recorded inside the timed region.
+  roofline  per-launch duration of the dominant kernel (t_pv: ELL SpMV + dot) from
+          CUDA events recorded around every launch in a second pass over the same steps.
   cpu_baseline  the oracle's Jacobi-BiCGStab port (scipy CSR, 1 thread) on a
           bounded sample of the same workload, rank 0, N = 1 only.
 """
@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 METRIC = "Backward-Euler steps/s at 12.6M CR DOFs"
 UNIT = "steps/s"
 # bytes per matrix row moved by each solver kernel in the ELL-4/unit-diagonal layout
-ROW_BYTES = {"init": 48 + 6 * 8, "pv": 48 + 6 * 8, "st": 48 + 4 * 8, "xr": 7 * 8, "p": 4 * 8, "s": 3 * 8, "residual": 48 + 2 * 8,
+ROW_BYTES = {"init": 48 + 7 * 8, "pv": 48 + 3 * 8, "st": 48 + 3 * 8, "xr": 8 * 8, "p": 4 * 8, "s": 3 * 8, "residual": 48 + 2 * 8,
              "extrapolate": 4 * 8}
 KINDS = ["init", "pv", "st", "xr", "p", "s", "residual", "extrapolate"]
 
@@ -52,7 +52,6 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", "--n", dest="n", type=int, default=int(os.environ.get("CRBE_BENCH_N", 2048)), help="cells per axis (per GPU strip)")
     ap.add_argument("--regime", default="P-ref", choices=["P-ref", "P-T10", "P-stiff"])
-    ap.add_argument("--fused", action="store_true", help="fuse the p/s updates into the SpMV kernels (3-kernel iteration)")
     ap.add_argument("--no-extrapolate", action="store_true", help="start every solve from u^n instead of 2u^n - u^(n-1)")
     ap.add_argument("--classic", action="store_true", help="register-load kernels instead of the bulk-copy (TMA) pipeline")
     ap.add_argument("--e2e-steps", type=int, default=24)
@@ -327,7 +326,7 @@ def main():
     mesh = wl.mesh()
     dom, prob = wl.domain(), wl.problem()
     md = crbe.MeshData(mesh, dom, wl.nt)
-    solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", fused=args.fused, tma=not args.classic, extrapolate=not args.no_extrapolate, progress=False)
+    solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", tma=not args.classic, extrapolate=not args.no_extrapolate, progress=False)
     rt = Runtime.get(device)
     solver.set_initial_condition()
     u = rt.upload(np.asarray(solver.u_prev, dtype=np.float64))
@@ -380,17 +379,13 @@ def main():
             for k in range(8) if pcnt[k] > 0}
     steps_per_s = K / (ms * 1e-3)
     it_mean = float(np.mean(iters))
-    if not args.fused:   # unfused SpMV kernels move fewer vectors: p,rh in / v out and s in / t out
-        for nm, rb in (("pv", 48 + 3 * 8), ("st", 48 + 2 * 8)):
-            kern[nm]["GBps"] = rb * n / (kern[nm]["ms_per_launch"] * 1e-3) / 1e9
-            ROW_BYTES[nm] = rb
     dom_k = "pv"
     achieved = kern[dom_k]["GBps"]
-    # whole-step traffic in this layout: per iteration pv+st+xr (unfused: +p+s), per step init + residual
-    per_it = ROW_BYTES["pv"] + ROW_BYTES["st"] + ROW_BYTES["xr"] + (0 if args.fused else ROW_BYTES["p"] + ROW_BYTES["s"] - 3 * 8)
+    # whole-step traffic in this layout: per iteration pv+s+st+xrp, per step init + residual (+ extrapolation)
+    per_it = ROW_BYTES["pv"] + ROW_BYTES["s"] + ROW_BYTES["st"] + ROW_BYTES["xr"]      # 232 B per row and iteration
     step_bytes = (it_mean * per_it + ROW_BYTES["init"] + ROW_BYTES["residual"]
                   + (0 if args.no_extrapolate else ROW_BYTES["extrapolate"])) * n
-    # SURVEY 8(d) CSR accounting of the same work, for comparison
+    # SURVEY 8(d) CSR accounting of a textbook BiCGStab iteration (2 CSR SpMV + 19 vector passes), for comparison
     csr_spmv = 12 * counts["nnz_sys"] + 4 * (n + 1)
     csr_iter = 2 * csr_spmv + 19 * 8 * n
 
@@ -399,7 +394,8 @@ def main():
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl.name, **counts, "regime": wl.regime, "dt": wl.dt, "rtol": solver.rtol,
-                   "solver": "Jacobi-BiCGStab " + ("fused 3-kernel" if args.fused else "5-kernel") + (", register loads" if args.classic else ", bulk-copy pipeline"),
+                   "solver": "Jacobi-BiCGStab, merged-reduction 4-kernel iteration" + (", register loads" if args.classic else ", bulk-copy pipeline")
+                             + ("" if args.no_extrapolate else ", extrapolated initial guess"),
                    "iters_per_step": it_mean, "l2": "inputs larger than L2 (1.9 GB touched per iteration vs 126 MB L2)",
                    "setup_s": t_setup},
         "dof_updates_per_s": steps_per_s * n,
@@ -409,10 +405,10 @@ def main():
         "kernels": kern,
         "step_GBps": step_bytes / (ms / K * 1e-3) / 1e9,
         "step_GBps_csr_equiv": (it_mean * csr_iter + csr_spmv + 16 * n + 8 * 8 * n) / (ms / K * 1e-3) / 1e9,
-        "roofline": {"bound": "hbm", "kernel": "pv fused: p-update + ELL SpMV + dot" if args.fused else "pv: ELL SpMV v = A p + dot (r^,v)",
+        "roofline": {"bound": "hbm", "kernel": "pv: ELL SpMV v = A p + dot (r^,v)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "frac_of_8TBps_nominal": achieved / 8000.0, "peak_source": peak_src,
-                     "bytes_per_launch": ROW_BYTES[dom_k] * n, "traffic": ncu_traffic("t_pv<1>" if args.fused else "t_pv<0>", args, n)},
+                     "bytes_per_launch": ROW_BYTES[dom_k] * n, "traffic": ncu_traffic("t_pv", args, n)},
     }
 
     # ---- e2e: the public API with host buffers ---------------------------------
@@ -420,7 +416,7 @@ def main():
         E = max(2, min(args.e2e_steps, K))
         wl_e = workloads.unit_square(args.n, steps=E, regime=args.regime)
         md_e = crbe.MeshData(mesh, wl_e.domain(), wl_e.nt)
-        s_e = crbe.BESCRFEM(wl_e.domain(), prob, md_e, crbe.ElementCR(), 1, history="all", fused=args.fused, tma=not args.classic, extrapolate=not args.no_extrapolate, progress=False)
+        s_e = crbe.BESCRFEM(wl_e.domain(), prob, md_e, crbe.ElementCR(), 1, history="all", tma=not args.classic, extrapolate=not args.no_extrapolate, progress=False)
         import contextlib
         import io
         with contextlib.redirect_stdout(io.StringIO()):

@@ -134,7 +134,7 @@ typedef struct crbe_solve_info {
     double bnorm;            /* ||b|| (Jacobi-scaled)                                  */
 } crbe_solve_info;
 
-#define CRBE_SOLVER_FUSED 1u          /* fuse the p- and s-updates into the SpMV kernels       */
+#define CRBE_SOLVER_FUSED 1u          /* reserved (the iteration is the merged-reduction form)   */
 #define CRBE_SOLVER_VERIFY 2u         /* recompute the true residual after convergence         */
 #define CRBE_SOLVER_GRAPH 4u          /* replay iterations from a CUDA graph                   */
 #define CRBE_SOLVER_EXTRAPOLATE 16u   /* crbe_solver_step: start from 2 u^n - u^(n-1) (linear extrapolation in

@@ -242,8 +242,8 @@ def test_dot_and_errors(rt):
         assert e3[2] == np.max(np.abs(x - y))
 
 
-@pytest.mark.parametrize("fused,tma", [(False, True), (True, True), (False, False), (True, False)])
-def test_linear_solve_vs_superlu(rt, fused, tma):
+@pytest.mark.parametrize("tma", [True, False], ids=["bulk-copy", "register-loads"])
+def test_linear_solve_vs_superlu(rt, tma):
     """crbe_solver_solve on an assembled Dirichlet system against scipy's direct solve."""
     import torch
     from airpollution_b200 import _lib, crbe
@@ -251,7 +251,7 @@ def test_linear_solve_vs_superlu(rt, fused, tma):
     from airpollution_b200.runtime import ptr
     dom = crbe.Domain(1, 1, T=0.5)
     md = crbe.MeshData(delaunay_mesh(4000, seed=4), dom, 6)
-    s = crbe.BESCRFEM(dom, crbe.Problem(v=[0.7, -0.3], D=0.05), md, crbe.ElementCR(), fused=fused, tma=tma)
+    s = crbe.BESCRFEM(dom, crbe.Problem(v=[0.7, -0.3], D=0.05), md, crbe.ElementCR(), tma=tma)
     s.build_global_matrices()
     A = orc.dirichlet_system_fast(s.base_system, md.boundary_segments)
     rng = np.random.default_rng(5)
@@ -268,12 +268,13 @@ def test_linear_solve_vs_superlu(rt, fused, tma):
 
 # ------------------------------------------------------------------ a-7 .. a-12: the full path
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-@pytest.mark.parametrize("fused,tma", [(False, True), (True, True), (False, False), (True, False)])
-def test_solve_matches_reference_fixture(name, fused, tma):
+@pytest.mark.parametrize("tma,extrapolate", [(True, True), (True, False), (False, True)],
+                         ids=["bulk-copy", "bulk-copy-noextrap", "register-loads"])
+def test_solve_matches_reference_fixture(name, tma, extrapolate):
     g = load_golden(name)
     crbe, dom, md = _product(g)
     prob = golden_problem(name, g)
-    s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), fused=fused, tma=tma, progress=False)
+    s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), tma=tma, extrapolate=extrapolate, progress=False)
     sol = s.solve()
     assert s.dt == float(g["dt"])
     assert sol.shape == (int(g["nt"]), len(g["segments"]))
@@ -341,7 +342,7 @@ def test_unsupported_order_raises_like_reference():
 
 def test_large_mesh_properties():
     """n = 1024 (3.1 M DOFs): size-independent checks -- closed-form numbering, pattern
-    counts, Dirichlet rows, residual of the exported system, agreement of fused/unfused."""
+    counts, Dirichlet rows, residual of the exported system, agreement of the kernel variants."""
     import torch
     from airpollution_b200 import crbe
     from airpollution_b200.meshgen import structured_counts, structured_mesh
@@ -360,8 +361,8 @@ def test_large_mesh_properties():
     s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), progress=False, history="last")
     sol = s.solve()
     assert s._nnz == nnz and s.n_colours <= 4
-    for fused, tma in ((True, True), (False, False), (True, False)):
-        s2 = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), progress=False, history="last", fused=fused, tma=tma)
+    for tma, ex in ((True, False), (False, True)):
+        s2 = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), progress=False, history="last", tma=tma, extrapolate=ex)
         sol2 = s2.solve()
         assert rel_err(sol[-1], sol2[-1]) <= 1e-12
         del s2
