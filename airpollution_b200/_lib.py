@@ -61,6 +61,7 @@ _SIGNATURES = {
     "crbe_solver_set_system": [vp, vp, vp, vp],
     "crbe_solver_set_options": [vp, C.c_double, C.c_int32, C.c_uint32],
     "crbe_solver_step": [vp, vp, vp, C.c_double, C.POINTER(SolveInfo)],
+    "crbe_solver_step_pingpong": [vp, vp, vp, vp, C.c_double, C.POINTER(SolveInfo)],
     "crbe_solver_solve": [vp, vp, vp, C.POINTER(SolveInfo)],
     "crbe_solver_rhs": [vp, vp, vp, C.c_double, vp],
     "crbe_solver_lift": [vp, vp, vp, vp],

@@ -488,9 +488,16 @@ class BESCRFEM:
         u = rt.upload(np.asarray(self.u_prev, dtype=np.float64))
         # 2. global matrices and the solver (crbe.py:415)
         self.build_global_matrices()
-        # 3. time stepping (crbe.py:418-431)
-        stage = [rt.empty((n,), torch.float64), rt.empty((n,), torch.float64)]
-        stage_free = [None, None]
+        # 3. time stepping (crbe.py:418-431).  Two solution vectors alternate (crbe_solver_step_pingpong): the step
+        # builds u^(n+1) in one while u^n stays intact in the other, so a stored step is downloaded straight from
+        # its vector during the NEXT step, on a copy stream, without a staging copy.
+        vlen = C.c_int64()
+        rt.call("crbe_solver_vector_length", self._solver, C.byref(vlen), None)
+        ubuf = [rt.zeros((vlen.value,), torch.float64), rt.zeros((vlen.value,), torch.float64)]
+        ubuf[0][:n] = u
+        del u
+        cur = 0
+        copied = [None, None]
         copy_stream = torch.cuda.Stream(device=rt.device)
         main = torch.cuda.current_stream(rt.device)
         info = _lib.SolveInfo()
@@ -501,64 +508,49 @@ class BESCRFEM:
             steps = _tqdm(steps, desc="Time-stepping")
         dt = float(self.dt)
         reassemble = self.velocity_field is not None
-        # The boundary data of the lift (crbe.py:367-379) is the user's numpy callback on the Nb boundary midpoints.
-        # It is evaluated and uploaded one stored step ahead by a helper thread while the GPU solves the current
-        # step (the C call releases the GIL), so the host work is off the critical path.
-        nb = md.boundary_segments.shape[0]
-        mid_b = md.midpoints[md.boundary_segments] if nb else np.zeros((0, 2))
-        bc_host = [torch.zeros((max(nb, 1),), dtype=torch.float64, pin_memory=True) for _ in range(2)]
-        bc_dev = [rt.empty((max(nb, 1),), torch.float64) for _ in range(2)]
-        bc_ready = [None, None]
+        # The lift (crbe.py:367-379, :429) adds the user's boundary data on the Nb Dirichlet DOFs, where the solved
+        # vector is exactly zero.  The callback is numpy on the host like in the reference; it runs on a helper
+        # thread while the GPU solves (the C call releases the GIL) and is applied to the downloaded rows at the end.
+        bnd = md.boundary_segments
+        nb = bnd.shape[0]
+        mid_b = md.midpoints[bnd] if nb else np.zeros((0, 2))
+        stored = [st for st in range(1, n_steps) if st in row_of]
 
-        def prepare_bc(slot, t_out):
-            vals = self.problem.boundary_fn(np.hstack((mid_b, t_out * np.ones((nb, 1))))) if nb else np.zeros(0)
-            if bc_ready[slot] is not None:
-                bc_ready[slot].synchronize()       # the previous upload from this pinned slot has left the host
-            bc_host[slot][:nb].copy_(torch.from_numpy(np.ascontiguousarray(vals, dtype=np.float64)))
-            with torch.cuda.device(rt.device), torch.cuda.stream(copy_stream):
-                bc_dev[slot].copy_(bc_host[slot], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            bc_ready[slot] = ev
+        def boundary_values(t_out):
+            return np.asarray(self.problem.boundary_fn(np.hstack((mid_b, t_out * np.ones((nb, 1))))), dtype=np.float64)
 
         from concurrent.futures import ThreadPoolExecutor
-        stored = [st for st in range(1, n_steps) if st in row_of]
         pool = ThreadPoolExecutor(max_workers=1)
-        pending = pool.submit(prepare_bc, 0, stored[0] * self.dt) if stored else None
+        bc_jobs = [pool.submit(boundary_values, st * self.dt) for st in stored] if nb else []
         start = time.time()
-        k_out = 0
         try:
             for step in steps:
                 t = step * self.dt                                               # crbe.py:420
                 if reassemble:
                     self._reassemble_advection(t, export=(step == n_steps - 1))
                 src = self._source_on_device(t)
-                rt.call("crbe_solver_step", self._solver, ptr(u), ptr(src), dt, C.byref(info))
+                nxt = cur ^ 1
+                if copied[nxt] is not None:
+                    main.wait_event(copied[nxt])          # its download (two steps back) must be through before it is reused
+                rt.call("crbe_solver_step_pingpong", self._solver, ptr(ubuf[cur]), ptr(ubuf[nxt]), ptr(src), dt, C.byref(info))
+                cur = nxt
                 self.step_info.append((info.iterations, info.relres, info.true_relres, info.restarts))
                 if step in row_of:
-                    # lifted copy of the step's solution (crbe.py:429), staged so the download overlaps the next step
-                    sb = k_out & 1
-                    pending.result()
-                    if k_out + 1 < len(stored):
-                        pending = pool.submit(prepare_bc, sb ^ 1, stored[k_out + 1] * self.dt)
-                    main.wait_event(bc_ready[sb])
-                    if stage_free[sb] is not None:
-                        main.wait_event(stage_free[sb])
-                    rt.call("crbe_solver_lift", self._solver, ptr(u), ptr(bc_dev[sb]), ptr(stage[sb]))
-                    ready = torch.cuda.Event()
-                    ready.record(main)
-                    with torch.cuda.stream(copy_stream):
-                        copy_stream.wait_event(ready)
-                        sol_t[row_of[step]].copy_(stage[sb], non_blocking=True)
-                        done = torch.cuda.Event()
-                        done.record(copy_stream)
-                    stage_free[sb] = done
-                    k_out += 1
+                    with torch.cuda.stream(copy_stream):  # the step call has synchronised: the vector is final
+                        sol_t[row_of[step]].copy_(ubuf[cur][:n], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                    copied[cur] = ev
+            copy_stream.synchronize()
+            rt.synchronize()
+            if nb:
+                rows_idx = np.array([row_of[st] for st in stored], dtype=np.int64)
+                bc_all = np.stack([j.result() for j in bc_jobs]) if stored else np.zeros((0, nb))
+                self.solutions[rows_idx[:, None], bnd[None, :]] += bc_all   # u_prev + set_boundary_fn(t), crbe.py:429
         finally:
             pool.shutdown(wait=True)
-        copy_stream.synchronize()
-        rt.synchronize()
         self.solve_time = time.time() - start
+        u = ubuf[cur][:n]
         self.u_prev = to_numpy(u)
         self._dev["u"] = u
         print(f"Solve completed in {self.solve_time:.2f}s")

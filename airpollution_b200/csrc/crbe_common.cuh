@@ -138,38 +138,4 @@ __device__ __forceinline__ void block_sum(double (&v)[NV]) {
     }
 }
 
-// Grid-wide deterministic sum: every CTA stores its partial, the last CTA to
-// arrive adds the partials in index order and writes out[k].  No floating-point
-// atomics, so the result does not depend on CTA scheduling.  `counter` wraps
-// back to zero by itself (atomicInc), so the scratch is reusable by the next
-// kernel in the stream.
-template <int NV>
-__device__ __forceinline__ void grid_sum(double (&v)[NV], double* partials, unsigned int* counter,
-                                         double* const (&out)[NV]) {
-    block_sum<NV>(v);
-    __shared__ bool last;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) partials[k * CRBE_MAX_PARTIAL_BLOCKS + blockIdx.x] = v[k];
-        __threadfence();
-        unsigned int t = atomicInc(counter, gridDim.x - 1);
-        last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    double acc[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        acc[k] = 0.0;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
-            acc[k] += __ldcg(&partials[k * CRBE_MAX_PARTIAL_BLOCKS + b]);
-    }
-    block_sum<NV>(acc);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) *out[k] = acc[k];
-    }
-}
-
 #endif  // __CUDACC__

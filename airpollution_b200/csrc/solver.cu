@@ -14,10 +14,9 @@
 //   for the bulk-copy pipeline (solver_tiles.cuh), and x is gathered through
 //   L1/L2.  The CSR arrays stay the exchange format with the host (scipy) side.
 //
-// Kernels per BiCGStab iteration (FUSED):   bytes per row (fp64 vectors)
-//   k_pv : p = r + beta (p - omega v) recomputed at the neighbours, v = A p, (r^,v)   48 + 6*8
-//   k_st : s = r - alpha v recomputed at the neighbours,          t = A s, (t,s),(t,t) 48 + 4*8
-//   k_xr : x += alpha p + omega s, r = s - omega t, (r^,r), (r,r)                            7*8
+// Kernels per BiCGStab iteration (merged-reduction form, see "BiCGStab kernels" below): pv, s, st, xrp --
+// 232 bytes per row.  The SpMV-type kernels come in two flavours: register loads (k_*, this file) and the
+// bulk-copy / mbarrier shared-memory pipeline (t_*, solver_tiles.cuh, default).
 // Scalars (alpha, beta, omega) never visit the host: each kernel derives them
 // from a small device buffer of dot products written by the last CTA of the
 // producing kernel (deterministic two-stage reduction, no float atomics).
@@ -66,8 +65,9 @@ struct crbe_solver {
     double *b = nullptr, *r = nullptr, *rh = nullptr, *s = nullptr, *t = nullptr, *tmp = nullptr;
     double* hist = nullptr;            // u^n of the running time loop (right-hand side / extrapolation of the initial guess)
     bool hist_valid = false;
-    double* p[2] = {nullptr, nullptr};
-    double* v[2] = {nullptr, nullptr};
+    const double* pp_prev = nullptr;   // ping-pong stepping: the buffer that held u^n in the previous call
+    double* p[1] = {nullptr};
+    double* v[1] = {nullptr};
     double* sums = nullptr;
     int* dstate = nullptr;
     double* sums_h = nullptr;  // pinned: CRBE_NSUMS doubles followed by 2 ints
@@ -348,6 +348,11 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate(int64_t n, double* _
         hist[i] = un;
         u[i] = fma(2.0, un, -uo);
     }
+}
+
+// ping-pong form: nxt holds u^(n-1) and becomes the initial guess 2 u^n - u^(n-1); cur (u^n) is left untouched
+__global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate_pp(int64_t n, const double* __restrict__ cur, double* __restrict__ nxt) {
+    ROW_LOOP(i, n) nxt[i] = fma(2.0, cur[i], -nxt[i]);
 }
 
 __global__ void k_lift(const double* __restrict__ bc, const int* __restrict__ bnd, int64_t nb, double* __restrict__ out) {
@@ -669,9 +674,7 @@ static int solver_release(crbe_solver* s) {
     cudaFree(s->tmp);
     cudaFree(s->hist);
     cudaFree(s->p[0]);
-    cudaFree(s->p[1]);
     cudaFree(s->v[0]);
-    cudaFree(s->v[1]);
     cudaFree(s->sums);
     cudaFree(s->red);
     if (s->window) {
@@ -802,7 +805,7 @@ extern "C" int crbe_solver_create_partitioned(crbe_ctx* ctx, crbe_comm* comm, in
 // number of doubles a solution vector handed to crbe_solver_step / _solve must hold (owned rows, padding, halo)
 extern "C" int crbe_solver_vector_length(crbe_solver* s, int64_t* len_h, int64_t* halo_offset_h) {
     CRBE_REQUIRE(s && len_h, "null argument");
-    *len_h = s->world > 1 ? s->veclen : s->n;
+    *len_h = s->veclen;      // owned rows padded to whole tiles (+ halo entries in the partitioned solver)
     if (halo_offset_h) *halo_offset_h = s->ld;
     return CRBE_OK;
 }
@@ -1196,54 +1199,84 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
     return CRBE_OK;
 }
 
-extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* source_d, double dt, crbe_solve_info* info_h) {
-    CRBE_REQUIRE(s && u_d && info_h, "null argument");
+// One time step.  u_cur holds u^n.  In place (u_next == u_cur): u^n is saved in the solver's history vector and the
+// iterate is built in u_cur.  Ping-pong (u_next != u_cur, both padded to crbe_solver_vector_length): the iterate is
+// built in u_next and u_cur stays intact during the NEXT step as well, so the host can download it while the GPU is
+// already solving -- no staging copy; u_next is expected to hold u^(n-1) when the buffers simply alternate.
+static int step_impl(crbe_solver* s, double* u_cur, double* u_next, const double* source_d, double dt, crbe_solve_info* info_h) {
     CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
     crbe_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
+    const bool pp = u_next != u_cur;
+    CRBE_REQUIRE(!(pp && s->world > 1), "ping-pong stepping is for the single-GPU solver");
     memset(info_h, 0, sizeof(*info_h));
     int launches = 0;
     if (s->rhs_val) {   // Crank-Nicolson: (M - c(K+A)) u_prev with u_prev as given, boundary values included (crbe.py:386)
-        CRBE_CHECK(halo_exchange(s, u_d, &launches));
+        CRBE_CHECK(halo_exchange(s, u_cur, &launches));
         if (s->p2p) k_p2p_wait<<<1, 32, 0, st>>>(0, s->d_comm);
-        k_spmv_csr<<<s->g_spmv, CRBE_BLOCK, 0, st>>>(s->n, s->indptr, s->indices, s->rhs_val, u_d, s->tmp);
+        k_spmv_csr<<<s->g_spmv, CRBE_BLOCK, 0, st>>>(s->n, s->indptr, s->indices, s->rhs_val, u_cur, s->tmp);
         ++launches;
     }
     if (s->nb > 0) {    // the solution of the Dirichlet system is exactly 0 on its identity rows: start there
-        k_zero_rows<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, st>>>(u_d, s->bnd, s->nb);
+        k_zero_rows<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, st>>>(u_cur, s->bnd, s->nb);
         ++launches;
     }
-    // hist <- u^n for the right-hand side; with one step of history the initial guess is extrapolated linearly in time
-    // (2 u^n - u^(n-1)): the first residual drops by 2-3 orders of magnitude, which saves about one iteration per step
-    if (!s->rhs_val) {
-        if (s->hist_valid && (s->flags & CRBE_SOLVER_EXTRAPOLATE)) {
-            PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, u_d, s->hist)));
+    // Right-hand side from u^n; with one step of history the initial guess is extrapolated linearly in time
+    // (2 u^n - u^(n-1)): the first residual drops by 2-3 orders of magnitude, which saves about one iteration per step.
+    const bool extrap = !s->rhs_val && (s->flags & CRBE_SOLVER_EXTRAPOLATE);
+    double* x = u_next;
+    const double* xb = u_cur;
+    if (pp) {
+        if (extrap && s->hist_valid && s->pp_prev == u_next) {
+            PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate_pp<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, u_cur, u_next)));
             ++launches;
         } else {
-            CRBE_CUDA(cudaMemcpyAsync(s->hist, u_d, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
+            CRBE_CUDA(cudaMemcpyAsync(u_next, u_cur, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
         }
+        s->pp_prev = u_cur;
         s->hist_valid = true;
+    } else if (!s->rhs_val) {
+        if (extrap && s->hist_valid && s->pp_prev == nullptr) {
+            PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, u_cur, s->hist)));
+            ++launches;
+        } else {
+            CRBE_CUDA(cudaMemcpyAsync(s->hist, u_cur, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
+        }
+        s->pp_prev = nullptr;
+        s->hist_valid = true;
+        xb = s->hist;
     }
-    CRBE_CHECK(halo_exchange(s, u_d, &launches));
+    CRBE_CHECK(halo_exchange(s, x, &launches));
     if (s->rhs_val)
-        PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, s->tmp, source_d, dt,
+        PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->tmp, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<<<s->gt_init, CRBE_TILE, TilePipe<2>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->ell_val, s->ell_col, u_d, s->hist, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
+                                     s->n, s->ntiles, s->ell_val, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
                                      s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else
-        PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, u_d, s->hist, source_d, dt,
+        PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, xb, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     ++launches;
     CRBE_KERNEL_CHECK();
     CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, -1, &launches));
-    int rc = run_bicgstab(s, u_d, info_h, &launches);
+    int rc = run_bicgstab(s, x, info_h, &launches);
     info_h->launches = launches;
     ctx->launches += launches;
     return rc;
+}
+
+extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* source_d, double dt, crbe_solve_info* info_h) {
+    CRBE_REQUIRE(s && u_d && info_h, "null argument");
+    return step_impl(s, u_d, u_d, source_d, dt, info_h);
+}
+
+extern "C" int crbe_solver_step_pingpong(crbe_solver* s, double* u_cur_d, double* u_next_d, const double* source_d, double dt,
+                                         crbe_solve_info* info_h) {
+    CRBE_REQUIRE(s && u_cur_d && u_next_d && u_cur_d != u_next_d && info_h, "bad argument");
+    return step_impl(s, u_cur_d, u_next_d, source_d, dt, info_h);
 }
 
 extern "C" int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d, crbe_solve_info* info_h) {

@@ -389,7 +389,6 @@ def bench_partitioned(args, K, W, device):
     rt.call("crbe_solver_profile_read", part._solver, pms, pcnt)
     n_own = part.n_own
     rb = dict(B.ROW_BYTES)
-    rb["pv"], rb["st"] = 48 + 3 * 8, 48 + 2 * 8
     kern = {B.KINDS[k]: {"launches": int(pcnt[k]), "ms_per_launch": pms[k] / pcnt[k],
                          "GBps": rb[B.KINDS[k]] * n_own / (pms[k] / pcnt[k] * 1e-3) / 1e9} for k in range(8) if pcnt[k] > 0}
     steps_per_s = K / (ms * 1e-3)
@@ -420,7 +419,7 @@ def bench_partitioned(args, K, W, device):
                    "rtol": 1e-13, "dofs_per_gpu": n_own, "halo_dofs_rank0": part.n_halo,
                    "value_definition": ("n_gpus x steps/s of the partitioned mesh: every GPU advances a 12.6M-DOF strip per step"
                                         if scaling == "weak" else "steps/s of the fixed mesh"),
-                   "solver": "Jacobi-BiCGStab 5-kernel, halo exchange + allreduce over " + part.transport,
+                   "solver": "Jacobi-BiCGStab, merged-reduction 4-kernel iteration, halo exchange + allreduce over " + part.transport,
                    "iters_per_step": float(np.mean(iters)), "l2": "inputs larger than L2", "setup_s": setup_s},
         "dof_updates_per_s": steps_per_s * counts["dofs"],
         "clocks": clocks, "gpu_launches": int(l1.value - l0.value), "kernels": kern,

@@ -136,7 +136,7 @@ typedef struct crbe_solve_info {
 
 #define CRBE_SOLVER_FUSED 1u          /* reserved (the iteration is the merged-reduction form)   */
 #define CRBE_SOLVER_VERIFY 2u         /* recompute the true residual after convergence         */
-#define CRBE_SOLVER_GRAPH 4u          /* replay iterations from a CUDA graph                   */
+#define CRBE_SOLVER_GRAPH 4u          /* reserved                                                */
 #define CRBE_SOLVER_EXTRAPOLATE 16u   /* crbe_solver_step: start from 2 u^n - u^(n-1) (linear extrapolation in
                                          time) instead of u^n once one step of history exists        */
 #define CRBE_SOLVER_TMA 8u            /* SpMV-type kernels fed by bulk async copies (cp.async.bulk
@@ -158,6 +158,12 @@ int crbe_solver_set_options(crbe_solver* s, double rtol, int32_t max_iterations,
  * dt*source_d if not NULL), solves the Dirichlet system, leaves the un-lifted
  * solution in u_d. */
 int crbe_solver_step(crbe_solver* s, double* u_d, const double* source_d, double dt, crbe_solve_info* info_h);
+/* The same step with two alternating vectors (single GPU; both crbe_solver_vector_length long, zero padded):
+ * u_cur_d holds u^n and is left intact, the new solution is built in u_next_d (which should still hold u^(n-1)
+ * from the call before, for the extrapolated initial guess).  u^n can therefore be downloaded by the host
+ * during the whole next step without a staging copy. */
+int crbe_solver_step_pingpong(crbe_solver* s, double* u_cur_d, double* u_next_d, const double* source_d, double dt,
+                              crbe_solve_info* info_h);
 /* Solve  A x = b  for the loaded system (Dirichlet rows applied); x_d holds the initial guess. */
 int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d, crbe_solve_info* info_h);
 /* b of crbe.py:384-402 for inspection: b_d (out). */
