@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--regime", default="P-ref", choices=["P-ref", "P-T10", "P-stiff"])
     ap.add_argument("--no-extrapolate", action="store_true", help="start every solve from u^n instead of 2u^n - u^(n-1)")
     ap.add_argument("--classic", action="store_true", help="register-load kernels instead of the bulk-copy (TMA) pipeline")
-    ap.add_argument("--e2e-steps", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -329,18 +329,25 @@ def main():
     solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", tma=not args.classic, extrapolate=not args.no_extrapolate, progress=False)
     rt = Runtime.get(device)
     solver.set_initial_condition()
-    u = rt.upload(np.asarray(solver.u_prev, dtype=np.float64))
     solver.build_global_matrices()
     rt.synchronize()
     t_setup = time.time() - t_setup
     n = md.number_of_segments
     assert n == counts["dofs"]
+    # two alternating solution vectors, as BESCRFEM.solve() uses them (crbe_solver_step_pingpong)
+    vlen = C.c_int64()
+    rt.call("crbe_solver_vector_length", solver._solver, C.byref(vlen), None)
+    ubuf = [rt.zeros((vlen.value,), torch.float64), rt.zeros((vlen.value,), torch.float64)]
+    ubuf[0][:n] = rt.upload(np.asarray(solver.u_prev, dtype=np.float64))
+    state = {"cur": 0}
 
     info = _lib.SolveInfo()
     dt = float(solver.dt)
 
     def step():
-        rt.call("crbe_solver_step", solver._solver, ptr(u), ptr(None), dt, C.byref(info))
+        c = state["cur"]
+        rt.call("crbe_solver_step_pingpong", solver._solver, ptr(ubuf[c]), ptr(ubuf[c ^ 1]), ptr(None), dt, C.byref(info))
+        state["cur"] = c ^ 1
         return info.iterations
 
     l0 = C.c_int64()
