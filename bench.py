@@ -40,7 +40,7 @@ METRIC = "Backward-Euler steps/s at 12.6M CR DOFs"
 UNIT = "steps/s"
 # bytes per matrix row moved by each solver kernel in the ELL-4/unit-diagonal layout
 ROW_BYTES = {"init": 48 + 7 * 8, "pv": 48 + 3 * 8, "st": 48 + 3 * 8, "xr": 8 * 8, "p": 4 * 8, "s": 3 * 8, "residual": 48 + 2 * 8,
-             "extrapolate": 4 * 8}
+             "extrapolate": 3 * 8}
 KINDS = ["init", "pv", "st", "xr", "p", "s", "residual", "extrapolate"]
 
 
