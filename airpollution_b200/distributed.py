@@ -90,6 +90,39 @@ def strip_offsets(nx, ny, world):
 
 
 # --------------------------------------------------------------------------
+# geometric partition of an arbitrary mesh: recursive coordinate bisection of the DOF (edge-midpoint) cloud
+# --------------------------------------------------------------------------
+def rcb_partition(midpoints, world):
+    """Recursive coordinate bisection into ``world`` parts of (almost) equal size.
+
+    Returns ``(order, offsets)``: ``order`` lists the DOF ids part by part (ascending reference id inside a part, so
+    the result is deterministic), ``offsets[r]:offsets[r+1]`` is the slice of part r.  Each cut halves the current
+    point set along its longer bounding-box axis at the weighted median; parts need not be powers of two."""
+    mid = np.asarray(midpoints, dtype=np.float64)
+    n = len(mid)
+    parts = []
+
+    def split(ids, k):
+        if k == 1:
+            parts.append(np.sort(ids))
+            return
+        kl = k // 2
+        pts = mid[ids]
+        ext = pts.max(axis=0) - pts.min(axis=0) if len(ids) else np.zeros(2)
+        axis = int(ext[1] > ext[0])
+        nl = (len(ids) * kl) // k
+        # stable: ties broken by reference id
+        o = np.lexsort((ids, pts[:, axis]))
+        split(ids[o[:nl]], kl)
+        split(ids[o[nl:]], k - kl)
+
+    split(np.arange(n, dtype=np.int64), world)
+    order = np.concatenate(parts) if parts else np.zeros(0, np.int64)
+    offsets = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.int64).tolist()
+    return order, offsets
+
+
+# --------------------------------------------------------------------------
 # localisation of the owned rows: global column ids -> [owned | halo]
 # --------------------------------------------------------------------------
 def localize_columns(cols_global, d0, d1):
@@ -169,8 +202,9 @@ class Comm:
 class PartitionedCRBE:
     """Backward-Euler / Crank-Nicolson stepping of a structured ``Workload``
     (``airpollution_b200.workloads``) split into strips of cell rows, or of an
-    arbitrary mesh (``mesh=``) with the global system assembled redundantly and
-    split into equal blocks of rows."""
+    arbitrary mesh (``mesh=``) partitioned geometrically by recursive coordinate
+    bisection of the edge midpoints (the global system is assembled redundantly
+    on every rank in that case; each rank keeps the rows of its part)."""
 
     def __init__(self, workload=None, *, mesh=None, domain=None, problem=None, nt=None, order=1, rank=None, world=None,
                  device=None, comm=None, rtol=1e-13, max_iterations=10000, tma=True, verify=True, p2p=None,
@@ -199,10 +233,15 @@ class PartitionedCRBE:
             gid = structured_global_dof(nx, md._dev["segments"], j0)
             self.n_global = structured_total_dofs(nx, ny)
         else:
+            # arbitrary mesh: geometric partition (recursive coordinate bisection of the edge midpoints); the solver
+            # works in the partition's numbering (part after part), results are mapped back to the reference's
             md = crbe.MeshData(mesh, domain, nt, device=rt.device)
             n = md.number_of_segments
-            self.offsets = [(n * r) // self.world for r in range(self.world + 1)]
-            gid = torch.arange(n, device=rt.device, dtype=torch.int64)
+            order, self.offsets = rcb_partition(md.midpoints, self.world)
+            self.partition_order = order                       # partition id -> reference DOF id
+            gid_np = np.empty(n, dtype=np.int64)
+            gid_np[order] = np.arange(n, dtype=np.int64)       # reference DOF id -> partition id
+            gid = torch.from_numpy(gid_np).to(rt.device)
             self.n_global = n
         self.domain, self.problem, self.nt, self.order = domain, problem, nt, order
         self.dt = domain.T / (nt - 1)
@@ -327,7 +366,13 @@ class PartitionedCRBE:
             return mine
         parts = [None] * self.world
         dist.all_gather_object(parts, mine)
-        return np.concatenate(parts)
+        full = np.concatenate(parts)
+        order = getattr(self, "partition_order", None)
+        if order is not None:                  # back from the partition's numbering to the reference's
+            out = np.empty_like(full)
+            out[order] = full
+            return out
+        return full
 
     def close(self):
         from . import _lib

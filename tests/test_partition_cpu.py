@@ -121,3 +121,27 @@ def test_halo_plan_between_gloo_ranks(world):
         for k, qq in enumerate(neigh):
             other = by_rank[qq]
             assert ns[k] == other[5][other[3].index(rank)]
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_rcb_partition_is_balanced_and_local(world):
+    from airpollution_b200.meshgen import delaunay_mesh
+    mesh = delaunay_mesh(4000, seed=21, shuffle=True)
+    om = orc.OracleMesh(mesh.points, mesh.triangles, 1.0, 3)
+    order, offsets = D.rcb_partition(om.midpoints, world)
+    n = om.number_of_segments
+    assert sorted(order.tolist()) == list(range(n))
+    sizes = np.diff(offsets)
+    assert sizes.max() - sizes.min() <= world                      # balanced
+    order2, offsets2 = D.rcb_partition(om.midpoints, world)
+    assert np.array_equal(order, order2) and offsets == offsets2   # deterministic
+    # locality: far fewer coupled DOF pairs are cut than by equal blocks of the (shuffled) reference numbering
+    M, K, A = orc.assemble_global(om.points, om.triangles, om.triangle_to_segments, om.triangle_areas, 0.1, (1.0, 0.5), n)
+    coo = K.tocoo()
+    part = np.empty(n, dtype=np.int64)
+    for r in range(world):
+        part[order[offsets[r]:offsets[r + 1]]] = r
+    cut_rcb = np.count_nonzero(part[coo.row] != part[coo.col])
+    blocks = (np.arange(n) * world) // n
+    cut_blocks = np.count_nonzero(blocks[coo.row] != blocks[coo.col])
+    assert cut_rcb < 0.25 * cut_blocks
