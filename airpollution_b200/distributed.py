@@ -237,10 +237,10 @@ class PartitionedCRBE:
             # works in the partition's numbering (part after part), results are mapped back to the reference's
             md = crbe.MeshData(mesh, domain, nt, device=rt.device)
             n = md.number_of_segments
-            order, self.offsets = rcb_partition(md.midpoints, self.world)
-            self.partition_order = order                       # partition id -> reference DOF id
+            part_order, self.offsets = rcb_partition(md.midpoints, self.world)
+            self.partition_order = part_order                  # partition id -> reference DOF id
             gid_np = np.empty(n, dtype=np.int64)
-            gid_np[order] = np.arange(n, dtype=np.int64)       # reference DOF id -> partition id
+            gid_np[part_order] = np.arange(n, dtype=np.int64)  # reference DOF id -> partition id
             gid = torch.from_numpy(gid_np).to(rt.device)
             self.n_global = n
         self.domain, self.problem, self.nt, self.order = domain, problem, nt, order

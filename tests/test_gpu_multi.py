@@ -68,7 +68,20 @@ def test_partitioned_solve_matches_single_gpu(case, p2p):
     procs = [ctx.Process(target=_worker, args=(r, world, port, case, p2p, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = sorted(q.get(timeout=600) for _ in range(world))
+    import queue
+    import time
+    results, deadline = [], time.time() + 420
+    while len(results) < world:          # fail fast if a rank dies instead of waiting for the queue
+        try:
+            results.append(q.get(timeout=2))
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() > deadline:
+                for p in procs:
+                    if p.is_alive():
+                        p.kill()
+                pytest.fail(f"a rank exited with {dead}" if dead else "timed out waiting for the ranks")
+    results.sort()
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
