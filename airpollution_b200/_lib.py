@@ -57,6 +57,8 @@ _SIGNATURES = {
     "crbe_spmv_csr": [vp, C.c_int64, vp, vp, vp, vp, vp],
     "crbe_dot": [vp, C.c_int64, vp, vp, c_f64p],
     "crbe_errors": [vp, C.c_int64, vp, vp, c_f64p],
+    "crbe_moments": [vp, C.c_int64, vp, vp, vp, c_f64p],
+    "crbe_solver_mass_diagonal": [vp, C.POINTER(vp)],
     "crbe_solver_create": [vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, C.POINTER(vp)],
     "crbe_solver_set_system": [vp, vp, vp, vp],
     "crbe_solver_set_options": [vp, C.c_double, C.c_int32, C.c_uint32],

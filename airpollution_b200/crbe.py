@@ -584,6 +584,35 @@ class BESCRFEM:
         rt.call("crbe_errors", rt.ctx, md.number_of_segments, ptr(u_exact), ptr(u_num), out)
         return np.float64(out[0]), np.float64(out[1]), np.float64(out[2])
 
+    # ---- plume diagnostics (scripts/problem3_comprehensive_analysis2.py:60-302) ---------
+    @staticmethod
+    def _moments_dict(raw, midpoints_of):
+        s0, sx, sy, sxx, syy, peak, idx = raw[:7]
+        if s0 > 1e-10:                                  # the reference's guard (…analysis2.py:156)
+            cx, cy = sx / s0, sy / s0
+            vx, vy = sxx / s0 - cx * cx, syy / s0 - cy * cy
+        else:
+            cx = cy = vx = vy = 0.0
+        return {"mass": s0, "com_x": cx, "com_y": cy, "var_x": vx, "var_y": vy, "peak": peak,
+                "peak_xy": tuple(midpoints_of(int(idx)))}
+
+    def moments(self, time_index=-1):
+        """Mass, centre of mass, spread (variance about the centre of mass) and peak of a stored solution row,
+        integrated with the CR quadrature (area/3 per edge midpoint) -- the reductions of the reference's
+        analysis scripts, as one pass on the device (``crbe_moments``)."""
+        md, rt = self.mesh_data, self._rt
+        rt.bind_stream()
+        u = rt.upload(np.ascontiguousarray(self.solutions[time_index, :]))
+        return self._moments_of(u)
+
+    def _moments_of(self, u_dev):
+        md, rt = self.mesh_data, self._rt
+        w = C.c_void_p()
+        rt.call("crbe_solver_mass_diagonal", self._solver, C.byref(w))
+        out = (C.c_double * 8)()
+        rt.call("crbe_moments", rt.ctx, md.number_of_segments, ptr(u_dev), w, ptr(md._dev["midpoints"]), out)
+        return self._moments_dict(list(out), lambda i: to_numpy(md._dev["midpoints"][i]))
+
     # ---- plotting (crbe.py:485-660): host-side, needs matplotlib -----------
     def plot_solution(self, analytical_sol_fn=None, time_index=None, save_dir="results"):
         from .plotting import plot_solution

@@ -34,7 +34,7 @@ extern "C" int crbe_ctx_create(int device, crbe_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->stream = nullptr;   // the (legacy) default stream until the host binds its own
-    CRBE_CUDA(cudaMalloc(&c->partials, sizeof(double) * 4 * CRBE_MAX_PARTIAL_BLOCKS));
+    CRBE_CUDA(cudaMalloc(&c->partials, sizeof(double) * 8 * CRBE_MAX_PARTIAL_BLOCKS));
     CRBE_CUDA(cudaMalloc(&c->counter, sizeof(unsigned int) * 4));
     CRBE_CUDA(cudaMemset(c->counter, 0, sizeof(unsigned int) * 4));
     CRBE_CUDA(cudaMalloc(&c->dev_scalars, sizeof(double) * 64));

@@ -638,6 +638,80 @@ extern "C" int crbe_errors(crbe_ctx* ctx, int64_t n, const double* u_exact_d, co
     return CRBE_OK;
 }
 
+// ---------------------------------------------------------------- plume diagnostics
+// The analysis scripts of the reference integrate the solution triangle by triangle with the CR quadrature
+// (area/3 per edge midpoint): mass, first and second moments, peak (scripts/problem3_comprehensive_analysis2.py:60-302).
+// Those are linear functionals with weight w_e = sum over the triangles of e of area/3 = diag(M): one pass over the
+// DOFs gives sum w u, sum w u x, sum w u y, sum w u x^2, sum w u y^2 and the peak value.
+__device__ __forceinline__ unsigned long long ordered_bits(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(CRBE_BLOCK) k_moments(int64_t n, const double* __restrict__ u, const double* __restrict__ w,
+                                                        const double* __restrict__ mid, double* out, unsigned long long* peak_bits,
+                                                        double* partials, unsigned int* counter) {
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    unsigned long long pk = 0ull;
+    ROW_LOOP(i, n) {
+        const double ui = u[i], wu = w[i] * ui, x = mid[2 * i], y = mid[2 * i + 1];
+        acc[0] += wu;
+        acc[1] = fma(wu, x, acc[1]);
+        acc[2] = fma(wu, y, acc[2]);
+        acc[3] = fma(wu * x, x, acc[3]);
+        acc[4] = fma(wu * y, y, acc[4]);
+        const unsigned long long ob = ordered_bits(ui);
+        pk = ob > pk ? ob : pk;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_down_sync(0xffffffffu, pk, d);
+        pk = o > pk ? o : pk;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(peak_bits, pk);
+    double* const o5[5] = {out, out + 1, out + 2, out + 3, out + 4};
+    grid_sum_last<5>(acc, partials, counter, o5, nullptr);
+}
+
+__global__ void __launch_bounds__(CRBE_BLOCK) k_peak_index(int64_t n, const double* __restrict__ u, const unsigned long long* peak_bits,
+                                                           unsigned long long* index) {
+    const unsigned long long pk = *peak_bits;
+    ROW_LOOP(i, n) if (ordered_bits(u[i]) == pk) atomicMin(index, (unsigned long long)i);
+}
+
+// out8_h: mass, moment_x, moment_y, moment_xx, moment_yy, peak value, peak DOF index, (unused)
+extern "C" int crbe_moments(crbe_ctx* ctx, int64_t n, const double* u_d, const double* weights_d, const double* midpoints_d, double* out8_h) {
+    CRBE_REQUIRE(ctx && out8_h && n > 0 && u_d && weights_d && midpoints_d, "bad argument");
+    cudaStream_t st = ctx->stream;
+    unsigned long long* bits = (unsigned long long*)(ctx->dev_scalars + 8);
+    const unsigned long long init[2] = {0ull, ~0ull};
+    CRBE_CUDA(cudaMemcpyAsync(bits, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const int g = crbe_grid_for(ctx, n);
+    k_moments<<<g, CRBE_BLOCK, 0, st>>>(n, u_d, weights_d, midpoints_d, ctx->dev_scalars, bits, ctx->partials, ctx->counter);
+    k_peak_index<<<g, CRBE_BLOCK, 0, st>>>(n, u_d, bits, bits + 1);
+    CRBE_KERNEL_CHECK();
+    ctx->launches += 2;
+    CRBE_CUDA(cudaMemcpyAsync(ctx->host_scalars, ctx->dev_scalars, 10 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CRBE_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < 5; ++k) out8_h[k] = ctx->host_scalars[k];
+    unsigned long long hb[2];
+    memcpy(hb, ctx->host_scalars + 8, sizeof(hb));
+    const unsigned long long raw = (hb[0] & 0x8000000000000000ull) ? (hb[0] & 0x7fffffffffffffffull) : ~hb[0];
+    double peak;
+    memcpy(&peak, &raw, sizeof(peak));
+    out8_h[5] = peak;
+    out8_h[6] = (double)hb[1];
+    out8_h[7] = 0.0;
+    return CRBE_OK;
+}
+
+// diag(M) of the loaded system: the quadrature weights of crbe_moments
+extern "C" int crbe_solver_mass_diagonal(crbe_solver* s, const double** mdiag_d) {
+    CRBE_REQUIRE(s && mdiag_d && s->system_loaded, "no system loaded");
+    *mdiag_d = s->mdiag;
+    return CRBE_OK;
+}
+
 // ---------------------------------------------------------------- solver object
 template <class Kern>
 static int tile_grid(crbe_ctx* ctx, Kern kernel, int smem_bytes, int64_t ntiles, int* grid) {

@@ -123,6 +123,13 @@ int crbe_dot(crbe_ctx* ctx, int64_t n, const double* x_d, const double* y_d, dou
 /* (rel_l2, l2, max) of crbe.py:447-453 */
 int crbe_errors(crbe_ctx* ctx, int64_t n, const double* u_exact_d, const double* u_num_d, double* out3_h);
 
+/* Plume diagnostics of the reference's analysis scripts (scripts/problem3_comprehensive_analysis2.py:60-302:
+ * mass, centre of mass, spread, peak) in one pass over the DOFs: with the CR quadrature they are weighted sums
+ * with weights_d = diag(M).  out8_h: sum w u, sum w u x, sum w u y, sum w u x^2, sum w u y^2, peak value,
+ * peak DOF index, 0. */
+int crbe_moments(crbe_ctx* ctx, int64_t n, const double* u_d, const double* weights_d, const double* midpoints_d,
+                 double* out8_h);
+
 /* ---- a-9..a-11: the per-step linear solve ------------------------------- */
 typedef struct crbe_solve_info {
     int32_t iterations;      /* BiCGStab iterations of this solve                     */
@@ -170,6 +177,8 @@ int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d, crbe_solve
 int crbe_solver_rhs(crbe_solver* s, const double* u_d, const double* source_d, double dt, double* b_d);
 /* out = u with out[bnd[k]] += bc[k]   (the lift of crbe.py:429) */
 int crbe_solver_lift(crbe_solver* s, const double* u_d, const double* bc_values_d, double* out_d);
+int crbe_solver_mass_diagonal(crbe_solver* s, const double** mdiag_d_out);   /* diag(M), the weights of crbe_moments */
+int crbe_solver_mass_diagonal(crbe_solver* s, const double** mdiag_d_out);   /* diag(M), the weights of crbe_moments */
 int crbe_solver_destroy(crbe_solver* s);
 
 /* ---- row-block partitioned solve over several GPUs (one process per GPU) -- */

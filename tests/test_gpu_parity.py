@@ -465,3 +465,27 @@ def test_constant_velocity_field_reduces_to_reference_path():
     b = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), progress=False, velocity_field=const).solve()
     np.testing.assert_array_equal(a, b)
     assert rel_err(b[-1], g["final"]) <= SOLUTION_RTOL
+
+
+def test_moments_match_triangle_integration():
+    """crbe_moments against the triangle loop of the reference's analysis script
+    (scripts/problem3_comprehensive_analysis2.py:60-302), restated with numpy."""
+    g = load_golden("delaunay40_o1")
+    crbe, dom, md = _product(g)
+    prob = golden_problem("delaunay40_o1", g)
+    s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), progress=False)
+    sol = s.solve()
+    t2s, area, mid = md.triangle_to_segments, md.triangle_areas, md.midpoints
+    for ti in (0, 5, -1):
+        u = sol[ti]
+        mass = float(np.sum(area * u[t2s].sum(axis=1) / 3))
+        mx = float(np.sum(area * (u[t2s] * mid[t2s, 0]).sum(axis=1) / 3))
+        my = float(np.sum(area * (u[t2s] * mid[t2s, 1]).sum(axis=1) / 3))
+        cx, cy = mx / mass, my / mass
+        vx = float(np.sum(area * (u[t2s] * (mid[t2s, 0] - cx) ** 2).sum(axis=1) / 3)) / mass
+        vy = float(np.sum(area * (u[t2s] * (mid[t2s, 1] - cy) ** 2).sum(axis=1) / 3)) / mass
+        m = s.moments(ti)
+        np.testing.assert_allclose([m["mass"], m["com_x"], m["com_y"], m["var_x"], m["var_y"]], [mass, cx, cy, vx, vy],
+                                   rtol=1e-10, atol=1e-13)
+        assert m["peak"] == u.max()
+        assert tuple(m["peak_xy"]) == tuple(mid[int(np.argmax(u))])
