@@ -773,11 +773,27 @@ static int solver_release(crbe_solver* s) {
     return CRBE_OK;
 }
 
+static int solver_init(crbe_solver* s, crbe_ctx* ctx, crbe_comm* comm, int64_t n, int64_t n_halo, const int32_t* indptr_d,
+                       const int32_t* indices_d, int64_t nnz, const int32_t* bnd_seg_d, int64_t nb);
+
+// allocation failures half way must not leak the solver: build into a fresh object, release it on any error
 static int solver_create_impl(crbe_ctx* ctx, crbe_comm* comm, int64_t n, int64_t n_halo, const int32_t* indptr_d,
                               const int32_t* indices_d, int64_t nnz, const int32_t* bnd_seg_d, int64_t nb, crbe_solver** out) {
     CRBE_REQUIRE(ctx && out && n > 0 && indptr_d && indices_d && nnz > 0 && nb >= 0 && (nb == 0 || bnd_seg_d) && n_halo >= 0,
                  "bad argument");
     crbe_solver* s = new crbe_solver();
+    const int rc = solver_init(s, ctx, comm, n, n_halo, indptr_d, indices_d, nnz, bnd_seg_d, nb);
+    if (rc != CRBE_OK) {
+        solver_release(s);
+        *out = nullptr;
+        return rc;
+    }
+    *out = s;
+    return CRBE_OK;
+}
+
+static int solver_init(crbe_solver* s, crbe_ctx* ctx, crbe_comm* comm, int64_t n, int64_t n_halo, const int32_t* indptr_d,
+                       const int32_t* indices_d, int64_t nnz, const int32_t* bnd_seg_d, int64_t nb) {
     s->ctx = ctx;
     s->comm = comm;
     s->world = crbe_comm_world(comm);
@@ -788,7 +804,6 @@ static int solver_create_impl(crbe_ctx* ctx, crbe_comm* comm, int64_t n, int64_t
     s->nb = nb;
     s->indptr = indptr_d;
     s->indices = indices_d;
-    *out = s;
     // internal vectors: owned rows padded to whole tiles (padding stays zero), then the halo entries
     s->veclen = s->ld + (n_halo + 31) / 32 * 32;
     const size_t vb = sizeof(double) * (size_t)s->veclen;
