@@ -33,6 +33,7 @@ SOLVER_VERIFY = 2
 SOLVER_GRAPH = 4
 SOLVER_TMA = 8
 SOLVER_EXTRAPOLATE = 16
+SOLVER_VERIFY_AUTO = 32
 
 # name -> (argtypes)   every function returns int unless listed in _RESTYPE
 _SIGNATURES = {

@@ -198,6 +198,8 @@ class BESCRFEM:
     ``history``         ``"all"`` (reference: ``solutions`` is nt x N), ``"last"``
                         (``solutions`` holds only the initial and final rows) or an
                         int stride -- 1001 x 12.6 M doubles do not fit in host memory.
+    ``verify``          recompute the true residual ``b - A x`` after convergence: ``True`` always, ``"auto"`` (default)
+                        after solves of more than 12 iterations or a restart, ``False`` never.
     ``extrapolate``     start each solve from ``2 u^n - u^(n-1)`` instead of ``u^n`` (same stopping rule, about one
                         BiCGStab iteration less per step).
     ``tma``             feed the SpMV-type kernels through the bulk-copy/mbarrier shared-memory
@@ -209,7 +211,7 @@ class BESCRFEM:
     """
 
     def __init__(self, domain, problem, mesh_data, element, time_scheme_order=1, *, rtol=1e-13,
-                 max_iterations=10000, history="all", tma=True, verify=True, extrapolate=True,
+                 max_iterations=10000, history="all", tma=True, verify="auto", extrapolate=True,
                  progress=None, velocity_field=None):
         self.domain = domain
         self.problem = problem
@@ -356,7 +358,7 @@ class BESCRFEM:
             rt.call("crbe_solver_create", rt.ctx, md.number_of_segments, ptr(d["indptr"]), ptr(d["indices"]), self._nnz,
                     ptr(md._dev["bnd"]), md._dev["bnd"].numel(), C.byref(h))
             self._solver = h
-        flags = ((_lib.SOLVER_VERIFY if self.verify else 0)
+        flags = ((_lib.SOLVER_VERIFY_AUTO if self.verify == "auto" else (_lib.SOLVER_VERIFY if self.verify else 0))
                  | (_lib.SOLVER_TMA if self.tma else 0) | (_lib.SOLVER_EXTRAPOLATE if self.extrapolate else 0))
         rt.call("crbe_solver_set_options", self._solver, float(self.rtol), int(self.max_iterations), flags)
         rt.call("crbe_solver_set_system", self._solver, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))

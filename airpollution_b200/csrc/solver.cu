@@ -73,7 +73,7 @@ struct crbe_solver {
     double* sums_h = nullptr;  // pinned: CRBE_NSUMS doubles followed by 2 ints
     double rtol = 1e-13;
     int maxit = 10000;
-    unsigned flags = CRBE_SOLVER_TMA | CRBE_SOLVER_VERIFY | CRBE_SOLVER_EXTRAPOLATE;
+    unsigned flags = CRBE_SOLVER_TMA | CRBE_SOLVER_VERIFY_AUTO | CRBE_SOLVER_EXTRAPOLATE;
     int last_iters = 8;
     bool system_loaded = false;
     // persistent grids: SMs x resident CTAs of each kernel (a grid-stride sweep must be one full wave)
@@ -1209,17 +1209,24 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
     const int* dst_h = (const int*)(s->sums_h + CRBE_NSUMS);
     int total_iters = 0, restarts = 0, status = 0;
     double true_rr = -1.0;
-    const bool verify = (s->flags & CRBE_SOLVER_VERIFY) != 0;
+    // Verification of the true residual: always (CRBE_SOLVER_VERIFY) or only for long recurrences
+    // (CRBE_SOLVER_VERIFY_AUTO): the gap between recurrence and true residual grows like k * eps * ||A|| ||x||, so a
+    // solve of <= VERIFY_AUTO_ITERS iterations cannot be off by anything near rtol; longer solves and restarts are checked.
+    constexpr int VERIFY_AUTO_ITERS = 12;
+    const bool verify_always = (s->flags & CRBE_SOLVER_VERIFY) != 0;
+    const bool verify_auto = !verify_always && (s->flags & CRBE_SOLVER_VERIFY_AUTO) != 0;
     for (;;) {
         int k = 0;
         int target = s->last_iters + 1;
         if (target > s->maxit - total_iters) target = s->maxit - total_iters;
         if (target < 1) target = 1;
-        bool done = false;
+        bool done = false, speculated_last = false;
         for (;;) {
             for (; k < target; ++k) CRBE_CHECK(launch_iteration(s, k, x, launches));
             // the verification rides behind the batch (it returns at once unless the batch converged): one sync per step
-            if (verify) CRBE_CHECK(launch_residual(s, x, 1, launches));
+            const bool speculate = verify_always || (verify_auto && (total_iters + target > VERIFY_AUTO_ITERS || restarts > 0));
+            if (speculate) CRBE_CHECK(launch_residual(s, x, 1, launches));
+            speculated_last = speculate;
             CRBE_KERNEL_CHECK();
             CRBE_CHECK(fetch_state(s));
             const double rr = s->sums_h[S_RR], bb = s->sums_h[S_BB];
@@ -1244,8 +1251,14 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
             status = 0;
             break;
         }
-        if (status == 0 && !verify) break;
         if (status == 0) {
+            const bool need = verify_always || (verify_auto && (total_iters > VERIFY_AUTO_ITERS || restarts > 0));
+            if (!need) break;
+            if (!speculated_last) {          // converged in a batch that did not carry the verification kernel
+                CRBE_CHECK(launch_residual(s, x, 1, launches));
+                CRBE_CHECK(fetch_state(s));
+                prof_collect(s, 0, true);
+            }
             true_rr = s->sums_h[S_RRTRUE];
             if (true_rr <= accept2 * s->sums_h[S_BB]) break;
         }

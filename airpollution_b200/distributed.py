@@ -207,7 +207,7 @@ class PartitionedCRBE:
     on every rank in that case; each rank keeps the rows of its part)."""
 
     def __init__(self, workload=None, *, mesh=None, domain=None, problem=None, nt=None, order=1, rank=None, world=None,
-                 device=None, comm=None, rtol=1e-13, max_iterations=10000, tma=True, verify=True, p2p=None,
+                 device=None, comm=None, rtol=1e-13, max_iterations=10000, tma=True, verify="auto", p2p=None,
                  extrapolate=True):
         from . import _lib, crbe
         from .runtime import Runtime, ptr
@@ -294,7 +294,8 @@ class PartitionedCRBE:
                 (C.c_int64 * max(nn, 1))(*[len(s) for s in send_ids]), ptr(d["send_idx"]),
                 (C.c_int64 * max(nn, 1))(*recv_counts), C.byref(h))
         self._solver = h
-        flags = (_lib.SOLVER_VERIFY if verify else 0) | (_lib.SOLVER_TMA if tma else 0) | \
+        flags = (_lib.SOLVER_VERIFY_AUTO if verify == "auto" else (_lib.SOLVER_VERIFY if verify else 0)) | \
+                (_lib.SOLVER_TMA if tma else 0) | \
                 (_lib.SOLVER_EXTRAPOLATE if extrapolate else 0)
         rt.call("crbe_solver_set_options", h, float(rtol), int(max_iterations), flags)
         rt.call("crbe_solver_set_system", h, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))

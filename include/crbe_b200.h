@@ -142,7 +142,9 @@ typedef struct crbe_solve_info {
 } crbe_solve_info;
 
 #define CRBE_SOLVER_FUSED 1u          /* reserved (the iteration is the merged-reduction form)   */
-#define CRBE_SOLVER_VERIFY 2u         /* recompute the true residual after convergence         */
+#define CRBE_SOLVER_VERIFY 2u         /* recompute the true residual after every convergence   */
+#define CRBE_SOLVER_VERIFY_AUTO 32u   /* ... only after solves of more than 12 iterations or a restart (the gap between
+                                         recurrence and true residual grows with the length of the recurrence) */
 #define CRBE_SOLVER_GRAPH 4u          /* reserved                                                */
 #define CRBE_SOLVER_EXTRAPOLATE 16u   /* crbe_solver_step: start from 2 u^n - u^(n-1) (linear extrapolation in
                                          time) instead of u^n once one step of history exists        */

@@ -251,7 +251,7 @@ def test_linear_solve_vs_superlu(rt, tma):
     from airpollution_b200.runtime import ptr
     dom = crbe.Domain(1, 1, T=0.5)
     md = crbe.MeshData(delaunay_mesh(4000, seed=4), dom, 6)
-    s = crbe.BESCRFEM(dom, crbe.Problem(v=[0.7, -0.3], D=0.05), md, crbe.ElementCR(), tma=tma)
+    s = crbe.BESCRFEM(dom, crbe.Problem(v=[0.7, -0.3], D=0.05), md, crbe.ElementCR(), tma=tma, verify=True)
     s.build_global_matrices()
     A = orc.dirichlet_system_fast(s.base_system, md.boundary_segments)
     rng = np.random.default_rng(5)
@@ -264,6 +264,20 @@ def test_linear_solve_vs_superlu(rt, tma):
     assert info.status == 0 and info.iterations > 0
     assert info.true_relres <= 1e-12
     assert rel_err(x.cpu().numpy(), ref) <= 1e-10
+
+
+@pytest.mark.parametrize("verify", [True, "auto", False])
+def test_verification_policies_agree(verify):
+    """The true-residual check only ever confirms a converged solve on these problems: the three policies
+    (always / after long recurrences / never) must produce the same bits."""
+    g = load_golden("struct_n32_o1")
+    crbe, dom, md = _product(g)
+    prob = golden_problem("struct_n32_o1", g)
+    s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), verify=verify, progress=False)
+    sol = s.solve()
+    assert rel_err(sol[-1], g["final"]) <= SOLUTION_RTOL
+    ref = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), verify=True, progress=False).solve()
+    assert np.array_equal(sol, ref)
 
 
 # ------------------------------------------------------------------ a-7 .. a-12: the full path
