@@ -68,6 +68,7 @@ _SIGNATURES = {
     "crbe_solver_solve": [vp, vp, vp, C.POINTER(SolveInfo)],
     "crbe_solver_rhs": [vp, vp, vp, C.c_double, vp],
     "crbe_solver_lift": [vp, vp, vp, vp],
+    "crbe_solver_store_lifted_async": [vp, vp, vp, vp, vp],
     "crbe_solver_destroy": [vp],
     "crbe_solver_profile": [vp, C.c_int],
     "crbe_solver_profile_read": [vp, c_f64p, c_i64p],

@@ -204,6 +204,8 @@ class BESCRFEM:
                         BiCGStab iteration less per step).
     ``tma``             feed the SpMV-type kernels through the bulk-copy/mbarrier shared-memory
                         pipeline (default) instead of per-thread register loads.
+    ``graph``           replay each step as one CUDA graph once its shape repeats (default; the launches of a step
+                        then no longer travel over PCIe one by one while a solution row is being downloaded).
     ``progress``        tqdm bar like the reference (default: only for nt*N < 2e7).
     ``velocity_field``  ``f(centroids[Nt,2], t) -> v[Nt,2]`` (torch tensors on the device): a velocity that varies in
                         space and time, one value per triangle, re-assembled every step (BASELINE config 5).  The
@@ -212,7 +214,7 @@ class BESCRFEM:
 
     def __init__(self, domain, problem, mesh_data, element, time_scheme_order=1, *, rtol=1e-13,
                  max_iterations=10000, history="all", tma=True, verify="auto", extrapolate=True,
-                 progress=None, velocity_field=None):
+                 graph=True, progress=None, velocity_field=None):
         self.domain = domain
         self.problem = problem
         self.mesh_data = mesh_data
@@ -226,6 +228,7 @@ class BESCRFEM:
         self.tma = tma
         self.extrapolate = extrapolate
         self.verify = verify
+        self.graph = graph
         self.progress = progress
         self.velocity_field = velocity_field
         self._rt = mesh_data._rt
@@ -359,7 +362,8 @@ class BESCRFEM:
                     ptr(md._dev["bnd"]), md._dev["bnd"].numel(), C.byref(h))
             self._solver = h
         flags = ((_lib.SOLVER_VERIFY_AUTO if self.verify == "auto" else (_lib.SOLVER_VERIFY if self.verify else 0))
-                 | (_lib.SOLVER_TMA if self.tma else 0) | (_lib.SOLVER_EXTRAPOLATE if self.extrapolate else 0))
+                 | (_lib.SOLVER_TMA if self.tma else 0) | (_lib.SOLVER_EXTRAPOLATE if self.extrapolate else 0)
+                 | (_lib.SOLVER_GRAPH if self.graph else 0))
         rt.call("crbe_solver_set_options", self._solver, float(self.rtol), int(self.max_iterations), flags)
         rt.call("crbe_solver_set_system", self._solver, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
 
@@ -483,8 +487,10 @@ class BESCRFEM:
         row_of = {s: k for k, s in enumerate(rows)}
         try:
             sol_t = torch.zeros((len(rows), n), dtype=torch.float64, pin_memory=True)
-        except RuntimeError:
+            pinned = True
+        except RuntimeError:         # not enough lockable memory: pageable history, slower downloads
             sol_t = torch.zeros((len(rows), n), dtype=torch.float64)
+            pinned = False
         self.solutions = sol_t.numpy()
         self.solutions[0, :] = self.u_prev
         u = rt.upload(np.asarray(self.u_prev, dtype=np.float64))
@@ -512,7 +518,9 @@ class BESCRFEM:
         reassemble = self.velocity_field is not None
         # The lift (crbe.py:367-379, :429) adds the user's boundary data on the Nb Dirichlet DOFs, where the solved
         # vector is exactly zero.  The callback is numpy on the host like in the reference; it runs on a helper
-        # thread while the GPU solves (the C call releases the GIL) and is applied to the downloaded rows at the end.
+        # thread while the GPU solves (the C call releases the GIL).  Its Nb values go up with the row's download
+        # and the device stores the lifted boundary entries straight into the page-locked history row
+        # (crbe_solver_store_lifted_async); with a pageable history they are added on the host at the end.
         bnd = md.boundary_segments
         nb = bnd.shape[0]
         mid_b = md.midpoints[bnd] if nb else np.zeros((0, 2))
@@ -524,6 +532,13 @@ class BESCRFEM:
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(max_workers=1)
         bc_jobs = [pool.submit(boundary_values, st * self.dt) for st in stored] if nb else []
+        lift_on_device = pinned and nb > 0
+        if lift_on_device:
+            ring = 4
+            bc_pin = torch.zeros((ring, nb), dtype=torch.float64, pin_memory=True)
+            bc_np = bc_pin.numpy()
+            ring_ev = [None] * ring
+        n_stored = 0
         start = time.time()
         try:
             for step in steps:
@@ -537,15 +552,26 @@ class BESCRFEM:
                 rt.call("crbe_solver_step_pingpong", self._solver, ptr(ubuf[cur]), ptr(ubuf[nxt]), ptr(src), dt, C.byref(info))
                 cur = nxt
                 self.step_info.append((info.iterations, info.relres, info.true_relres, info.restarts))
-                if step in row_of:
-                    with torch.cuda.stream(copy_stream):  # the step call has synchronised: the vector is final
-                        sol_t[row_of[step]].copy_(ubuf[cur][:n], non_blocking=True)
-                        ev = torch.cuda.Event()
+                if step in row_of:                        # the step call has synchronised: the vector is final
+                    ev = torch.cuda.Event()
+                    if lift_on_device:
+                        slot = n_stored % ring
+                        if ring_ev[slot] is not None:
+                            ring_ev[slot].synchronize()   # its upload (4 rows back) is long through
+                        bc_np[slot, :] = bc_jobs[n_stored].result()
+                        rt.call("crbe_solver_store_lifted_async", self._solver, ptr(ubuf[cur]), bc_pin[slot].data_ptr(),
+                                sol_t[row_of[step]].data_ptr(), copy_stream.cuda_stream)
                         ev.record(copy_stream)
+                        ring_ev[slot] = ev
+                    else:
+                        with torch.cuda.stream(copy_stream):
+                            sol_t[row_of[step]].copy_(ubuf[cur][:n], non_blocking=True)
+                            ev.record(copy_stream)
                     copied[cur] = ev
+                    n_stored += 1
             copy_stream.synchronize()
             rt.synchronize()
-            if nb:
+            if nb and not lift_on_device:
                 rows_idx = np.array([row_of[st] for st in stored], dtype=np.int64)
                 bc_all = np.stack([j.result() for j in bc_jobs]) if stored else np.zeros((0, nb))
                 self.solutions[rows_idx[:, None], bnd[None, :]] += bc_all   # u_prev + set_boundary_fn(t), crbe.py:429

@@ -51,6 +51,17 @@ enum { D_STATUS = 0, D_ITERS = 1 };
 struct P2PHeader;
 struct CommArgs;
 
+// One instantiated step: everything crbe_solver_step enqueues before its first synchronisation, for one combination of
+// buffers and batch length.  A key is captured the second time it is asked for (one-off calls are launched directly).
+struct StepGraph {
+    const double *u_cur, *u_next, *source;
+    double dt;
+    int mode, target, speculate;
+    cudaGraphExec_t exec;
+    int launches;
+    uint64_t stamp;
+};
+
 struct crbe_solver {
     crbe_ctx* ctx = nullptr;
     int64_t n = 0, ld = 0, nnz = 0, nb = 0;
@@ -73,7 +84,7 @@ struct crbe_solver {
     double* sums_h = nullptr;  // pinned: CRBE_NSUMS doubles followed by 2 ints
     double rtol = 1e-13;
     int maxit = 10000;
-    unsigned flags = CRBE_SOLVER_TMA | CRBE_SOLVER_VERIFY_AUTO | CRBE_SOLVER_EXTRAPOLATE;
+    unsigned flags = CRBE_SOLVER_TMA | CRBE_SOLVER_VERIFY_AUTO | CRBE_SOLVER_EXTRAPOLATE | CRBE_SOLVER_GRAPH;
     int last_iters = 8;
     bool system_loaded = false;
     // persistent grids: SMs x resident CTAs of each kernel (a grid-stride sweep must be one full wave)
@@ -101,6 +112,11 @@ struct crbe_solver {
     double* saved_p0 = nullptr;                // the stand-alone p, s allocations replaced by window storage
     double* saved_s = nullptr;
     crbe_profile* prof = nullptr;
+    // CUDA graphs of whole steps (CRBE_SOLVER_GRAPH): head kernels + first batch of iterations + state download
+    std::vector<StepGraph> graphs;
+    cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the context's may be the legacy default stream)
+    uint64_t graph_clock = 0;
+    double* bc_stage = nullptr;          // crbe_solver_store_lifted_async: boundary values on the device
 };
 
 // ---------------------------------------------------------------- helpers
@@ -357,6 +373,12 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate_pp(int64_t n, const 
 
 __global__ void k_lift(const double* __restrict__ bc, const int* __restrict__ bnd, int64_t nb, double* __restrict__ out) {
     ROW_LOOP(k, nb) out[bnd[k]] += bc[k];
+}
+
+// the lifted boundary entries of a row that lives elsewhere (page-locked host memory seen through its device mapping)
+__global__ void k_lift_to(const double* __restrict__ u, const double* __restrict__ bc, const int* __restrict__ bnd, int64_t nb,
+                          double* __restrict__ out) {
+    ROW_LOOP(k, nb) out[bnd[k]] = __dadd_rn(u[bnd[k]], bc[k]);
 }
 
 // ---------------------------------------------------------------- BiCGStab kernels
@@ -726,8 +748,17 @@ static int tile_grid(crbe_ctx* ctx, Kern kernel, int smem_bytes, int64_t ntiles,
     return CRBE_OK;
 }
 
+static void drop_step_graphs(crbe_solver* s) {
+    for (StepGraph& g : s->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    s->graphs.clear();
+}
+
 static int solver_release(crbe_solver* s) {
     if (!s) return CRBE_OK;
+    drop_step_graphs(s);
+    if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
+    cudaFree(s->bc_stage);
     if (s->window) {               // p and s live in the window: free the stand-alone allocations they replaced
         s->p[0] = s->saved_p0;
         s->s = s->saved_s;
@@ -1009,6 +1040,7 @@ extern "C" int crbe_solver_set_options(crbe_solver* s, double rtol, int32_t max_
     s->rtol = rtol;
     s->maxit = max_iterations;
     s->flags = flags;
+    drop_step_graphs(s);   // tolerances and kernel variants are baked into the captured launches
     return CRBE_OK;
 }
 
@@ -1016,6 +1048,7 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
     CRBE_REQUIRE(s && s_val_d && m_val_d, "null argument");
     crbe_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
+    drop_step_graphs(s);   // rhs_val / tmp may be (de)allocated below
     int* err = s->dstate + 2;
     CRBE_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
     k_build_ell<<<crbe_grid_for(ctx, s->n), CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->indptr, s->indices, s_val_d, m_val_d, s->is_bnd,
@@ -1173,11 +1206,16 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
     return CRBE_OK;
 }
 
-static int fetch_state(crbe_solver* s) {
+static int enqueue_fetch(crbe_solver* s) {
     cudaStream_t st = s->ctx->stream;
     CRBE_CUDA(cudaMemcpyAsync(s->sums_h, s->sums, sizeof(double) * CRBE_NSUMS, cudaMemcpyDeviceToHost, st));
     CRBE_CUDA(cudaMemcpyAsync(s->sums_h + CRBE_NSUMS, s->dstate, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
-    CRBE_CUDA(cudaStreamSynchronize(st));
+    return CRBE_OK;
+}
+
+static int fetch_state(crbe_solver* s) {
+    CRBE_CHECK(enqueue_fetch(s));
+    CRBE_CUDA(cudaStreamSynchronize(s->ctx->stream));
     return CRBE_OK;
 }
 
@@ -1200,8 +1238,35 @@ static int launch_residual(crbe_solver* s, double* x, int guard, int* launches) 
     return reduce_dots(s, S_RRTRUE, 1, S_RRTRUE, -1, -1, -1, launches);
 }
 
+// Verification of the true residual: always (CRBE_SOLVER_VERIFY) or only for long recurrences
+// (CRBE_SOLVER_VERIFY_AUTO): the gap between recurrence and true residual grows like k * eps * ||A|| ||x||, so a
+// solve of <= VERIFY_AUTO_ITERS iterations cannot be off by anything near rtol; longer solves and restarts are checked.
+constexpr int VERIFY_AUTO_ITERS = 12;
+
+static inline bool verify_wanted(const crbe_solver* s, int iterations, int restarts) {
+    if (s->flags & CRBE_SOLVER_VERIFY) return true;
+    return (s->flags & CRBE_SOLVER_VERIFY_AUTO) != 0 && (iterations > VERIFY_AUTO_ITERS || restarts > 0);
+}
+
+// first batch of a solve: one iteration more than the previous solve needed
+static inline int first_batch_target(const crbe_solver* s, int total_iters) {
+    int target = s->last_iters + 1;
+    if (target > s->maxit - total_iters) target = s->maxit - total_iters;
+    return target < 1 ? 1 : target;
+}
+
+// iterations [k0, target) + the speculative verification + the download of the state, no synchronisation
+static int enqueue_batch(crbe_solver* s, double* x, int k0, int target, bool speculate, int* launches) {
+    for (int k = k0; k < target; ++k) CRBE_CHECK(launch_iteration(s, k, x, launches));
+    // the verification rides behind the batch (it returns at once unless the batch converged): one sync per step
+    if (speculate) CRBE_CHECK(launch_residual(s, x, 1, launches));
+    CRBE_KERNEL_CHECK();
+    return enqueue_fetch(s);
+}
+
 // Iterate from the state left by k_init until converged.  b, r, r^ and the sums are on the device.
-static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* launches) {
+// first_enqueued: the first batch (first_batch_target iterations, verification as verify_wanted says) is already in flight.
+static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* launches, bool first_enqueued = false) {
     crbe_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     const double rtol2 = s->rtol * s->rtol;
@@ -1209,26 +1274,17 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
     const int* dst_h = (const int*)(s->sums_h + CRBE_NSUMS);
     int total_iters = 0, restarts = 0, status = 0;
     double true_rr = -1.0;
-    // Verification of the true residual: always (CRBE_SOLVER_VERIFY) or only for long recurrences
-    // (CRBE_SOLVER_VERIFY_AUTO): the gap between recurrence and true residual grows like k * eps * ||A|| ||x||, so a
-    // solve of <= VERIFY_AUTO_ITERS iterations cannot be off by anything near rtol; longer solves and restarts are checked.
-    constexpr int VERIFY_AUTO_ITERS = 12;
-    const bool verify_always = (s->flags & CRBE_SOLVER_VERIFY) != 0;
-    const bool verify_auto = !verify_always && (s->flags & CRBE_SOLVER_VERIFY_AUTO) != 0;
     for (;;) {
         int k = 0;
-        int target = s->last_iters + 1;
-        if (target > s->maxit - total_iters) target = s->maxit - total_iters;
-        if (target < 1) target = 1;
+        int target = first_batch_target(s, total_iters);
         bool done = false, speculated_last = false;
         for (;;) {
-            for (; k < target; ++k) CRBE_CHECK(launch_iteration(s, k, x, launches));
-            // the verification rides behind the batch (it returns at once unless the batch converged): one sync per step
-            const bool speculate = verify_always || (verify_auto && (total_iters + target > VERIFY_AUTO_ITERS || restarts > 0));
-            if (speculate) CRBE_CHECK(launch_residual(s, x, 1, launches));
+            const bool speculate = verify_wanted(s, total_iters + target, restarts);
+            if (!first_enqueued) CRBE_CHECK(enqueue_batch(s, x, k, target, speculate, launches));
+            first_enqueued = false;
+            k = target;
             speculated_last = speculate;
-            CRBE_KERNEL_CHECK();
-            CRBE_CHECK(fetch_state(s));
+            CRBE_CUDA(cudaStreamSynchronize(st));
             const double rr = s->sums_h[S_RR], bb = s->sums_h[S_BB];
             status = dst_h[D_STATUS];
             done = status != 0 || !(rr > rtol2 * bb) || !isfinite(rr);
@@ -1252,8 +1308,7 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
             break;
         }
         if (status == 0) {
-            const bool need = verify_always || (verify_auto && (total_iters > VERIFY_AUTO_ITERS || restarts > 0));
-            if (!need) break;
+            if (!verify_wanted(s, total_iters, restarts)) break;
             if (!speculated_last) {          // converged in a batch that did not carry the verification kernel
                 CRBE_CHECK(launch_residual(s, x, 1, launches));
                 CRBE_CHECK(fetch_state(s));
@@ -1301,55 +1356,49 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
     return CRBE_OK;
 }
 
-// One time step.  u_cur holds u^n.  In place (u_next == u_cur): u^n is saved in the solver's history vector and the
-// iterate is built in u_cur.  Ping-pong (u_next != u_cur, both padded to crbe_solver_vector_length): the iterate is
-// built in u_next and u_cur stays intact during the NEXT step as well, so the host can download it while the GPU is
-// already solving -- no staging copy; u_next is expected to hold u^(n-1) when the buffers simply alternate.
-static int step_impl(crbe_solver* s, double* u_cur, double* u_next, const double* source_d, double dt, crbe_solve_info* info_h) {
-    CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
+// How a step prepares its right-hand side and initial guess
+enum StepMode { SM_PP_EXTRAP = 0, SM_PP_COPY, SM_IP_EXTRAP, SM_IP_COPY, SM_CN };
+
+// Everything a step enqueues before the iterations: Dirichlet rows of u^n, history / initial guess, b, r, r^, p and the first norms.
+static int enqueue_step_head(crbe_solver* s, double* u_cur, double* u_next, const double* source_d, double dt, int mode, int* launches) {
     crbe_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    const bool pp = u_next != u_cur;
-    CRBE_REQUIRE(!(pp && s->world > 1), "ping-pong stepping is for the single-GPU solver");
-    memset(info_h, 0, sizeof(*info_h));
-    int launches = 0;
-    if (s->rhs_val) {   // Crank-Nicolson: (M - c(K+A)) u_prev with u_prev as given, boundary values included (crbe.py:386)
-        CRBE_CHECK(halo_exchange(s, u_cur, &launches));
+    if (mode == SM_CN) {   // Crank-Nicolson: (M - c(K+A)) u_prev with u_prev as given, boundary values included (crbe.py:386)
+        CRBE_CHECK(halo_exchange(s, u_cur, launches));
         if (s->p2p) k_p2p_wait<<<1, 32, 0, st>>>(0, s->d_comm);
         k_spmv_csr<<<s->g_spmv, CRBE_BLOCK, 0, st>>>(s->n, s->indptr, s->indices, s->rhs_val, u_cur, s->tmp);
-        ++launches;
+        *launches += 1;
     }
     if (s->nb > 0) {    // the solution of the Dirichlet system is exactly 0 on its identity rows: start there
         k_zero_rows<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, st>>>(u_cur, s->bnd, s->nb);
-        ++launches;
+        *launches += 1;
     }
     // Right-hand side from u^n; with one step of history the initial guess is extrapolated linearly in time
     // (2 u^n - u^(n-1)): the first residual drops by 2-3 orders of magnitude, which saves about one iteration per step.
-    const bool extrap = !s->rhs_val && (s->flags & CRBE_SOLVER_EXTRAPOLATE);
     double* x = u_next;
     const double* xb = u_cur;
-    if (pp) {
-        if (extrap && s->hist_valid && s->pp_prev == u_next) {
+    switch (mode) {
+        case SM_PP_EXTRAP:
             PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate_pp<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, u_cur, u_next)));
-            ++launches;
-        } else {
+            *launches += 1;
+            break;
+        case SM_PP_COPY:
             CRBE_CUDA(cudaMemcpyAsync(u_next, u_cur, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
-        }
-        s->pp_prev = u_cur;
-        s->hist_valid = true;
-    } else if (!s->rhs_val) {
-        if (extrap && s->hist_valid && s->pp_prev == nullptr) {
+            break;
+        case SM_IP_EXTRAP:
             PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, u_cur, s->hist)));
-            ++launches;
-        } else {
+            *launches += 1;
+            xb = s->hist;
+            break;
+        case SM_IP_COPY:
             CRBE_CUDA(cudaMemcpyAsync(s->hist, u_cur, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
-        }
-        s->pp_prev = nullptr;
-        s->hist_valid = true;
-        xb = s->hist;
+            xb = s->hist;
+            break;
+        default:
+            break;
     }
-    CRBE_CHECK(halo_exchange(s, x, &launches));
-    if (s->rhs_val)
+    CRBE_CHECK(halo_exchange(s, x, launches));
+    if (mode == SM_CN)
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->tmp, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
@@ -1361,10 +1410,111 @@ static int step_impl(crbe_solver* s, double* u_cur, double* u_next, const double
         PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, xb, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
-    ++launches;
+    *launches += 1;
     CRBE_KERNEL_CHECK();
-    CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, -1, &launches));
-    int rc = run_bicgstab(s, x, info_h, &launches);
+    return reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, -1, launches);
+}
+
+// ---- CUDA graphs of whole steps ---------------------------------------------------------------------------
+// A step is ~25 short launches; their descriptors are fetched by the GPU front end from host memory, which costs
+// several microseconds per launch while a solution row is travelling over the same PCIe link (measured: +6 % per
+// step during BESCRFEM.solve(history="all")).  An instantiated graph keeps the whole step on the device side.
+constexpr size_t STEP_GRAPH_SLOTS = 12;
+
+static StepGraph* find_step_graph(crbe_solver* s, const StepGraph& key) {
+    for (StepGraph& g : s->graphs)
+        if (g.u_cur == key.u_cur && g.u_next == key.u_next && g.source == key.source && g.dt == key.dt && g.mode == key.mode &&
+            g.target == key.target && g.speculate == key.speculate)
+            return &g;
+    return nullptr;
+}
+
+static int capture_step(crbe_solver* s, double* u_cur, double* u_next, const double* source_d, double dt, StepGraph* g) {
+    crbe_ctx* ctx = s->ctx;
+    if (!s->cap_stream) CRBE_CUDA(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+    cudaStream_t launch_stream = ctx->stream;
+    ctx->stream = s->cap_stream;
+    int launches = 0;
+    int rc = CRBE_OK;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        rc = enqueue_step_head(s, u_cur, u_next, source_d, dt, g->mode, &launches);
+        if (rc == CRBE_OK) rc = enqueue_batch(s, u_next, 0, g->target, g->speculate != 0, &launches);
+        const cudaError_t e2 = cudaStreamEndCapture(s->cap_stream, &graph);   // always close the capture
+        if (rc == CRBE_OK && e2 != cudaSuccess) e = e2;
+    }
+    ctx->stream = launch_stream;
+    if (rc != CRBE_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        crbe_set_error("CUDA graph capture of a step failed: %s", cudaGetErrorString(e));
+        return CRBE_ERR_CUDA;
+    }
+    e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        g->exec = nullptr;
+        crbe_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        return CRBE_ERR_CUDA;
+    }
+    g->launches = launches;
+    return CRBE_OK;
+}
+
+// One time step.  u_cur holds u^n.  In place (u_next == u_cur): u^n is saved in the solver's history vector and the
+// iterate is built in u_cur.  Ping-pong (u_next != u_cur, both padded to crbe_solver_vector_length): the iterate is
+// built in u_next and u_cur stays intact during the NEXT step as well, so the host can download it while the GPU is
+// already solving -- no staging copy; u_next is expected to hold u^(n-1) when the buffers simply alternate.
+static int step_impl(crbe_solver* s, double* u_cur, double* u_next, const double* source_d, double dt, crbe_solve_info* info_h) {
+    CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
+    crbe_ctx* ctx = s->ctx;
+    const bool pp = u_next != u_cur;
+    CRBE_REQUIRE(!(pp && s->world > 1), "ping-pong stepping is for the single-GPU solver");
+    memset(info_h, 0, sizeof(*info_h));
+    int launches = 0;
+    const bool extrap = !s->rhs_val && (s->flags & CRBE_SOLVER_EXTRAPOLATE);
+    int mode = SM_CN;
+    if (pp) {
+        mode = (extrap && s->hist_valid && s->pp_prev == u_next) ? SM_PP_EXTRAP : SM_PP_COPY;
+        s->pp_prev = u_cur;
+        s->hist_valid = true;
+    } else if (!s->rhs_val) {
+        mode = (extrap && s->hist_valid && s->pp_prev == nullptr) ? SM_IP_EXTRAP : SM_IP_COPY;
+        s->pp_prev = nullptr;
+        s->hist_valid = true;
+    }
+    // Steady state on one GPU: replay the step as one graph (captured the second time the same step shape is asked for)
+    bool in_flight = false;
+    const bool graphs_on = (s->flags & CRBE_SOLVER_GRAPH) && s->world == 1 && !(s->prof && s->prof->on);
+    if (graphs_on) {
+        StepGraph key = {u_cur, u_next, source_d, dt, mode, first_batch_target(s, 0), 0, nullptr, 0, 0};
+        key.speculate = verify_wanted(s, key.target, 0) ? 1 : 0;
+        StepGraph* g = find_step_graph(s, key);
+        if (!g) {                       // first sighting: remember the shape, launch directly
+            if (s->graphs.size() >= STEP_GRAPH_SLOTS) {
+                size_t oldest = 0;
+                for (size_t i = 1; i < s->graphs.size(); ++i)
+                    if (s->graphs[i].stamp < s->graphs[oldest].stamp) oldest = i;
+                if (s->graphs[oldest].exec) cudaGraphExecDestroy(s->graphs[oldest].exec);
+                s->graphs.erase(s->graphs.begin() + oldest);
+            }
+            key.stamp = ++s->graph_clock;
+            s->graphs.push_back(key);
+        } else {
+            g->stamp = ++s->graph_clock;
+            if (!g->exec) CRBE_CHECK(capture_step(s, u_cur, u_next, source_d, dt, g));
+            CRBE_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+            launches += g->launches;
+            in_flight = true;
+        }
+    }
+    if (!in_flight) CRBE_CHECK(enqueue_step_head(s, u_cur, u_next, source_d, dt, mode, &launches));
+    int rc = run_bicgstab(s, u_next, info_h, &launches, in_flight);
     info_h->launches = launches;
     ctx->launches += launches;
     return rc;
@@ -1430,6 +1580,32 @@ extern "C" int crbe_solver_lift(crbe_solver* s, const double* u_d, const double*
     if (out_d != u_d) CRBE_CUDA(cudaMemcpyAsync(out_d, u_d, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, ctx->stream));
     if (s->nb > 0) {
         k_lift<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, ctx->stream>>>(bc_values_d, s->bnd, s->nb, out_d);
+        CRBE_KERNEL_CHECK();
+        ctx->launches += 1;
+    }
+    return CRBE_OK;
+}
+
+// solutions[step] = u_prev + lift (crbe.py:429) straight into the host's history array, asynchronously on `stream` (the
+// caller's copy stream, so the transfer overlaps the next step): the N values go down with one copy-engine transfer,
+// the Nb boundary values go up and the device stores the lifted boundary entries through the mapping of row_h.
+extern "C" int crbe_solver_store_lifted_async(crbe_solver* s, const double* u_d, const double* bc_values_h, double* row_h, void* stream) {
+    CRBE_REQUIRE(s && u_d && row_h && (s->nb == 0 || bc_values_h), "null argument");
+    crbe_ctx* ctx = s->ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* row_dev = nullptr;
+    if (s->nb > 0) {
+        if (cudaHostGetDevicePointer((void**)&row_dev, row_h, 0) != cudaSuccess || !row_dev) {
+            cudaGetLastError();
+            crbe_set_error("crbe_solver_store_lifted_async: row_h is not page-locked, mapped host memory");
+            return CRBE_ERR_ARG;
+        }
+        if (!s->bc_stage) CRBE_CUDA(cudaMalloc(&s->bc_stage, sizeof(double) * s->nb));
+    }
+    CRBE_CUDA(cudaMemcpyAsync(row_h, u_d, sizeof(double) * s->n, cudaMemcpyDeviceToHost, st));
+    if (s->nb > 0) {
+        CRBE_CUDA(cudaMemcpyAsync(s->bc_stage, bc_values_h, sizeof(double) * s->nb, cudaMemcpyHostToDevice, st));
+        k_lift_to<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, st>>>(u_d, s->bc_stage, s->bnd, s->nb, row_dev);
         CRBE_KERNEL_CHECK();
         ctx->launches += 1;
     }

@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--regime", default="P-ref", choices=["P-ref", "P-T10", "P-stiff"])
     ap.add_argument("--no-extrapolate", action="store_true", help="start every solve from u^n instead of 2u^n - u^(n-1)")
     ap.add_argument("--verify-always", action="store_true", help="recompute the true residual after every solve (default: auto)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")
     ap.add_argument("--classic", action="store_true", help="register-load kernels instead of the bulk-copy (TMA) pipeline")
     ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--cpu-steps", type=int, default=2)
@@ -327,7 +328,7 @@ def main():
     mesh = wl.mesh()
     dom, prob = wl.domain(), wl.problem()
     md = crbe.MeshData(mesh, dom, wl.nt)
-    solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", tma=not args.classic, extrapolate=not args.no_extrapolate, verify=True if args.verify_always else "auto", progress=False)
+    solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", tma=not args.classic, extrapolate=not args.no_extrapolate, verify=True if args.verify_always else "auto", graph=not args.no_graph, progress=False)
     rt = Runtime.get(device)
     solver.set_initial_condition()
     solver.build_global_matrices()
@@ -405,6 +406,7 @@ def main():
                    "solver": "Jacobi-BiCGStab, merged-reduction 4-kernel iteration" + (", register loads" if args.classic else ", bulk-copy pipeline")
                              + ("" if args.no_extrapolate else ", extrapolated initial guess"),
                    "verify": "always" if args.verify_always else "auto (true residual recomputed after solves of > 12 iterations or a restart)",
+                   "launch": "kernel by kernel" if args.no_graph else "one CUDA graph per step (head + first batch of iterations + state download)",
                    "iters_per_step": it_mean, "l2": "inputs larger than L2 (1.9 GB touched per iteration vs 126 MB L2)",
                    "setup_s": t_setup},
         "dof_updates_per_s": steps_per_s * n,
@@ -425,7 +427,7 @@ def main():
         E = max(2, min(args.e2e_steps, K))
         wl_e = workloads.unit_square(args.n, steps=E, regime=args.regime)
         md_e = crbe.MeshData(mesh, wl_e.domain(), wl_e.nt)
-        s_e = crbe.BESCRFEM(wl_e.domain(), prob, md_e, crbe.ElementCR(), 1, history="all", tma=not args.classic, extrapolate=not args.no_extrapolate, verify=True if args.verify_always else "auto", progress=False)
+        s_e = crbe.BESCRFEM(wl_e.domain(), prob, md_e, crbe.ElementCR(), 1, history="all", tma=not args.classic, extrapolate=not args.no_extrapolate, verify=True if args.verify_always else "auto", graph=not args.no_graph, progress=False)
         import contextlib
         import io
         with contextlib.redirect_stdout(io.StringIO()):

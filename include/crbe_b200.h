@@ -145,7 +145,8 @@ typedef struct crbe_solve_info {
 #define CRBE_SOLVER_VERIFY 2u         /* recompute the true residual after every convergence   */
 #define CRBE_SOLVER_VERIFY_AUTO 32u   /* ... only after solves of more than 12 iterations or a restart (the gap between
                                          recurrence and true residual grows with the length of the recurrence) */
-#define CRBE_SOLVER_GRAPH 4u          /* reserved                                                */
+#define CRBE_SOLVER_GRAPH 4u          /* single GPU: replay a step (head kernels, first batch of iterations, state download)
+                                         as one CUDA graph once the same step shape has been seen twice            */
 #define CRBE_SOLVER_EXTRAPOLATE 16u   /* crbe_solver_step: start from 2 u^n - u^(n-1) (linear extrapolation in
                                          time) instead of u^n once one step of history exists        */
 #define CRBE_SOLVER_TMA 8u            /* SpMV-type kernels fed by bulk async copies (cp.async.bulk
@@ -179,7 +180,13 @@ int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d, crbe_solve
 int crbe_solver_rhs(crbe_solver* s, const double* u_d, const double* source_d, double dt, double* b_d);
 /* out = u with out[bnd[k]] += bc[k]   (the lift of crbe.py:429) */
 int crbe_solver_lift(crbe_solver* s, const double* u_d, const double* bc_values_d, double* out_d);
-int crbe_solver_mass_diagonal(crbe_solver* s, const double** mdiag_d_out);   /* diag(M), the weights of crbe_moments */
+/* solutions[step, :] = u_prev + lift (crbe.py:429) written straight into the host's history array, asynchronously on
+ * `stream` (a cudaStream_t of the caller, normally NOT the context's stream, so that the transfer overlaps the next
+ * step): the N values of u_d go down with one copy-engine transfer, the Nb boundary values bc_values_h go up, and the
+ * device stores the lifted boundary entries through the device mapping of row_h.  row_h: page-locked host memory
+ * (cudaHostAlloc / cudaHostRegister), N doubles; bc_values_h: page-locked, must stay valid until the stream has
+ * passed this call.  Calls on one stream are ordered; do not issue it on two streams at once. */
+int crbe_solver_store_lifted_async(crbe_solver* s, const double* u_d, const double* bc_values_h, double* row_h, void* stream);
 int crbe_solver_mass_diagonal(crbe_solver* s, const double** mdiag_d_out);   /* diag(M), the weights of crbe_moments */
 int crbe_solver_destroy(crbe_solver* s);
 

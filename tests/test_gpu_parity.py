@@ -280,6 +280,60 @@ def test_verification_policies_agree(verify):
     assert np.array_equal(sol, ref)
 
 
+@pytest.mark.parametrize("name", ["struct_n32_o1", "struct_n16_o2", "source_delaunay80"])
+def test_graph_replay_is_bit_identical(name):
+    """Steps replayed as CUDA graphs (default) against the same steps launched kernel by kernel."""
+    g = load_golden(name)
+    crbe, dom, md = _product(g)
+    prob = golden_problem(name, g)
+    a = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), graph=True, progress=False)
+    sa = a.solve()
+    b = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), graph=False, progress=False)
+    sb = b.solve()
+    assert np.array_equal(sa, sb)
+    assert [i[0] for i in a.step_info] == [i[0] for i in b.step_info]
+    assert rel_err(sa[-1], g["final"]) <= SOLUTION_RTOL
+    # in-place stepping through the C ABI, graph on: same bits as the ping-pong loop of solve()
+    import torch
+    from airpollution_b200 import _lib
+    from airpollution_b200.runtime import ptr
+    if int(g["order"]) == 1 and "source" not in name:
+        c = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, graph=True, progress=False)
+        c.set_initial_condition()
+        c.build_global_matrices()
+        rt = c._rt
+        u = rt.upload(np.asarray(c.u_prev, dtype=np.float64))
+        info = _lib.SolveInfo()
+        for _ in range(1, md.nt):
+            rt.call("crbe_solver_step", c._solver, ptr(u), None, float(c.dt), C.byref(info))
+        assert np.array_equal(u.cpu().numpy(), a.u_prev)
+
+
+def test_store_lifted_async_rejects_pageable_rows(rt):
+    import torch
+    from airpollution_b200 import crbe
+    from airpollution_b200.meshgen import structured_mesh
+    from airpollution_b200.runtime import ptr
+    dom = crbe.Domain(1, 1, T=0.1)
+    md = crbe.MeshData(structured_mesh(8, 8), dom, 3)
+    s = crbe.BESCRFEM(dom, crbe.Problem(), md, crbe.ElementCR(), progress=False)
+    s.build_global_matrices()
+    n, nb = md.number_of_segments, len(md.boundary_segments)
+    u = rt.zeros((n,), torch.float64)
+    row = np.zeros(n)
+    bc = torch.ones(nb, dtype=torch.float64, pin_memory=True)
+    with pytest.raises(RuntimeError, match="page-locked"):
+        rt.call("crbe_solver_store_lifted_async", s._solver, ptr(u), bc.data_ptr(), row.ctypes.data, 0)
+    # and the page-locked case: u + lift, boundary entries only
+    rowp = torch.full((n,), -1.0, dtype=torch.float64, pin_memory=True)
+    u[:] = torch.arange(n, dtype=torch.float64, device=u.device)
+    rt.call("crbe_solver_store_lifted_async", s._solver, ptr(u), bc.data_ptr(), rowp.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = np.arange(n, dtype=np.float64)
+    want[md.boundary_segments] += 1.0
+    assert np.array_equal(rowp.numpy(), want)
+
+
 # ------------------------------------------------------------------ a-7 .. a-12: the full path
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 @pytest.mark.parametrize("tma,extrapolate", [(True, True), (True, False), (False, True)],
