@@ -1357,13 +1357,14 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
 }
 
 // How a step prepares its right-hand side and initial guess
-enum StepMode { SM_PP_EXTRAP = 0, SM_PP_COPY, SM_IP_EXTRAP, SM_IP_COPY, SM_CN };
+enum StepMode { SM_PP_EXTRAP = 0, SM_PP_COPY, SM_IP_EXTRAP, SM_IP_COPY, SM_IP_PLAIN };
 
 // Everything a step enqueues before the iterations: Dirichlet rows of u^n, history / initial guess, b, r, r^, p and the first norms.
 static int enqueue_step_head(crbe_solver* s, double* u_cur, double* u_next, const double* source_d, double dt, int mode, int* launches) {
     crbe_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    if (mode == SM_CN) {   // Crank-Nicolson: (M - c(K+A)) u_prev with u_prev as given, boundary values included (crbe.py:386)
+    const bool cn = s->rhs_val != nullptr;
+    if (cn) {   // Crank-Nicolson: (M - c(K+A)) u_prev with u_prev as given, boundary values included (crbe.py:386)
         CRBE_CHECK(halo_exchange(s, u_cur, launches));
         if (s->p2p) k_p2p_wait<<<1, 32, 0, st>>>(0, s->d_comm);
         k_spmv_csr<<<s->g_spmv, CRBE_BLOCK, 0, st>>>(s->n, s->indptr, s->indices, s->rhs_val, u_cur, s->tmp);
@@ -1398,7 +1399,7 @@ static int enqueue_step_head(crbe_solver* s, double* u_cur, double* u_next, cons
             break;
     }
     CRBE_CHECK(halo_exchange(s, x, launches));
-    if (mode == SM_CN)
+    if (cn)
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->tmp, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
@@ -1478,7 +1479,7 @@ static int step_impl(crbe_solver* s, double* u_cur, double* u_next, const double
     memset(info_h, 0, sizeof(*info_h));
     int launches = 0;
     const bool extrap = !s->rhs_val && (s->flags & CRBE_SOLVER_EXTRAPOLATE);
-    int mode = SM_CN;
+    int mode = SM_IP_PLAIN;   // Crank-Nicolson in place: the right-hand side comes from the SpMV, the guess is u^n itself
     if (pp) {
         mode = (extrap && s->hist_valid && s->pp_prev == u_next) ? SM_PP_EXTRAP : SM_PP_COPY;
         s->pp_prev = u_cur;
