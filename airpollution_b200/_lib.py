@@ -34,6 +34,7 @@ SOLVER_GRAPH = 4
 SOLVER_TMA = 8
 SOLVER_EXTRAPOLATE = 16
 SOLVER_VERIFY_AUTO = 32
+SOLVER_INDEX32 = 64
 
 # name -> (argtypes)   every function returns int unless listed in _RESTYPE
 _SIGNATURES = {
@@ -69,6 +70,7 @@ _SIGNATURES = {
     "crbe_solver_rhs": [vp, vp, vp, C.c_double, vp],
     "crbe_solver_lift": [vp, vp, vp, vp],
     "crbe_solver_store_lifted_async": [vp, vp, vp, vp, vp],
+    "crbe_solver_index_bits": [vp, C.POINTER(C.c_int32)],
     "crbe_solver_destroy": [vp],
     "crbe_solver_profile": [vp, C.c_int],
     "crbe_solver_profile_read": [vp, c_f64p, c_i64p],

@@ -204,6 +204,8 @@ class BESCRFEM:
                         BiCGStab iteration less per step).
     ``tma``             feed the SpMV-type kernels through the bulk-copy/mbarrier shared-memory
                         pipeline (default) instead of per-thread register loads.
+    ``index16``         stream 16-bit ``column - row`` offsets instead of 32-bit columns when every offset of the
+                        matrix fits (default; same arithmetic, 8 bytes per row and SpMV less).
     ``graph``           replay each step as one CUDA graph once its shape repeats (default; the launches of a step
                         then no longer travel over PCIe one by one while a solution row is being downloaded).
     ``progress``        tqdm bar like the reference (default: only for nt*N < 2e7).
@@ -214,7 +216,7 @@ class BESCRFEM:
 
     def __init__(self, domain, problem, mesh_data, element, time_scheme_order=1, *, rtol=1e-13,
                  max_iterations=10000, history="all", tma=True, verify="auto", extrapolate=True,
-                 graph=True, progress=None, velocity_field=None):
+                 graph=True, index16=True, progress=None, velocity_field=None):
         self.domain = domain
         self.problem = problem
         self.mesh_data = mesh_data
@@ -229,6 +231,7 @@ class BESCRFEM:
         self.extrapolate = extrapolate
         self.verify = verify
         self.graph = graph
+        self.index16 = index16
         self.progress = progress
         self.velocity_field = velocity_field
         self._rt = mesh_data._rt
@@ -363,9 +366,16 @@ class BESCRFEM:
             self._solver = h
         flags = ((_lib.SOLVER_VERIFY_AUTO if self.verify == "auto" else (_lib.SOLVER_VERIFY if self.verify else 0))
                  | (_lib.SOLVER_TMA if self.tma else 0) | (_lib.SOLVER_EXTRAPOLATE if self.extrapolate else 0)
-                 | (_lib.SOLVER_GRAPH if self.graph else 0))
+                 | (_lib.SOLVER_GRAPH if self.graph else 0) | (0 if self.index16 else _lib.SOLVER_INDEX32))
         rt.call("crbe_solver_set_options", self._solver, float(self.rtol), int(self.max_iterations), flags)
         rt.call("crbe_solver_set_system", self._solver, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
+
+    @property
+    def index_bits(self):
+        """16 or 32: width of the column indices the SpMV kernels stream (after build_global_matrices)."""
+        bits = C.c_int32()
+        self._rt.call("crbe_solver_index_bits", self._solver, C.byref(bits))
+        return bits.value
 
     def _csr(self, key):
         import scipy.sparse as sp

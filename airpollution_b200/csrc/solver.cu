@@ -70,6 +70,8 @@ struct crbe_solver {
     int32_t* bnd = nullptr;            // Dirichlet row ids (copy)
     unsigned char* is_bnd = nullptr;
     int32_t* ell_col = nullptr;
+    int16_t* ell_col16 = nullptr;      // column - row, same tile-major layout (bulk-copy kernels, when every offset fits)
+    bool idx16 = false;
     double* ell_val = nullptr;
     double *mdiag = nullptr, *mscale = nullptr, *dscale = nullptr;
     double* rhs_val = nullptr;         // CN: values of M - c(K+A) on the structural pattern
@@ -90,6 +92,7 @@ struct crbe_solver {
     // persistent grids: SMs x resident CTAs of each kernel (a grid-stride sweep must be one full wave)
     int g_init = 1, g_pv = 1, g_st = 1, g_xr = 1, g_vec = 1, g_res = 1, g_spmv = 1;
     int gt_pv = 1, gt_st = 1, gt_init = 1, gt_res = 1;   // tile (bulk-copy) kernels
+    int gs_pv = 1, gs_st = 1, gs_init = 1, gs_res = 1;   // ... their 16-bit-offset variants (smaller stages, maybe more CTAs per SM)
     int64_t ntiles = 0;
     // row-block partition (world > 1): this solver holds the rows [0, n) of its rank; gathered vectors carry the
     // halo entries (values owned by other ranks) behind the padded owned part, at [ld, ld + n_halo)
@@ -350,6 +353,20 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_build_ell(int64_t n, int64_t ld,
         mdiag[i] = m;
         mscale[i] = bd ? 0.0 : m / d;
         dscale[i] = bd ? 0.0 : 1.0 / d;
+    }
+}
+
+// 16-bit form of the column indices for the bulk-copy kernels: column - row (0 for padding rows).  *overflow is raised
+// when an offset does not fit; the kernels then keep the 32-bit indices.
+__global__ void __launch_bounds__(CRBE_BLOCK) k_pack_col16(int64_t n, int64_t ld, const int* __restrict__ ecol, int16_t* __restrict__ ecol16,
+                                                           int* __restrict__ overflow) {
+    ROW_LOOP(i, ld) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t off = i < n ? (int64_t)ecol[ell_at(i, k)] - i : 0;
+            if (off < -32767 || off > 32767) *overflow = 1;
+            ecol16[ell_at(i, k)] = (int16_t)off;
+        }
     }
 }
 
@@ -766,6 +783,7 @@ static int solver_release(crbe_solver* s) {
     cudaFree(s->bnd);
     cudaFree(s->is_bnd);
     cudaFree(s->ell_col);
+    cudaFree(s->ell_col16);
     cudaFree(s->ell_val);
     cudaFree(s->mdiag);
     cudaFree(s->mscale);
@@ -854,6 +872,8 @@ static int solver_init(crbe_solver* s, crbe_ctx* ctx, crbe_comm* comm, int64_t n
         CRBE_CUDA(cudaMemsetAsync(*vp, 0, vb, ctx->stream));
     }
     CRBE_CUDA(cudaMemsetAsync(s->ell_col, 0, sizeof(int32_t) * 4 * s->ld, ctx->stream));
+    CRBE_CUDA(cudaMalloc(&s->ell_col16, sizeof(int16_t) * 4 * s->ld));
+    CRBE_CUDA(cudaMemsetAsync(s->ell_col16, 0, sizeof(int16_t) * 4 * s->ld, ctx->stream));
     CRBE_CUDA(cudaMemsetAsync(s->ell_val, 0, sizeof(double) * 4 * s->ld, ctx->stream));
     CRBE_CUDA(cudaMalloc(&s->sums, sizeof(double) * CRBE_NSUMS));
     CRBE_CUDA(cudaMemsetAsync(s->sums, 0, sizeof(double) * CRBE_NSUMS, ctx->stream));
@@ -878,10 +898,14 @@ static int solver_init(crbe_solver* s, crbe_ctx* ctx, crbe_comm* comm, int64_t n
         s->g_spmv = crbe_persistent_grid(ctx, k_spmv_csr, n);
         // bulk-copy kernels: opt in to their dynamic shared memory, then size one resident wave over the tiles
         s->ntiles = s->ld / CRBE_TILE;
-        CRBE_CHECK(tile_grid(ctx, t_pv, TilePipe<2, SPMV_STAGES>::SMEM_BYTES, s->ntiles, &s->gt_pv));
-        CRBE_CHECK(tile_grid(ctx, t_st, TilePipe<2, SPMV_STAGES>::SMEM_BYTES, s->ntiles, &s->gt_st));
-        CRBE_CHECK(tile_grid(ctx, t_init_be, TilePipe<2>::SMEM_BYTES, s->ntiles, &s->gt_init));
-        CRBE_CHECK(tile_grid(ctx, t_residual, TilePipe<1>::SMEM_BYTES, s->ntiles, &s->gt_res));
+        CRBE_CHECK(tile_grid(ctx, t_pv<int>, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_pv));
+        CRBE_CHECK(tile_grid(ctx, t_st<int>, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_st));
+        CRBE_CHECK(tile_grid(ctx, t_init_be<int>, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_init));
+        CRBE_CHECK(tile_grid(ctx, t_residual<int>, TilePipe<1, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_res));
+        CRBE_CHECK(tile_grid(ctx, t_pv<short>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_pv));
+        CRBE_CHECK(tile_grid(ctx, t_st<short>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_st));
+        CRBE_CHECK(tile_grid(ctx, t_init_be<short>, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_init));
+        CRBE_CHECK(tile_grid(ctx, t_residual<short>, TilePipe<1, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_res));
     }
     CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
     return CRBE_OK;
@@ -1030,6 +1054,14 @@ int crbe_solver_get_arrays(crbe_solver* s, crbe_solver_arrays* out) {
     return CRBE_OK;
 }
 
+// 16 or 32: the width of the column indices the bulk-copy kernels stream for the loaded system
+extern "C" int crbe_solver_index_bits(crbe_solver* s, int32_t* bits_h) {
+    CRBE_REQUIRE(s && bits_h, "null argument");
+    CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
+    *bits_h = (s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32) && (s->flags & CRBE_SOLVER_TMA)) ? 16 : 32;
+    return CRBE_OK;
+}
+
 extern "C" int crbe_solver_destroy(crbe_solver* s) {
     if (s) cudaStreamSynchronize(s->ctx->stream);
     return solver_release(s);
@@ -1063,9 +1095,16 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
         cudaFree(s->rhs_val);
         s->rhs_val = nullptr;
     }
-    int err_h = 0;
+    int* overflow = s->dstate + 3;
+    CRBE_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
+    k_pack_col16<<<crbe_grid_for(ctx, s->ld), CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_col, s->ell_col16, overflow);
+    CRBE_KERNEL_CHECK();
+    ctx->launches += 1;
+    int err_h = 0, overflow_h = 0;
     CRBE_CUDA(cudaMemcpyAsync(&err_h, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CRBE_CUDA(cudaMemcpyAsync(&overflow_h, overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
     CRBE_CUDA(cudaStreamSynchronize(st));
+    s->idx16 = overflow_h == 0;
     if (err_h) {
         crbe_set_error("system matrix unusable: %s%s%s", (err_h & 1) ? "row without diagonal; " : "",
                        (err_h & 2) ? "row with more than 5 entries (not a CR pattern); " : "", (err_h & 4) ? "zero diagonal; " : "");
@@ -1181,8 +1220,13 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
     double *p = s->p[0], *v = s->v[0];
     // p is up to date (written by the init / restart kernel at k = 0, by k_xrp afterwards), its halo refreshed
     CRBE_CHECK(halo_exchange(s, p, launches));
-    if (tma)
-        PROF_LAUNCH(PK_PV, k, (t_pv<<<s->gt_pv, CRBE_TILE, TilePipe<2, SPMV_STAGES>::SMEM_BYTES, st>>>(
+    const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
+    if (tma && i16)
+        PROF_LAUNCH(PK_PV, k, (t_pv<short><<<s->gs_pv, CRBE_TILE, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, st>>>(
+                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col16, p, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
+                                  ctx->counter, s->d_comm)));
+    else if (tma)
+        PROF_LAUNCH(PK_PV, k, (t_pv<int><<<s->gt_pv, CRBE_TILE, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, st>>>(
                                   s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, p, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
                                   ctx->counter, s->d_comm)));
     else
@@ -1191,8 +1235,12 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
     CRBE_CHECK(reduce_dots(s, S_RHV, 1, S_RHV, -1, -1, -1, launches));
     PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, s->s, s->sums, s->dstate, s->d_comm)));
     CRBE_CHECK(halo_exchange(s, s->s, launches));
-    if (tma)
-        PROF_LAUNCH(PK_ST, k, (t_st<<<s->gt_st, CRBE_TILE, TilePipe<2, SPMV_STAGES>::SMEM_BYTES, st>>>(
+    if (tma && i16)
+        PROF_LAUNCH(PK_ST, k, (t_st<short><<<s->gs_st, CRBE_TILE, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, st>>>(
+                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col16, s->s, s->t, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
+                                  ctx->counter, s->d_comm)));
+    else if (tma)
+        PROF_LAUNCH(PK_ST, k, (t_st<int><<<s->gt_st, CRBE_TILE, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, st>>>(
                                   s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, s->s, s->t, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
                                   ctx->counter, s->d_comm)));
     else
@@ -1225,8 +1273,13 @@ static int launch_residual(crbe_solver* s, double* x, int guard, int* launches) 
     cudaStream_t st = ctx->stream;
     const double rtol2 = s->rtol * s->rtol;
     CRBE_CHECK(halo_exchange(s, x, launches));
-    if (s->flags & CRBE_SOLVER_TMA)
-        PROF_LAUNCH(PK_RES, guard ? -2 : -1, (t_residual<<<s->gt_res, CRBE_TILE, TilePipe<1>::SMEM_BYTES, st>>>(
+    const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
+    if ((s->flags & CRBE_SOLVER_TMA) && i16)
+        PROF_LAUNCH(PK_RES, guard ? -2 : -1, (t_residual<short><<<s->gs_res, CRBE_TILE, TilePipe<1, TILE_STAGES, short>::SMEM_BYTES, st>>>(
+                                                 s->n, s->ntiles, s->ell_val, s->ell_col16, x, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
+                                                 ctx->partials, ctx->counter, s->d_comm, s->dstate, guard, rtol2)));
+    else if (s->flags & CRBE_SOLVER_TMA)
+        PROF_LAUNCH(PK_RES, guard ? -2 : -1, (t_residual<int><<<s->gt_res, CRBE_TILE, TilePipe<1, TILE_STAGES, int>::SMEM_BYTES, st>>>(
                                                  s->n, s->ntiles, s->ell_val, s->ell_col, x, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                  ctx->partials, ctx->counter, s->d_comm, s->dstate, guard, rtol2)));
     else
@@ -1403,8 +1456,12 @@ static int enqueue_step_head(crbe_solver* s, double* u_cur, double* u_next, cons
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->tmp, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
+    else if ((s->flags & CRBE_SOLVER_TMA) && s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32))
+        PROF_LAUNCH(PK_INIT, -1, (t_init_be<short><<<s->gs_init, CRBE_TILE, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, st>>>(
+                                     s->n, s->ntiles, s->ell_val, s->ell_col16, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
+                                     s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if (s->flags & CRBE_SOLVER_TMA)
-        PROF_LAUNCH(PK_INIT, -1, (t_init_be<<<s->gt_init, CRBE_TILE, TilePipe<2>::SMEM_BYTES, st>>>(
+        PROF_LAUNCH(PK_INIT, -1, (t_init_be<int><<<s->gt_init, CRBE_TILE, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, st>>>(
                                      s->n, s->ntiles, s->ell_val, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
                                      s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else

@@ -58,19 +58,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
-// One stage holds, for the 256 rows of a tile:  val[4][256] f64 | vec[NVEC][256] f64 | col[4][256] i32
-template <int NVEC, int STAGES = TILE_STAGES>
+// One stage holds, for the 256 rows of a tile:  val[4][256] f64 | vec[NVEC][256] f64 | col[4][256] IDX
+// IDX = int: absolute column indices.  IDX = short: column - row (every neighbour of a CR row of a mesh numbered with
+// some locality lies within +-32767 rows; chosen per matrix at crbe_solver_set_system), 8 bytes per row less to stream.
+template <int NVEC, int STAGES = TILE_STAGES, class IDX = int>
 struct TilePipe {
     static constexpr int VAL_BYTES = 4 * CRBE_TILE * 8;
     static constexpr int VEC_BYTES = CRBE_TILE * 8;
-    static constexpr int COL_BYTES = 4 * CRBE_TILE * 4;
+    static constexpr int COL_BYTES = 4 * CRBE_TILE * (int)sizeof(IDX);
     static constexpr int STAGE_BYTES = VAL_BYTES + NVEC * VEC_BYTES + COL_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES;
 
     unsigned char* smem;
     uint64_t* bars;
     const double* eval;
-    const int* ecol;
+    const IDX* ecol;
     const double* vec[NVEC > 0 ? NVEC : 1];
     int64_t first, stride, count;   // tiles first, first+stride, ... (count of them) belong to this CTA
 
@@ -114,18 +116,22 @@ struct TilePipe {
 
     __device__ __forceinline__ const double* sval(int64_t m) const { return (const double*)(smem + (m % STAGES) * STAGE_BYTES); }
     __device__ __forceinline__ const double* svec(int64_t m, int v) const { return sval(m) + 4 * CRBE_TILE + v * CRBE_TILE; }
-    __device__ __forceinline__ const int* scol(int64_t m) const { return (const int*)(sval(m) + (4 + NVEC) * CRBE_TILE); }
+    __device__ __forceinline__ const IDX* scol(int64_t m) const { return (const IDX*)(sval(m) + (4 + NVEC) * CRBE_TILE); }
+    // what to add to a stored index of thread tr's row in tile m to get the column
+    __device__ __forceinline__ int col_base(int64_t m, int tr) const {
+        return sizeof(IDX) == 2 ? (int)(tile_of(m) * CRBE_TILE) + tr : 0;
+    }
 };
 
 // y = x_own + sum_k a_k * x(col_k) with the tile's values/indices read from shared memory
-template <class F>
-__device__ __forceinline__ double tile_row(const double* __restrict__ sval, const int* __restrict__ scol, int r, double xi, F xat) {
+template <class IDX, class F>
+__device__ __forceinline__ double tile_row(const double* __restrict__ sval, const IDX* __restrict__ scol, int base, int r, double xi, F xat) {
     double a[4];
     int c[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         a[k] = sval[k * CRBE_TILE + r];
-        c[k] = scol[k * CRBE_TILE + r];
+        c[k] = base + (int)scol[k * CRBE_TILE + r];
     }
     double g[4];
 #pragma unroll
@@ -139,14 +145,15 @@ __device__ __forceinline__ double tile_row(const double* __restrict__ sval, cons
 // SpMV over the tiles of this CTA with the gathers software-pipelined one tile ahead: the x[col] loads of tile m+1
 // are issued before tile m is finished, so gather latency overlaps arithmetic, stores and the barrier.
 // body(m, row, tr, own, y) consumes the row result y = own + sum a_k x[col_k]; own = staged vector 0.
-template <int NV, int ST, class Body>
-__device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST>& pipe, const double* __restrict__ x, int64_t n, Body body) {
+template <int NV, int ST, class IDX, class Body>
+__device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, const double* __restrict__ x, int64_t n, Body body) {
     const int tr = threadIdx.x;
     double g[4], gn[4];
     auto gather = [&](int64_t m, double (&dst)[4]) {
-        const int* sc = pipe.scol(m);
+        const IDX* sc = pipe.scol(m);
+        const double* xb = x + pipe.col_base(m, tr);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dst[k] = __ldg(x + sc[k * CRBE_TILE + tr]);
+        for (int k = 0; k < 4; ++k) dst[k] = __ldg(xb + (int)sc[k * CRBE_TILE + tr]);
     };
     if (pipe.count > 0) {
         pipe.wait(0);
@@ -173,14 +180,15 @@ __device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST>& pipe, const
 }
 
 // ---- v = A p, (r^, v) ------------------------------------------------------------------------------------
+template <class IDX>
 __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, double rtol2, const double* __restrict__ eval,
-                                                  const int* __restrict__ ecol, const double* __restrict__ p, double* __restrict__ v,
+                                                  const IDX* __restrict__ ecol, const double* __restrict__ p, double* __restrict__ v,
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[SPMV_STAGES];
     if (solver_idle(sums, dstate, rtol2)) return;
-    TilePipe<2, SPMV_STAGES> pipe;
+    TilePipe<2, SPMV_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
     pipe.vec[0] = p;
@@ -197,14 +205,15 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, dou
 }
 
 // ---- t = A s, (t,s), (t,t), (r^,s), (r^,t) -----------------------------------------------------------------
+template <class IDX>
 __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, double rtol2, const double* __restrict__ eval,
-                                                  const int* __restrict__ ecol, const double* __restrict__ s, double* __restrict__ t,
+                                                  const IDX* __restrict__ ecol, const double* __restrict__ s, double* __restrict__ t,
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[SPMV_STAGES];
     if (solver_idle(sums, dstate, rtol2)) return;
-    TilePipe<2, SPMV_STAGES> pipe;
+    TilePipe<2, SPMV_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
     pipe.vec[0] = s;
@@ -225,7 +234,8 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, dou
 }
 
 // ---- Backward-Euler step start: b = mscale*u^n (+ dscale*dt*f), r = r^ = p = b - A x0, (b,b), (r,r) --------
-__global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles, const double* __restrict__ eval, const int* __restrict__ ecol,
+template <class IDX>
+__global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles, const double* __restrict__ eval, const IDX* __restrict__ ecol,
                                                        const double* __restrict__ x, const double* __restrict__ xb,
                                                        const double* __restrict__ src, double dt,
                                                        const double* __restrict__ mscale, const double* __restrict__ dscale,
@@ -238,7 +248,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
         dstate[D_STATUS] = 0;
         dstate[D_ITERS] = 0;
     }
-    TilePipe<2> pipe;
+    TilePipe<2, TILE_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
     pipe.vec[0] = mscale;
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
         pipe.wait(m);
         if (row < n) {
             const double bi = fma(pipe.svec(m, 0)[tr], pipe.svec(m, 1)[tr], extra);
-            const double ax = tile_row(pipe.sval(m), pipe.scol(m), tr, xi, [&](int j) { return __ldg(x + j); });
+            const double ax = tile_row(pipe.sval(m), pipe.scol(m), pipe.col_base(m, tr), tr, xi, [&](int j) { return __ldg(x + j); });
             const double ri = bi - ax;
             b[row] = bi;
             r[row] = ri;
@@ -275,7 +285,8 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
 }
 
 // ---- true residual b - A x and its norm (guard = 1: verification, norm only; guard = 0: restart, r = r^ = p) ----
-__global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntiles, const double* __restrict__ eval, const int* __restrict__ ecol,
+template <class IDX>
+__global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntiles, const double* __restrict__ eval, const IDX* __restrict__ ecol,
                                                         const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
                                                         double* __restrict__ rh, double* __restrict__ p, double* sums, double* dots,
                                                         double* partials, unsigned int* counter, const CommArgs* __restrict__ ca,
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntile
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
     if (guard && (dstate[D_STATUS] != 0 || sums[S_RR] > rtol2 * sums[S_BB])) return;
-    TilePipe<1> pipe;
+    TilePipe<1, TILE_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
     pipe.vec[0] = b;
@@ -296,7 +307,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntile
         const double xi = row < n ? x[row] : 0.0;
         pipe.wait(m);
         if (row < n) {
-            const double ax = tile_row(pipe.sval(m), pipe.scol(m), tr, xi, [&](int j) { return __ldg(x + j); });
+            const double ax = tile_row(pipe.sval(m), pipe.scol(m), pipe.col_base(m, tr), tr, xi, [&](int j) { return __ldg(x + j); });
             const double ri = pipe.svec(m, 0)[tr] - ax;
             if (!guard) {
                 r[row] = ri;

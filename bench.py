@@ -41,6 +41,12 @@ UNIT = "steps/s"
 # bytes per matrix row moved by each solver kernel in the ELL-4/unit-diagonal layout
 ROW_BYTES = {"init": 48 + 7 * 8, "pv": 48 + 3 * 8, "st": 48 + 3 * 8, "xr": 8 * 8, "p": 4 * 8, "s": 3 * 8, "residual": 48 + 2 * 8,
              "extrapolate": 3 * 8}
+
+
+def set_index_bits(bits):
+    """The matrix part of a row is 4 values + 4 indices: 48 B with 32-bit columns, 40 B with 16-bit offsets."""
+    mat = 32 + 4 * bits // 8
+    ROW_BYTES.update({"init": mat + 7 * 8, "pv": mat + 3 * 8, "st": mat + 3 * 8, "residual": mat + 2 * 8})
 KINDS = ["init", "pv", "st", "xr", "p", "s", "residual", "extrapolate"]
 
 
@@ -54,6 +60,7 @@ def parse_args():
     ap.add_argument("--regime", default="P-ref", choices=["P-ref", "P-T10", "P-stiff"])
     ap.add_argument("--no-extrapolate", action="store_true", help="start every solve from u^n instead of 2u^n - u^(n-1)")
     ap.add_argument("--verify-always", action="store_true", help="recompute the true residual after every solve (default: auto)")
+    ap.add_argument("--index32", action="store_true", help="stream 32-bit column indices even when 16-bit offsets fit")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")
     ap.add_argument("--classic", action="store_true", help="register-load kernels instead of the bulk-copy (TMA) pipeline")
     ap.add_argument("--e2e-steps", type=int, default=60)
@@ -74,14 +81,14 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel, args, n):
+def ncu_traffic(kernel, args, n, bits=32):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` capture (profiles/r01_traffic.json); only valid for the configuration it was taken on."""
     if args.classic or args.n != 2048:
         return None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return json.load(f).get(kernel)
+            return json.load(f).get(kernel if bits == 32 else f"{kernel}_idx{bits}")
     except Exception:
         return None
 
@@ -328,12 +335,14 @@ def main():
     mesh = wl.mesh()
     dom, prob = wl.domain(), wl.problem()
     md = crbe.MeshData(mesh, dom, wl.nt)
-    solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", tma=not args.classic, extrapolate=not args.no_extrapolate, verify=True if args.verify_always else "auto", graph=not args.no_graph, progress=False)
+    solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", tma=not args.classic, extrapolate=not args.no_extrapolate, verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False)
     rt = Runtime.get(device)
     solver.set_initial_condition()
     solver.build_global_matrices()
     rt.synchronize()
     t_setup = time.time() - t_setup
+    bits = solver.index_bits
+    set_index_bits(bits)
     n = md.number_of_segments
     assert n == counts["dofs"]
     # two alternating solution vectors, as BESCRFEM.solve() uses them (crbe_solver_step_pingpong)
@@ -391,7 +400,7 @@ def main():
     dom_k = "pv"
     achieved = kern[dom_k]["GBps"]
     # whole-step traffic in this layout: per iteration pv+s+st+xrp, per step init + residual (+ extrapolation)
-    per_it = ROW_BYTES["pv"] + ROW_BYTES["s"] + ROW_BYTES["st"] + ROW_BYTES["xr"]      # 232 B per row and iteration
+    per_it = ROW_BYTES["pv"] + ROW_BYTES["s"] + ROW_BYTES["st"] + ROW_BYTES["xr"]      # 232 B per row and iteration (216 with 16-bit offsets)
     step_bytes = (it_mean * per_it + ROW_BYTES["init"] + (ROW_BYTES["residual"] if "residual" in kern else 0)
                   + (0 if args.no_extrapolate else ROW_BYTES["extrapolate"])) * n
     # SURVEY 8(d) CSR accounting of a textbook BiCGStab iteration (2 CSR SpMV + 19 vector passes), for comparison
@@ -407,6 +416,7 @@ def main():
                              + ("" if args.no_extrapolate else ", extrapolated initial guess"),
                    "verify": "always" if args.verify_always else "auto (true residual recomputed after solves of > 12 iterations or a restart)",
                    "launch": "kernel by kernel" if args.no_graph else "one CUDA graph per step (head + first batch of iterations + state download)",
+                   "index_bits": bits,
                    "iters_per_step": it_mean, "l2": "inputs larger than L2 (1.9 GB touched per iteration vs 126 MB L2)",
                    "setup_s": t_setup},
         "dof_updates_per_s": steps_per_s * n,
@@ -419,7 +429,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "pv: ELL SpMV v = A p + dot (r^,v)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "frac_of_8TBps_nominal": achieved / 8000.0, "peak_source": peak_src,
-                     "bytes_per_launch": ROW_BYTES[dom_k] * n, "traffic": ncu_traffic("t_pv", args, n)},
+                     "bytes_per_launch": ROW_BYTES[dom_k] * n, "traffic": ncu_traffic("t_pv", args, n, bits)},
     }
 
     # ---- e2e: the public API with host buffers ---------------------------------
@@ -427,7 +437,7 @@ def main():
         E = max(2, min(args.e2e_steps, K))
         wl_e = workloads.unit_square(args.n, steps=E, regime=args.regime)
         md_e = crbe.MeshData(mesh, wl_e.domain(), wl_e.nt)
-        s_e = crbe.BESCRFEM(wl_e.domain(), prob, md_e, crbe.ElementCR(), 1, history="all", tma=not args.classic, extrapolate=not args.no_extrapolate, verify=True if args.verify_always else "auto", graph=not args.no_graph, progress=False)
+        s_e = crbe.BESCRFEM(wl_e.domain(), prob, md_e, crbe.ElementCR(), 1, history="all", tma=not args.classic, extrapolate=not args.no_extrapolate, verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False)
         import contextlib
         import io
         with contextlib.redirect_stdout(io.StringIO()):

@@ -143,6 +143,8 @@ typedef struct crbe_solve_info {
 
 #define CRBE_SOLVER_FUSED 1u          /* reserved (the iteration is the merged-reduction form)   */
 #define CRBE_SOLVER_VERIFY 2u         /* recompute the true residual after every convergence   */
+#define CRBE_SOLVER_INDEX32 64u       /* keep 32-bit column indices in the bulk-copy kernels even when every column - row offset
+                                         of the matrix fits 16 bits (default: the 16-bit form, 8 bytes per row and SpMV less) */
 #define CRBE_SOLVER_VERIFY_AUTO 32u   /* ... only after solves of more than 12 iterations or a restart (the gap between
                                          recurrence and true residual grows with the length of the recurrence) */
 #define CRBE_SOLVER_GRAPH 4u          /* single GPU: replay a step (head kernels, first batch of iterations, state download)
@@ -188,6 +190,8 @@ int crbe_solver_lift(crbe_solver* s, const double* u_d, const double* bc_values_
  * passed this call.  Calls on one stream are ordered; do not issue it on two streams at once. */
 int crbe_solver_store_lifted_async(crbe_solver* s, const double* u_d, const double* bc_values_h, double* row_h, void* stream);
 int crbe_solver_mass_diagonal(crbe_solver* s, const double** mdiag_d_out);   /* diag(M), the weights of crbe_moments */
+/* 16 or 32: width of the column indices the SpMV kernels stream for the loaded system and options */
+int crbe_solver_index_bits(crbe_solver* s, int32_t* bits_h);
 int crbe_solver_destroy(crbe_solver* s);
 
 /* ---- row-block partitioned solve over several GPUs (one process per GPU) -- */

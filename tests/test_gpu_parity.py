@@ -309,6 +309,46 @@ def test_graph_replay_is_bit_identical(name):
         assert np.array_equal(u.cpu().numpy(), a.u_prev)
 
 
+@pytest.mark.parametrize("name", ["struct_n32_o1", "delaunay150_o2", "source_delaunay80"])
+def test_index16_and_index32_agree(name):
+    """16-bit column offsets are only another encoding of the same columns: identical bits."""
+    g = load_golden(name)
+    crbe, dom, md = _product(g)
+    prob = golden_problem(name, g)
+    a = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), index16=True, progress=False)
+    sa = a.solve()
+    assert a.index_bits == 16
+    b = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), index16=False, progress=False)
+    sb = b.solve()
+    assert b.index_bits == 32
+    assert np.array_equal(sa, sb)
+    c = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), tma=False, progress=False)
+    c.build_global_matrices()
+    assert c.index_bits == 32          # the register-load kernels always read 32-bit columns
+
+
+def test_index16_falls_back_when_offsets_do_not_fit():
+    """A randomly numbered mesh with more than 2^15 DOFs has neighbours further than +-32767 rows away."""
+    from airpollution_b200 import crbe
+    from airpollution_b200.meshgen import delaunay_mesh, structured_mesh
+    dom = crbe.Domain(1, 1, T=0.01)
+    mesh = delaunay_mesh(15000, seed=3, shuffle=True)
+    md = crbe.MeshData(mesh, dom, 4)
+    assert md.number_of_segments > 40000
+    prob = crbe.Problem(v=[0.5, 0.2], D=0.05)
+    s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), progress=False)
+    sol = s.solve()
+    assert s.index_bits == 32
+    om = orc.OracleMesh(mesh.points, mesh.triangles, dom.T, md.nt)
+    ref = orc.OracleSolver(dom.T, prob, om, 1, linear_solver="splu").solve()
+    assert rel_err(sol[-1], ref[-1]) <= SOLUTION_RTOL
+    # the structured numbering has its fourth neighbour 3 nx + 1 rows away: fits up to nx ~ 10900
+    md2 = crbe.MeshData(structured_mesh(200, 200), dom, 3)
+    s2 = crbe.BESCRFEM(dom, prob, md2, crbe.ElementCR(), progress=False)
+    s2.build_global_matrices()
+    assert s2.index_bits == 16
+
+
 def test_store_lifted_async_rejects_pageable_rows(rt):
     import torch
     from airpollution_b200 import crbe
