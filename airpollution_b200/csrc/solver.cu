@@ -47,6 +47,7 @@ struct crbe_profile {
 
 enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RS = 7, S_RT = 8, S_RRTRUE = 10 };
 enum { D_STATUS = 0, D_ITERS = 1 };
+constexpr int IDX16_ESCAPE = -32768;   // 16-bit column offset that does not fit: read the 32-bit column instead
 
 struct P2PHeader;
 struct CommArgs;
@@ -356,15 +357,18 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_build_ell(int64_t n, int64_t ld,
     }
 }
 
-// 16-bit form of the column indices for the bulk-copy kernels: column - row (0 for padding rows).  *overflow is raised
-// when an offset does not fit; the kernels then keep the 32-bit indices.
+// 16-bit form of the column indices for the bulk-copy kernels: column - row (0 for padding rows).  Offsets that do not
+// fit are stored as IDX16_ESCAPE (the kernels then read the 32-bit column) and counted in *escapes.
 __global__ void __launch_bounds__(CRBE_BLOCK) k_pack_col16(int64_t n, int64_t ld, const int* __restrict__ ecol, int16_t* __restrict__ ecol16,
-                                                           int* __restrict__ overflow) {
+                                                           int* __restrict__ escapes) {
     ROW_LOOP(i, ld) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int64_t off = i < n ? (int64_t)ecol[ell_at(i, k)] - i : 0;
-            if (off < -32767 || off > 32767) *overflow = 1;
+            int64_t off = i < n ? (int64_t)ecol[ell_at(i, k)] - i : 0;
+            if (off < -32767 || off > 32767) {
+                atomicAdd(escapes, 1);
+                off = IDX16_ESCAPE;
+            }
             ecol16[ell_at(i, k)] = (int16_t)off;
         }
     }
@@ -1104,7 +1108,7 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
     CRBE_CUDA(cudaMemcpyAsync(&err_h, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     CRBE_CUDA(cudaMemcpyAsync(&overflow_h, overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
     CRBE_CUDA(cudaStreamSynchronize(st));
-    s->idx16 = overflow_h == 0;
+    s->idx16 = (int64_t)overflow_h * 64 <= s->n;   // escaped entries cost a dependent load: worth it only while they are rare
     if (err_h) {
         crbe_set_error("system matrix unusable: %s%s%s", (err_h & 1) ? "row without diagonal; " : "",
                        (err_h & 2) ? "row with more than 5 entries (not a CR pattern); " : "", (err_h & 4) ? "zero diagonal; " : "");
@@ -1223,11 +1227,11 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
     const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
     if (tma && i16)
         PROF_LAUNCH(PK_PV, k, (t_pv<short><<<s->gs_pv, CRBE_TILE, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col16, p, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
+                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col16, s->ell_col, p, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
                                   ctx->counter, s->d_comm)));
     else if (tma)
         PROF_LAUNCH(PK_PV, k, (t_pv<int><<<s->gt_pv, CRBE_TILE, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, p, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
+                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, nullptr, p, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
                                   ctx->counter, s->d_comm)));
     else
         PROF_LAUNCH(PK_PV, k, (k_pv<<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, rtol2, s->ell_val, s->ell_col, p, v, s->rh, s->sums, s->dots,
@@ -1237,11 +1241,11 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
     CRBE_CHECK(halo_exchange(s, s->s, launches));
     if (tma && i16)
         PROF_LAUNCH(PK_ST, k, (t_st<short><<<s->gs_st, CRBE_TILE, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col16, s->s, s->t, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
+                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col16, s->ell_col, s->s, s->t, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
                                   ctx->counter, s->d_comm)));
     else if (tma)
         PROF_LAUNCH(PK_ST, k, (t_st<int><<<s->gt_st, CRBE_TILE, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, s->s, s->t, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
+                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, nullptr, s->s, s->t, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
                                   ctx->counter, s->d_comm)));
     else
         PROF_LAUNCH(PK_ST, k, (k_st<<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, rtol2, s->ell_val, s->ell_col, s->s, s->t, s->rh, s->sums,
@@ -1276,11 +1280,11 @@ static int launch_residual(crbe_solver* s, double* x, int guard, int* launches) 
     const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
     if ((s->flags & CRBE_SOLVER_TMA) && i16)
         PROF_LAUNCH(PK_RES, guard ? -2 : -1, (t_residual<short><<<s->gs_res, CRBE_TILE, TilePipe<1, TILE_STAGES, short>::SMEM_BYTES, st>>>(
-                                                 s->n, s->ntiles, s->ell_val, s->ell_col16, x, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
+                                                 s->n, s->ntiles, s->ell_val, s->ell_col16, s->ell_col, x, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                  ctx->partials, ctx->counter, s->d_comm, s->dstate, guard, rtol2)));
     else if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_RES, guard ? -2 : -1, (t_residual<int><<<s->gt_res, CRBE_TILE, TilePipe<1, TILE_STAGES, int>::SMEM_BYTES, st>>>(
-                                                 s->n, s->ntiles, s->ell_val, s->ell_col, x, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
+                                                 s->n, s->ntiles, s->ell_val, s->ell_col, nullptr, x, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                  ctx->partials, ctx->counter, s->d_comm, s->dstate, guard, rtol2)));
     else
         PROF_LAUNCH(PK_RES, guard ? -2 : -1, (k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->b, s->r,
@@ -1458,11 +1462,11 @@ static int enqueue_step_head(crbe_solver* s, double* u_cur, double* u_next, cons
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if ((s->flags & CRBE_SOLVER_TMA) && s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32))
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<short><<<s->gs_init, CRBE_TILE, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->ell_val, s->ell_col16, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
+                                     s->n, s->ntiles, s->ell_val, s->ell_col16, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
                                      s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<int><<<s->gt_init, CRBE_TILE, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->ell_val, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
+                                     s->n, s->ntiles, s->ell_val, s->ell_col, nullptr, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
                                      s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else
         PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, xb, source_d, dt,

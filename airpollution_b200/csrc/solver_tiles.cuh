@@ -59,8 +59,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // One stage holds, for the 256 rows of a tile:  val[4][256] f64 | vec[NVEC][256] f64 | col[4][256] IDX
-// IDX = int: absolute column indices.  IDX = short: column - row (every neighbour of a CR row of a mesh numbered with
-// some locality lies within +-32767 rows; chosen per matrix at crbe_solver_set_system), 8 bytes per row less to stream.
+// IDX = int: absolute column indices.  IDX = short: column - row, 8 bytes per row less to stream (the neighbours of a CR
+// row of a mesh numbered with some locality lie within +-32767 rows).  The few entries that do not fit -- halo columns
+// of a partitioned matrix, the odd far neighbour -- carry the escape value IDX16_ESCAPE and are looked up in the 32-bit
+// array; crbe_solver_set_system picks the 16-bit form when such entries are rare.
 template <int NVEC, int STAGES = TILE_STAGES, class IDX = int>
 struct TilePipe {
     static constexpr int VAL_BYTES = 4 * CRBE_TILE * 8;
@@ -73,6 +75,7 @@ struct TilePipe {
     uint64_t* bars;
     const double* eval;
     const IDX* ecol;
+    const int* ecol32;              // IDX = short: absolute columns of the escaped entries
     const double* vec[NVEC > 0 ? NVEC : 1];
     int64_t first, stride, count;   // tiles first, first+stride, ... (count of them) belong to this CTA
 
@@ -117,21 +120,26 @@ struct TilePipe {
     __device__ __forceinline__ const double* sval(int64_t m) const { return (const double*)(smem + (m % STAGES) * STAGE_BYTES); }
     __device__ __forceinline__ const double* svec(int64_t m, int v) const { return sval(m) + 4 * CRBE_TILE + v * CRBE_TILE; }
     __device__ __forceinline__ const IDX* scol(int64_t m) const { return (const IDX*)(sval(m) + (4 + NVEC) * CRBE_TILE); }
-    // what to add to a stored index of thread tr's row in tile m to get the column
-    __device__ __forceinline__ int col_base(int64_t m, int tr) const {
-        return sizeof(IDX) == 2 ? (int)(tile_of(m) * CRBE_TILE) + tr : 0;
+    // column of slot k of thread tr's row in the staged tile m
+    __device__ __forceinline__ int column(int64_t m, int k, int tr) const {
+        const int raw = (int)scol(m)[k * CRBE_TILE + tr];
+        if (sizeof(IDX) == 4) return raw;
+        const int64_t tile = tile_of(m);
+        if (raw == IDX16_ESCAPE) return __ldg(ecol32 + tile * (4 * CRBE_TILE) + k * CRBE_TILE + tr);
+        return (int)(tile * CRBE_TILE) + tr + raw;
     }
 };
 
 // y = x_own + sum_k a_k * x(col_k) with the tile's values/indices read from shared memory
-template <class IDX, class F>
-__device__ __forceinline__ double tile_row(const double* __restrict__ sval, const IDX* __restrict__ scol, int base, int r, double xi, F xat) {
+template <class Pipe, class F>
+__device__ __forceinline__ double tile_row(const Pipe& pipe, int64_t m, int r, double xi, F xat) {
+    const double* __restrict__ sval = pipe.sval(m);
     double a[4];
     int c[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         a[k] = sval[k * CRBE_TILE + r];
-        c[k] = base + (int)scol[k * CRBE_TILE + r];
+        c[k] = pipe.column(m, k, r);
     }
     double g[4];
 #pragma unroll
@@ -150,10 +158,8 @@ __device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, 
     const int tr = threadIdx.x;
     double g[4], gn[4];
     auto gather = [&](int64_t m, double (&dst)[4]) {
-        const IDX* sc = pipe.scol(m);
-        const double* xb = x + pipe.col_base(m, tr);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dst[k] = __ldg(xb + (int)sc[k * CRBE_TILE + tr]);
+        for (int k = 0; k < 4; ++k) dst[k] = __ldg(x + pipe.column(m, k, tr));
     };
     if (pipe.count > 0) {
         pipe.wait(0);
@@ -182,7 +188,7 @@ __device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, 
 // ---- v = A p, (r^, v) ------------------------------------------------------------------------------------
 template <class IDX>
 __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, double rtol2, const double* __restrict__ eval,
-                                                  const IDX* __restrict__ ecol, const double* __restrict__ p, double* __restrict__ v,
+                                                  const IDX* __restrict__ ecol, const int* __restrict__ ecol32, const double* __restrict__ p, double* __restrict__ v,
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
@@ -191,6 +197,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, dou
     TilePipe<2, SPMV_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
+    pipe.ecol32 = ecol32;
     pipe.vec[0] = p;
     pipe.vec[1] = rh;
     pipe.start(tile_smem, bars, ntiles);
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, dou
 // ---- t = A s, (t,s), (t,t), (r^,s), (r^,t) -----------------------------------------------------------------
 template <class IDX>
 __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, double rtol2, const double* __restrict__ eval,
-                                                  const IDX* __restrict__ ecol, const double* __restrict__ s, double* __restrict__ t,
+                                                  const IDX* __restrict__ ecol, const int* __restrict__ ecol32, const double* __restrict__ s, double* __restrict__ t,
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
@@ -216,6 +223,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, dou
     TilePipe<2, SPMV_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
+    pipe.ecol32 = ecol32;
     pipe.vec[0] = s;
     pipe.vec[1] = rh;
     pipe.start(tile_smem, bars, ntiles);
@@ -235,7 +243,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, dou
 
 // ---- Backward-Euler step start: b = mscale*u^n (+ dscale*dt*f), r = r^ = p = b - A x0, (b,b), (r,r) --------
 template <class IDX>
-__global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles, const double* __restrict__ eval, const IDX* __restrict__ ecol,
+__global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles, const double* __restrict__ eval, const IDX* __restrict__ ecol, const int* __restrict__ ecol32,
                                                        const double* __restrict__ x, const double* __restrict__ xb,
                                                        const double* __restrict__ src, double dt,
                                                        const double* __restrict__ mscale, const double* __restrict__ dscale,
@@ -251,6 +259,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
     TilePipe<2, TILE_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
+    pipe.ecol32 = ecol32;
     pipe.vec[0] = mscale;
     pipe.vec[1] = xb;     // previous solution u^n (right-hand side); x is the initial guess, possibly extrapolated
     pipe.start(tile_smem, bars, ntiles);
@@ -267,7 +276,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
         pipe.wait(m);
         if (row < n) {
             const double bi = fma(pipe.svec(m, 0)[tr], pipe.svec(m, 1)[tr], extra);
-            const double ax = tile_row(pipe.sval(m), pipe.scol(m), pipe.col_base(m, tr), tr, xi, [&](int j) { return __ldg(x + j); });
+            const double ax = tile_row(pipe, m, tr, xi, [&](int j) { return __ldg(x + j); });
             const double ri = bi - ax;
             b[row] = bi;
             r[row] = ri;
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
 
 // ---- true residual b - A x and its norm (guard = 1: verification, norm only; guard = 0: restart, r = r^ = p) ----
 template <class IDX>
-__global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntiles, const double* __restrict__ eval, const IDX* __restrict__ ecol,
+__global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntiles, const double* __restrict__ eval, const IDX* __restrict__ ecol, const int* __restrict__ ecol32,
                                                         const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
                                                         double* __restrict__ rh, double* __restrict__ p, double* sums, double* dots,
                                                         double* partials, unsigned int* counter, const CommArgs* __restrict__ ca,
@@ -297,6 +306,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntile
     TilePipe<1, TILE_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
+    pipe.ecol32 = ecol32;
     pipe.vec[0] = b;
     pipe.start(tile_smem, bars, ntiles);
     halo_wait(0, ca);
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntile
         const double xi = row < n ? x[row] : 0.0;
         pipe.wait(m);
         if (row < n) {
-            const double ax = tile_row(pipe.sval(m), pipe.scol(m), pipe.col_base(m, tr), tr, xi, [&](int j) { return __ldg(x + j); });
+            const double ax = tile_row(pipe, m, tr, xi, [&](int j) { return __ldg(x + j); });
             const double ri = pipe.svec(m, 0)[tr] - ax;
             if (!guard) {
                 r[row] = ri;

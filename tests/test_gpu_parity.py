@@ -349,6 +349,52 @@ def test_index16_falls_back_when_offsets_do_not_fit():
     assert s2.index_bits == 16
 
 
+@pytest.mark.parametrize("tma", [True, False], ids=["bulk-copy", "register-loads"])
+def test_index16_escape_entries(rt, tma):
+    """A banded matrix with a few couplings 50 000 rows away: those entries do not fit a 16-bit offset, are stored as
+    escapes and looked up in the 32-bit array; everything else streams 16-bit offsets."""
+    import torch
+    import scipy.sparse as sp
+    from airpollution_b200 import _lib
+    from airpollution_b200.runtime import ptr
+    n = 100_000
+    i = np.arange(n)
+    far = i[(i % 997 == 0) & (i < n // 2)]
+    rows = np.concatenate([i, i[1:], i[:-1], far, far + n // 2])
+    cols = np.concatenate([i, i[:-1], i[1:], far + n // 2, far])
+    rng = np.random.default_rng(11)
+    vals = np.concatenate([4.0 + rng.random(n), -1.0 - 0.1 * rng.random(n - 1), -1.0 + 0.1 * rng.random(n - 1),
+                           -0.5 * np.ones(len(far)), -0.25 * np.ones(len(far))])
+    A = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+    A.sort_indices()
+    M = sp.csr_matrix((np.where(A.tocoo().row == A.tocoo().col, 1.0, 0.0), A.indices, A.indptr), shape=(n, n))
+    indptr, indices = rt.upload(A.indptr.astype(np.int32)), rt.upload(A.indices.astype(np.int32))
+    sval, mval = rt.upload(A.data), rt.upload(M.data)
+    h = C.c_void_p()
+    rt.call("crbe_solver_create", rt.ctx, n, ptr(indptr), ptr(indices), A.nnz, None, 0, C.byref(h))
+    try:
+        flags = _lib.SOLVER_VERIFY | (_lib.SOLVER_TMA if tma else 0)
+        rt.call("crbe_solver_set_options", h, 1e-13, 1000, flags)
+        rt.call("crbe_solver_set_system", h, ptr(sval), ptr(mval), None)
+        bits = C.c_int32()
+        rt.call("crbe_solver_index_bits", h, C.byref(bits))
+        assert bits.value == (16 if tma else 32)
+        b = rng.standard_normal(n)
+        bd, x = rt.upload(b), rt.zeros((n,), torch.float64)
+        info = _lib.SolveInfo()
+        rt.call("crbe_solver_solve", h, ptr(bd), ptr(x), C.byref(info))
+        ref = spla.spsolve(A.tocsc(), b)
+        assert info.status == 0 and info.true_relres <= 1e-12
+        assert rel_err(x.cpu().numpy(), ref) <= 1e-11
+        # the same system with 32-bit columns: identical bits
+        rt.call("crbe_solver_set_options", h, 1e-13, 1000, flags | _lib.SOLVER_INDEX32)
+        x2 = rt.zeros((n,), torch.float64)
+        rt.call("crbe_solver_solve", h, ptr(bd), ptr(x2), C.byref(info))
+        assert torch.equal(x, x2)
+    finally:
+        rt.call("crbe_solver_destroy", h)
+
+
 def test_store_lifted_async_rejects_pageable_rows(rt):
     import torch
     from airpollution_b200 import crbe
