@@ -35,6 +35,22 @@ SOLVER_TMA = 8
 SOLVER_EXTRAPOLATE = 16
 SOLVER_VERIFY_AUTO = 32
 SOLVER_INDEX32 = 64
+MAX_EXTRAP_ORDER = 4
+
+
+def extrapolation_flags(extrapolate):
+    """False/0: start from u^n; True: the default order (4); 1..4: that order."""
+    if extrapolate is True:
+        q = MAX_EXTRAP_ORDER
+    else:
+        q = int(extrapolate or 0)
+    if not 0 <= q <= MAX_EXTRAP_ORDER:
+        raise ValueError(f"extrapolate must be a bool or an order 0..{MAX_EXTRAP_ORDER}")
+    return (SOLVER_EXTRAPOLATE | (q << 8)) if q else 0
+
+
+def extrapolation_order(extrapolate):
+    return (extrapolation_flags(extrapolate) >> 8) & 7
 
 # name -> (argtypes)   every function returns int unless listed in _RESTYPE
 _SIGNATURES = {
@@ -66,6 +82,7 @@ _SIGNATURES = {
     "crbe_solver_set_options": [vp, C.c_double, C.c_int32, C.c_uint32],
     "crbe_solver_step": [vp, vp, vp, C.c_double, C.POINTER(SolveInfo)],
     "crbe_solver_step_pingpong": [vp, vp, vp, vp, C.c_double, C.POINTER(SolveInfo)],
+    "crbe_solver_step_ring": [vp, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, vp, C.c_double, C.POINTER(SolveInfo)],
     "crbe_solver_solve": [vp, vp, vp, C.POINTER(SolveInfo)],
     "crbe_solver_rhs": [vp, vp, vp, C.c_double, vp],
     "crbe_solver_lift": [vp, vp, vp, vp],

@@ -47,6 +47,7 @@ struct crbe_profile {
 
 enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RS = 7, S_RT = 8, S_RRTRUE = 10 };
 enum { D_STATUS = 0, D_ITERS = 1 };
+constexpr int CRBE_MAX_EXTRAP = 4;      // highest order of the extrapolated initial guess
 constexpr int IDX16_ESCAPE = -32768;   // 16-bit column offset that does not fit: read the 32-bit column instead
 
 struct P2PHeader;
@@ -55,9 +56,9 @@ struct CommArgs;
 // One instantiated step: everything crbe_solver_step enqueues before its first synchronisation, for one combination of
 // buffers and batch length.  A key is captured the second time it is asked for (one-off calls are launched directly).
 struct StepGraph {
-    const double *u_cur, *u_next, *source;
+    const double *u0, *x, *save, *h[4], *source;
     double dt;
-    int mode, target, speculate;
+    int q, target, speculate;
     cudaGraphExec_t exec;
     int launches;
     uint64_t stamp;
@@ -77,9 +78,13 @@ struct crbe_solver {
     double *mdiag = nullptr, *mscale = nullptr, *dscale = nullptr;
     double* rhs_val = nullptr;         // CN: values of M - c(K+A) on the structural pattern
     double *b = nullptr, *r = nullptr, *rh = nullptr, *s = nullptr, *t = nullptr, *tmp = nullptr;
-    double* hist = nullptr;            // u^n of the running time loop (right-hand side / extrapolation of the initial guess)
-    bool hist_valid = false;
-    const double* pp_prev = nullptr;   // ping-pong stepping: the buffer that held u^n in the previous call
+    // History of the running time loop: the initial guess of a step is the polynomial extrapolation of the last
+    // order+1 solutions.  In-place stepping keeps copies in hist[] (hist[(hist_head + k) % hist_slots] = u^(n-1-k));
+    // ring stepping reads the caller's own buffers and only tracks how many of them hold consecutive solutions.
+    double* hist[CRBE_MAX_EXTRAP] = {nullptr};
+    int hist_head = 0, hist_count = 0;
+    const double* ring_sig[CRBE_MAX_EXTRAP + 1] = {nullptr};
+    int ring_n = 0, ring_expect = -1, ring_valid = 0;
     double* p[1] = {nullptr};
     double* v[1] = {nullptr};
     double* sums = nullptr;
@@ -87,7 +92,7 @@ struct crbe_solver {
     double* sums_h = nullptr;  // pinned: CRBE_NSUMS doubles followed by 2 ints
     double rtol = 1e-13;
     int maxit = 10000;
-    unsigned flags = CRBE_SOLVER_TMA | CRBE_SOLVER_VERIFY_AUTO | CRBE_SOLVER_EXTRAPOLATE | CRBE_SOLVER_GRAPH;
+    unsigned flags = CRBE_SOLVER_TMA | CRBE_SOLVER_VERIFY_AUTO | CRBE_SOLVER_EXTRAPOLATE | CRBE_SOLVER_EXTRAP_ORDER(4u) | CRBE_SOLVER_GRAPH;
     int last_iters = 8;
     bool system_loaded = false;
     // persistent grids: SMs x resident CTAs of each kernel (a grid-stride sweep must be one full wave)
@@ -378,18 +383,33 @@ __global__ void k_zero_rows(double* __restrict__ u, const int* __restrict__ bnd,
     ROW_LOOP(k, nb) u[bnd[k]] = 0.0;
 }
 
-// u holds u^n, hist holds u^(n-1):  hist <- u^n,  u <- 2 u^n - u^(n-1)  (initial guess of the next solve)
-__global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate(int64_t n, double* __restrict__ u, double* __restrict__ hist) {
-    ROW_LOOP(i, n) {
-        const double un = u[i], uo = hist[i];
-        hist[i] = un;
-        u[i] = fma(2.0, un, -uo);
-    }
-}
+// Initial guess of a step: the polynomial through the last Q+1 solutions evaluated one step ahead,
+//   x0 = sum_{j=0..Q} (-1)^j C(Q+1, j+1) u^(n-j)      (Q = 1: 2 u^n - u^(n-1);  Q = 4: 5, -10, 10, -5, 1).
+// The solution varies smoothly over the tiny steps of the reference's regime, so every order gains 2-3 digits of initial
+// residual until the rounding noise of the earlier solves (~rtol x sum |c_j|) is reached.  u0 = u^n, h[j-1] = u^(n-j);
+// x0 may alias u0 (in-place stepping) or h[Q-1] (ring stepping: the oldest solution makes room); save (optional)
+// receives u^n.  Element-wise, so the aliasing is safe; no __restrict__.
+struct ExtrapArgs {
+    const double* u0;
+    const double* h[CRBE_MAX_EXTRAP];
+    double* x0;
+    double* save;
+};
 
-// ping-pong form: nxt holds u^(n-1) and becomes the initial guess 2 u^n - u^(n-1); cur (u^n) is left untouched
-__global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate_pp(int64_t n, const double* __restrict__ cur, double* __restrict__ nxt) {
-    ROW_LOOP(i, n) nxt[i] = fma(2.0, cur[i], -nxt[i]);
+template <int Q>
+__global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate(int64_t n, ExtrapArgs a) {
+    constexpr double C[5][5] = {{1, 0, 0, 0, 0}, {2, -1, 0, 0, 0}, {3, -3, 1, 0, 0}, {4, -6, 4, -1, 0}, {5, -10, 10, -5, 1}};
+    ROW_LOOP(i, n) {
+        const double un = a.u0[i];
+        double hv[Q > 0 ? Q : 1];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) hv[j] = a.h[j][i];
+        double acc = C[Q][0] * un;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) acc = fma(C[Q][j + 1], hv[j], acc);
+        if (a.save) a.save[i] = un;
+        a.x0[i] = acc;
+    }
 }
 
 __global__ void k_lift(const double* __restrict__ bc, const int* __restrict__ bnd, int64_t nb, double* __restrict__ out) {
@@ -799,7 +819,7 @@ static int solver_release(crbe_solver* s) {
     cudaFree(s->s);
     cudaFree(s->t);
     cudaFree(s->tmp);
-    cudaFree(s->hist);
+    for (double* h : s->hist) cudaFree(h);
     cudaFree(s->p[0]);
     cudaFree(s->v[0]);
     cudaFree(s->sums);
@@ -870,7 +890,7 @@ static int solver_init(crbe_solver* s, crbe_ctx* ctx, crbe_comm* comm, int64_t n
     }
     CRBE_CUDA(cudaMalloc(&s->ell_col, sizeof(int32_t) * 4 * s->ld));
     CRBE_CUDA(cudaMalloc(&s->ell_val, sizeof(double) * 4 * s->ld));
-    double** vecs[] = {&s->mdiag, &s->mscale, &s->dscale, &s->b, &s->r, &s->rh, &s->s, &s->t, &s->p[0], &s->v[0], &s->hist};
+    double** vecs[] = {&s->mdiag, &s->mscale, &s->dscale, &s->b, &s->r, &s->rh, &s->s, &s->t, &s->p[0], &s->v[0], &s->hist[0]};
     for (double** vp : vecs) {
         CRBE_CUDA(cudaMalloc(vp, vb));
         CRBE_CUDA(cudaMemsetAsync(*vp, 0, vb, ctx->stream));
@@ -1115,7 +1135,9 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
         return CRBE_ERR_ARG;
     }
     s->system_loaded = true;
-    s->hist_valid = false;      // a new system starts a new time loop
+    s->hist_count = 0;          // a new system starts a new time loop
+    s->ring_valid = 0;
+    s->ring_expect = -1;
     return CRBE_OK;
 }
 
@@ -1413,61 +1435,78 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
     return CRBE_OK;
 }
 
-// How a step prepares its right-hand side and initial guess
-enum StepMode { SM_PP_EXTRAP = 0, SM_PP_COPY, SM_IP_EXTRAP, SM_IP_COPY, SM_IP_PLAIN };
+// What a step works on: u0 = u^n, h[j-1] = u^(n-j) (q of them), the iterate x (may alias u0 or h[q-1]), and where a
+// copy of u^n goes when x overwrites it (save; the right-hand side is then built from the copy).
+struct StepPlan {
+    double* u0;
+    double* x;
+    double* save;
+    const double* h[CRBE_MAX_EXTRAP];
+    int q;
+};
+
+static inline int extrap_order(const crbe_solver* s) {
+    if (!(s->flags & CRBE_SOLVER_EXTRAPOLATE)) return 0;
+    const int q = (int)((s->flags >> 8) & 7u);
+    return q == 0 ? 1 : (q > CRBE_MAX_EXTRAP ? CRBE_MAX_EXTRAP : q);
+}
+
+static int launch_extrapolate(crbe_solver* s, const StepPlan& pl, int* launches) {
+    cudaStream_t st = s->ctx->stream;
+    ExtrapArgs a;
+    a.u0 = pl.u0;
+    a.x0 = pl.x;
+    a.save = pl.save;
+    for (int j = 0; j < CRBE_MAX_EXTRAP; ++j) a.h[j] = j < pl.q ? pl.h[j] : nullptr;
+    switch (pl.q) {
+        case 1: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<1><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a))); break;
+        case 2: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<2><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a))); break;
+        case 3: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<3><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a))); break;
+        default: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<4><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a))); break;
+    }
+    *launches += 1;
+    CRBE_KERNEL_CHECK();
+    return CRBE_OK;
+}
 
 // Everything a step enqueues before the iterations: Dirichlet rows of u^n, history / initial guess, b, r, r^, p and the first norms.
-static int enqueue_step_head(crbe_solver* s, double* u_cur, double* u_next, const double* source_d, double dt, int mode, int* launches) {
+static int enqueue_step_head(crbe_solver* s, const StepPlan& pl, const double* source_d, double dt, int* launches) {
     crbe_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     const bool cn = s->rhs_val != nullptr;
     if (cn) {   // Crank-Nicolson: (M - c(K+A)) u_prev with u_prev as given, boundary values included (crbe.py:386)
-        CRBE_CHECK(halo_exchange(s, u_cur, launches));
+        CRBE_CHECK(halo_exchange(s, pl.u0, launches));
         if (s->p2p) k_p2p_wait<<<1, 32, 0, st>>>(0, s->d_comm);
-        k_spmv_csr<<<s->g_spmv, CRBE_BLOCK, 0, st>>>(s->n, s->indptr, s->indices, s->rhs_val, u_cur, s->tmp);
+        k_spmv_csr<<<s->g_spmv, CRBE_BLOCK, 0, st>>>(s->n, s->indptr, s->indices, s->rhs_val, pl.u0, s->tmp);
         *launches += 1;
     }
     if (s->nb > 0) {    // the solution of the Dirichlet system is exactly 0 on its identity rows: start there
-        k_zero_rows<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, st>>>(u_cur, s->bnd, s->nb);
+        k_zero_rows<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, st>>>(pl.u0, s->bnd, s->nb);
         *launches += 1;
     }
-    // Right-hand side from u^n; with one step of history the initial guess is extrapolated linearly in time
-    // (2 u^n - u^(n-1)): the first residual drops by 2-3 orders of magnitude, which saves about one iteration per step.
-    double* x = u_next;
-    const double* xb = u_cur;
-    switch (mode) {
-        case SM_PP_EXTRAP:
-            PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate_pp<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, u_cur, u_next)));
-            *launches += 1;
-            break;
-        case SM_PP_COPY:
-            CRBE_CUDA(cudaMemcpyAsync(u_next, u_cur, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
-            break;
-        case SM_IP_EXTRAP:
-            PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, u_cur, s->hist)));
-            *launches += 1;
-            xb = s->hist;
-            break;
-        case SM_IP_COPY:
-            CRBE_CUDA(cudaMemcpyAsync(s->hist, u_cur, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
-            xb = s->hist;
-            break;
-        default:
-            break;
+    // Right-hand side from u^n; the initial guess is extrapolated from the history (see k_extrapolate)
+    double* x = pl.x;
+    const double* xb = pl.save ? pl.save : pl.u0;
+    if (pl.q > 0) {
+        CRBE_CHECK(launch_extrapolate(s, pl, launches));
+    } else if (!cn) {
+        if (pl.save) CRBE_CUDA(cudaMemcpyAsync(pl.save, pl.u0, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
+        if (x != pl.u0) CRBE_CUDA(cudaMemcpyAsync(x, pl.u0, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
     }
     CRBE_CHECK(halo_exchange(s, x, launches));
+    const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
     if (cn)
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->tmp, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
-    else if ((s->flags & CRBE_SOLVER_TMA) && s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32))
+    else if ((s->flags & CRBE_SOLVER_TMA) && i16)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<short><<<s->gs_init, CRBE_TILE, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->ell_val, s->ell_col16, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
-                                     s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
+                                     s->n, s->ntiles, s->ell_val, s->ell_col16, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r,
+                                     s->rh, s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<int><<<s->gt_init, CRBE_TILE, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->ell_val, s->ell_col, nullptr, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r, s->rh,
-                                     s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
+                                     s->n, s->ntiles, s->ell_val, s->ell_col, nullptr, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r,
+                                     s->rh, s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else
         PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, xb, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
@@ -1478,20 +1517,21 @@ static int enqueue_step_head(crbe_solver* s, double* u_cur, double* u_next, cons
 }
 
 // ---- CUDA graphs of whole steps ---------------------------------------------------------------------------
-// A step is ~25 short launches; their descriptors are fetched by the GPU front end from host memory, which costs
+// A step is ~10-25 short launches; their descriptors are fetched by the GPU front end from host memory, which costs
 // several microseconds per launch while a solution row is travelling over the same PCIe link (measured: +6 % per
 // step during BESCRFEM.solve(history="all")).  An instantiated graph keeps the whole step on the device side.
-constexpr size_t STEP_GRAPH_SLOTS = 12;
+constexpr size_t STEP_GRAPH_SLOTS = 32;
 
 static StepGraph* find_step_graph(crbe_solver* s, const StepGraph& key) {
     for (StepGraph& g : s->graphs)
-        if (g.u_cur == key.u_cur && g.u_next == key.u_next && g.source == key.source && g.dt == key.dt && g.mode == key.mode &&
-            g.target == key.target && g.speculate == key.speculate)
+        if (g.u0 == key.u0 && g.x == key.x && g.save == key.save && g.h[0] == key.h[0] && g.h[1] == key.h[1] && g.h[2] == key.h[2] &&
+            g.h[3] == key.h[3] && g.source == key.source && g.dt == key.dt && g.q == key.q && g.target == key.target &&
+            g.speculate == key.speculate)
             return &g;
     return nullptr;
 }
 
-static int capture_step(crbe_solver* s, double* u_cur, double* u_next, const double* source_d, double dt, StepGraph* g) {
+static int capture_step(crbe_solver* s, const StepPlan& pl, const double* source_d, double dt, StepGraph* g) {
     crbe_ctx* ctx = s->ctx;
     if (!s->cap_stream) CRBE_CUDA(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
     cudaStream_t launch_stream = ctx->stream;
@@ -1501,8 +1541,8 @@ static int capture_step(crbe_solver* s, double* u_cur, double* u_next, const dou
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
-        rc = enqueue_step_head(s, u_cur, u_next, source_d, dt, g->mode, &launches);
-        if (rc == CRBE_OK) rc = enqueue_batch(s, u_next, 0, g->target, g->speculate != 0, &launches);
+        rc = enqueue_step_head(s, pl, source_d, dt, &launches);
+        if (rc == CRBE_OK) rc = enqueue_batch(s, pl.x, 0, g->target, g->speculate != 0, &launches);
         const cudaError_t e2 = cudaStreamEndCapture(s->cap_stream, &graph);   // always close the capture
         if (rc == CRBE_OK && e2 != cudaSuccess) e = e2;
     }
@@ -1528,33 +1568,16 @@ static int capture_step(crbe_solver* s, double* u_cur, double* u_next, const dou
     return CRBE_OK;
 }
 
-// One time step.  u_cur holds u^n.  In place (u_next == u_cur): u^n is saved in the solver's history vector and the
-// iterate is built in u_cur.  Ping-pong (u_next != u_cur, both padded to crbe_solver_vector_length): the iterate is
-// built in u_next and u_cur stays intact during the NEXT step as well, so the host can download it while the GPU is
-// already solving -- no staging copy; u_next is expected to hold u^(n-1) when the buffers simply alternate.
-static int step_impl(crbe_solver* s, double* u_cur, double* u_next, const double* source_d, double dt, crbe_solve_info* info_h) {
-    CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
+// One time step as planned by the entry points below.
+static int step_impl(crbe_solver* s, const StepPlan& pl, const double* source_d, double dt, crbe_solve_info* info_h) {
     crbe_ctx* ctx = s->ctx;
-    const bool pp = u_next != u_cur;
-    CRBE_REQUIRE(!(pp && s->world > 1), "ping-pong stepping is for the single-GPU solver");
     memset(info_h, 0, sizeof(*info_h));
     int launches = 0;
-    const bool extrap = !s->rhs_val && (s->flags & CRBE_SOLVER_EXTRAPOLATE);
-    int mode = SM_IP_PLAIN;   // Crank-Nicolson in place: the right-hand side comes from the SpMV, the guess is u^n itself
-    if (pp) {
-        mode = (extrap && s->hist_valid && s->pp_prev == u_next) ? SM_PP_EXTRAP : SM_PP_COPY;
-        s->pp_prev = u_cur;
-        s->hist_valid = true;
-    } else if (!s->rhs_val) {
-        mode = (extrap && s->hist_valid && s->pp_prev == nullptr) ? SM_IP_EXTRAP : SM_IP_COPY;
-        s->pp_prev = nullptr;
-        s->hist_valid = true;
-    }
     // Steady state on one GPU: replay the step as one graph (captured the second time the same step shape is asked for)
     bool in_flight = false;
     const bool graphs_on = (s->flags & CRBE_SOLVER_GRAPH) && s->world == 1 && !(s->prof && s->prof->on);
     if (graphs_on) {
-        StepGraph key = {u_cur, u_next, source_d, dt, mode, first_batch_target(s, 0), 0, nullptr, 0, 0};
+        StepGraph key = {pl.u0, pl.x, pl.save, {pl.h[0], pl.h[1], pl.h[2], pl.h[3]}, source_d, dt, pl.q, first_batch_target(s, 0), 0, nullptr, 0, 0};
         key.speculate = verify_wanted(s, key.target, 0) ? 1 : 0;
         StepGraph* g = find_step_graph(s, key);
         if (!g) {                       // first sighting: remember the shape, launch directly
@@ -1569,28 +1592,102 @@ static int step_impl(crbe_solver* s, double* u_cur, double* u_next, const double
             s->graphs.push_back(key);
         } else {
             g->stamp = ++s->graph_clock;
-            if (!g->exec) CRBE_CHECK(capture_step(s, u_cur, u_next, source_d, dt, g));
+            if (!g->exec) CRBE_CHECK(capture_step(s, pl, source_d, dt, g));
             CRBE_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
             launches += g->launches;
             in_flight = true;
         }
     }
-    if (!in_flight) CRBE_CHECK(enqueue_step_head(s, u_cur, u_next, source_d, dt, mode, &launches));
-    int rc = run_bicgstab(s, u_next, info_h, &launches, in_flight);
+    if (!in_flight) CRBE_CHECK(enqueue_step_head(s, pl, source_d, dt, &launches));
+    int rc = run_bicgstab(s, pl.x, info_h, &launches, in_flight);
     info_h->launches = launches;
     ctx->launches += launches;
     return rc;
 }
 
+// In place: u_d holds u^n and receives u^(n+1); the solver keeps copies of the last solutions for the right-hand side
+// and the extrapolated initial guess.
+static int step_in_place(crbe_solver* s, double* u_d, const double* source_d, double dt, crbe_solve_info* info_h) {
+    CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
+    StepPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.u0 = u_d;
+    pl.x = u_d;
+    s->ring_valid = 0;     // the caller left the ring protocol
+    s->ring_expect = -1;
+    if (s->rhs_val) return step_impl(s, pl, source_d, dt, info_h);   // Crank-Nicolson: right-hand side from the SpMV, guess u^n
+    const int order = extrap_order(s);
+    const int slots = order > 1 ? order : 1;                          // one copy of u^n is always needed for the right-hand side
+    const size_t vb = sizeof(double) * (size_t)s->veclen;
+    for (int k = 0; k < slots; ++k)
+        if (!s->hist[k]) {
+            CRBE_CUDA(cudaMalloc(&s->hist[k], vb));
+            CRBE_CUDA(cudaMemsetAsync(s->hist[k], 0, vb, s->ctx->stream));
+        }
+    if (s->hist_head >= slots) s->hist_head = 0;
+    pl.q = s->hist_count < order ? s->hist_count : order;
+    for (int j = 0; j < pl.q; ++j) pl.h[j] = s->hist[(s->hist_head + j) % slots];
+    const int dst = (s->hist_head + slots - 1) % slots;              // the oldest copy (or a free slot) makes room for u^n
+    pl.save = s->hist[dst];
+    s->hist_head = dst;
+    if (s->hist_count < slots) s->hist_count += 1;
+    return step_impl(s, pl, source_d, dt, info_h);
+}
+
+// Ring of caller-owned vectors (each crbe_solver_vector_length long, zero padded): bufs[cur] holds u^n, the buffers before
+// it (cyclically) the earlier solutions of this time loop; u^(n+1) is built in bufs[(cur + 1) % count], which held the
+// oldest one.  Nothing is copied, and every solution stays intact for count - 1 further steps (downloads overlap them).
+static int step_ring(crbe_solver* s, double* const* bufs, int count, int cur, const double* source_d, double dt, crbe_solve_info* info_h) {
+    CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
+    CRBE_REQUIRE(s->world == 1, "ring stepping is for the single-GPU solver");
+    CRBE_REQUIRE(count >= 2 && count <= CRBE_MAX_EXTRAP + 1 && cur >= 0 && cur < count, "bad ring");
+    bool same = s->ring_n == count && s->ring_expect == cur;
+    for (int k = 0; k < count; ++k) {
+        CRBE_REQUIRE(bufs[k] != nullptr, "null ring buffer");
+        same = same && s->ring_sig[k] == bufs[k];
+        s->ring_sig[k] = bufs[k];
+    }
+    s->ring_n = count;
+    s->ring_valid = same ? (s->ring_valid + 1 < count - 1 ? s->ring_valid + 1 : count - 1) : 0;
+    s->ring_expect = (cur + 1) % count;
+    s->hist_count = 0;     // the caller left the in-place protocol
+    StepPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.u0 = bufs[cur];
+    pl.x = bufs[(cur + 1) % count];
+    if (s->rhs_val) {
+        pl.q = 0;
+        CRBE_CUDA(cudaMemcpyAsync(pl.x, pl.u0, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, s->ctx->stream));
+        // Crank-Nicolson works in place on the copy (its right-hand side needs u^n with the boundary values as given)
+        pl.u0 = pl.x;
+        return step_impl(s, pl, source_d, dt, info_h);
+    }
+    const int order = extrap_order(s);
+    pl.q = s->ring_valid < order ? s->ring_valid : order;
+    for (int j = 0; j < pl.q; ++j) pl.h[j] = bufs[((cur - 1 - j) % count + count) % count];
+    return step_impl(s, pl, source_d, dt, info_h);
+}
+
 extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* source_d, double dt, crbe_solve_info* info_h) {
     CRBE_REQUIRE(s && u_d && info_h, "null argument");
-    return step_impl(s, u_d, u_d, source_d, dt, info_h);
+    return step_in_place(s, u_d, source_d, dt, info_h);
 }
 
 extern "C" int crbe_solver_step_pingpong(crbe_solver* s, double* u_cur_d, double* u_next_d, const double* source_d, double dt,
                                          crbe_solve_info* info_h) {
     CRBE_REQUIRE(s && u_cur_d && u_next_d && u_cur_d != u_next_d && info_h, "bad argument");
-    return step_impl(s, u_cur_d, u_next_d, source_d, dt, info_h);
+    // a ring of two: keep a canonical order of the pair so that alternating calls are recognised as one time loop
+    const bool fwd = s->ring_n == 2 && s->ring_sig[0] == u_cur_d && s->ring_sig[1] == u_next_d;
+    const bool bwd = s->ring_n == 2 && s->ring_sig[1] == u_cur_d && s->ring_sig[0] == u_next_d;
+    double* bufs[2] = {bwd ? u_next_d : u_cur_d, bwd ? u_cur_d : u_next_d};
+    (void)fwd;
+    return step_ring(s, bufs, 2, bwd ? 1 : 0, source_d, dt, info_h);
+}
+
+extern "C" int crbe_solver_step_ring(crbe_solver* s, double* const* bufs_h, int32_t count, int32_t cur, const double* source_d, double dt,
+                                     crbe_solve_info* info_h) {
+    CRBE_REQUIRE(s && bufs_h && info_h, "null argument");
+    return step_ring(s, bufs_h, count, cur, source_d, dt, info_h);
 }
 
 extern "C" int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d, crbe_solve_info* info_h) {

@@ -296,7 +296,7 @@ class PartitionedCRBE:
         self._solver = h
         flags = (_lib.SOLVER_VERIFY_AUTO if verify == "auto" else (_lib.SOLVER_VERIFY if verify else 0)) | \
                 (_lib.SOLVER_TMA if tma else 0) | \
-                (_lib.SOLVER_EXTRAPOLATE if extrapolate else 0)
+                _lib.extrapolation_flags(extrapolate)
         rt.call("crbe_solver_set_options", h, float(rtol), int(max_iterations), flags)
         rt.call("crbe_solver_set_system", h, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
         vlen = C.c_int64()

@@ -53,18 +53,19 @@ KINDS = ["init", "pv", "st", "xr", "p", "s", "residual", "extrapolate"]
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=1000, help="timed steps (default: the whole 1000-step job of config 3)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", "--n", dest="n", type=int, default=int(os.environ.get("CRBE_BENCH_N", 2048)), help="cells per axis (per GPU strip)")
     ap.add_argument("--regime", default="P-ref", choices=["P-ref", "P-T10", "P-stiff"])
-    ap.add_argument("--no-extrapolate", action="store_true", help="start every solve from u^n instead of 2u^n - u^(n-1)")
+    ap.add_argument("--no-extrapolate", action="store_true", help="start every solve from u^n instead of the extrapolated guess")
+    ap.add_argument("--extrapolate-order", type=int, default=4, help="order of the extrapolated initial guess (1..4; 1 = 2u^n - u^(n-1))")
     ap.add_argument("--verify-always", action="store_true", help="recompute the true residual after every solve (default: auto)")
     ap.add_argument("--index32", action="store_true", help="stream 32-bit column indices even when 16-bit offsets fit")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")
     ap.add_argument("--classic", action="store_true", help="register-load kernels instead of the bulk-copy (TMA) pipeline")
-    ap.add_argument("--e2e-steps", type=int, default=60)
-    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=120)
+    ap.add_argument("--cpu-steps", type=int, default=30, help="steps of the CPU port (cpu_baseline / --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--strong", action="store_true", help="fixed n x n mesh split over the ranks (config 4 style)")
@@ -146,12 +147,14 @@ class ClockSampler:
 # --------------------------------------------------------------------------
 # CPU legs (the only place bench.py touches oracle/)
 # --------------------------------------------------------------------------
-def cpu_port_steps_per_s(wl, steps):
+def cpu_port_steps_per_s(wl, steps, order=0):
     """Oracle port of the same algorithm (Jacobi-BiCGStab, rtol 1e-13) on the host cores.
 
     Set-up (numbering, assembly, Dirichlet rows) uses the numpy/scipy oracle and is not timed.  The time
     loop runs in the OpenMP C leg of the oracle (oracle/crbe_oracle_omp.c) with the thread count that
     proves fastest on this host; if that cannot be built, in numpy/scipy on one thread.
+    order: the product's extrapolated initial guess (same algorithm on both sides; it only pays once the history is
+    there and the start-up transient of the time loop has died down, so the sample covers a few dozen steps).
     Returns (steps/s, iterations per step, threads used, description)."""
     from oracle import crbe_oracle as orc
     mesh = wl.mesh()
@@ -180,9 +183,10 @@ def cpu_port_steps_per_s(wl, steps):
             best, best_t = t, el
     lib.crbe_omp_set_threads(best)
     t0 = time.time()
-    _, its = omp.be_steps(A, md, om.boundary_segments, u0, steps)
+    _, its = omp.be_steps(A, md, om.boundary_segments, u0, steps, order=order)
     el = time.time() - t0
-    return steps / el, its, best, f"OpenMP C leg of the oracle, {best} of {ncpu} host threads (fastest of 1, n/4, n/2, n)"
+    return steps / el, its, best, (f"OpenMP C leg of the oracle, {best} of {ncpu} host threads (fastest of 1, n/4, n/2, n), "
+                                   f"initial guess of order {order}")
 
 
 def run_reference_arm(args):
@@ -197,7 +201,7 @@ def run_reference_arm(args):
     wl = workloads.unit_square(args.n, steps=args.steps, regime=args.regime)
     steps = max(1, min(args.steps, args.cpu_steps))
     t0 = time.time()
-    v, its, cores, how = cpu_port_steps_per_s(wl, steps)
+    v, its, cores, how = cpu_port_steps_per_s(wl, steps, 0 if args.no_extrapolate else args.extrapolate_order)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": 0, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -335,7 +339,7 @@ def main():
     mesh = wl.mesh()
     dom, prob = wl.domain(), wl.problem()
     md = crbe.MeshData(mesh, dom, wl.nt)
-    solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", tma=not args.classic, extrapolate=not args.no_extrapolate, verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False)
+    solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", tma=not args.classic, extrapolate=0 if args.no_extrapolate else args.extrapolate_order, verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False)
     rt = Runtime.get(device)
     solver.set_initial_condition()
     solver.build_global_matrices()
@@ -345,10 +349,14 @@ def main():
     set_index_bits(bits)
     n = md.number_of_segments
     assert n == counts["dofs"]
-    # two alternating solution vectors, as BESCRFEM.solve() uses them (crbe_solver_step_pingpong)
+    # a ring of solution vectors, as BESCRFEM.solve() uses them (crbe_solver_step_ring)
     vlen = C.c_int64()
     rt.call("crbe_solver_vector_length", solver._solver, C.byref(vlen), None)
-    ubuf = [rt.zeros((vlen.value,), torch.float64), rt.zeros((vlen.value,), torch.float64)]
+    q = 0 if args.no_extrapolate else args.extrapolate_order
+    nring = max(2, q + 1)
+    ROW_BYTES["extrapolate"] = (q + 2) * 8        # reads u^n ... u^(n-q), writes the guess over the oldest
+    ubuf = [rt.zeros((vlen.value,), torch.float64) for _ in range(nring)]
+    ring = (C.c_void_p * nring)(*[b.data_ptr() for b in ubuf])
     ubuf[0][:n] = rt.upload(np.asarray(solver.u_prev, dtype=np.float64))
     state = {"cur": 0}
 
@@ -357,8 +365,8 @@ def main():
 
     def step():
         c = state["cur"]
-        rt.call("crbe_solver_step_pingpong", solver._solver, ptr(ubuf[c]), ptr(ubuf[c ^ 1]), ptr(None), dt, C.byref(info))
-        state["cur"] = c ^ 1
+        rt.call("crbe_solver_step_ring", solver._solver, ring, nring, c, ptr(None), dt, C.byref(info))
+        state["cur"] = (c + 1) % nring
         return info.iterations
 
     l0 = C.c_int64()
@@ -413,7 +421,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl.name, **counts, "regime": wl.regime, "dt": wl.dt, "rtol": solver.rtol,
                    "solver": "Jacobi-BiCGStab, merged-reduction 4-kernel iteration" + (", register loads" if args.classic else ", bulk-copy pipeline")
-                             + ("" if args.no_extrapolate else ", extrapolated initial guess"),
+                             + ("" if args.no_extrapolate else f", initial guess extrapolated from the last {q + 1} solutions (order {q})"),
                    "verify": "always" if args.verify_always else "auto (true residual recomputed after solves of > 12 iterations or a restart)",
                    "launch": "kernel by kernel" if args.no_graph else "one CUDA graph per step (head + first batch of iterations + state download)",
                    "index_bits": bits,
@@ -437,7 +445,7 @@ def main():
         E = max(2, min(args.e2e_steps, K))
         wl_e = workloads.unit_square(args.n, steps=E, regime=args.regime)
         md_e = crbe.MeshData(mesh, wl_e.domain(), wl_e.nt)
-        s_e = crbe.BESCRFEM(wl_e.domain(), prob, md_e, crbe.ElementCR(), 1, history="all", tma=not args.classic, extrapolate=not args.no_extrapolate, verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False)
+        s_e = crbe.BESCRFEM(wl_e.domain(), prob, md_e, crbe.ElementCR(), 1, history="all", tma=not args.classic, extrapolate=0 if args.no_extrapolate else args.extrapolate_order, verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False)
         import contextlib
         import io
         with contextlib.redirect_stdout(io.StringIO()):
@@ -450,7 +458,7 @@ def main():
     # ---- CPU baseline on the same box ------------------------------------------
     if not args.no_cpu_baseline:
         cs = max(1, args.cpu_steps)
-        v, its, cores, how = cpu_port_steps_per_s(wl, cs)
+        v, its, cores, how = cpu_port_steps_per_s(wl, cs, q)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{cs} BE steps of the same {wl.name} problem, Jacobi-BiCGStab rtol 1e-13, {how}; "
                                           f"its/step {its}"}

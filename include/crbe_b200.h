@@ -149,8 +149,9 @@ typedef struct crbe_solve_info {
                                          recurrence and true residual grows with the length of the recurrence) */
 #define CRBE_SOLVER_GRAPH 4u          /* single GPU: replay a step (head kernels, first batch of iterations, state download)
                                          as one CUDA graph once the same step shape has been seen twice            */
-#define CRBE_SOLVER_EXTRAPOLATE 16u   /* crbe_solver_step: start from 2 u^n - u^(n-1) (linear extrapolation in
-                                         time) instead of u^n once one step of history exists        */
+#define CRBE_SOLVER_EXTRAPOLATE 16u   /* start each step from the polynomial extrapolation of the last q+1 solutions instead of
+                                         u^n (q = 1: 2 u^n - u^(n-1)), as far as the history of the time loop reaches    */
+#define CRBE_SOLVER_EXTRAP_ORDER(q) (((q) & 7u) << 8)   /* q = 1..4 with CRBE_SOLVER_EXTRAPOLATE; 0 means 1 */
 #define CRBE_SOLVER_TMA 8u            /* SpMV-type kernels fed by bulk async copies (cp.async.bulk
                                          + mbarrier pipeline through shared memory)               */
 
@@ -176,6 +177,13 @@ int crbe_solver_step(crbe_solver* s, double* u_d, const double* source_d, double
  * during the whole next step without a staging copy. */
 int crbe_solver_step_pingpong(crbe_solver* s, double* u_cur_d, double* u_next_d, const double* source_d, double dt,
                               crbe_solve_info* info_h);
+/* The general form: a ring of count = 2..5 such vectors (bufs_h: host array of device pointers).  bufs[cur] holds u^n,
+ * the buffers before it (cyclically) the earlier solutions of this time loop; u^(n+1) is built in bufs[(cur+1) % count],
+ * which held the oldest one.  Call with cur advancing by one each step; the solver notices a new loop by itself.
+ * Nothing is copied, an extrapolation of order q needs count >= q+1, and every solution stays intact for count-1
+ * further steps. */
+int crbe_solver_step_ring(crbe_solver* s, double* const* bufs_h, int32_t count, int32_t cur, const double* source_d, double dt,
+                          crbe_solve_info* info_h);
 /* Solve  A x = b  for the loaded system (Dirichlet rows applied); x_d holds the initial guess. */
 int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d, crbe_solve_info* info_h);
 /* b of crbe.py:384-402 for inspection: b_d (out). */

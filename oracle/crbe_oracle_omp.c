@@ -97,26 +97,48 @@ done:
 }
 
 /* n_steps Backward-Euler steps: b = mdiag .* u (Dirichlet rows zeroed), solve, u <- x.  Zero source (the stock Problem).
+ * order > 0: the initial guess of a step is the polynomial extrapolation of the last order+1 solutions (as far as the
+ * history reaches), x0 = sum_j (-1)^j C(q+1, j+1) u^(n-j) -- the product's initial guess, same stopping rule.
  * iters_out[n_steps].  Returns 0 or a negative step index on failure. */
-int crbe_omp_be_steps(int64_t n, const int32_t* ip, const int32_t* ix, const double* a, const double* dinv, const double* mdiag,
-                      const uint8_t* is_bnd, double* u, int n_steps, double rtol, int maxit, int* iters_out) {
+int crbe_omp_be_steps_extrap(int64_t n, const int32_t* ip, const int32_t* ix, const double* a, const double* dinv, const double* mdiag,
+                             const uint8_t* is_bnd, double* u, int n_steps, double rtol, int maxit, int order, int* iters_out) {
+    static const double C[5][5] = {{1, 0, 0, 0, 0}, {2, -1, 0, 0, 0}, {3, -3, 1, 0, 0}, {4, -6, 4, -1, 0}, {5, -10, 10, -5, 1}};
+    if (order < 0 || order > 4) return -1000001;
     double* b = malloc(8 * n);
-    if (!b) return -1000000;
-    for (int st = 0; st < n_steps; ++st) {
+    double* hist[4] = {0, 0, 0, 0};
+    int ok = b != 0;
+    for (int k = 0; k < order && ok; ++k) ok = (hist[k] = malloc(8 * n)) != 0;
+    int rc = ok ? 0 : -1000000;
+    int have = 0;                 /* hist[0 .. have) = u^(n-1), u^(n-2), ... */
+    for (int st = 0; st < n_steps && rc == 0; ++st) {
+        const int q = have < order ? have : order;
+        double* oldest = order > 0 ? hist[order - 1] : 0;
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < n; ++i) {
-            b[i] = is_bnd[i] ? 0.0 : mdiag[i] * u[i];
-            if (is_bnd[i]) u[i] = 0.0;
+            const double un = is_bnd[i] ? 0.0 : u[i];
+            b[i] = is_bnd[i] ? 0.0 : mdiag[i] * un;
+            double acc = C[q][0] * un;
+            for (int j = 0; j < q; ++j) acc = fma(C[q][j + 1], hist[j][i], acc);
+            if (oldest) oldest[i] = un;     /* the slot of the oldest solution receives u^n (read above when q == order) */
+            u[i] = acc;
+        }
+        if (order > 0) {                    /* rotate: the slot just written becomes hist[0] */
+            for (int k = order - 1; k > 0; --k) hist[k] = hist[k - 1];
+            hist[0] = oldest;
+            if (have < order) ++have;
         }
         const int it = crbe_omp_bicgstab(n, ip, ix, a, dinv, b, u, rtol, maxit);
-        if (it < 0) {
-            free(b);
-            return -(st + 1);
-        }
-        iters_out[st] = it;
+        if (it < 0) rc = -(st + 1);
+        else iters_out[st] = it;
     }
     free(b);
-    return 0;
+    for (int k = 0; k < 4; ++k) free(hist[k]);
+    return rc;
+}
+
+int crbe_omp_be_steps(int64_t n, const int32_t* ip, const int32_t* ix, const double* a, const double* dinv, const double* mdiag,
+                      const uint8_t* is_bnd, double* u, int n_steps, double rtol, int maxit, int* iters_out) {
+    return crbe_omp_be_steps_extrap(n, ip, ix, a, dinv, mdiag, is_bnd, u, n_steps, rtol, maxit, 0, iters_out);
 }
 
 void crbe_omp_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }

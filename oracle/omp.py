@@ -54,8 +54,9 @@ def bicgstab(A, b, x0, dinv, rtol=1e-13, maxit=10000):
     return x, it
 
 
-def be_steps(A, mdiag, boundary, u0, n_steps, rtol=1e-13, maxit=10000):
-    """n_steps Backward-Euler steps with zero source; returns (u, iterations per step)."""
+def be_steps(A, mdiag, boundary, u0, n_steps, rtol=1e-13, maxit=10000, order=0):
+    """n_steps Backward-Euler steps with zero source; returns (u, iterations per step).
+    order: initial guess extrapolated from the last order+1 solutions (0: u^n itself)."""
     lib = load()
     A = A.tocsr()
     n = A.shape[0]
@@ -66,9 +67,9 @@ def be_steps(A, mdiag, boundary, u0, n_steps, rtol=1e-13, maxit=10000):
     isb[boundary] = 1
     u = np.array(u0, dtype=np.float64)
     its = np.zeros(n_steps, dtype=np.int32)
-    rc = lib.crbe_omp_be_steps(C.c_int64(n), _p(ip, C.c_int32), _p(ix, C.c_int32), _p(data, C.c_double), _p(dinv, C.c_double),
+    rc = lib.crbe_omp_be_steps_extrap(C.c_int64(n), _p(ip, C.c_int32), _p(ix, C.c_int32), _p(data, C.c_double), _p(dinv, C.c_double),
                                _p(np.ascontiguousarray(mdiag, dtype=np.float64), C.c_double), _p(isb, C.c_uint8), _p(u, C.c_double),
-                               C.c_int(n_steps), C.c_double(rtol), C.c_int(maxit), _p(its, C.c_int32))
+                               C.c_int(n_steps), C.c_double(rtol), C.c_int(maxit), C.c_int(order), _p(its, C.c_int32))
     if rc != 0:
         raise RuntimeError(f"OpenMP oracle failed at step {-rc}")
     return u, its.tolist()

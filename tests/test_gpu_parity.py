@@ -395,6 +395,53 @@ def test_index16_escape_entries(rt, tma):
         rt.call("crbe_solver_destroy", h)
 
 
+@pytest.mark.parametrize("order", [0, 1, 2, 3, 4])
+def test_extrapolation_orders_match_reference_fixture(order):
+    """The order of the extrapolated initial guess changes where BiCGStab starts, not where it stops."""
+    for name in ("struct_n32_o1", "delaunay40_o1", "source_delaunay80"):
+        g = load_golden(name)
+        crbe, dom, md = _product(g)
+        prob = golden_problem(name, g)
+        s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), extrapolate=order, progress=False)
+        sol = s.solve()
+        assert rel_err(sol[-1], g["final"]) <= SOLUTION_RTOL
+        assert rel_err(s.u_prev, g["u_prev_final"]) <= SOLUTION_RTOL
+
+
+def test_extrapolated_guess_saves_iterations_in_the_benchmark_regime():
+    """dt = 0.08 h^2/D (the reference's own regime): the solution is smooth in time, the order-4 guess leaves
+    one or two BiCGStab iterations per step where u^n as the guess needs six; same solution."""
+    from airpollution_b200 import crbe, workloads
+    wl = workloads.unit_square(96, steps=60, regime="P-ref")
+    md = crbe.MeshData(wl.mesh(), wl.domain(), wl.nt)
+    sols, its = {}, {}
+    for order in (0, 1, 4):
+        s = crbe.BESCRFEM(wl.domain(), wl.problem(), md, crbe.ElementCR(), 1, extrapolate=order, progress=False)
+        sols[order] = s.solve()
+        its[order] = [i[0] for i in s.step_info]
+    assert rel_err(sols[4][-1], sols[0][-1]) <= 1e-11 and rel_err(sols[1][-1], sols[0][-1]) <= 1e-11
+    assert sum(its[4][-20:]) < sum(its[1][-20:]) < sum(its[0][-20:])
+    assert max(its[4][-20:]) <= 3
+    # in-place stepping through the C ABI keeps its own history: same bits as the ring of solve()
+    import torch
+    from airpollution_b200 import _lib
+    from airpollution_b200.runtime import ptr
+    c = crbe.BESCRFEM(wl.domain(), wl.problem(), md, crbe.ElementCR(), 1, extrapolate=4, progress=False)
+    c.set_initial_condition()
+    c.build_global_matrices()
+    rt = c._rt
+    u = rt.upload(np.asarray(c.u_prev, dtype=np.float64))
+    info = _lib.SolveInfo()
+    it_ip = []
+    for _ in range(1, md.nt):
+        rt.call("crbe_solver_step", c._solver, ptr(u), None, float(c.dt), C.byref(info))
+        it_ip.append(info.iterations)
+    assert it_ip == its[4]
+    s4 = crbe.BESCRFEM(wl.domain(), wl.problem(), md, crbe.ElementCR(), 1, extrapolate=4, progress=False)
+    s4.solve()
+    assert np.array_equal(u.cpu().numpy(), s4.u_prev)
+
+
 def test_store_lifted_async_rejects_pageable_rows(rt):
     import torch
     from airpollution_b200 import crbe

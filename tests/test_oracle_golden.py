@@ -197,3 +197,33 @@ def test_openmp_leg_matches_numpy_oracle():
     assert rel_err(u, g["u_prev_final"]) <= 1e-10
     assert rel_err(u, s.u_prev) <= 1e-12
     assert its == s.iterations
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_openmp_leg_extrapolated_guess(order):
+    """The extrapolated initial guess changes where BiCGStab starts, not where it stops: same solution as the
+    fixture, and in a smooth regime (tiny steps) markedly fewer iterations once the history is there."""
+    from oracle import omp
+    from airpollution_b200 import workloads
+    g = load_golden("struct_n16_o1")
+    m = _mesh(g)
+    prob = golden_problem("struct_n16_o1", g)
+    s = orc.OracleSolver(float(g["T"]), prob, m, order=1, linear_solver="bicgstab")
+    s.build_global_matrices()
+    omp.load().crbe_omp_set_threads(2)
+    A = orc.dirichlet_system_fast(s.base_system, m.boundary_segments)
+    u, its = omp.be_steps(A, s.global_mass.diagonal(), m.boundary_segments, prob.initial_condition_fn(m.midpoints), int(g["nt"]) - 1,
+                          order=order)
+    assert rel_err(u, g["u_prev_final"]) <= 1e-10
+    # the benchmark regime on a small mesh: dt = 0.08 h^2 / D
+    wl = workloads.unit_square(64, steps=40, regime="P-ref")
+    mesh = wl.mesh()
+    om = orc.OracleMesh(mesh.points, mesh.triangles, wl.domain().T, wl.nt)
+    so = orc.OracleSolver(wl.domain().T, wl.problem(), om, order=1, linear_solver="bicgstab")
+    so.build_global_matrices()
+    A = orc.dirichlet_system_fast(so.base_system, om.boundary_segments)
+    u0 = wl.problem().initial_condition_fn(om.midpoints)
+    ua, ia = omp.be_steps(A, so.global_mass.diagonal(), om.boundary_segments, u0, 40, order=0)
+    ub, ib = omp.be_steps(A, so.global_mass.diagonal(), om.boundary_segments, u0, 40, order=order)
+    assert rel_err(ub, ua) <= 1e-11
+    assert sum(ib[-10:]) < sum(ia[-10:])
