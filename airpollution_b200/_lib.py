@@ -22,7 +22,7 @@ vp = C.c_void_p   # device pointers are passed as plain addresses
 class SolveInfo(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("restarts", C.c_int32), ("status", C.c_int32),
                 ("launches", C.c_int32), ("relres", C.c_double), ("true_relres", C.c_double),
-                ("bnorm", C.c_double)]
+                ("bnorm", C.c_double), ("initial_relres", C.c_double), ("guess_order", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -35,15 +35,15 @@ SOLVER_TMA = 8
 SOLVER_EXTRAPOLATE = 16
 SOLVER_VERIFY_AUTO = 32
 SOLVER_INDEX32 = 64
+SOLVER_EXTRAP_ADAPT = 128
 MAX_EXTRAP_ORDER = 4
 
 
 def extrapolation_flags(extrapolate):
-    """False/0: start from u^n; True: the default order (4); 1..4: that order."""
+    """False/0: start from u^n; True: order chosen per step, up to 4; 1..4: that order, fixed."""
     if extrapolate is True:
-        q = MAX_EXTRAP_ORDER
-    else:
-        q = int(extrapolate or 0)
+        return SOLVER_EXTRAPOLATE | SOLVER_EXTRAP_ADAPT | (MAX_EXTRAP_ORDER << 8)
+    q = int(extrapolate or 0)
     if not 0 <= q <= MAX_EXTRAP_ORDER:
         raise ValueError(f"extrapolate must be a bool or an order 0..{MAX_EXTRAP_ORDER}")
     return (SOLVER_EXTRAPOLATE | (q << 8)) if q else 0

@@ -201,9 +201,10 @@ class BESCRFEM:
     ``verify``          recompute the true residual ``b - A x`` after convergence: ``True`` always, ``"auto"`` (default)
                         after solves of more than 12 iterations or a restart, ``False`` never.
     ``extrapolate``     start each solve from the polynomial extrapolation of the last solutions instead of ``u^n``:
-                        ``True`` (default) order 4, an int 1..4 that order (1: ``2 u^n - u^(n-1)``), ``False`` none.
-                        Same stopping rule; in the reference's regime of tiny steps the solution is so smooth in
-                        time that order 4 leaves one BiCGStab iteration per step instead of six.
+                        ``True`` (default) order 1..4 chosen per step from the measured initial residuals, an int
+                        1..4 that order, fixed (1: ``2 u^n - u^(n-1)``), ``False`` none.  Same stopping rule; in the
+                        reference's regime of tiny steps the solution is so smooth in time that a cubic or quartic
+                        guess leaves one BiCGStab iteration per step instead of six.
     ``tma``             feed the SpMV-type kernels through the bulk-copy/mbarrier shared-memory
                         pipeline (default) instead of per-thread register loads.
     ``index16``         stream 16-bit ``column - row`` offsets instead of 32-bit columns when every offset of the
@@ -566,7 +567,7 @@ class BESCRFEM:
                     main.wait_event(copied[nxt])          # its download (nring - 1 steps back) must be through before it is reused
                 rt.call("crbe_solver_step_ring", self._solver, ring, nring, cur, ptr(src), dt, C.byref(info))
                 cur = nxt
-                self.step_info.append((info.iterations, info.relres, info.true_relres, info.restarts))
+                self.step_info.append((info.iterations, info.relres, info.true_relres, info.restarts, info.guess_order, info.initial_relres))
                 if step in row_of:                        # the step call has synchronised: the vector is final
                     ev = torch.cuda.Event()
                     if lift_on_device:

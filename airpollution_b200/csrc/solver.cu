@@ -45,7 +45,7 @@ struct crbe_profile {
 };
 
 
-enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RS = 7, S_RT = 8, S_RRTRUE = 10 };
+enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RS = 7, S_RT = 8, S_RR0 = 9, S_RRTRUE = 10 };
 enum { D_STATUS = 0, D_ITERS = 1 };
 constexpr int CRBE_MAX_EXTRAP = 4;      // highest order of the extrapolated initial guess
 constexpr int IDX16_ESCAPE = -32768;   // 16-bit column offset that does not fit: read the 32-bit column instead
@@ -62,6 +62,20 @@ struct StepGraph {
     cudaGraphExec_t exec;
     int launches;
     uint64_t stamp;
+};
+
+// Which order of the extrapolated initial guess to use (CRBE_SOLVER_EXTRAP_ADAPT).  The truncation error of the
+// guess falls with the order, the amplified rounding noise of the earlier solves (sum |c_j| = 3, 7, 15, 31) rises,
+// and during the start-up transient of a time loop low orders are as good as high ones: the policy starts at order 1,
+// keeps a smoothed log10 of the measured initial residual per order, probes a neighbouring order every `interval`
+// steps (4 after a move, doubling up to 64 after a probe that did not pay) and moves when that order is better by a
+// clear margin (scratch/policy_sim.py replays it on the CPU oracle).  Decisions depend only on reduced sums, which are
+// identical on every rank of a partitioned solve.
+struct GuessPolicy {
+    double score[CRBE_MAX_EXTRAP + 1] = {0};
+    bool seen[CRBE_MAX_EXTRAP + 1] = {false};
+    int cur = 1, probe = -1, dir = +1, interval = 8, since = 0;
+    void reset() { *this = GuessPolicy(); }
 };
 
 struct crbe_solver {
@@ -85,6 +99,7 @@ struct crbe_solver {
     int hist_head = 0, hist_count = 0;
     const double* ring_sig[CRBE_MAX_EXTRAP + 1] = {nullptr};
     int ring_n = 0, ring_expect = -1, ring_valid = 0;
+    GuessPolicy guess;
     double* p[1] = {nullptr};
     double* v[1] = {nullptr};
     double* sums = nullptr;
@@ -92,7 +107,7 @@ struct crbe_solver {
     double* sums_h = nullptr;  // pinned: CRBE_NSUMS doubles followed by 2 ints
     double rtol = 1e-13;
     int maxit = 10000;
-    unsigned flags = CRBE_SOLVER_TMA | CRBE_SOLVER_VERIFY_AUTO | CRBE_SOLVER_EXTRAPOLATE | CRBE_SOLVER_EXTRAP_ORDER(4u) | CRBE_SOLVER_GRAPH;
+    unsigned flags = CRBE_SOLVER_TMA | CRBE_SOLVER_VERIFY_AUTO | CRBE_SOLVER_EXTRAPOLATE | CRBE_SOLVER_EXTRAP_ORDER(4u) | CRBE_SOLVER_EXTRAP_ADAPT | CRBE_SOLVER_GRAPH;
     int last_iters = 8;
     bool system_loaded = false;
     // persistent grids: SMs x resident CTAs of each kernel (a grid-stride sweep must be one full wave)
@@ -560,6 +575,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_xrp(int64_t n, int k, double rto
     double* const out[1] = {dots + S_RR};
     if (grid_sum_last<1>(acc, partials, counter, out, ca)) {
         dstate[D_ITERS] += 1;
+        if (k == 0) sums[S_RR0] = rho;      // (r^, r0) = ||r0||^2 of the initial guess, kept for the host (guess-order policy)
         sums[S_RHO0 + ((k + 1) & 1)] = rho_next;
         if (!isfinite(beta) && (ca == nullptr || ca->world <= 1 || dots == sums) && *out[0] > thr) dstate[D_STATUS] = 2;
     }
@@ -1136,6 +1152,7 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
     }
     s->system_loaded = true;
     s->hist_count = 0;          // a new system starts a new time loop
+    s->guess.reset();
     s->ring_valid = 0;
     s->ring_expect = -1;
     return CRBE_OK;
@@ -1451,6 +1468,53 @@ static inline int extrap_order(const crbe_solver* s) {
     return q == 0 ? 1 : (q > CRBE_MAX_EXTRAP ? CRBE_MAX_EXTRAP : q);
 }
 
+// order of the guess for this step, given how many earlier solutions are at hand
+static int choose_guess_order(crbe_solver* s, int avail) {
+    const int order_max = extrap_order(s);
+    if (order_max == 0 || avail == 0) return 0;
+    if (!(s->flags & CRBE_SOLVER_EXTRAP_ADAPT)) return avail < order_max ? avail : order_max;
+    GuessPolicy& g = s->guess;
+    if (g.cur > order_max) g.cur = order_max;
+    int q = g.cur;
+    g.probe = -1;
+    if (++g.since >= g.interval) {
+        g.since = 0;
+        int cand = g.cur + g.dir;
+        if (cand < 1 || cand > order_max) cand = g.cur - g.dir;
+        g.dir = cand < g.cur ? +1 : -1;      // next time the other side, unless this probe wins
+        if (cand >= 1 && cand <= order_max && cand <= avail && cand != g.cur) {
+            q = cand;
+            g.probe = cand;
+        }
+    }
+    return q < avail ? q : avail;
+}
+
+static void record_guess(crbe_solver* s, int q, crbe_solve_info* info) {
+    const double bb = s->sums_h[S_BB];
+    const double rr0 = info->iterations > 0 ? s->sums_h[S_RR0] : s->sums_h[S_RR];
+    info->guess_order = q;
+    info->initial_relres = (bb > 0.0 && info->restarts == 0) ? sqrt(rr0 / bb) : -1.0;
+    if (!(s->flags & CRBE_SOLVER_EXTRAP_ADAPT) || q < 1 || !(info->initial_relres > 0.0)) return;
+    GuessPolicy& g = s->guess;
+    const double val = log10(info->initial_relres);
+    if (g.probe == q) {
+        g.score[q] = val;
+        g.seen[q] = true;
+        if (g.seen[g.cur] && val < g.score[g.cur] - 0.1) {   // clearly better: move there and look further the same way soon
+            g.dir = q > g.cur ? +1 : -1;
+            g.cur = q;
+            g.interval = 4;
+        } else {
+            g.interval = g.interval < 64 ? 2 * g.interval : 64;
+        }
+        g.probe = -1;
+    } else {
+        g.score[q] = g.seen[q] ? 0.5 * (g.score[q] + val) : val;
+        g.seen[q] = true;
+    }
+}
+
 static int launch_extrapolate(crbe_solver* s, const StepPlan& pl, int* launches) {
     cudaStream_t st = s->ctx->stream;
     ExtrapArgs a;
@@ -1625,13 +1689,15 @@ static int step_in_place(crbe_solver* s, double* u_d, const double* source_d, do
             CRBE_CUDA(cudaMemsetAsync(s->hist[k], 0, vb, s->ctx->stream));
         }
     if (s->hist_head >= slots) s->hist_head = 0;
-    pl.q = s->hist_count < order ? s->hist_count : order;
+    pl.q = choose_guess_order(s, s->hist_count < order ? s->hist_count : order);
     for (int j = 0; j < pl.q; ++j) pl.h[j] = s->hist[(s->hist_head + j) % slots];
     const int dst = (s->hist_head + slots - 1) % slots;              // the oldest copy (or a free slot) makes room for u^n
     pl.save = s->hist[dst];
     s->hist_head = dst;
     if (s->hist_count < slots) s->hist_count += 1;
-    return step_impl(s, pl, source_d, dt, info_h);
+    const int rc = step_impl(s, pl, source_d, dt, info_h);
+    if (rc == CRBE_OK) record_guess(s, pl.q, info_h);
+    return rc;
 }
 
 // Ring of caller-owned vectors (each crbe_solver_vector_length long, zero padded): bufs[cur] holds u^n, the buffers before
@@ -1663,9 +1729,11 @@ static int step_ring(crbe_solver* s, double* const* bufs, int count, int cur, co
         return step_impl(s, pl, source_d, dt, info_h);
     }
     const int order = extrap_order(s);
-    pl.q = s->ring_valid < order ? s->ring_valid : order;
+    pl.q = choose_guess_order(s, s->ring_valid < order ? s->ring_valid : order);
     for (int j = 0; j < pl.q; ++j) pl.h[j] = bufs[((cur - 1 - j) % count + count) % count];
-    return step_impl(s, pl, source_d, dt, info_h);
+    const int rc = step_impl(s, pl, source_d, dt, info_h);
+    if (rc == CRBE_OK) record_guess(s, pl.q, info_h);
+    return rc;
 }
 
 extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* source_d, double dt, crbe_solve_info* info_h) {

@@ -59,7 +59,8 @@ def parse_args():
     ap.add_argument("--cells", "--n", dest="n", type=int, default=int(os.environ.get("CRBE_BENCH_N", 2048)), help="cells per axis (per GPU strip)")
     ap.add_argument("--regime", default="P-ref", choices=["P-ref", "P-T10", "P-stiff"])
     ap.add_argument("--no-extrapolate", action="store_true", help="start every solve from u^n instead of the extrapolated guess")
-    ap.add_argument("--extrapolate-order", type=int, default=4, help="order of the extrapolated initial guess (1..4; 1 = 2u^n - u^(n-1))")
+    ap.add_argument("--extrapolate-order", type=int, default=0,
+                    help="fixed order of the extrapolated initial guess (1..4; 1 = 2u^n - u^(n-1)); default 0: chosen per step, up to 4")
     ap.add_argument("--verify-always", action="store_true", help="recompute the true residual after every solve (default: auto)")
     ap.add_argument("--index32", action="store_true", help="stream 32-bit column indices even when 16-bit offsets fit")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")
@@ -201,7 +202,7 @@ def run_reference_arm(args):
     wl = workloads.unit_square(args.n, steps=args.steps, regime=args.regime)
     steps = max(1, min(args.steps, args.cpu_steps))
     t0 = time.time()
-    v, its, cores, how = cpu_port_steps_per_s(wl, steps, 0 if args.no_extrapolate else args.extrapolate_order)
+    v, its, cores, how = cpu_port_steps_per_s(wl, steps, 0 if args.no_extrapolate else (args.extrapolate_order or 3))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": 0, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -339,7 +340,7 @@ def main():
     mesh = wl.mesh()
     dom, prob = wl.domain(), wl.problem()
     md = crbe.MeshData(mesh, dom, wl.nt)
-    solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", tma=not args.classic, extrapolate=0 if args.no_extrapolate else args.extrapolate_order, verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False)
+    solver = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, history="last", tma=not args.classic, extrapolate=False if args.no_extrapolate else (args.extrapolate_order or True), verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False)
     rt = Runtime.get(device)
     solver.set_initial_condition()
     solver.build_global_matrices()
@@ -352,9 +353,8 @@ def main():
     # a ring of solution vectors, as BESCRFEM.solve() uses them (crbe_solver_step_ring)
     vlen = C.c_int64()
     rt.call("crbe_solver_vector_length", solver._solver, C.byref(vlen), None)
-    q = 0 if args.no_extrapolate else args.extrapolate_order
+    q = 0 if args.no_extrapolate else (args.extrapolate_order or 4)
     nring = max(2, q + 1)
-    ROW_BYTES["extrapolate"] = (q + 2) * 8        # reads u^n ... u^(n-q), writes the guess over the oldest
     ubuf = [rt.zeros((vlen.value,), torch.float64) for _ in range(nring)]
     ring = (C.c_void_p * nring)(*[b.data_ptr() for b in ubuf])
     ubuf[0][:n] = rt.upload(np.asarray(solver.u_prev, dtype=np.float64))
@@ -362,11 +362,13 @@ def main():
 
     info = _lib.SolveInfo()
     dt = float(solver.dt)
+    orders = []
 
     def step():
         c = state["cur"]
         rt.call("crbe_solver_step_ring", solver._solver, ring, nring, c, ptr(None), dt, C.byref(info))
         state["cur"] = (c + 1) % nring
+        orders.append(info.guess_order)
         return info.iterations
 
     l0 = C.c_int64()
@@ -378,10 +380,14 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    del orders[:]
     iters = [step() for _ in range(K)]
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    timed_orders = list(orders)
+    q_mean = float(np.mean(timed_orders)) if timed_orders else 0.0
+    ROW_BYTES["extrapolate"] = (q_mean + 2) * 8   # reads u^n ... u^(n-q), writes the guess over the oldest
     l1 = C.c_int64()
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l1))
     # same region once more with a CUDA event pair around every kernel launch: per-kernel durations for the roofline
@@ -421,7 +427,9 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl.name, **counts, "regime": wl.regime, "dt": wl.dt, "rtol": solver.rtol,
                    "solver": "Jacobi-BiCGStab, merged-reduction 4-kernel iteration" + (", register loads" if args.classic else ", bulk-copy pipeline")
-                             + ("" if args.no_extrapolate else f", initial guess extrapolated from the last {q + 1} solutions (order {q})"),
+                             + ("" if args.no_extrapolate else ", initial guess extrapolated from the last solutions ("
+                                + (f"order {args.extrapolate_order}" if args.extrapolate_order else "order 1..4 chosen per step from the measured initial residuals")
+                                + f"; mean order {q_mean:.2f}, orders of the last 16 steps {timed_orders[-16:]})"),
                    "verify": "always" if args.verify_always else "auto (true residual recomputed after solves of > 12 iterations or a restart)",
                    "launch": "kernel by kernel" if args.no_graph else "one CUDA graph per step (head + first batch of iterations + state download)",
                    "index_bits": bits,
@@ -445,7 +453,7 @@ def main():
         E = max(2, min(args.e2e_steps, K))
         wl_e = workloads.unit_square(args.n, steps=E, regime=args.regime)
         md_e = crbe.MeshData(mesh, wl_e.domain(), wl_e.nt)
-        s_e = crbe.BESCRFEM(wl_e.domain(), prob, md_e, crbe.ElementCR(), 1, history="all", tma=not args.classic, extrapolate=0 if args.no_extrapolate else args.extrapolate_order, verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False)
+        s_e = crbe.BESCRFEM(wl_e.domain(), prob, md_e, crbe.ElementCR(), 1, history="all", tma=not args.classic, extrapolate=False if args.no_extrapolate else (args.extrapolate_order or True), verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False)
         import contextlib
         import io
         with contextlib.redirect_stdout(io.StringIO()):
@@ -458,7 +466,7 @@ def main():
     # ---- CPU baseline on the same box ------------------------------------------
     if not args.no_cpu_baseline:
         cs = max(1, args.cpu_steps)
-        v, its, cores, how = cpu_port_steps_per_s(wl, cs, q)
+        v, its, cores, how = cpu_port_steps_per_s(wl, cs, 0 if args.no_extrapolate else (args.extrapolate_order or max(1, int(round(q_mean)))))
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{cs} BE steps of the same {wl.name} problem, Jacobi-BiCGStab rtol 1e-13, {how}; "
                                           f"its/step {its}"}

@@ -139,6 +139,9 @@ typedef struct crbe_solve_info {
     double relres;           /* recurrence residual  ||r|| / ||b||  (Jacobi-scaled)   */
     double true_relres;      /* ||b - A x|| / ||b|| recomputed after convergence      */
     double bnorm;            /* ||b|| (Jacobi-scaled)                                  */
+    double initial_relres;   /* ||b - A x0|| / ||b|| of the initial guess (crbe_solver_step*)  */
+    int32_t guess_order;     /* order of the extrapolated initial guess used by this step      */
+    int32_t reserved;
 } crbe_solve_info;
 
 #define CRBE_SOLVER_FUSED 1u          /* reserved (the iteration is the merged-reduction form)   */
@@ -152,6 +155,9 @@ typedef struct crbe_solve_info {
 #define CRBE_SOLVER_EXTRAPOLATE 16u   /* start each step from the polynomial extrapolation of the last q+1 solutions instead of
                                          u^n (q = 1: 2 u^n - u^(n-1)), as far as the history of the time loop reaches    */
 #define CRBE_SOLVER_EXTRAP_ORDER(q) (((q) & 7u) << 8)   /* q = 1..4 with CRBE_SOLVER_EXTRAPOLATE; 0 means 1 */
+#define CRBE_SOLVER_EXTRAP_ADAPT 128u /* treat the order as an upper bound and pick the order per step from the measured
+                                         initial residuals: which order wins depends on how smooth the solution is in
+                                         time against the rounding noise of the earlier solves (higher orders amplify it) */
 #define CRBE_SOLVER_TMA 8u            /* SpMV-type kernels fed by bulk async copies (cp.async.bulk
                                          + mbarrier pipeline through shared memory)               */
 
