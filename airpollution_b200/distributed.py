@@ -347,7 +347,8 @@ class PartitionedCRBE:
         from .runtime import ptr
         self.step_index += 1
         self.rt.call("crbe_solver_step", self._solver, ptr(self.u), ptr(source), float(self.dt), C.byref(self.info))
-        self.step_info.append((self.info.iterations, self.info.relres, self.info.true_relres, self.info.restarts))
+        self.step_info.append((self.info.iterations, self.info.relres, self.info.true_relres, self.info.restarts,
+                               self.info.guess_order, self.info.initial_relres))
         return self.info.iterations
 
     def owned_solution(self, lifted=True):
@@ -434,7 +435,12 @@ def bench_partitioned(args, K, W, device):
     pms, pcnt = (C.c_double * 8)(), (C.c_int64 * 8)()
     rt.call("crbe_solver_profile_read", part._solver, pms, pcnt)
     n_own = part.n_own
+    bits = C.c_int32()
+    rt.call("crbe_solver_index_bits", part._solver, C.byref(bits))
+    B.set_index_bits(bits.value)
+    q_mean = float(np.mean([i[4] for i in part.step_info[-K:]])) if part.step_info else 0.0
     rb = dict(B.ROW_BYTES)
+    rb["extrapolate"] = (q_mean + 3) * 8      # in-place form: reads u^n ... u^(n-q), writes the guess and the copy of u^n
     kern = {B.KINDS[k]: {"launches": int(pcnt[k]), "ms_per_launch": pms[k] / pcnt[k],
                          "GBps": rb[B.KINDS[k]] * n_own / (pms[k] / pcnt[k] * 1e-3) / 1e9} for k in range(8) if pcnt[k] > 0}
     steps_per_s = K / (ms * 1e-3)
@@ -466,6 +472,7 @@ def bench_partitioned(args, K, W, device):
                    "value_definition": ("n_gpus x steps/s of the partitioned mesh: every GPU advances a 12.6M-DOF strip per step"
                                         if scaling == "weak" else "steps/s of the fixed mesh"),
                    "solver": "Jacobi-BiCGStab, merged-reduction 4-kernel iteration, halo exchange + allreduce over " + part.transport,
+                   "index_bits": bits.value, "guess_order_mean": q_mean,
                    "iters_per_step": float(np.mean(iters)), "l2": "inputs larger than L2", "setup_s": setup_s},
         "dof_updates_per_s": steps_per_s * counts["dofs"],
         "clocks": clocks, "gpu_launches": int(l1.value - l0.value), "kernels": kern,
