@@ -113,7 +113,8 @@ struct crbe_solver {
     // persistent grids: SMs x resident CTAs of each kernel (a grid-stride sweep must be one full wave)
     int g_init = 1, g_pv = 1, g_st = 1, g_xr = 1, g_vec = 1, g_res = 1, g_spmv = 1;
     int gt_pv = 1, gt_st = 1, gt_init = 1, gt_res = 1;   // tile (bulk-copy) kernels
-    int gs_pv = 1, gs_st = 1, gs_init = 1, gs_res = 1;   // ... their 16-bit-offset variants (smaller stages, maybe more CTAs per SM)
+    int gs_pv = 1, gs_st = 1, gs_init = 1, gs_res = 1;
+    int gt_pv0 = 1, gs_pv0 = 1;                          // first-iteration SpMV (one vector stream)   // ... their 16-bit-offset variants (smaller stages, maybe more CTAs per SM)
     int64_t ntiles = 0;
     // row-block partition (world > 1): this solver holds the rows [0, n) of its rank; gathered vectors carry the
     // halo entries (values owned by other ranks) behind the padded owned part, at [ld, ld + n_halo)
@@ -480,13 +481,15 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
         const double ax = ell_row(eval, ecol, ld, i, xi, [&](int j) { return __ldg(x + j); });
         const double ri = bi - ax;
         b[i] = bi;
-        r[i] = ri;
         rh[i] = ri;
-        p[i] = ri;
+        if (r) {            // single GPU: the first iteration reads r and p through r^ (all three are r0), see launch_iteration
+            r[i] = ri;
+            p[i] = ri;
+        }
         acc[0] = fma(bi, bi, acc[0]);
         acc[1] = fma(ri, ri, acc[1]);
     }
-    halo_push_tail(p, 1, ca);
+    if (r) halo_push_tail(p, 1, ca);
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
     grid_sum_last<3>(acc, partials, counter, out, ca);
@@ -546,9 +549,10 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, double
 
 // x += alpha p + omega s;  r = s - omega t;  p = r + beta (p - omega v);  (r, r);
 // rho_{k+1} = (r^,s) - omega (r^,t) is published by the last CTA (every rank computes the same value).
+// p_in: where the old p is read (p itself, or r^ in the first iteration on a single GPU; may alias p: no __restrict__)
 __global__ void __launch_bounds__(CRBE_BLOCK) k_xrp(int64_t n, int k, double rtol2, const double* __restrict__ s, const double* __restrict__ t,
                                                     const double* __restrict__ v, double* __restrict__ x, double* __restrict__ r,
-                                                    double* __restrict__ p, double* sums, double* dots, int* dstate, double* partials,
+                                                    const double* p_in, double* p, double* sums, double* dots, int* dstate, double* partials,
                                                     unsigned int* counter, const CommArgs* __restrict__ ca) {
     if (solver_idle(sums, dstate, rtol2)) return;
     const double rho = sums[S_RHO0 + (k & 1)];
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_xrp(int64_t n, int k, double rto
     const double thr = rtol2 * sums[S_BB];
     double acc[1] = {0.0};
     ROW_LOOP(i, n) {
-        const double si = s[i], pi = p[i];
+        const double si = s[i], pi = p_in[i];
         x[i] = fma(alpha, pi, fma(omega, si, x[i]));
         const double ri = fma(-omega, t[i], si);
         r[i] = ri;
@@ -938,11 +942,13 @@ static int solver_init(crbe_solver* s, crbe_ctx* ctx, crbe_comm* comm, int64_t n
         s->g_spmv = crbe_persistent_grid(ctx, k_spmv_csr, n);
         // bulk-copy kernels: opt in to their dynamic shared memory, then size one resident wave over the tiles
         s->ntiles = s->ld / CRBE_TILE;
-        CRBE_CHECK(tile_grid(ctx, t_pv<int>, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_pv));
+        CRBE_CHECK(tile_grid(ctx, t_pv<int, false>, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_pv));
+        CRBE_CHECK(tile_grid(ctx, t_pv<int, true>, TilePipe<1, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_pv0));
         CRBE_CHECK(tile_grid(ctx, t_st<int>, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_st));
         CRBE_CHECK(tile_grid(ctx, t_init_be<int>, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_init));
         CRBE_CHECK(tile_grid(ctx, t_residual<int>, TilePipe<1, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_res));
-        CRBE_CHECK(tile_grid(ctx, t_pv<short>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_pv));
+        CRBE_CHECK(tile_grid(ctx, t_pv<short, false>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_pv));
+        CRBE_CHECK(tile_grid(ctx, t_pv<short, true>, TilePipe<1, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_pv0));
         CRBE_CHECK(tile_grid(ctx, t_st<short>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_st));
         CRBE_CHECK(tile_grid(ctx, t_init_be<short>, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_init));
         CRBE_CHECK(tile_grid(ctx, t_residual<short>, TilePipe<1, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_res));
@@ -1261,22 +1267,36 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
     const double rtol2 = s->rtol * s->rtol;
     const bool tma = (s->flags & CRBE_SOLVER_TMA) != 0;
     double *p = s->p[0], *v = s->v[0];
+    // At k = 0 the init / restart kernel has just set r = r^ = p = r0.  On a single GPU the first iteration reads all
+    // three through r^ (the init kernels then do not write r and p at all: 16 B per row less, and the two operands of
+    // the first SpMV are one stream).  The partitioned solver keeps p apart: its halo entries live behind p.
+    const bool first = k == 0 && s->world == 1;
+    const double* p_in = first ? s->rh : p;
+    const double* r_in = first ? s->rh : s->r;
     // p is up to date (written by the init / restart kernel at k = 0, by k_xrp afterwards), its halo refreshed
     CRBE_CHECK(halo_exchange(s, p, launches));
     const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
-    if (tma && i16)
-        PROF_LAUNCH(PK_PV, k, (t_pv<short><<<s->gs_pv, CRBE_TILE, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col16, s->ell_col, p, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
-                                  ctx->counter, s->d_comm)));
+    if (tma && i16 && first)
+        PROF_LAUNCH(PK_PV, k, (t_pv<short, true><<<s->gs_pv0, CRBE_TILE, TilePipe<1, SPMV_STAGES, short>::SMEM_BYTES, st>>>(
+                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col16, s->ell_col, p_in, v, s->rh, s->sums, s->dots, s->dstate,
+                                  ctx->partials, ctx->counter, s->d_comm)));
+    else if (tma && i16)
+        PROF_LAUNCH(PK_PV, k, (t_pv<short, false><<<s->gs_pv, CRBE_TILE, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, st>>>(
+                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col16, s->ell_col, p_in, v, s->rh, s->sums, s->dots, s->dstate,
+                                  ctx->partials, ctx->counter, s->d_comm)));
+    else if (tma && first)
+        PROF_LAUNCH(PK_PV, k, (t_pv<int, true><<<s->gt_pv0, CRBE_TILE, TilePipe<1, SPMV_STAGES, int>::SMEM_BYTES, st>>>(
+                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, nullptr, p_in, v, s->rh, s->sums, s->dots, s->dstate,
+                                  ctx->partials, ctx->counter, s->d_comm)));
     else if (tma)
-        PROF_LAUNCH(PK_PV, k, (t_pv<int><<<s->gt_pv, CRBE_TILE, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, nullptr, p, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
-                                  ctx->counter, s->d_comm)));
+        PROF_LAUNCH(PK_PV, k, (t_pv<int, false><<<s->gt_pv, CRBE_TILE, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, st>>>(
+                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, nullptr, p_in, v, s->rh, s->sums, s->dots, s->dstate,
+                                  ctx->partials, ctx->counter, s->d_comm)));
     else
-        PROF_LAUNCH(PK_PV, k, (k_pv<<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, rtol2, s->ell_val, s->ell_col, p, v, s->rh, s->sums, s->dots,
+        PROF_LAUNCH(PK_PV, k, (k_pv<<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, rtol2, s->ell_val, s->ell_col, p_in, v, s->rh, s->sums, s->dots,
                                                                  s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     CRBE_CHECK(reduce_dots(s, S_RHV, 1, S_RHV, -1, -1, -1, launches));
-    PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->r, v, s->s, s->sums, s->dstate, s->d_comm)));
+    PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, r_in, v, s->s, s->sums, s->dstate, s->d_comm)));
     CRBE_CHECK(halo_exchange(s, s->s, launches));
     if (tma && i16)
         PROF_LAUNCH(PK_ST, k, (t_st<short><<<s->gs_st, CRBE_TILE, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, st>>>(
@@ -1290,7 +1310,7 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
         PROF_LAUNCH(PK_ST, k, (k_st<<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, rtol2, s->ell_val, s->ell_col, s->s, s->t, s->rh, s->sums,
                                                                  s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     CRBE_CHECK(reduce_dots(s, S_TS, 4, S_TS, S_TT, S_RS, S_RT, launches));
-    PROF_LAUNCH(PK_XR, k, (k_xrp<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->s, s->t, v, x, s->r, p, s->sums, s->dots, s->dstate,
+    PROF_LAUNCH(PK_XR, k, (k_xrp<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->s, s->t, v, x, s->r, p_in, p, s->sums, s->dots, s->dstate,
                                                               ctx->partials, ctx->counter, s->d_comm)));
     *launches += 4;
     CRBE_CHECK(reduce_dots(s, S_RR, 1, S_RR, -1, -1, -1, launches));
@@ -1559,21 +1579,22 @@ static int enqueue_step_head(crbe_solver* s, const StepPlan& pl, const double* s
     }
     CRBE_CHECK(halo_exchange(s, x, launches));
     const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
+    double* r_w = s->world == 1 ? nullptr : s->r;   // single GPU: r and p are not written, the first iteration reads r^ (launch_iteration)
     if (cn)
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->tmp, source_d, dt,
-                                                                             s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
+                                                                             s->mscale, s->dscale, s->is_bnd, s->b, r_w, s->rh, s->p[0], s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if ((s->flags & CRBE_SOLVER_TMA) && i16)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<short><<<s->gs_init, CRBE_TILE, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->ell_val, s->ell_col16, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r,
+                                     s->n, s->ntiles, s->ell_val, s->ell_col16, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, s->b, r_w,
                                      s->rh, s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<int><<<s->gt_init, CRBE_TILE, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->ell_val, s->ell_col, nullptr, x, xb, source_d, dt, s->mscale, s->dscale, s->b, s->r,
+                                     s->n, s->ntiles, s->ell_val, s->ell_col, nullptr, x, xb, source_d, dt, s->mscale, s->dscale, s->b, r_w,
                                      s->rh, s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else
         PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, xb, source_d, dt,
-                                                                             s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
+                                                                             s->mscale, s->dscale, s->is_bnd, s->b, r_w, s->rh, s->p[0], s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     *launches += 1;
     CRBE_KERNEL_CHECK();
@@ -1766,7 +1787,7 @@ extern "C" int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d,
     int launches = 1;
     CRBE_CHECK(halo_exchange(s, x_d, &launches));
     k_init<2><<<s->g_init, CRBE_BLOCK, 0, ctx->stream>>>(s->n, s->ld, s->ell_val, s->ell_col, x_d, b_d, nullptr, 0.0,
-                                                                        s->mscale, s->dscale, s->is_bnd, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
+                                                                        s->mscale, s->dscale, s->is_bnd, s->b, s->world == 1 ? nullptr : s->r, s->rh, s->p[0], s->sums, s->dots,
                                                                         s->dstate, ctx->partials, ctx->counter, s->d_comm);
     CRBE_KERNEL_CHECK();
     CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, -1, &launches));

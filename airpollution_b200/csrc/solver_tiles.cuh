@@ -186,7 +186,8 @@ __device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, 
 }
 
 // ---- v = A p, (r^, v) ------------------------------------------------------------------------------------
-template <class IDX>
+// FIRST: the first iteration after an init / restart on a single GPU, where p = r^ = r0: one vector stream instead of two.
+template <class IDX, bool FIRST>
 __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, double rtol2, const double* __restrict__ eval,
                                                   const IDX* __restrict__ ecol, const int* __restrict__ ecol32, const double* __restrict__ p, double* __restrict__ v,
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
@@ -194,18 +195,18 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, dou
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[SPMV_STAGES];
     if (solver_idle(sums, dstate, rtol2)) return;
-    TilePipe<2, SPMV_STAGES, IDX> pipe;
+    TilePipe<FIRST ? 1 : 2, SPMV_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
     pipe.ecol32 = ecol32;
     pipe.vec[0] = p;
-    pipe.vec[1] = rh;
+    if (!FIRST) pipe.vec[FIRST ? 0 : 1] = rh;
     pipe.start(tile_smem, bars, ntiles);
     halo_wait(1, ca);   // the bulk copies are already in flight
     double acc[1] = {0.0};
     tile_spmv_prefetch(pipe, p, n, [&](int64_t m, int64_t row, int tr, double, double vi) {
         v[row] = vi;
-        acc[0] = fma(pipe.svec(m, 1)[tr], vi, acc[0]);
+        acc[0] = fma(pipe.svec(m, FIRST ? 0 : 1)[tr], vi, acc[0]);
     });
     double* const out[1] = {dots + S_RHV};
     grid_sum_last<1>(acc, partials, counter, out, ca);
@@ -279,15 +280,17 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
             const double ax = tile_row(pipe, m, tr, xi, [&](int j) { return __ldg(x + j); });
             const double ri = bi - ax;
             b[row] = bi;
-            r[row] = ri;
             rh[row] = ri;
-            p[row] = ri;
+            if (r) {        // see k_init
+                r[row] = ri;
+                p[row] = ri;
+            }
             acc[0] = fma(bi, bi, acc[0]);
             acc[1] = fma(ri, ri, acc[1]);
         }
         pipe.release(m);
     }
-    halo_push_tail(p, 1, ca);
+    if (r) halo_push_tail(p, 1, ca);
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
     grid_sum_last<3>(acc, partials, counter, out, ca);

@@ -437,7 +437,7 @@ def bench_partitioned(args, K, W, device):
     n_own = part.n_own
     bits = C.c_int32()
     rt.call("crbe_solver_index_bits", part._solver, C.byref(bits))
-    B.set_index_bits(bits.value)
+    B.set_index_bits(bits.value, single_gpu=False)
     q_mean = float(np.mean([i[4] for i in part.step_info[-K:]])) if part.step_info else 0.0
     rb = dict(B.ROW_BYTES)
     rb["extrapolate"] = (q_mean + 3) * 8      # in-place form: reads u^n ... u^(n-q), writes the guess and the copy of u^n
