@@ -26,6 +26,9 @@ def main(path, suffix=""):
     seen, traffic = set(), {}
     for r in data:
         kern = re.sub(r"^void ", "", r[col["Kernel Name"]]).split("(")[0]
+        dur = float(r[col["gpu__time_duration.sum"]].replace(",", ""))
+        if units[col["gpu__time_duration.sum"]] in ("us", "usecond") and dur < 10.0:
+            continue          # a launch past convergence: returns at once
         if kern in seen:
             continue
         seen.add(kern)
@@ -36,7 +39,9 @@ def main(path, suffix=""):
         rd = float(r[col["dram__bytes_read.sum"]].replace(",", "")) * SCALE[units[col["dram__bytes_read.sum"]]]
         wr = float(r[col["dram__bytes_write.sum"]].replace(",", "")) * SCALE[units[col["dram__bytes_write.sum"]]]
         print(f"  dram traffic (read+write) per launch: {(rd + wr) / 1e6:.1f} MB\n")
-        traffic[kern.split("<")[0] + suffix] = rd + wr
+        key = kern.replace("<short, 1>", "0").replace("<int, 1>", "0")
+        key = re.sub(r"<(short|int)(, 0)?>", "", key).replace("<", "").replace(">", "")
+        traffic[key + suffix] = rd + wr
     print("# traffic json:", json.dumps(traffic))
 
 
