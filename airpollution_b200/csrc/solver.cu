@@ -482,14 +482,12 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
         const double ri = bi - ax;
         b[i] = bi;
         rh[i] = ri;
-        if (r) {            // single GPU: the first iteration reads r and p through r^ (all three are r0), see launch_iteration
-            r[i] = ri;
-            p[i] = ri;
-        }
+        if (r) r[i] = ri;   // r = r^ = p = r0: the first iteration reads them through one vector (launch_iteration), so the
+        if (p) p[i] = ri;   // step kernels pass r = nullptr, and p only where its halo entries are needed (partitioned solver)
         acc[0] = fma(bi, bi, acc[0]);
         acc[1] = fma(ri, ri, acc[1]);
     }
-    if (r) halo_push_tail(p, 1, ca);
+    if (p) halo_push_tail(p, 1, ca);
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
     grid_sum_last<3>(acc, partials, counter, out, ca);
@@ -1267,12 +1265,12 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
     const double rtol2 = s->rtol * s->rtol;
     const bool tma = (s->flags & CRBE_SOLVER_TMA) != 0;
     double *p = s->p[0], *v = s->v[0];
-    // At k = 0 the init / restart kernel has just set r = r^ = p = r0.  On a single GPU the first iteration reads all
-    // three through r^ (the init kernels then do not write r and p at all: 16 B per row less, and the two operands of
-    // the first SpMV are one stream).  The partitioned solver keeps p apart: its halo entries live behind p.
-    const bool first = k == 0 && s->world == 1;
-    const double* p_in = first ? s->rh : p;
-    const double* r_in = first ? s->rh : s->r;
+    // At k = 0 the init / restart kernel has just set r = r^ = p = r0, so the first iteration reads all three through
+    // one vector and its SpMV streams one operand instead of two: r^ on a single GPU (the init kernels then write
+    // neither r nor p: 24 B per row less), p in the partitioned solver (its halo entries live behind p; r is not written).
+    const bool first = k == 0;
+    const double* p_in = first && s->world == 1 ? s->rh : p;
+    const double* r_in = first ? p_in : s->r;
     // p is up to date (written by the init / restart kernel at k = 0, by k_xrp afterwards), its halo refreshed
     CRBE_CHECK(halo_exchange(s, p, launches));
     const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
@@ -1579,22 +1577,23 @@ static int enqueue_step_head(crbe_solver* s, const StepPlan& pl, const double* s
     }
     CRBE_CHECK(halo_exchange(s, x, launches));
     const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
-    double* r_w = s->world == 1 ? nullptr : s->r;   // single GPU: r and p are not written, the first iteration reads r^ (launch_iteration)
+    double* const r_w = nullptr;                          // see launch_iteration: the first iteration does not read r,
+    double* const p_w = s->world == 1 ? nullptr : s->p[0];   // and p only in the partitioned solver
     if (cn)
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->tmp, source_d, dt,
-                                                                             s->mscale, s->dscale, s->is_bnd, s->b, r_w, s->rh, s->p[0], s->sums, s->dots,
+                                                                             s->mscale, s->dscale, s->is_bnd, s->b, r_w, s->rh, p_w, s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if ((s->flags & CRBE_SOLVER_TMA) && i16)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<short><<<s->gs_init, CRBE_TILE, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, st>>>(
                                      s->n, s->ntiles, s->ell_val, s->ell_col16, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, s->b, r_w,
-                                     s->rh, s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
+                                     s->rh, p_w, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<int><<<s->gt_init, CRBE_TILE, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, st>>>(
                                      s->n, s->ntiles, s->ell_val, s->ell_col, nullptr, x, xb, source_d, dt, s->mscale, s->dscale, s->b, r_w,
-                                     s->rh, s->p[0], s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
+                                     s->rh, p_w, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else
         PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, xb, source_d, dt,
-                                                                             s->mscale, s->dscale, s->is_bnd, s->b, r_w, s->rh, s->p[0], s->sums, s->dots,
+                                                                             s->mscale, s->dscale, s->is_bnd, s->b, r_w, s->rh, p_w, s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     *launches += 1;
     CRBE_KERNEL_CHECK();
@@ -1787,7 +1786,7 @@ extern "C" int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d,
     int launches = 1;
     CRBE_CHECK(halo_exchange(s, x_d, &launches));
     k_init<2><<<s->g_init, CRBE_BLOCK, 0, ctx->stream>>>(s->n, s->ld, s->ell_val, s->ell_col, x_d, b_d, nullptr, 0.0,
-                                                                        s->mscale, s->dscale, s->is_bnd, s->b, s->world == 1 ? nullptr : s->r, s->rh, s->p[0], s->sums, s->dots,
+                                                                        s->mscale, s->dscale, s->is_bnd, s->b, nullptr, s->rh, s->world == 1 ? nullptr : s->p[0], s->sums, s->dots,
                                                                         s->dstate, ctx->partials, ctx->counter, s->d_comm);
     CRBE_KERNEL_CHECK();
     CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, -1, &launches));

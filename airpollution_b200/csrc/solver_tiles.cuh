@@ -186,7 +186,7 @@ __device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, 
 }
 
 // ---- v = A p, (r^, v) ------------------------------------------------------------------------------------
-// FIRST: the first iteration after an init / restart on a single GPU, where p = r^ = r0: one vector stream instead of two.
+// FIRST: the first iteration after an init / restart, where p = r^ = r0: one vector stream instead of two.
 template <class IDX, bool FIRST>
 __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, double rtol2, const double* __restrict__ eval,
                                                   const IDX* __restrict__ ecol, const int* __restrict__ ecol32, const double* __restrict__ p, double* __restrict__ v,
@@ -281,16 +281,14 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
             const double ri = bi - ax;
             b[row] = bi;
             rh[row] = ri;
-            if (r) {        // see k_init
-                r[row] = ri;
-                p[row] = ri;
-            }
+            if (r) r[row] = ri;   // see k_init
+            if (p) p[row] = ri;
             acc[0] = fma(bi, bi, acc[0]);
             acc[1] = fma(ri, ri, acc[1]);
         }
         pipe.release(m);
     }
-    if (r) halo_push_tail(p, 1, ca);
+    if (p) halo_push_tail(p, 1, ca);
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
     grid_sum_last<3>(acc, partials, counter, out, ca);

@@ -440,6 +440,8 @@ def bench_partitioned(args, K, W, device):
     B.set_index_bits(bits.value, single_gpu=False)
     q_mean = float(np.mean([i[4] for i in part.step_info[-K:]])) if part.step_info else 0.0
     rb = dict(B.ROW_BYTES)
+    f0 = min(1.0, min(K, 30) / pcnt[1]) if pcnt[1] > 0 else 0.0     # share of first-iteration (one-stream) SpMV launches
+    rb["pv"] = f0 * rb["pv0"] + (1.0 - f0) * rb["pv"]
     rb["extrapolate"] = (q_mean + 3) * 8      # in-place form: reads u^n ... u^(n-q), writes the guess and the copy of u^n
     kern = {B.KINDS[k]: {"launches": int(pcnt[k]), "ms_per_launch": pms[k] / pcnt[k],
                          "GBps": rb[B.KINDS[k]] * n_own / (pms[k] / pcnt[k] * 1e-3) / 1e9} for k in range(8) if pcnt[k] > 0}

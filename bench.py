@@ -45,10 +45,10 @@ ROW_BYTES = {"init": 48 + 7 * 8, "pv": 48 + 3 * 8, "st": 48 + 3 * 8, "xr": 8 * 8
 
 def set_index_bits(bits, single_gpu=True):
     """The matrix part of a row is 4 values + 4 indices: 48 B with 32-bit columns, 40 B with 16-bit offsets.
-    On a single GPU the init kernel writes b and r^ only (the first iteration reads r and p through r^), and the
-    first SpMV of a solve streams one vector instead of two ("pv0")."""
+    The init kernel writes b and r^ only (plus p in the partitioned solver): the first iteration reads r and p
+    through one vector, and the first SpMV of a solve streams one vector instead of two ("pv0")."""
     mat = 32 + 4 * bits // 8
-    ROW_BYTES.update({"init": mat + (5 if single_gpu else 7) * 8, "pv": mat + 3 * 8, "pv0": mat + (2 if single_gpu else 3) * 8,
+    ROW_BYTES.update({"init": mat + (5 if single_gpu else 6) * 8, "pv": mat + 3 * 8, "pv0": mat + 2 * 8,
                       "st": mat + 3 * 8, "residual": mat + 2 * 8})
 KINDS = ["init", "pv", "st", "xr", "p", "s", "residual", "extrapolate"]
 
