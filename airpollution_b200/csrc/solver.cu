@@ -12,11 +12,15 @@
 //   so a warp reads 32 consecutive doubles / ints per slot (fully coalesced,
 //   48 B per row instead of CSR's 64 B), a whole tile is one contiguous burst
 //   for the bulk-copy pipeline (solver_tiles.cuh), and x is gathered through
-//   L1/L2.  The CSR arrays stay the exchange format with the host (scipy) side.
+//   L1/L2.  The bulk-copy kernels stream the columns as 16-bit (column - row)
+//   offsets when (nearly) all of them fit: ell_col16, same layout, 40 B per row.
+//   The CSR arrays stay the exchange format with the host (scipy) side.
 //
 // Kernels per BiCGStab iteration (merged-reduction form, see "BiCGStab kernels" below): pv, s, st, xrp --
-// 232 bytes per row.  The SpMV-type kernels come in two flavours: register loads (k_*, this file) and the
+// 216 bytes per row.  The SpMV-type kernels come in two flavours: register loads (k_*, this file) and the
 // bulk-copy / mbarrier shared-memory pipeline (t_*, solver_tiles.cuh, default).
+// A step starts from a guess extrapolated from the last solutions (k_extrapolate, GuessPolicy), which in the
+// reference's regime leaves about one iteration per step; whole steps are replayed as CUDA graphs (StepGraph).
 // Scalars (alpha, beta, omega) never visit the host: each kernel derives them
 // from a small device buffer of dot products written by the last CTA of the
 // producing kernel (deterministic two-stage reduction, no float atomics).
@@ -441,16 +445,17 @@ __global__ void k_lift_to(const double* __restrict__ u, const double* __restrict
 // ---------------------------------------------------------------- BiCGStab kernels
 // The iteration is the merged-reduction form of BiCGStab (Yang & Brent): (r^,s) and (r^,t) are taken together with
 // (t,s), (t,t), so rho_{k+1} = (r^,s) - omega (r^,t) and beta are known when x and r are updated and the p-update
-// joins that kernel.  Four kernels and 232 B per row and iteration (bulk-copy layout):
-//   pv : v = A p, (r^,v)                                              48 + 3*8
+// joins that kernel.  Four kernels and 216 B per row and iteration (bulk-copy layout, matrix part of a row = 4 f64
+// values + 4 16-bit column offsets = 40 B; 48 B and 232 B with 32-bit columns):
+//   pv : v = A p, (r^,v)                                              40 + 3*8   (first iteration: 40 + 2*8)
 //   s  : s = r - alpha v                                              3*8
-//   st : t = A s, (t,s), (t,t), (r^,s), (r^,t)                        48 + 3*8
+//   st : t = A s, (t,s), (t,t), (r^,s), (r^,t)                        40 + 3*8
 //   xrp: x += alpha p + omega s; r = s - omega t; p = r + beta (p - omega v); (r,r)      8*8
 //
 // MODE 0: Backward Euler right-hand side  b = (M_ii u^n_i + dt f_i) / d_i   (crbe.py:384,394,402); bin = u^n
 // MODE 1: b = scale_i * (bin_i + dt f_i), scale_i = 1/d_i (0 on Dirichlet rows)           (CN, crbe.py:386)
 // MODE 2: b = bin_i / d_i, Dirichlet rows keep bin_i                                    (generic solve)
-// then r = r^ = p = b - A x and the norms (b,b), (r,r).
+// then r^ (and r, p where asked for) = b - A x and the norms (b,b), (r,r).
 template <int MODE>
 __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, const double* __restrict__ eval, const int* __restrict__ ecol,
                                                      const double* __restrict__ x, const double* __restrict__ bin,
@@ -1764,12 +1769,10 @@ extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* sourc
 extern "C" int crbe_solver_step_pingpong(crbe_solver* s, double* u_cur_d, double* u_next_d, const double* source_d, double dt,
                                          crbe_solve_info* info_h) {
     CRBE_REQUIRE(s && u_cur_d && u_next_d && u_cur_d != u_next_d && info_h, "bad argument");
-    // a ring of two: keep a canonical order of the pair so that alternating calls are recognised as one time loop
-    const bool fwd = s->ring_n == 2 && s->ring_sig[0] == u_cur_d && s->ring_sig[1] == u_next_d;
-    const bool bwd = s->ring_n == 2 && s->ring_sig[1] == u_cur_d && s->ring_sig[0] == u_next_d;
-    double* bufs[2] = {bwd ? u_next_d : u_cur_d, bwd ? u_cur_d : u_next_d};
-    (void)fwd;
-    return step_ring(s, bufs, 2, bwd ? 1 : 0, source_d, dt, info_h);
+    // a ring of two: keep the order of the pair seen first, so that alternating calls are recognised as one time loop
+    const bool swapped = s->ring_n == 2 && s->ring_sig[1] == u_cur_d && s->ring_sig[0] == u_next_d;
+    double* bufs[2] = {swapped ? u_next_d : u_cur_d, swapped ? u_cur_d : u_next_d};
+    return step_ring(s, bufs, 2, swapped ? 1 : 0, source_d, dt, info_h);
 }
 
 extern "C" int crbe_solver_step_ring(crbe_solver* s, double* const* bufs_h, int32_t count, int32_t cur, const double* source_d, double dt,

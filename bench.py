@@ -429,7 +429,7 @@ def main():
     tot_share = sum(shares.values())
     shares = {k: round(v / tot_share, 3) for k, v in shares.items()}
     # whole-step traffic in this layout: per iteration pv+s+st+xrp, per step init + residual (+ extrapolation)
-    per_it = ROW_BYTES["pv"] + ROW_BYTES["s"] + ROW_BYTES["st"] + ROW_BYTES["xr"]      # 232 B per row and iteration (216 with 16-bit offsets)
+    per_it = ROW_BYTES["pv"] + ROW_BYTES["s"] + ROW_BYTES["st"] + ROW_BYTES["xr"]      # 216 B per row and iteration with 16-bit offsets (232 with 32-bit columns)
     step_bytes = (it_mean * per_it + ROW_BYTES["init"] + (ROW_BYTES["residual"] if "residual" in kern else 0)
                   + (0 if args.no_extrapolate else ROW_BYTES["extrapolate"])) * n
     # SURVEY 8(d) CSR accounting of a textbook BiCGStab iteration (2 CSR SpMV + 19 vector passes), for comparison
