@@ -407,7 +407,8 @@ def bench_partitioned(args, K, W, device):
     t0 = time.time()
     part = PartitionedCRBE(wl, device=device, tma=not args.classic, extrapolate=not args.no_extrapolate)
     setup_s = time.time() - t0
-    for _ in range(W):
+    spinup = B.spinup_steps(args, K)
+    for _ in range(spinup + W):
         part.step()
     sampler = B.ClockSampler(device.index)
     sampler.start()
@@ -451,7 +452,7 @@ def bench_partitioned(args, K, W, device):
     # e2e: every step the owned block of the solution is downloaded into pinned host memory
     e2e = None
     if not args.no_e2e:
-        E = max(2, min(args.e2e_steps, K))
+        E = max(2, min(args.e2e_steps, 120))
         host = torch.zeros((2, n_own), dtype=torch.float64, pin_memory=True)
         dist.barrier()
         torch.cuda.synchronize()
@@ -475,7 +476,7 @@ def bench_partitioned(args, K, W, device):
                                         if scaling == "weak" else "steps/s of the fixed mesh"),
                    "solver": "Jacobi-BiCGStab, merged-reduction 4-kernel iteration, halo exchange + allreduce over " + part.transport,
                    "index_bits": bits.value, "guess_order_mean": q_mean,
-                   "iters_per_step": float(np.mean(iters)), "l2": "inputs larger than L2", "setup_s": setup_s},
+                   "iters_per_step": float(np.mean(iters)), "l2": "inputs larger than L2", "setup_s": setup_s, **B.spinup_note(spinup)},
         "dof_updates_per_s": steps_per_s * counts["dofs"],
         "clocks": clocks, "gpu_launches": int(l1.value - l0.value), "kernels": kern,
         "roofline": {"bound": "hbm", "kernel": "pv: ELL SpMV v = A p + dot (r^,v), rank 0", "achieved": kern["pv"]["GBps"],
