@@ -85,7 +85,7 @@ def parse_args():
     ap.add_argument("--index32", action="store_true", help="stream 32-bit column indices even when 16-bit offsets fit")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")
     ap.add_argument("--classic", action="store_true", help="register-load kernels instead of the bulk-copy (TMA) pipeline")
-    ap.add_argument("--e2e-steps", type=int, default=240, help="time levels of the e2e BESCRFEM.solve() run (100.7 MB of pinned host memory each)")
+    ap.add_argument("--e2e-steps", type=int, default=120, help="time levels of the e2e BESCRFEM.solve() run (100.7 MB of pinned host memory each)")
     ap.add_argument("--spinup", type=int, default=-1,
                     help="steps of the time loop advanced during set-up, before warm-up (default: 0 when the whole job is timed, "
                          "--steps >= 500; 40 for shorter samples, so that they measure the developed loop and not its first steps)")
