@@ -172,10 +172,14 @@ int crbe_solver_create(crbe_ctx* ctx, int64_t n, const int32_t* indptr_d, const 
  * preconditioner into the stored rows. */
 int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, const double* m_val_d,
                            const double* rhs_val_d);
+/* Defaults: rtol 1e-13, 10000 iterations, flags = TMA | VERIFY_AUTO | GRAPH | EXTRAPOLATE | EXTRAP_ORDER(4) | EXTRAP_ADAPT.
+ * None of the flags changes the stopping rule ||r|| <= rtol ||b||. */
 int crbe_solver_set_options(crbe_solver* s, double rtol, int32_t max_iterations, uint32_t flags);
 /* One time step (crbe.py:419-426 without the lift): forms b from u_d (and
  * dt*source_d if not NULL), solves the Dirichlet system, leaves the un-lifted
- * solution in u_d. */
+ * solution in u_d.  The solver keeps copies of the last solutions of the loop
+ * (right-hand side, extrapolated initial guess); crbe_solver_set_system starts
+ * a new loop. */
 int crbe_solver_step(crbe_solver* s, double* u_d, const double* source_d, double dt, crbe_solve_info* info_h);
 /* The same step with two alternating vectors (single GPU; both crbe_solver_vector_length long, zero padded):
  * u_cur_d holds u^n and is left intact, the new solution is built in u_next_d (which should still hold u^(n-1)
