@@ -61,3 +61,27 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "/root/reference" not in text, f
+
+
+def test_extrapolation_flag_encoding():
+    """extrapolate=True/False/0..4 -> CRBE_SOLVER_EXTRAPOLATE, CRBE_SOLVER_EXTRAP_ORDER(q), CRBE_SOLVER_EXTRAP_ADAPT (header values)."""
+    import re
+    import pytest
+    from airpollution_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "crbe_b200.h")).read()
+    val = lambda name: int(re.search(r"#define %s (\d+)u" % name, hdr).group(1))
+    assert _lib.SOLVER_EXTRAPOLATE == val("CRBE_SOLVER_EXTRAPOLATE") and _lib.SOLVER_EXTRAP_ADAPT == val("CRBE_SOLVER_EXTRAP_ADAPT")
+    assert _lib.SOLVER_INDEX32 == val("CRBE_SOLVER_INDEX32") and _lib.SOLVER_GRAPH == val("CRBE_SOLVER_GRAPH")
+    assert _lib.SOLVER_VERIFY_AUTO == val("CRBE_SOLVER_VERIFY_AUTO") and _lib.SOLVER_TMA == val("CRBE_SOLVER_TMA")
+    assert _lib.extrapolation_flags(False) == 0 and _lib.extrapolation_flags(0) == 0
+    assert _lib.extrapolation_flags(True) == _lib.SOLVER_EXTRAPOLATE | _lib.SOLVER_EXTRAP_ADAPT | (4 << 8)
+    for q in (1, 2, 3, 4):
+        assert _lib.extrapolation_flags(q) == _lib.SOLVER_EXTRAPOLATE | (q << 8)
+        assert _lib.extrapolation_order(q) == q
+    assert _lib.extrapolation_order(True) == 4 and _lib.extrapolation_order(False) == 0
+    with pytest.raises(ValueError):
+        _lib.extrapolation_flags(5)
+    # the ctypes mirror of crbe_solve_info has the header's fields, in order
+    body = re.search(r"typedef struct crbe_solve_info \{(.*?)\} crbe_solve_info;", hdr, re.S).group(1)
+    fields = re.findall(r"(?:int32_t|double)\s+(\w+);", body)
+    assert fields == [f for f, _ in _lib.SolveInfo._fields_]
