@@ -1122,6 +1122,10 @@ extern "C" int crbe_solver_set_options(crbe_solver* s, double rtol, int32_t max_
     s->maxit = max_iterations;
     s->flags = flags;
     drop_step_graphs(s);   // tolerances and kernel variants are baked into the captured launches
+    s->hist_count = 0;     // the order of the guess may have changed: its history starts afresh
+    s->ring_valid = 0;
+    s->ring_expect = -1;
+    s->guess.reset();
     return CRBE_OK;
 }
 
