@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "crbe_common.cuh"
+#include "guess_policy.h"
 
 enum { PK_INIT = 0, PK_PV, PK_ST, PK_XR, PK_P, PK_S, PK_RES, PK_EXTRAP, PK_COUNT };
 
@@ -51,7 +52,6 @@ struct crbe_profile {
 
 enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RS = 7, S_RT = 8, S_RR0 = 9, S_RRTRUE = 10 };
 enum { D_STATUS = 0, D_ITERS = 1 };
-constexpr int CRBE_MAX_EXTRAP = 4;      // highest order of the extrapolated initial guess
 constexpr int IDX16_ESCAPE = -32768;   // 16-bit column offset that does not fit: read the 32-bit column instead
 
 struct P2PHeader;
@@ -66,20 +66,6 @@ struct StepGraph {
     cudaGraphExec_t exec;
     int launches;
     uint64_t stamp;
-};
-
-// Which order of the extrapolated initial guess to use (CRBE_SOLVER_EXTRAP_ADAPT).  The truncation error of the
-// guess falls with the order, the amplified rounding noise of the earlier solves (sum |c_j| = 3, 7, 15, 31) rises,
-// and during the start-up transient of a time loop low orders are as good as high ones: the policy starts at order 1,
-// keeps a smoothed log10 of the measured initial residual per order, probes a neighbouring order every `interval`
-// steps (4 after a move, doubling up to 64 after a probe that did not pay) and moves when that order is better by a
-// clear margin (scratch/policy_sim.py replays it on the CPU oracle).  Decisions depend only on reduced sums, which are
-// identical on every rank of a partitioned solve.
-struct GuessPolicy {
-    double score[CRBE_MAX_EXTRAP + 1] = {0};
-    bool seen[CRBE_MAX_EXTRAP + 1] = {false};
-    int cur = 1, probe = -1, dir = +1, interval = 8, since = 0;
-    void reset() { *this = GuessPolicy(); }
 };
 
 struct crbe_solver {
@@ -1500,21 +1486,7 @@ static int choose_guess_order(crbe_solver* s, int avail) {
     const int order_max = extrap_order(s);
     if (order_max == 0 || avail == 0) return 0;
     if (!(s->flags & CRBE_SOLVER_EXTRAP_ADAPT)) return avail < order_max ? avail : order_max;
-    GuessPolicy& g = s->guess;
-    if (g.cur > order_max) g.cur = order_max;
-    int q = g.cur;
-    g.probe = -1;
-    if (++g.since >= g.interval) {
-        g.since = 0;
-        int cand = g.cur + g.dir;
-        if (cand < 1 || cand > order_max) cand = g.cur - g.dir;
-        g.dir = cand < g.cur ? +1 : -1;      // next time the other side, unless this probe wins
-        if (cand >= 1 && cand <= order_max && cand <= avail && cand != g.cur) {
-            q = cand;
-            g.probe = cand;
-        }
-    }
-    return q < avail ? q : avail;
+    return s->guess.choose(order_max, avail);
 }
 
 static void record_guess(crbe_solver* s, int q, crbe_solve_info* info) {
@@ -1523,23 +1495,7 @@ static void record_guess(crbe_solver* s, int q, crbe_solve_info* info) {
     info->guess_order = q;
     info->initial_relres = (bb > 0.0 && info->restarts == 0) ? sqrt(rr0 / bb) : -1.0;
     if (!(s->flags & CRBE_SOLVER_EXTRAP_ADAPT) || q < 1 || !(info->initial_relres > 0.0)) return;
-    GuessPolicy& g = s->guess;
-    const double val = log10(info->initial_relres);
-    if (g.probe == q) {
-        g.score[q] = val;
-        g.seen[q] = true;
-        if (g.seen[g.cur] && val < g.score[g.cur] - 0.1) {   // clearly better: move there and look further the same way soon
-            g.dir = q > g.cur ? +1 : -1;
-            g.cur = q;
-            g.interval = 4;
-        } else {
-            g.interval = g.interval < 64 ? 2 * g.interval : 64;
-        }
-        g.probe = -1;
-    } else {
-        g.score[q] = g.seen[q] ? 0.5 * (g.score[q] + val) : val;
-        g.seen[q] = true;
-    }
+    s->guess.record(q, log10(info->initial_relres));
 }
 
 static int launch_extrapolate(crbe_solver* s, const StepPlan& pl, int* launches) {
