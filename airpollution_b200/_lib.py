@@ -85,6 +85,7 @@ _SIGNATURES = {
     "crbe_solver_step_ring": [vp, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, vp, C.c_double, C.POINTER(SolveInfo)],
     "crbe_solver_solve": [vp, vp, vp, C.POINTER(SolveInfo)],
     "crbe_solver_rhs": [vp, vp, vp, C.c_double, vp],
+    "crbe_solver_step_residual": [vp, vp, vp, vp, C.c_double, c_f64p, c_f64p],
     "crbe_solver_lift": [vp, vp, vp, vp],
     "crbe_solver_store_lifted_async": [vp, vp, vp, vp, vp],
     "crbe_solver_index_bits": [vp, C.POINTER(C.c_int32)],
@@ -105,14 +106,14 @@ _SIGNATURES = {
     "crbe_solver_x": [vp, C.POINTER(vp)],
     "crbe_solver_p2p_error": [vp, c_i32p],
 }
-# test / debug hooks (not in the public header)
+# test hooks (declared in the header's "test hooks" section)
 _DEBUG_SIGNATURES = {
     "crbe_test_exclusive_scan": [vp, vp, vp, C.c_int64, c_i64p],
     "crbe_solver_debug_ell": [vp, c_i64p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
     "crbe_comm_test_allreduce": [vp, vp, C.c_int],
 }
 
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["crbe_last_error"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_DEBUG_SIGNATURES) + ["crbe_last_error"])
 
 
 class CrbeError(RuntimeError):

@@ -448,8 +448,11 @@ class BESCRFEM:
                 if not isinstance(f, torch.Tensor):
                     raise TypeError("source_term did not return a tensor")
                 return f.to(torch.float64).contiguous()
-            except Exception:
-                self._source_mode = "host"   # the user's callback only understands numpy
+            except (TypeError, AttributeError, NotImplementedError):
+                # the user's callback only understands numpy (np.exp of a CUDA tensor raises TypeError, a numpy-only
+                # method is an AttributeError).  Anything else -- a bug in the callback, a CUDA error, out of memory --
+                # propagates instead of silently re-running the callback on the host for the rest of the solve.
+                self._source_mode = "host"
         xyt = np.hstack((md.midpoints, t * np.ones((n, 1))))               # crbe.py:391-392
         return rt.upload(np.asarray(prob.source_term(xyt), dtype=np.float64))
 
@@ -547,8 +550,25 @@ class BESCRFEM:
 
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(max_workers=1)
-        bc_jobs = [pool.submit(boundary_values, st * self.dt) for st in stored] if nb else []
+        # boundary_fn runs on the helper thread a bounded number of stored rows ahead of the time loop (not all nt
+        # evaluations up front: the results would pile up in memory and keep running after a failure)
+        bc_ahead = 8
+        bc_jobs = {}
+
+        def bc_submit(upto):
+            while nb and len(bc_jobs) + bc_taken[0] < min(len(stored), upto):
+                k = len(bc_jobs) + bc_taken[0]
+                bc_jobs[k] = pool.submit(boundary_values, stored[k] * self.dt)
+
+        def bc_result(k):
+            bc_submit(k + 1 + bc_ahead)
+            bc_taken[0] += 1
+            return bc_jobs.pop(k).result()
+
+        bc_taken = [0]
+        bc_submit(bc_ahead)
         lift_on_device = pinned and nb > 0
+        bc_host = [] if (nb and not lift_on_device) else None
         if lift_on_device:
             bc_ring = 4
             bc_pin = torch.zeros((bc_ring, nb), dtype=torch.float64, pin_memory=True)
@@ -574,7 +594,7 @@ class BESCRFEM:
                         slot = n_stored % bc_ring
                         if ring_ev[slot] is not None:
                             ring_ev[slot].synchronize()   # its upload (4 rows back) is long through
-                        bc_np[slot, :] = bc_jobs[n_stored].result()
+                        bc_np[slot, :] = bc_result(n_stored)
                         rt.call("crbe_solver_store_lifted_async", self._solver, ptr(ubuf[cur]), bc_pin[slot].data_ptr(),
                                 sol_t[row_of[step]].data_ptr(), copy_stream.cuda_stream)
                         ev.record(copy_stream)
@@ -583,14 +603,19 @@ class BESCRFEM:
                         with torch.cuda.stream(copy_stream):
                             sol_t[row_of[step]].copy_(ubuf[cur][:n], non_blocking=True)
                             ev.record(copy_stream)
+                        if bc_host is not None:
+                            bc_host.append(bc_result(n_stored))
                     copied[cur] = ev
                     n_stored += 1
             copy_stream.synchronize()
             rt.synchronize()
             if nb and not lift_on_device:
                 rows_idx = np.array([row_of[st] for st in stored], dtype=np.int64)
-                bc_all = np.stack([j.result() for j in bc_jobs]) if stored else np.zeros((0, nb))
+                bc_all = np.stack(bc_host) if stored else np.zeros((0, nb))
                 self.solutions[rows_idx[:, None], bnd[None, :]] += bc_all   # u_prev + set_boundary_fn(t), crbe.py:429
+        except BaseException:
+            pool.shutdown(wait=False, cancel_futures=True)   # do not evaluate the remaining callbacks after a failure
+            raise
         finally:
             pool.shutdown(wait=True)
         self.solve_time = time.time() - start

@@ -1784,6 +1784,47 @@ extern "C" int crbe_solver_rhs(crbe_solver* s, const double* u_d, const double* 
     return CRBE_OK;
 }
 
+// Independent check of a finished Backward-Euler step (crbe.py:384-426): the residual of u_next in the Dirichlet system built from
+// u_prev,  || (M u_prev + dt f)/d - A~ u_next || / || (M u_prev + dt f)/d ||  in the solver's (diagonally scaled) norm.  Reads
+// the loaded matrix and the two solutions only -- none of the solver's work vectors or sums -- so it can follow any step of
+// any stepping variant without disturbing the time loop.
+__global__ void __launch_bounds__(CRBE_BLOCK) k_step_residual(int64_t n, int64_t ld, const double* __restrict__ eval, const int* __restrict__ ecol,
+                                                              const double* __restrict__ up, const double* __restrict__ un,
+                                                              const double* __restrict__ src, double dt, const double* __restrict__ mscale,
+                                                              const double* __restrict__ dscale, double* out, double* partials,
+                                                              unsigned int* counter) {
+    double acc[2] = {0.0, 0.0};
+    ROW_LOOP(i, n) {
+        double bi = mscale[i] * up[i];
+        if (src) bi = fma(dscale[i] * dt, src[i], bi);
+        const double ax = ell_row(eval, ecol, ld, i, un[i], [&](int j) { return __ldg(un + j); });
+        const double ri = bi - ax;
+        acc[0] = fma(bi, bi, acc[0]);
+        acc[1] = fma(ri, ri, acc[1]);
+    }
+    double* const o[2] = {out, out + 1};
+    grid_sum_last<2>(acc, partials, counter, o, nullptr);
+}
+
+extern "C" int crbe_solver_step_residual(crbe_solver* s, const double* u_prev_d, const double* u_next_d, const double* source_d, double dt,
+                                         double* relres_h, double* bnorm_h) {
+    CRBE_REQUIRE(s && u_prev_d && u_next_d && relres_h, "null argument");
+    CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
+    CRBE_REQUIRE(s->rhs_val == nullptr, "the step check is for the Backward-Euler system");
+    CRBE_REQUIRE(s->world == 1, "single-GPU solver only (halo entries of u_next would have to be current)");
+    crbe_ctx* ctx = s->ctx;
+    k_step_residual<<<s->g_res, CRBE_BLOCK, 0, ctx->stream>>>(s->n, s->ld, s->ell_val, s->ell_col, u_prev_d, u_next_d, source_d, dt, s->mscale,
+                                                             s->dscale, ctx->dev_scalars, ctx->partials, ctx->counter);
+    CRBE_KERNEL_CHECK();
+    ctx->launches += 1;
+    CRBE_CUDA(cudaMemcpyAsync(ctx->host_scalars, ctx->dev_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double bb = ctx->host_scalars[0], rr = ctx->host_scalars[1];
+    *relres_h = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
+    if (bnorm_h) *bnorm_h = sqrt(bb);
+    return CRBE_OK;
+}
+
 extern "C" int crbe_solver_lift(crbe_solver* s, const double* u_d, const double* bc_values_d, double* out_d) {
     CRBE_REQUIRE(s && u_d && out_d && (s->nb == 0 || bc_values_d), "null argument");
     crbe_ctx* ctx = s->ctx;

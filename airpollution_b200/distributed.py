@@ -392,6 +392,84 @@ class PartitionedCRBE:
 # --------------------------------------------------------------------------
 # bench.py --gpus N
 # --------------------------------------------------------------------------
+def _timed_partitioned_steps(part, lead, K, device):
+    """lead untimed steps, then K timed ones: CUDA events on the launching stream between barrier + synchronize, max over
+    ranks.  Returns (ms, iterations per timed step)."""
+    for _ in range(lead):
+        part.step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    iters = [part.step() for _ in range(K)]
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    return float(ms_t.item()), iters
+
+
+def partition_parity_check(args, device, n=256, steps=30):
+    """Partitioned solve against the single-GPU solve of the same mesh, in this process group: ``steps`` steps of an
+    n x n-cell problem from the initial condition on all ranks (strips) and on rank 0 alone; relative difference of the
+    final vectors (rank 0's figure is broadcast).  Keeps partitioned parity in the driver-run record even where the GPU
+    tests that cover it are skipped for lack of a second GPU."""
+    import bench as B
+    from . import workloads
+    rank = dist.get_rank()
+    wl = workloads.unit_square(n, steps=steps, regime=args.regime)
+    part = PartitionedCRBE(wl, device=device, tma=not args.classic, extrapolate=not args.no_extrapolate)
+    its_p = [part.step() for _ in range(steps)]
+    full = part.gather_solution(lifted=False)
+    part.close()
+    out = [None]
+    if rank == 0:
+        loop = B.SingleGpuLoop(args, wl, device)
+        its_1 = [loop.step() for _ in range(steps)]
+        ref = loop.current_solution()
+        loop.close()
+        den = float(np.linalg.norm(ref))
+        out[0] = {"rel_diff_vs_1gpu": float(np.linalg.norm(full - ref) / den) if den > 0 else None, "bar": 1e-11,
+                  "workload": wl.name, "dofs": int(len(ref)), "steps_from_ic": steps, "iters_partitioned": int(sum(its_p)),
+                  "iters_1gpu": int(sum(its_1))}
+    dist.broadcast_object_list(out, src=0)
+    return out[0]
+
+
+def strong_block(args, device):
+    """BASELINE config 4: the 8192 x 8192-cell mesh (201 M DOFs) split into strips over the ranks, against the same mesh on
+    rank 0 alone, measured in the same process (the other ranks wait)."""
+    import bench as B
+    from . import workloads
+    rank, world = dist.get_rank(), dist.get_world_size()
+    K, W, spin = args.strong_steps, 3, 40
+    box = [None]
+    if rank == 0:
+        box[0] = B.strong_block_single(args, device)
+    dist.barrier()
+    dist.broadcast_object_list(box, src=0)
+    one = box[0]
+    try:
+        wl = workloads.unit_square(args.strong_n, steps=K + W + spin, regime=args.regime)
+        t0 = time.time()
+        part = PartitionedCRBE(wl, device=device, tma=not args.classic, extrapolate=not args.no_extrapolate)
+        setup_s = time.time() - t0
+        ms, iters = _timed_partitioned_steps(part, spin + W, K, device)
+        n_own = part.n_own
+        part.close()
+        sps = K / (ms * 1e-3)
+        out = {"workload": wl.name + f", {world} strips of cell rows", "dofs": wl.counts()["dofs"], "dofs_per_gpu_rank0": n_own,
+               "n_gpus": world, "steps": K, "lead_in_steps": spin + W, "steps_per_s": sps, "ms_per_step": ms / K,
+               "iters_per_step": float(np.mean(iters)), "setup_s": setup_s, "one_gpu": one,
+               "speedup_vs_1gpu": (sps / one["steps_per_s"]) if one and "steps_per_s" in one else None,
+               "target": ">= 6x at 8 GPUs (BASELINE north_star)"}
+    except Exception as e:       # all ranks fail alike (same sizes): report instead of taking the weak line down
+        torch.cuda.empty_cache()
+        out = {"unavailable": f"{type(e).__name__}: {e}", "one_gpu": one}
+    return out
+
+
 def bench_partitioned(args, K, W, device):
     import bench as B
     from . import workloads
@@ -404,6 +482,7 @@ def bench_partitioned(args, K, W, device):
     else:
         wl = workloads.unit_square(args.n, steps=K + W, regime=args.regime, ny=args.n * world)
         scaling = "weak"
+    win = B.time_window(args, K, W)
     t0 = time.time()
     part = PartitionedCRBE(wl, device=device, tma=not args.classic, extrapolate=not args.no_extrapolate)
     setup_s = time.time() - t0
@@ -414,17 +493,7 @@ def bench_partitioned(args, K, W, device):
     sampler.start()
     l0, l1 = C.c_int64(), C.c_int64()
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l0))
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    iters = [part.step() for _ in range(K)]
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms_t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
-    dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms = float(ms_t.item())
+    ms, iters = _timed_partitioned_steps(part, 0, K, device)
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l1))
     # the same steps once more with a CUDA event pair around every kernel launch (per-kernel durations)
     rt.call("crbe_solver_profile", part._solver, 1)
@@ -446,6 +515,7 @@ def bench_partitioned(args, K, W, device):
     rb["extrapolate"] = (q_mean + 3) * 8      # in-place form: reads u^n ... u^(n-q), writes the guess and the copy of u^n
     kern = {B.KINDS[k]: {"launches": int(pcnt[k]), "ms_per_launch": pms[k] / pcnt[k],
                          "GBps": rb[B.KINDS[k]] * n_own / (pms[k] / pcnt[k] * 1e-3) / 1e9} for k in range(8) if pcnt[k] > 0}
+    kernel_ms_per_step = sum(pms[k] for k in range(8)) / max(1, min(K, 30))
     steps_per_s = K / (ms * 1e-3)
     counts = wl.counts()
     units = world if scaling == "weak" else 1
@@ -466,23 +536,32 @@ def bench_partitioned(args, K, W, device):
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
         e2e = {"value": units * E / float(el.item()), "unit": B.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * n_own,
                "steps": E, "api": "PartitionedCRBE.step() + download of the owned solution block per rank"}
+    transport = part.transport
+    n_halo = part.n_halo
+    part.close()
+    del part
+    torch.cuda.empty_cache()
+    cfg = B.shared_config(wl, win)
+    cfg["workload"] = wl.name + f", {world} strips of cell rows"
     result = {
         "metric": B.METRIC, "value": units * steps_per_s, "unit": B.UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": wl.name + f", {world} strips of cell rows", **counts, "regime": wl.regime, "dt": wl.dt,
-                   "rtol": 1e-13, "dofs_per_gpu": n_own, "halo_dofs_rank0": part.n_halo,
-                   "value_definition": ("n_gpus x steps/s of the partitioned mesh: every GPU advances a 12.6M-DOF strip per step"
-                                        if scaling == "weak" else "steps/s of the fixed mesh"),
-                   "solver": "Jacobi-BiCGStab, merged-reduction 4-kernel iteration, halo exchange + allreduce over " + part.transport,
-                   "index_bits": bits.value, "guess_order_mean": q_mean,
-                   "iters_per_step": float(np.mean(iters)), "l2": "inputs larger than L2", "setup_s": setup_s, **B.spinup_note(spinup)},
+        "config": cfg,
+        "details": {"dofs_per_gpu": n_own, "halo_dofs_rank0": n_halo,
+                    "value_definition": ("n_gpus x steps/s of the partitioned mesh: every GPU advances a 12.6M-DOF strip per step"
+                                         if scaling == "weak" else "steps/s of the fixed mesh"),
+                    "solver": "Jacobi-BiCGStab, merged-reduction 4-kernel iteration, halo exchange + allreduce over " + transport,
+                    "index_bits": bits.value, "guess_order_mean": q_mean,
+                    "iters_per_step": float(np.mean(iters)), "setup_s": setup_s, **B.spinup_note(spinup)},
         "dof_updates_per_s": steps_per_s * counts["dofs"],
-        "clocks": clocks, "gpu_launches": int(l1.value - l0.value), "kernels": kern,
+        "clocks": clocks, "gpu_launches": int(l1.value - l0.value), "kernels": kern, "kernel_ms_per_step": kernel_ms_per_step,
         "roofline": {"bound": "hbm", "kernel": "pv: ELL SpMV v = A p + dot (r^,v), rank 0", "achieved": kern["pv"]["GBps"],
                      "unit": "GB/s", "bytes_per_launch": rb["pv"] * n_own, "traffic": None},
     }
     if e2e:
         result["e2e"] = e2e
-    part.close()
+    result["check"] = partition_parity_check(args, device)
+    if not args.no_strong:
+        result["strong"] = strong_block(args, device)
     return result

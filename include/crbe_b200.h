@@ -198,6 +198,11 @@ int crbe_solver_step_ring(crbe_solver* s, double* const* bufs_h, int32_t count, 
 int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d, crbe_solve_info* info_h);
 /* b of crbe.py:384-402 for inspection: b_d (out). */
 int crbe_solver_rhs(crbe_solver* s, const double* u_d, const double* source_d, double dt, double* b_d);
+/* Independent check of a finished Backward-Euler step (what crbe.py:426 must reproduce): the residual of u_next in the Dirichlet
+ * system whose right-hand side is built from u_prev (crbe.py:384-402),  ||b - A u_next|| / ||b||  in the solver's diagonally
+ * scaled norm.  Reads the loaded matrix and the two vectors only; the time loop is not disturbed.  bnorm_h may be NULL. */
+int crbe_solver_step_residual(crbe_solver* s, const double* u_prev_d, const double* u_next_d, const double* source_d, double dt,
+                              double* relres_h, double* bnorm_h);
 /* out = u with out[bnd[k]] += bc[k]   (the lift of crbe.py:429) */
 int crbe_solver_lift(crbe_solver* s, const double* u_d, const double* bc_values_d, double* out_d);
 /* solutions[step, :] = u_prev + lift (crbe.py:429) written straight into the host's history array, asynchronously on
@@ -254,6 +259,15 @@ int crbe_solver_profile(crbe_solver* s, int enable);
 int crbe_solver_profile_read(crbe_solver* s, double* ms_h, int64_t* count_h);
 /* kernels launched through this context so far */
 int crbe_ctx_launch_count(crbe_ctx* ctx, int64_t* count_h);
+
+/* ---- test hooks (used by tests/ only; no reference counterpart) ------------------------------------------ */
+/* int32 exclusive scan of the set-up kernels (mesh.cu), exposed for its unit test */
+int crbe_test_exclusive_scan(crbe_ctx* ctx, const int32_t* in_d, int32_t* out_d, int64_t n, int64_t* total_h);
+/* the solver's row-scaled ELL arrays (device pointers, tile-major layout) so that a test can compare them with scipy */
+int crbe_solver_debug_ell(crbe_solver* s, int64_t* ld_h, const int32_t** ell_col_d, const double** ell_val_d,
+                          const double** mscale_d, const double** dscale_d);
+/* in-place sum of buf_d[0..count) over the ranks of a communicator (NCCL path) */
+int crbe_comm_test_allreduce(crbe_comm* comm, double* buf_d, int count);
 
 #ifdef __cplusplus
 }

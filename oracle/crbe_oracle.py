@@ -274,6 +274,9 @@ class OracleSolver:
 
     ``linear_solver``:
       ``"spsolve"``  a fresh SuperLU solve every step, exactly crbe.py:426;
+      ``"literal"``  like ``"spsolve"`` and the Dirichlet system is rebuilt through LIL every step as well, which is
+                     what the reference's loop literally does (crbe.py:397-404 inside set_source_term, then :426):
+                     the timing of this mode is the reference's own per-step cost;
       ``"splu"``     factorise once, triangular solves per step (same matrix
                      every step, crbe.py:397-404 never changes A);
       ``"bicgstab"`` Jacobi-preconditioned BiCGStab on the host (the GPU
@@ -333,7 +336,7 @@ class OracleSolver:
             self.solutions = np.zeros((nsteps, n))
             self.solutions[0, :] = u_prev                               # :412
         self.build_global_matrices()                                    # :415
-        if self.linear_solver == "spsolve":
+        if self.linear_solver in ("spsolve", "literal"):
             A = dirichlet_system(self.base_system, m.boundary_segments)
         else:
             A = dirichlet_system_fast(self.base_system, m.boundary_segments)
@@ -355,7 +358,9 @@ class OracleSolver:
                 lu = spla.splu(A.tocsc()) if self.linear_solver == "splu" else None
                 dinv = 1.0 / A.diagonal()
             b = self.rhs(t, u_prev)
-            if self.linear_solver == "spsolve":
+            if self.linear_solver == "literal":
+                A = dirichlet_system(self.base_system, m.boundary_segments)   # :397-404, every step
+            if self.linear_solver in ("spsolve", "literal"):
                 u_prev = spla.spsolve(A, b)                             # :426
             elif self.linear_solver == "splu":
                 u_prev = lu.solve(b)

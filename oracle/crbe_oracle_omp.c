@@ -99,9 +99,12 @@ done:
 /* n_steps Backward-Euler steps: b = mdiag .* u (Dirichlet rows zeroed), solve, u <- x.  Zero source (the stock Problem).
  * order > 0: the initial guess of a step is the polynomial extrapolation of the last order+1 solutions (as far as the
  * history reaches), x0 = sum_j (-1)^j C(q+1, j+1) u^(n-j) -- the product's initial guess, same stopping rule.
- * iters_out[n_steps].  Returns 0 or a negative step index on failure. */
-int crbe_omp_be_steps_extrap(int64_t n, const int32_t* ip, const int32_t* ix, const double* a, const double* dinv, const double* mdiag,
-                             const uint8_t* is_bnd, double* u, int n_steps, double rtol, int maxit, int order, int* iters_out) {
+ * iters_out[n_steps].  Returns 0 or a negative step index on failure.
+ * seconds_out (optional, n_steps): wall time of every step, so that the caller can time any window of the loop (bench.py
+ * times the same steps of the loop on the host as on the GPU). */
+int crbe_omp_be_steps_timed(int64_t n, const int32_t* ip, const int32_t* ix, const double* a, const double* dinv, const double* mdiag,
+                            const uint8_t* is_bnd, double* u, int n_steps, double rtol, int maxit, int order, int* iters_out,
+                            double* seconds_out) {
     static const double C[5][5] = {{1, 0, 0, 0, 0}, {2, -1, 0, 0, 0}, {3, -3, 1, 0, 0}, {4, -6, 4, -1, 0}, {5, -10, 10, -5, 1}};
     if (order < 0 || order > 4) return -1000001;
     double* b = malloc(8 * n);
@@ -111,6 +114,7 @@ int crbe_omp_be_steps_extrap(int64_t n, const int32_t* ip, const int32_t* ix, co
     int rc = ok ? 0 : -1000000;
     int have = 0;                 /* hist[0 .. have) = u^(n-1), u^(n-2), ... */
     for (int st = 0; st < n_steps && rc == 0; ++st) {
+        const double t_begin = omp_get_wtime();
         const int q = have < order ? have : order;
         double* oldest = order > 0 ? hist[order - 1] : 0;
 #pragma omp parallel for schedule(static)
@@ -130,10 +134,16 @@ int crbe_omp_be_steps_extrap(int64_t n, const int32_t* ip, const int32_t* ix, co
         const int it = crbe_omp_bicgstab(n, ip, ix, a, dinv, b, u, rtol, maxit);
         if (it < 0) rc = -(st + 1);
         else iters_out[st] = it;
+        if (seconds_out) seconds_out[st] = omp_get_wtime() - t_begin;
     }
     free(b);
     for (int k = 0; k < 4; ++k) free(hist[k]);
     return rc;
+}
+
+int crbe_omp_be_steps_extrap(int64_t n, const int32_t* ip, const int32_t* ix, const double* a, const double* dinv, const double* mdiag,
+                             const uint8_t* is_bnd, double* u, int n_steps, double rtol, int maxit, int order, int* iters_out) {
+    return crbe_omp_be_steps_timed(n, ip, ix, a, dinv, mdiag, is_bnd, u, n_steps, rtol, maxit, order, iters_out, 0);
 }
 
 int crbe_omp_be_steps(int64_t n, const int32_t* ip, const int32_t* ix, const double* a, const double* dinv, const double* mdiag,

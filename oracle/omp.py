@@ -28,6 +28,7 @@ def load():
         lib.crbe_omp_threads.restype = C.c_int
         lib.crbe_omp_bicgstab.restype = C.c_int
         lib.crbe_omp_be_steps.restype = C.c_int
+        lib.crbe_omp_be_steps_timed.restype = C.c_int
         _lib = lib
     return _lib
 
@@ -54,9 +55,9 @@ def bicgstab(A, b, x0, dinv, rtol=1e-13, maxit=10000):
     return x, it
 
 
-def be_steps(A, mdiag, boundary, u0, n_steps, rtol=1e-13, maxit=10000, order=0):
-    """n_steps Backward-Euler steps with zero source; returns (u, iterations per step).
-    order: initial guess extrapolated from the last order+1 solutions (0: u^n itself)."""
+def be_steps(A, mdiag, boundary, u0, n_steps, rtol=1e-13, maxit=10000, order=0, timings=False):
+    """n_steps Backward-Euler steps with zero source; returns (u, iterations per step) -- with ``timings`` also the wall
+    seconds of every step.  order: initial guess extrapolated from the last order+1 solutions (0: u^n itself)."""
     lib = load()
     A = A.tocsr()
     n = A.shape[0]
@@ -67,9 +68,13 @@ def be_steps(A, mdiag, boundary, u0, n_steps, rtol=1e-13, maxit=10000, order=0):
     isb[boundary] = 1
     u = np.array(u0, dtype=np.float64)
     its = np.zeros(n_steps, dtype=np.int32)
-    rc = lib.crbe_omp_be_steps_extrap(C.c_int64(n), _p(ip, C.c_int32), _p(ix, C.c_int32), _p(data, C.c_double), _p(dinv, C.c_double),
+    secs = np.zeros(n_steps, dtype=np.float64)
+    rc = lib.crbe_omp_be_steps_timed(C.c_int64(n), _p(ip, C.c_int32), _p(ix, C.c_int32), _p(data, C.c_double), _p(dinv, C.c_double),
                                _p(np.ascontiguousarray(mdiag, dtype=np.float64), C.c_double), _p(isb, C.c_uint8), _p(u, C.c_double),
-                               C.c_int(n_steps), C.c_double(rtol), C.c_int(maxit), C.c_int(order), _p(its, C.c_int32))
+                               C.c_int(n_steps), C.c_double(rtol), C.c_int(maxit), C.c_int(order), _p(its, C.c_int32),
+                               _p(secs, C.c_double))
     if rc != 0:
         raise RuntimeError(f"OpenMP oracle failed at step {-rc}")
+    if timings:
+        return u, its.tolist(), secs
     return u, its.tolist()

@@ -37,6 +37,14 @@ def test_library_exports_every_declared_symbol(lib_path):
     assert lib.crbe_abi_version() == 1
 
 
+def test_library_exports_nothing_the_header_does_not_declare(lib_path):
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if re.search(r" [TW] crbe_", ln)})
+    extra = [n for n in exported if n not in header_functions()]
+    assert not extra, f"exported with C linkage but not declared in crbe_b200.h: {extra}"
+
+
 def test_python_binding_covers_the_header(lib_path):
     from airpollution_b200 import _lib
     assert set(header_functions()) == set(_lib.EXPORTED_SYMBOLS)
