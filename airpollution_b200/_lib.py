@@ -36,6 +36,7 @@ SOLVER_EXTRAPOLATE = 16
 SOLVER_VERIFY_AUTO = 32
 SOLVER_INDEX32 = 64
 SOLVER_EXTRAP_ADAPT = 128
+SOLVER_NO_PREDICT = 2048
 MAX_EXTRAP_ORDER = 4
 
 
@@ -83,6 +84,8 @@ _SIGNATURES = {
     "crbe_solver_step": [vp, vp, vp, C.c_double, C.POINTER(SolveInfo)],
     "crbe_solver_step_pingpong": [vp, vp, vp, vp, C.c_double, C.POINTER(SolveInfo)],
     "crbe_solver_step_ring": [vp, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, vp, C.c_double, C.POINTER(SolveInfo)],
+    "crbe_solver_steps_ring": [vp, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, vp, C.c_double, C.POINTER(SolveInfo),
+                               c_i32p],
     "crbe_solver_solve": [vp, vp, vp, C.POINTER(SolveInfo)],
     "crbe_solver_rhs": [vp, vp, vp, C.c_double, vp],
     "crbe_solver_step_residual": [vp, vp, vp, vp, C.c_double, c_f64p, c_f64p],
@@ -92,6 +95,7 @@ _SIGNATURES = {
     "crbe_solver_destroy": [vp],
     "crbe_solver_profile": [vp, C.c_int],
     "crbe_solver_profile_read": [vp, c_f64p, c_i64p],
+    "crbe_solver_counters": [vp, c_i64p],
     "crbe_ctx_launch_count": [vp, c_i64p],
     "crbe_comm_unique_id_bytes": [],
     "crbe_comm_unique_id": [vp],

@@ -211,6 +211,8 @@ class BESCRFEM:
                         matrix fits (default; same arithmetic, 8 bytes per row and SpMV less).
     ``graph``           replay each step as one CUDA graph once its shape repeats (default; the launches of a step
                         then no longer travel over PCIe one by one while a solution row is being downloaded).
+    ``predict``         let the update kernel skip the stores of r and p in the iteration it predicts to be the last of a
+                        solve (default; same solution bits, 24 bytes per row less).
     ``progress``        tqdm bar like the reference (default: only for nt*N < 2e7).
     ``velocity_field``  ``f(centroids[Nt,2], t) -> v[Nt,2]`` (torch tensors on the device): a velocity that varies in
                         space and time, one value per triangle, re-assembled every step (BASELINE config 5).  The
@@ -219,7 +221,7 @@ class BESCRFEM:
 
     def __init__(self, domain, problem, mesh_data, element, time_scheme_order=1, *, rtol=1e-13,
                  max_iterations=10000, history="all", tma=True, verify="auto", extrapolate=True,
-                 graph=True, index16=True, progress=None, velocity_field=None):
+                 graph=True, index16=True, progress=None, velocity_field=None, predict=True):
         self.domain = domain
         self.problem = problem
         self.mesh_data = mesh_data
@@ -235,6 +237,7 @@ class BESCRFEM:
         self.verify = verify
         self.graph = graph
         self.index16 = index16
+        self.predict = predict
         self.progress = progress
         self.velocity_field = velocity_field
         self._rt = mesh_data._rt
@@ -369,7 +372,8 @@ class BESCRFEM:
             self._solver = h
         flags = ((_lib.SOLVER_VERIFY_AUTO if self.verify == "auto" else (_lib.SOLVER_VERIFY if self.verify else 0))
                  | (_lib.SOLVER_TMA if self.tma else 0) | _lib.extrapolation_flags(self.extrapolate)
-                 | (_lib.SOLVER_GRAPH if self.graph else 0) | (0 if self.index16 else _lib.SOLVER_INDEX32))
+                 | (_lib.SOLVER_GRAPH if self.graph else 0) | (0 if self.index16 else _lib.SOLVER_INDEX32)
+                 | (0 if self.predict else _lib.SOLVER_NO_PREDICT))
         rt.call("crbe_solver_set_options", self._solver, float(self.rtol), int(self.max_iterations), flags)
         rt.call("crbe_solver_set_system", self._solver, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
 
@@ -527,12 +531,9 @@ class BESCRFEM:
         copied = [None] * nring
         copy_stream = torch.cuda.Stream(device=rt.device)
         main = torch.cuda.current_stream(rt.device)
-        info = _lib.SolveInfo()
         self.step_info = []
         show = self.progress if self.progress is not None else (n_steps * n < 2e7)
-        steps = range(1, n_steps)
-        if show and _tqdm is not None:
-            steps = _tqdm(steps, desc="Time-stepping")
+        bar = _tqdm(total=n_steps - 1, desc="Time-stepping") if (show and _tqdm is not None) else None
         dt = float(self.dt)
         reassemble = self.velocity_field is not None
         # The lift (crbe.py:367-379, :429) adds the user's boundary data on the Nb Dirichlet DOFs, where the solved
@@ -575,20 +576,40 @@ class BESCRFEM:
             bc_np = bc_pin.numpy()
             ring_ev = [None] * bc_ring
         n_stored = 0
+        # Between two stored rows the host has nothing to do unless the problem has a time-dependent source or velocity:
+        # those stretches go down as one call (crbe_solver_steps_ring: one synchronisation per chunk of steps, convergence
+        # enforced per step on the device).  With history="all" every step is stored and the call covers one step.
+        static_source = getattr(type(self.problem), "source_term", None) is Problem.source_term
+        max_run = 64 if (static_source and not reassemble) else 1
+        infos = (_lib.SolveInfo * max_run)()
+        done = C.c_int32()
         start = time.time()
         try:
-            for step in steps:
+            step = 1
+            while step < n_steps:
+                run = 1
+                while run < max_run and step + run - 1 < n_steps - 1 and (step + run - 1) not in row_of:
+                    run += 1
                 t = step * self.dt                                               # crbe.py:420
                 if reassemble:
                     self._reassemble_advection(t, export=(step == n_steps - 1))
-                src = self._source_on_device(t)
-                nxt = (cur + 1) % nring
-                if copied[nxt] is not None:
-                    main.wait_event(copied[nxt])          # its download (nring - 1 steps back) must be through before it is reused
-                rt.call("crbe_solver_step_ring", self._solver, ring, nring, cur, ptr(src), dt, C.byref(info))
-                cur = nxt
-                self.step_info.append((info.iterations, info.relres, info.true_relres, info.restarts, info.guess_order, info.initial_relres))
-                if step in row_of:                        # the step call has synchronised: the vector is final
+                src = None if static_source else self._source_on_device(t)
+                # every vector the run writes (cur+1 ... cur+run, cyclically) must have finished its download
+                for k in range(1, min(run, nring) + 1):
+                    slot = (cur + k) % nring
+                    if copied[slot] is not None:
+                        main.wait_event(copied[slot])
+                        copied[slot] = None
+                rt.call("crbe_solver_steps_ring", self._solver, ring, nring, cur, run, ptr(src), dt, infos, C.byref(done))
+                for k in range(run):
+                    i = infos[k]
+                    self.step_info.append((i.iterations, i.relres, i.true_relres, i.restarts, i.guess_order, i.initial_relres))
+                cur = (cur + run) % nring
+                step += run
+                if bar is not None:
+                    bar.update(run)
+                last = step - 1                           # the step the run ended with
+                if last in row_of:                        # the call has synchronised: the vector is final
                     ev = torch.cuda.Event()
                     if lift_on_device:
                         slot = n_stored % bc_ring
@@ -596,12 +617,12 @@ class BESCRFEM:
                             ring_ev[slot].synchronize()   # its upload (4 rows back) is long through
                         bc_np[slot, :] = bc_result(n_stored)
                         rt.call("crbe_solver_store_lifted_async", self._solver, ptr(ubuf[cur]), bc_pin[slot].data_ptr(),
-                                sol_t[row_of[step]].data_ptr(), copy_stream.cuda_stream)
+                                sol_t[row_of[last]].data_ptr(), copy_stream.cuda_stream)
                         ev.record(copy_stream)
                         ring_ev[slot] = ev
                     else:
                         with torch.cuda.stream(copy_stream):
-                            sol_t[row_of[step]].copy_(ubuf[cur][:n], non_blocking=True)
+                            sol_t[row_of[last]].copy_(ubuf[cur][:n], non_blocking=True)
                             ev.record(copy_stream)
                         if bc_host is not None:
                             bc_host.append(bc_result(n_stored))
@@ -618,6 +639,8 @@ class BESCRFEM:
             raise
         finally:
             pool.shutdown(wait=True)
+            if bar is not None:
+                bar.close()
         self.solve_time = time.time() - start
         u = ubuf[cur][:n]
         self.u_prev = to_numpy(u)

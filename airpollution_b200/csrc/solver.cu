@@ -50,8 +50,15 @@ struct crbe_profile {
 };
 
 
-enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RS = 7, S_RT = 8, S_RR0 = 9, S_RRTRUE = 10 };
-enum { D_STATUS = 0, D_ITERS = 1 };
+enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6, S_RS = 7, S_RT = 8, S_SS = 9, S_RR0 = 10, S_RRTRUE = 11 };
+// device-side solver state (ints).  D_STATUS: 0 running / converged, 1 iteration limit (host only), 2 breakdown (rho, omega -> 0),
+// 3 the update kernel skipped the r, p stores of an iteration it predicted to be the last one and the prediction failed
+// (restart from the true residual), 4 a peer never signalled (peer-memory transport).
+// D_CHAIN: steps enqueued back to back without host synchronisation (crbe_solver_steps_ring): set by the end-of-step
+// kernel when its step has not converged; every later kernel of the chunk then returns at once.
+enum { D_STATUS = 0, D_ITERS = 1, D_SETUP_ERR = 2, D_ESCAPES = 3, D_CHAIN = 4, D_LOGPOS = 5, D_NLAST = 6, D_NSTATE = 8 };
+constexpr int STEP_LOG_DOUBLES = CRBE_NSUMS + 2;   // one record of the step log: the sums, then status and iterations
+constexpr int MAX_CHUNK = 64;                      // steps enqueued between two host synchronisations
 constexpr int IDX16_ESCAPE = -32768;   // 16-bit column offset that does not fit: read the 32-bit column instead
 
 struct P2PHeader;
@@ -62,7 +69,7 @@ struct CommArgs;
 struct StepGraph {
     const double *u0, *x, *save, *h[4], *source;
     double dt;
-    int q, target, speculate;
+    int q, target, speculate, chained;
     cudaGraphExec_t exec;
     int launches;
     uint64_t stamp;
@@ -102,8 +109,8 @@ struct crbe_solver {
     bool system_loaded = false;
     // persistent grids: SMs x resident CTAs of each kernel (a grid-stride sweep must be one full wave)
     int g_init = 1, g_pv = 1, g_st = 1, g_xr = 1, g_vec = 1, g_res = 1, g_spmv = 1;
-    int gt_pv = 1, gt_st = 1, gt_init = 1, gt_res = 1;   // tile (bulk-copy) kernels
-    int gs_pv = 1, gs_st = 1, gs_init = 1, gs_res = 1;
+    int gt_pv = 1, gt_st = 1, gt_init = 1, gt_res = 1, gt_res_be = 1;   // tile (bulk-copy) kernels
+    int gs_pv = 1, gs_st = 1, gs_init = 1, gs_res = 1, gs_res_be = 1;
     int gt_pv0 = 1, gs_pv0 = 1;                          // first-iteration SpMV (one vector stream)   // ... their 16-bit-offset variants (smaller stages, maybe more CTAs per SM)
     int64_t ntiles = 0;
     // row-block partition (world > 1): this solver holds the rows [0, n) of its rank; gathered vectors carry the
@@ -132,11 +139,23 @@ struct crbe_solver {
     cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the context's may be the legacy default stream)
     uint64_t graph_clock = 0;
     double* bc_stage = nullptr;          // crbe_solver_store_lifted_async: boundary values on the device
+    // Right-hand side of the running Backward-Euler step.  It is never stored: b_i = mscale_i u^n_i + dt dscale_i f_i is one
+    // multiply-add from vectors that stay intact through the step, so the init kernel does not write it (8 B per row) and
+    // the rare kernels that need it again (verification, restart) rebuild it.  be_u == nullptr: b is the stored vector
+    // (Crank-Nicolson, crbe_solver_solve).
+    const double* be_u = nullptr;
+    const double* be_src = nullptr;
+    double be_dt = 0.0;
+    // steps enqueued back to back (crbe_solver_steps_ring): one record per step, written by the end-of-step kernel
+    double* step_log = nullptr;
+    double* step_log_h = nullptr;        // pinned
+    int chunk_len = 1, stable_steps = 0; // how many steps the next chunk may hold (grows while the iteration count is steady)
+    int64_t n_chunks = 0, n_chunk_steps = 0, n_chain_breaks = 0;   // statistics (crbe_solver_counters)
 };
 
 // ---------------------------------------------------------------- helpers
 __device__ __forceinline__ bool solver_idle(const double* __restrict__ sums, const int* __restrict__ dstate, double rtol2) {
-    return dstate[D_STATUS] != 0 || !(sums[S_RR] > rtol2 * sums[S_BB]);
+    return dstate[D_STATUS] != 0 || dstate[D_CHAIN] != 0 || !(sums[S_RR] > rtol2 * sums[S_BB]);
 }
 
 // y_i = x_i + sum_k val[k][i] * x[col[k][i]]   (unit diagonal implicit)
@@ -385,7 +404,8 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_pack_col16(int64_t n, int64_t ld
     }
 }
 
-__global__ void k_zero_rows(double* __restrict__ u, const int* __restrict__ bnd, int64_t nb) {
+__global__ void k_zero_rows(double* __restrict__ u, const int* __restrict__ bnd, int64_t nb, const int* __restrict__ dstate) {
+    if (dstate[D_CHAIN] != 0) return;
     ROW_LOOP(k, nb) u[bnd[k]] = 0.0;
 }
 
@@ -403,8 +423,9 @@ struct ExtrapArgs {
 };
 
 template <int Q>
-__global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate(int64_t n, ExtrapArgs a) {
+__global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate(int64_t n, ExtrapArgs a, const int* __restrict__ dstate) {
     constexpr double C[5][5] = {{1, 0, 0, 0, 0}, {2, -1, 0, 0, 0}, {3, -3, 1, 0, 0}, {4, -6, 4, -1, 0}, {5, -10, 10, -5, 1}};
+    if (dstate[D_CHAIN] != 0) return;     // an earlier step of this chunk has not converged: leave every vector as it is
     ROW_LOOP(i, n) {
         const double un = a.u0[i];
         double hv[Q > 0 ? Q : 1];
@@ -450,6 +471,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
                                                      double* __restrict__ b, double* __restrict__ r, double* __restrict__ rh,
                                                      double* __restrict__ p, double* sums, double* dots, int* dstate, double* partials,
                                                      unsigned int* counter, const CommArgs* __restrict__ ca) {
+    if (dstate[D_CHAIN] != 0) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         dstate[D_STATUS] = 0;
         dstate[D_ITERS] = 0;
@@ -471,7 +493,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
         }
         const double ax = ell_row(eval, ecol, ld, i, xi, [&](int j) { return __ldg(x + j); });
         const double ri = bi - ax;
-        b[i] = bi;
+        if (b) b[i] = bi;   // Backward-Euler steps do not store b (crbe_solver::be_u)
         rh[i] = ri;
         if (r) r[i] = ri;   // r = r^ = p = r0: the first iteration reads them through one vector (launch_iteration), so the
         if (p) p[i] = ri;   // step kernels pass r = nullptr, and p only where its halo entries are needed (partitioned solver)
@@ -514,14 +536,14 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_s(int64_t n, int k, double rtol2
     halo_push_tail(s, 2, ca);
 }
 
-// t = A s, (t,s), (t,t), (r^,s), (r^,t)
+// t = A s, (t,s), (t,t), (r^,s), (r^,t), (s,s)
 __global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, double rtol2, const double* __restrict__ eval,
                                                    const int* __restrict__ ecol, const double* __restrict__ s, double* __restrict__ t,
                                                    const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                    unsigned int* counter, const CommArgs* __restrict__ ca) {
     if (solver_idle(sums, dstate, rtol2)) return;
     halo_wait(2, ca);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     ROW_LOOP(i, n) {
         const double si = s[i];
         const double ti = ell_row(eval, ecol, ld, i, si, [&](int j) { return __ldg(s + j); });
@@ -531,18 +553,25 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, double
         acc[1] = fma(ti, ti, acc[1]);
         acc[2] = fma(rhi, si, acc[2]);
         acc[3] = fma(rhi, ti, acc[3]);
+        acc[4] = fma(si, si, acc[4]);
     }
-    double* const out[4] = {dots + S_TS, dots + S_TT, dots + S_RS, dots + S_RT};
-    grid_sum_last<4>(acc, partials, counter, out, ca);
+    double* const out[5] = {dots + S_TS, dots + S_TT, dots + S_RS, dots + S_RT, dots + S_SS};
+    grid_sum_last<5>(acc, partials, counter, out, ca);
 }
 
 // x += alpha p + omega s;  r = s - omega t;  p = r + beta (p - omega v);  (r, r);
 // rho_{k+1} = (r^,s) - omega (r^,t) is published by the last CTA (every rank computes the same value).
 // p_in: where the old p is read (p itself, or r^ in the first iteration on a single GPU; may alias p: no __restrict__)
+//
+// Last iteration of a solve: ||r||^2 = (s,s) - (t,s)^2/(t,t) is known from the sums of the previous kernel before r exists.
+// When it lies clearly below the stopping threshold (factor 4: the formula cancels, its relative error is ~1e-16 (s,s)/||r||^2)
+// nobody will read this iteration's r and p, and the kernel neither stores them nor reads v: 40 instead of 64 bytes per
+// row.  x and the accumulated (r,r) are the same bits either way.  Should the accumulated norm contradict the prediction
+// the recurrence is gone: status 3, and the host restarts the solve from the true residual.
 __global__ void __launch_bounds__(CRBE_BLOCK) k_xrp(int64_t n, int k, double rtol2, const double* __restrict__ s, const double* __restrict__ t,
                                                     const double* __restrict__ v, double* __restrict__ x, double* __restrict__ r,
                                                     const double* p_in, double* p, double* sums, double* dots, int* dstate, double* partials,
-                                                    unsigned int* counter, const CommArgs* __restrict__ ca) {
+                                                    unsigned int* counter, const CommArgs* __restrict__ ca, int predict) {
     if (solver_idle(sums, dstate, rtol2)) return;
     const double rho = sums[S_RHO0 + (k & 1)];
     const double alpha = rho / sums[S_RHV];
@@ -555,38 +584,71 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_xrp(int64_t n, int k, double rto
     const double rho_next = fma(-omega, sums[S_RT], sums[S_RS]);
     const double beta = (rho_next / rho) * (alpha / omega);
     const double thr = rtol2 * sums[S_BB];
+    const double rr_pred = tt > 0.0 ? sums[S_SS] - sums[S_TS] * sums[S_TS] / tt : sums[S_SS];
+    const bool last = predict && rr_pred <= 0.25 * thr;
     double acc[1] = {0.0};
-    ROW_LOOP(i, n) {
-        const double si = s[i], pi = p_in[i];
-        x[i] = fma(alpha, pi, fma(omega, si, x[i]));
-        const double ri = fma(-omega, t[i], si);
-        r[i] = ri;
-        p[i] = fma(beta, fma(-omega, v[i], pi), ri);
-        acc[0] = fma(ri, ri, acc[0]);
+    if (last) {
+        ROW_LOOP(i, n) {
+            const double si = s[i];
+            x[i] = fma(alpha, p_in[i], fma(omega, si, x[i]));
+            const double ri = fma(-omega, t[i], si);
+            acc[0] = fma(ri, ri, acc[0]);
+        }
+    } else {
+        ROW_LOOP(i, n) {
+            const double si = s[i], pi = p_in[i];
+            x[i] = fma(alpha, pi, fma(omega, si, x[i]));
+            const double ri = fma(-omega, t[i], si);
+            r[i] = ri;
+            p[i] = fma(beta, fma(-omega, v[i], pi), ri);
+            acc[0] = fma(ri, ri, acc[0]);
+        }
+        halo_push_tail(p, 1, ca);
     }
-    halo_push_tail(p, 1, ca);
     double* const out[1] = {dots + S_RR};
     if (grid_sum_last<1>(acc, partials, counter, out, ca)) {
         dstate[D_ITERS] += 1;
+        if (last) dstate[D_NLAST] += 1;     // statistics: update kernels that ran in their short, last-iteration form
         if (k == 0) sums[S_RR0] = rho;      // (r^, r0) = ||r0||^2 of the initial guess, kept for the host (guess-order policy)
         sums[S_RHO0 + ((k + 1) & 1)] = rho_next;
-        if (!isfinite(beta) && (ca == nullptr || ca->world <= 1 || dots == sums) && *out[0] > thr) dstate[D_STATUS] = 2;
+        const bool own_total = ca == nullptr || ca->world <= 1 || dots == sums;     // *out[0] is the sum over all ranks
+        if (own_total && last && *out[0] > thr) dstate[D_STATUS] = 3;
+        else if (!isfinite(beta) && own_total && *out[0] > thr) dstate[D_STATUS] = 2;
     }
+}
+
+// Where the right-hand side of the running solve comes from: a stored vector (b != nullptr), or the Backward-Euler formula
+// b_i = mscale_i u^n_i + dt dscale_i f_i evaluated on the fly (see crbe_solver::be_u).
+struct RhsSource {
+    const double* b;
+    const double* u;        // u^n
+    const double* src;      // f(t^{n+1}) or nullptr
+    const double* mscale;
+    const double* dscale;
+    double dt;
+};
+
+__device__ __forceinline__ double rhs_at(const RhsSource& q, int64_t i) {
+    if (q.b) return q.b[i];
+    double bi = q.mscale[i] * q.u[i];
+    if (q.src) bi = fma(q.dscale[i] * q.dt, q.src[i], bi);
+    return bi;
 }
 
 // true residual b - A x and its norm.  guard = 1: verification enqueued speculatively behind the iterations -- runs
 // only once they have converged, writes nothing but the norm.  guard = 0: restart -- r = r^ = p = b - A x.
 __global__ void __launch_bounds__(CRBE_BLOCK) k_residual(int64_t n, int64_t ld, const double* __restrict__ eval, const int* __restrict__ ecol,
-                                                         const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
+                                                         const double* __restrict__ x, RhsSource rhs, double* __restrict__ r,
                                                          double* __restrict__ rh, double* __restrict__ p, double* sums, double* dots,
                                                          double* partials, unsigned int* counter, const CommArgs* __restrict__ ca,
                                                          const int* dstate, int guard, double rtol2) {
+    if (dstate[D_CHAIN] != 0) return;
     if (guard && (dstate[D_STATUS] != 0 || sums[S_RR] > rtol2 * sums[S_BB])) return;
     halo_wait(0, ca);
     double acc[1] = {0.0};
     ROW_LOOP(i, n) {
         const double ax = ell_row(eval, ecol, ld, i, x[i], [&](int j) { return __ldg(x + j); });
-        const double ri = b[i] - ax;
+        const double ri = rhs_at(rhs, i) - ax;
         if (!guard) {
             r[i] = ri;
             rh[i] = ri;
@@ -842,6 +904,8 @@ static int solver_release(crbe_solver* s) {
     cudaFree(s->send_idx);
     cudaFree(s->sendbuf);
     cudaFree(s->dstate);
+    cudaFree(s->step_log);
+    cudaFreeHost(s->step_log_h);
     cudaFreeHost(s->sums_h);
     if (s->prof) {
         for (ProfRecord& r : s->prof->pending) {
@@ -910,8 +974,10 @@ static int solver_init(crbe_solver* s, crbe_ctx* ctx, crbe_comm* comm, int64_t n
     CRBE_CUDA(cudaMemsetAsync(s->ell_val, 0, sizeof(double) * 4 * s->ld, ctx->stream));
     CRBE_CUDA(cudaMalloc(&s->sums, sizeof(double) * CRBE_NSUMS));
     CRBE_CUDA(cudaMemsetAsync(s->sums, 0, sizeof(double) * CRBE_NSUMS, ctx->stream));
-    CRBE_CUDA(cudaMalloc(&s->dstate, sizeof(int) * 4));
-    CRBE_CUDA(cudaMemsetAsync(s->dstate, 0, sizeof(int) * 4, ctx->stream));
+    CRBE_CUDA(cudaMalloc(&s->dstate, sizeof(int) * D_NSTATE));
+    CRBE_CUDA(cudaMemsetAsync(s->dstate, 0, sizeof(int) * D_NSTATE, ctx->stream));
+    CRBE_CUDA(cudaMalloc(&s->step_log, sizeof(double) * STEP_LOG_DOUBLES * MAX_CHUNK));
+    CRBE_CUDA(cudaMallocHost(&s->step_log_h, sizeof(double) * STEP_LOG_DOUBLES * MAX_CHUNK));
     CRBE_CUDA(cudaMallocHost(&s->sums_h, sizeof(double) * (CRBE_NSUMS + 2)));
     s->dots = s->sums;
     if (s->world > 1) {
@@ -935,12 +1001,14 @@ static int solver_init(crbe_solver* s, crbe_ctx* ctx, crbe_comm* comm, int64_t n
         CRBE_CHECK(tile_grid(ctx, t_pv<int, true>, TilePipe<1, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_pv0));
         CRBE_CHECK(tile_grid(ctx, t_st<int>, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_st));
         CRBE_CHECK(tile_grid(ctx, t_init_be<int>, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_init));
-        CRBE_CHECK(tile_grid(ctx, t_residual<int>, TilePipe<1, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_res));
+        CRBE_CHECK(tile_grid(ctx, t_residual<int, false>, TilePipe<1, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_res));
+        CRBE_CHECK(tile_grid(ctx, t_residual<int, true>, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_res_be));
         CRBE_CHECK(tile_grid(ctx, t_pv<short, false>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_pv));
         CRBE_CHECK(tile_grid(ctx, t_pv<short, true>, TilePipe<1, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_pv0));
         CRBE_CHECK(tile_grid(ctx, t_st<short>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_st));
         CRBE_CHECK(tile_grid(ctx, t_init_be<short>, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_init));
-        CRBE_CHECK(tile_grid(ctx, t_residual<short>, TilePipe<1, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_res));
+        CRBE_CHECK(tile_grid(ctx, t_residual<short, false>, TilePipe<1, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_res));
+        CRBE_CHECK(tile_grid(ctx, t_residual<short, true>, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_res_be));
     }
     CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
     return CRBE_OK;
@@ -1120,7 +1188,7 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
     crbe_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     drop_step_graphs(s);   // rhs_val / tmp may be (de)allocated below
-    int* err = s->dstate + 2;
+    int* err = s->dstate + D_SETUP_ERR;
     CRBE_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
     k_build_ell<<<crbe_grid_for(ctx, s->n), CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->indptr, s->indices, s_val_d, m_val_d, s->is_bnd,
                                                                  s->ell_col, s->ell_val, s->mdiag, s->mscale, s->dscale, err);
@@ -1134,7 +1202,7 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
         cudaFree(s->rhs_val);
         s->rhs_val = nullptr;
     }
-    int* overflow = s->dstate + 3;
+    int* overflow = s->dstate + D_ESCAPES;
     CRBE_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
     k_pack_col16<<<crbe_grid_for(ctx, s->ld), CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_col, s->ell_col16, overflow);
     CRBE_KERNEL_CHECK();
@@ -1206,11 +1274,12 @@ __global__ void k_pack(const double* __restrict__ vec, const int* __restrict__ i
     ROW_LOOP(q, cnt) out[q] = vec[idx[q]];
 }
 
-__global__ void k_commit(const double* __restrict__ red, double* __restrict__ sums, int a, int b, int c, int d) {
+__global__ void k_commit(const double* __restrict__ red, double* __restrict__ sums, int a, int b, int c, int d, int e) {
     if (a >= 0) sums[a] = red[a];
     if (b >= 0) sums[b] = red[b];
     if (c >= 0) sums[c] = red[c];
     if (d >= 0) sums[d] = red[d];
+    if (e >= 0) sums[e] = red[e];
 }
 
 __global__ void k_p2p_wait(int kind, const CommArgs* __restrict__ ca) { halo_wait(kind, ca); }
@@ -1245,10 +1314,10 @@ static int halo_exchange(crbe_solver* s, double* vec, int* launches) {
 }
 
 // sum the freshly written dot products red[first .. first+count) over the ranks, then publish slots a, b, c, d
-static int reduce_dots(crbe_solver* s, int first, int count, int a, int b, int c, int d, int* launches) {
+static int reduce_dots(crbe_solver* s, int first, int count, int a, int b, int c, int d, int* launches, int e = -1) {
     if (s->world <= 1 || s->p2p) return CRBE_OK;   // peer-memory transport: done in the tail of the dot kernel (grid_sum_last)
     CRBE_CHECK(crbe_comm_allreduce_sum(s->comm, s->red + first, count, s->ctx->stream));
-    k_commit<<<1, 1, 0, s->ctx->stream>>>(s->red, s->sums, a, b, c, d);
+    k_commit<<<1, 1, 0, s->ctx->stream>>>(s->red, s->sums, a, b, c, d, e);
     CRBE_KERNEL_CHECK();
     *launches += 1;
     return CRBE_OK;
@@ -1302,9 +1371,11 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
     else
         PROF_LAUNCH(PK_ST, k, (k_st<<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, rtol2, s->ell_val, s->ell_col, s->s, s->t, s->rh, s->sums,
                                                                  s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
-    CRBE_CHECK(reduce_dots(s, S_TS, 4, S_TS, S_TT, S_RS, S_RT, launches));
+    CRBE_CHECK(reduce_dots(s, S_TS, 5, S_TS, S_TT, S_RS, S_RT, launches, S_SS));
+    // the last-iteration shortcut needs the reduced (r,r) inside the kernel: single GPU and peer-memory transport
+    const int predict = (s->world == 1 || s->p2p) && !(s->flags & CRBE_SOLVER_NO_PREDICT) ? 1 : 0;
     PROF_LAUNCH(PK_XR, k, (k_xrp<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->s, s->t, v, x, s->r, p_in, p, s->sums, s->dots, s->dstate,
-                                                              ctx->partials, ctx->counter, s->d_comm)));
+                                                              ctx->partials, ctx->counter, s->d_comm, predict)));
     *launches += 4;
     CRBE_CHECK(reduce_dots(s, S_RR, 1, S_RR, -1, -1, -1, launches));
     return CRBE_OK;
@@ -1330,18 +1401,26 @@ static int launch_residual(crbe_solver* s, double* x, int guard, int* launches) 
     const double rtol2 = s->rtol * s->rtol;
     CRBE_CHECK(halo_exchange(s, x, launches));
     const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
-    if ((s->flags & CRBE_SOLVER_TMA) && i16)
-        PROF_LAUNCH(PK_RES, guard ? -2 : -1, (t_residual<short><<<s->gs_res, CRBE_TILE, TilePipe<1, TILE_STAGES, short>::SMEM_BYTES, st>>>(
-                                                 s->n, s->ntiles, s->ell_val, s->ell_col16, s->ell_col, x, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
-                                                 ctx->partials, ctx->counter, s->d_comm, s->dstate, guard, rtol2)));
+    const bool be = s->be_u != nullptr;     // Backward-Euler step: b is rebuilt from u^n (and the source), not stored
+    const RhsSource rhs = {be ? nullptr : s->b, s->be_u, s->be_src, s->mscale, s->dscale, s->be_dt};
+    const int pk = guard ? -2 : -1;
+#define CRBE_TRES(IDX, BE, GRID, NV, COL, COL32)                                                                                     \
+    PROF_LAUNCH(PK_RES, pk, (t_residual<IDX, BE><<<GRID, CRBE_TILE, TilePipe<NV, TILE_STAGES, IDX>::SMEM_BYTES, st>>>(                 \
+                                s->n, s->ntiles, s->ell_val, COL, COL32, x, rhs, s->r, s->rh, s->p[0], s->sums, s->dots, ctx->partials, \
+                                ctx->counter, s->d_comm, s->dstate, guard, rtol2)))
+    if ((s->flags & CRBE_SOLVER_TMA) && i16 && be)
+        CRBE_TRES(short, true, s->gs_res_be, 2, s->ell_col16, s->ell_col);
+    else if ((s->flags & CRBE_SOLVER_TMA) && i16)
+        CRBE_TRES(short, false, s->gs_res, 1, s->ell_col16, s->ell_col);
+    else if ((s->flags & CRBE_SOLVER_TMA) && be)
+        CRBE_TRES(int, true, s->gt_res_be, 2, s->ell_col, nullptr);
     else if (s->flags & CRBE_SOLVER_TMA)
-        PROF_LAUNCH(PK_RES, guard ? -2 : -1, (t_residual<int><<<s->gt_res, CRBE_TILE, TilePipe<1, TILE_STAGES, int>::SMEM_BYTES, st>>>(
-                                                 s->n, s->ntiles, s->ell_val, s->ell_col, nullptr, x, s->b, s->r, s->rh, s->p[0], s->sums, s->dots,
-                                                 ctx->partials, ctx->counter, s->d_comm, s->dstate, guard, rtol2)));
+        CRBE_TRES(int, false, s->gt_res, 1, s->ell_col, nullptr);
     else
-        PROF_LAUNCH(PK_RES, guard ? -2 : -1, (k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->b, s->r,
-                                                                                         s->rh, s->p[0], s->sums, s->dots, ctx->partials,
-                                                                                         ctx->counter, s->d_comm, s->dstate, guard, rtol2)));
+        PROF_LAUNCH(PK_RES, pk, (k_residual<<<s->g_res, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, rhs, s->r, s->rh, s->p[0],
+                                                                            s->sums, s->dots, ctx->partials, ctx->counter, s->d_comm,
+                                                                            s->dstate, guard, rtol2)));
+#undef CRBE_TRES
     *launches += 1;
     CRBE_KERNEL_CHECK();
     return reduce_dots(s, S_RRTRUE, 1, S_RRTRUE, -1, -1, -1, launches);
@@ -1364,18 +1443,50 @@ static inline int first_batch_target(const crbe_solver* s, int total_iters) {
     return target < 1 ? 1 : target;
 }
 
-// iterations [k0, target) + the speculative verification + the download of the state, no synchronisation
-static int enqueue_batch(crbe_solver* s, double* x, int k0, int target, bool speculate, int* launches) {
+// End of a step enqueued without host synchronisation (crbe_solver_steps_ring): append the state of the solve to the step log
+// and, if the step has not converged, raise D_CHAIN so that every later kernel of the chunk returns at once and the host finds
+// the device exactly where this step stopped.  Steps skipped that way are logged with status -1.
+__global__ void k_step_end(const double* __restrict__ sums, int* dstate, double rtol2, double* __restrict__ log) {
+    const int pos = dstate[D_LOGPOS];
+    const bool skipped = dstate[D_CHAIN] != 0;
+    const int status = dstate[D_STATUS], iters = dstate[D_ITERS];
+    const double rr = sums[S_RR], bb = sums[S_BB];
+    __syncthreads();
+    if (pos < MAX_CHUNK) {
+        double* rec = log + (size_t)pos * STEP_LOG_DOUBLES;
+        if (threadIdx.x < CRBE_NSUMS) rec[threadIdx.x] = sums[threadIdx.x];
+        if (threadIdx.x == CRBE_NSUMS) rec[CRBE_NSUMS] = skipped ? -1.0 : (double)status;
+        if (threadIdx.x == CRBE_NSUMS + 1) rec[CRBE_NSUMS + 1] = (double)iters;
+    }
+    if (threadIdx.x == 0) {
+        dstate[D_LOGPOS] = pos + 1;
+        if (!skipped && (status != 0 || !(rr <= rtol2 * bb))) dstate[D_CHAIN] = 1;
+    }
+}
+
+// iterations [k0, target) + the speculative verification + the download of the state (or, in a chunk of steps, the
+// end-of-step record), no synchronisation
+static int enqueue_batch(crbe_solver* s, double* x, int k0, int target, bool speculate, int* launches, bool chained = false) {
     for (int k = k0; k < target; ++k) CRBE_CHECK(launch_iteration(s, k, x, launches));
     // the verification rides behind the batch (it returns at once unless the batch converged): one sync per step
     if (speculate) CRBE_CHECK(launch_residual(s, x, 1, launches));
     CRBE_KERNEL_CHECK();
+    if (chained) {
+        k_step_end<<<1, 32, 0, s->ctx->stream>>>(s->sums, s->dstate, s->rtol * s->rtol, s->step_log);
+        CRBE_KERNEL_CHECK();
+        *launches += 1;
+        return CRBE_OK;
+    }
     return enqueue_fetch(s);
 }
 
 // Iterate from the state left by k_init until converged.  b, r, r^ and the sums are on the device.
-// first_enqueued: the first batch (first_batch_target iterations, verification as verify_wanted says) is already in flight.
-static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* launches, bool first_enqueued = false) {
+// first: FIRST_FRESH nothing is enqueued yet; FIRST_IN_FLIGHT the first batch (first_target iterations, verification as
+// verify_wanted says) is already in flight; FIRST_DONE it has run and its state is in sums_h already (a step of a chunk that
+// did not converge in the iterations enqueued for it).
+enum { FIRST_FRESH = 0, FIRST_IN_FLIGHT = 1, FIRST_DONE = 2 };
+
+static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* launches, int first = FIRST_FRESH, int first_target = 0) {
     crbe_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     const double rtol2 = s->rtol * s->rtol;
@@ -1385,15 +1496,15 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
     double true_rr = -1.0;
     for (;;) {
         int k = 0;
-        int target = first_batch_target(s, total_iters);
+        int target = first != FIRST_FRESH && first_target > 0 ? first_target : first_batch_target(s, total_iters);
         bool done = false, speculated_last = false;
         for (;;) {
-            const bool speculate = verify_wanted(s, total_iters + target, restarts);
-            if (!first_enqueued) CRBE_CHECK(enqueue_batch(s, x, k, target, speculate, launches));
-            first_enqueued = false;
+            const bool speculate = first == FIRST_DONE ? false : verify_wanted(s, total_iters + target, restarts);
+            if (first == FIRST_FRESH) CRBE_CHECK(enqueue_batch(s, x, k, target, speculate, launches));
             k = target;
             speculated_last = speculate;
-            CRBE_CUDA(cudaStreamSynchronize(st));
+            if (first != FIRST_DONE) CRBE_CUDA(cudaStreamSynchronize(st));
+            first = FIRST_FRESH;
             const double rr = s->sums_h[S_RR], bb = s->sums_h[S_BB];
             status = dst_h[D_STATUS];
             done = status != 0 || !(rr > rtol2 * bb) || !isfinite(rr);
@@ -1506,10 +1617,10 @@ static int launch_extrapolate(crbe_solver* s, const StepPlan& pl, int* launches)
     a.save = pl.save;
     for (int j = 0; j < CRBE_MAX_EXTRAP; ++j) a.h[j] = j < pl.q ? pl.h[j] : nullptr;
     switch (pl.q) {
-        case 1: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<1><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a))); break;
-        case 2: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<2><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a))); break;
-        case 3: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<3><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a))); break;
-        default: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<4><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a))); break;
+        case 1: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<1><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a, s->dstate))); break;
+        case 2: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<2><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a, s->dstate))); break;
+        case 3: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<3><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a, s->dstate))); break;
+        default: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<4><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a, s->dstate))); break;
     }
     *launches += 1;
     CRBE_KERNEL_CHECK();
@@ -1528,7 +1639,7 @@ static int enqueue_step_head(crbe_solver* s, const StepPlan& pl, const double* s
         *launches += 1;
     }
     if (s->nb > 0) {    // the solution of the Dirichlet system is exactly 0 on its identity rows: start there
-        k_zero_rows<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, st>>>(pl.u0, s->bnd, s->nb);
+        k_zero_rows<<<crbe_grid_for(ctx, s->nb), CRBE_BLOCK, 0, st>>>(pl.u0, s->bnd, s->nb, s->dstate);
         *launches += 1;
     }
     // Right-hand side from u^n; the initial guess is extrapolated from the history (see k_extrapolate)
@@ -1544,21 +1655,23 @@ static int enqueue_step_head(crbe_solver* s, const StepPlan& pl, const double* s
     const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
     double* const r_w = nullptr;                          // see launch_iteration: the first iteration does not read r,
     double* const p_w = s->world == 1 ? nullptr : s->p[0];   // and p only in the partitioned solver
+    // Backward Euler: b is not stored, the verification / restart kernels rebuild it from u^n (bind_rhs, crbe_solver::be_u)
+    double* const b_w = cn ? s->b : nullptr;
     if (cn)
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->tmp, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, r_w, s->rh, p_w, s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if ((s->flags & CRBE_SOLVER_TMA) && i16)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<short><<<s->gs_init, CRBE_TILE, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->ell_val, s->ell_col16, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, s->b, r_w,
+                                     s->n, s->ntiles, s->ell_val, s->ell_col16, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, b_w, r_w,
                                      s->rh, p_w, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<int><<<s->gt_init, CRBE_TILE, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->ell_val, s->ell_col, nullptr, x, xb, source_d, dt, s->mscale, s->dscale, s->b, r_w,
+                                     s->n, s->ntiles, s->ell_val, s->ell_col, nullptr, x, xb, source_d, dt, s->mscale, s->dscale, b_w, r_w,
                                      s->rh, p_w, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else
         PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, xb, source_d, dt,
-                                                                             s->mscale, s->dscale, s->is_bnd, s->b, r_w, s->rh, p_w, s->sums, s->dots,
+                                                                             s->mscale, s->dscale, s->is_bnd, b_w, r_w, s->rh, p_w, s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     *launches += 1;
     CRBE_KERNEL_CHECK();
@@ -1575,7 +1688,7 @@ static StepGraph* find_step_graph(crbe_solver* s, const StepGraph& key) {
     for (StepGraph& g : s->graphs)
         if (g.u0 == key.u0 && g.x == key.x && g.save == key.save && g.h[0] == key.h[0] && g.h[1] == key.h[1] && g.h[2] == key.h[2] &&
             g.h[3] == key.h[3] && g.source == key.source && g.dt == key.dt && g.q == key.q && g.target == key.target &&
-            g.speculate == key.speculate)
+            g.speculate == key.speculate && g.chained == key.chained)
             return &g;
     return nullptr;
 }
@@ -1591,7 +1704,7 @@ static int capture_step(crbe_solver* s, const StepPlan& pl, const double* source
     cudaError_t e = cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
         rc = enqueue_step_head(s, pl, source_d, dt, &launches);
-        if (rc == CRBE_OK) rc = enqueue_batch(s, pl.x, 0, g->target, g->speculate != 0, &launches);
+        if (rc == CRBE_OK) rc = enqueue_batch(s, pl.x, 0, g->target, g->speculate != 0, &launches, g->chained != 0);
         const cudaError_t e2 = cudaStreamEndCapture(s->cap_stream, &graph);   // always close the capture
         if (rc == CRBE_OK && e2 != cudaSuccess) e = e2;
     }
@@ -1617,17 +1730,25 @@ static int capture_step(crbe_solver* s, const StepPlan& pl, const double* source
     return CRBE_OK;
 }
 
-// One time step as planned by the entry points below.
-static int step_impl(crbe_solver* s, const StepPlan& pl, const double* source_d, double dt, crbe_solve_info* info_h) {
+// where the right-hand side of this step comes from, for the kernels launched outside the step's own enqueue (restart,
+// late verification): a replayed graph does not pass through enqueue_step_head
+static void bind_rhs(crbe_solver* s, const StepPlan& pl, const double* source_d, double dt) {
+    s->be_u = s->rhs_val ? nullptr : (pl.save ? pl.save : pl.u0);
+    s->be_src = source_d;
+    s->be_dt = dt;
+}
+
+// Enqueue one planned step without synchronising: head kernels + `target` iterations (+ the speculative verification) + the
+// state download, or, chained, the end-of-step record.  Steady state on one GPU: replayed as one graph (captured the second
+// time the same step shape is asked for).
+static int enqueue_step(crbe_solver* s, const StepPlan& pl, const double* source_d, double dt, int target, bool speculate, bool chained,
+                        int* launches) {
     crbe_ctx* ctx = s->ctx;
-    memset(info_h, 0, sizeof(*info_h));
-    int launches = 0;
-    // Steady state on one GPU: replay the step as one graph (captured the second time the same step shape is asked for)
-    bool in_flight = false;
+    bind_rhs(s, pl, source_d, dt);
     const bool graphs_on = (s->flags & CRBE_SOLVER_GRAPH) && s->world == 1 && !(s->prof && s->prof->on);
     if (graphs_on) {
-        StepGraph key = {pl.u0, pl.x, pl.save, {pl.h[0], pl.h[1], pl.h[2], pl.h[3]}, source_d, dt, pl.q, first_batch_target(s, 0), 0, nullptr, 0, 0};
-        key.speculate = verify_wanted(s, key.target, 0) ? 1 : 0;
+        StepGraph key = {pl.u0, pl.x, pl.save, {pl.h[0], pl.h[1], pl.h[2], pl.h[3]}, source_d, dt, pl.q, target, speculate ? 1 : 0,
+                         chained ? 1 : 0, nullptr, 0, 0};
         StepGraph* g = find_step_graph(s, key);
         if (!g) {                       // first sighting: remember the shape, launch directly
             if (s->graphs.size() >= STEP_GRAPH_SLOTS) {
@@ -1643,14 +1764,23 @@ static int step_impl(crbe_solver* s, const StepPlan& pl, const double* source_d,
             g->stamp = ++s->graph_clock;
             if (!g->exec) CRBE_CHECK(capture_step(s, pl, source_d, dt, g));
             CRBE_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
-            launches += g->launches;
-            in_flight = true;
+            *launches += g->launches;
+            return CRBE_OK;
         }
     }
-    if (!in_flight) CRBE_CHECK(enqueue_step_head(s, pl, source_d, dt, &launches));
-    int rc = run_bicgstab(s, pl.x, info_h, &launches, in_flight);
+    CRBE_CHECK(enqueue_step_head(s, pl, source_d, dt, launches));
+    return enqueue_batch(s, pl.x, 0, target, speculate, launches, chained);
+}
+
+// One time step as planned by the entry points below.
+static int step_impl(crbe_solver* s, const StepPlan& pl, const double* source_d, double dt, crbe_solve_info* info_h) {
+    memset(info_h, 0, sizeof(*info_h));
+    int launches = 0;
+    const int target = first_batch_target(s, 0);
+    CRBE_CHECK(enqueue_step(s, pl, source_d, dt, target, verify_wanted(s, target, 0), false, &launches));
+    int rc = run_bicgstab(s, pl.x, info_h, &launches, FIRST_IN_FLIGHT, target);
     info_h->launches = launches;
-    ctx->launches += launches;
+    s->ctx->launches += launches;
     return rc;
 }
 
@@ -1688,7 +1818,8 @@ static int step_in_place(crbe_solver* s, double* u_d, const double* source_d, do
 // Ring of caller-owned vectors (each crbe_solver_vector_length long, zero padded): bufs[cur] holds u^n, the buffers before
 // it (cyclically) the earlier solutions of this time loop; u^(n+1) is built in bufs[(cur + 1) % count], which held the
 // oldest one.  Nothing is copied, and every solution stays intact for count - 1 further steps (downloads overlap them).
-static int step_ring(crbe_solver* s, double* const* bufs, int count, int cur, const double* source_d, double dt, crbe_solve_info* info_h) {
+// plan_ring_step does the bookkeeping of one such step (which buffers hold consecutive solutions, the order of the guess).
+static int plan_ring_step(crbe_solver* s, double* const* bufs, int count, int cur, StepPlan* out) {
     CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
     CRBE_REQUIRE(s->world == 1, "ring stepping is for the single-GPU solver");
     CRBE_REQUIRE(count >= 2 && count <= CRBE_MAX_EXTRAP + 1 && cur >= 0 && cur < count, "bad ring");
@@ -1702,10 +1833,20 @@ static int step_ring(crbe_solver* s, double* const* bufs, int count, int cur, co
     s->ring_valid = same ? (s->ring_valid + 1 < count - 1 ? s->ring_valid + 1 : count - 1) : 0;
     s->ring_expect = (cur + 1) % count;
     s->hist_count = 0;     // the caller left the in-place protocol
-    StepPlan pl;
+    StepPlan& pl = *out;
     memset(&pl, 0, sizeof(pl));
     pl.u0 = bufs[cur];
     pl.x = bufs[(cur + 1) % count];
+    if (s->rhs_val) return CRBE_OK;     // Crank-Nicolson: see step_ring
+    const int order = extrap_order(s);
+    pl.q = choose_guess_order(s, s->ring_valid < order ? s->ring_valid : order);
+    for (int j = 0; j < pl.q; ++j) pl.h[j] = bufs[((cur - 1 - j) % count + count) % count];
+    return CRBE_OK;
+}
+
+static int step_ring(crbe_solver* s, double* const* bufs, int count, int cur, const double* source_d, double dt, crbe_solve_info* info_h) {
+    StepPlan pl;
+    CRBE_CHECK(plan_ring_step(s, bufs, count, cur, &pl));
     if (s->rhs_val) {
         pl.q = 0;
         CRBE_CUDA(cudaMemcpyAsync(pl.x, pl.u0, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, s->ctx->stream));
@@ -1713,12 +1854,144 @@ static int step_ring(crbe_solver* s, double* const* bufs, int count, int cur, co
         pl.u0 = pl.x;
         return step_impl(s, pl, source_d, dt, info_h);
     }
-    const int order = extrap_order(s);
-    pl.q = choose_guess_order(s, s->ring_valid < order ? s->ring_valid : order);
-    for (int j = 0; j < pl.q; ++j) pl.h[j] = bufs[((cur - 1 - j) % count + count) % count];
     const int rc = step_impl(s, pl, source_d, dt, info_h);
     if (rc == CRBE_OK) record_guess(s, pl.q, info_h);
     return rc;
+}
+
+// ---- several steps per host synchronisation -----------------------------------------------------------------
+// With about one BiCGStab iteration per step the host round trip after every step (launch, synchronise, read the norms,
+// decide) is a tenth of the step.  crbe_solver_steps_ring enqueues a chunk of steps back to back, each with the iterations
+// the previous steps needed plus one, and synchronises once.  Convergence is still enforced step by step, on the device:
+// the end-of-step kernel (k_step_end) logs the norms of every step and raises D_CHAIN when a step has not met the
+// stopping rule, which turns the rest of the chunk into no-ops; the host then finds the device exactly where that step
+// stopped, finishes it with the ordinary iteration loop and goes on.  Chunks grow (2, 4, ... MAX_CHUNK/2) while the
+// iteration count is steady, and end at a step whose guess order is a probe of the policy (its result must be recorded
+// before the next order is chosen).  Same kernels, same arguments, same order as step-by-step calls: identical bits.
+struct RingSnapshot {
+    GuessPolicy guess;
+    int ring_valid, ring_expect;
+};
+
+static void fill_info_from_log(crbe_solver* s, const double* rec, crbe_solve_info* info) {
+    memset(info, 0, sizeof(*info));
+    const double bb = rec[S_BB], rr = rec[S_RR];
+    info->iterations = (int)rec[CRBE_NSUMS + 1];
+    info->status = 0;
+    info->bnorm = sqrt(bb);
+    info->relres = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+    info->true_relres = -1.0;
+}
+
+static bool chunking_allowed(const crbe_solver* s, const double* source_d) {
+    (void)source_d;
+    if (s->world != 1 || s->rhs_val || (s->prof && s->prof->on)) return false;
+    if (s->flags & CRBE_SOLVER_VERIFY) return false;                    // every solve is followed by a host decision
+    return first_batch_target(s, 0) <= VERIFY_AUTO_ITERS;              // beyond that the verification policy wants a look
+}
+
+static void chunk_feedback(crbe_solver* s, int iterations, int iterations_before) {
+    if (iterations == iterations_before) {
+        if (++s->stable_steps >= 3) {
+            s->chunk_len = s->chunk_len < 2 ? 2 : (2 * s->chunk_len > MAX_CHUNK / 2 ? MAX_CHUNK / 2 : 2 * s->chunk_len);
+            s->stable_steps = 2;
+        }
+    } else {
+        s->stable_steps = 0;
+        s->chunk_len = 1;
+    }
+}
+
+static int steps_ring(crbe_solver* s, double* const* bufs, int count, int cur, int n_steps, const double* source_d, double dt,
+                      crbe_solve_info* infos, int* done) {
+    crbe_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const double rtol2 = s->rtol * s->rtol;
+    *done = 0;
+    int i = 0;
+    while (i < n_steps) {
+        int m = n_steps - i < s->chunk_len ? n_steps - i : s->chunk_len;
+        if (m > MAX_CHUNK) m = MAX_CHUNK;
+        const int before = s->last_iters;
+        if (m <= 1 || !chunking_allowed(s, source_d)) {
+            CRBE_CHECK(step_ring(s, bufs, count, (cur + i) % count, source_d, dt, &infos[i]));
+            chunk_feedback(s, infos[i].iterations, before);
+            ++i;
+            *done = i;
+            continue;
+        }
+        // ---- a chunk: plan and enqueue m steps, one synchronisation
+        CRBE_CUDA(cudaMemsetAsync(s->dstate + D_CHAIN, 0, sizeof(int) * 2, st));     // D_CHAIN, D_LOGPOS
+        StepPlan plans[MAX_CHUNK];
+        RingSnapshot snaps[MAX_CHUNK];
+        int launches_of[MAX_CHUNK];
+        const int target = first_batch_target(s, 0);
+        int enq = 0;
+        for (int j = 0; j < m; ++j) {
+            CRBE_CHECK(plan_ring_step(s, bufs, count, (cur + i + j) % count, &plans[j]));
+            snaps[j] = {s->guess, s->ring_valid, s->ring_expect};
+            launches_of[j] = 0;
+            CRBE_CHECK(enqueue_step(s, plans[j], source_d, dt, target, false, true, &launches_of[j]));
+            ++enq;
+            if ((s->flags & CRBE_SOLVER_EXTRAP_ADAPT) && s->guess.probe >= 0) break;   // a probe ends the chunk
+        }
+        CRBE_CUDA(cudaMemcpyAsync(s->step_log_h, s->step_log, sizeof(double) * STEP_LOG_DOUBLES * enq, cudaMemcpyDeviceToHost, st));
+        CRBE_CUDA(cudaStreamSynchronize(st));
+        s->n_chunks += 1;
+        // first step of the chunk that did not meet the stopping rule (the steps behind it were skipped on the device)
+        int jb = enq;
+        for (int j = 0; j < enq && jb == enq; ++j) {
+            const double* rec = s->step_log_h + (size_t)j * STEP_LOG_DOUBLES;
+            if (!((int)rec[CRBE_NSUMS] == 0 && rec[S_RR] <= rtol2 * rec[S_BB])) jb = j;
+        }
+        s->n_chunk_steps += jb;
+        if (jb < enq) s->n_chain_breaks += 1;
+        if (jb < enq) {     // host bookkeeping back to where that step was planned (choices for the skipped steps never happened)
+            s->guess = snaps[jb].guess;
+            s->ring_valid = snaps[jb].ring_valid;
+            s->ring_expect = snaps[jb].ring_expect;
+        }
+        int finished = 0;
+        for (int j = 0; j < jb; ++j) {
+            const double* rec = s->step_log_h + (size_t)j * STEP_LOG_DOUBLES;
+            memcpy(s->sums_h, rec, sizeof(double) * CRBE_NSUMS);    // what a step-by-step call would have downloaded
+            fill_info_from_log(s, rec, &infos[i + j]);
+            infos[i + j].launches = launches_of[j];
+            ctx->launches += launches_of[j];
+            if (infos[i + j].iterations > 0) s->last_iters = infos[i + j].iterations;
+            record_guess(s, plans[j].q, &infos[i + j]);
+            ++finished;
+        }
+        if (jb < enq) {
+            // this step needs more iterations (or a restart): continue it from the state the device stopped in
+            const double* rec = s->step_log_h + (size_t)jb * STEP_LOG_DOUBLES;
+            memcpy(s->sums_h, rec, sizeof(double) * CRBE_NSUMS);
+            int* dst_h = (int*)(s->sums_h + CRBE_NSUMS);
+            dst_h[D_STATUS] = (int)rec[CRBE_NSUMS] < 0 ? 0 : (int)rec[CRBE_NSUMS];
+            dst_h[D_ITERS] = (int)rec[CRBE_NSUMS + 1];
+            CRBE_CUDA(cudaMemsetAsync(s->dstate + D_CHAIN, 0, sizeof(int) * 2, st));
+            bind_rhs(s, plans[jb], source_d, dt);
+            int launches = 0;
+            memset(&infos[i + jb], 0, sizeof(crbe_solve_info));
+            const int rc = run_bicgstab(s, plans[jb].x, &infos[i + jb], &launches, FIRST_DONE, target);
+            infos[i + jb].launches = launches_of[jb] + launches;
+            ctx->launches += launches_of[jb] + launches;
+            if (rc != CRBE_OK) {
+                *done = i + finished;
+                return rc;
+            }
+            record_guess(s, plans[jb].q, &infos[i + jb]);
+            ++finished;
+            s->chunk_len = 1;
+            s->stable_steps = 0;
+        } else {
+            // the chunk went through: the iteration counts of its steps decide how long the next one may be
+            for (int j = 0; j < enq; ++j) chunk_feedback(s, infos[i + j].iterations, j == 0 ? before : infos[i + j - 1].iterations);
+        }
+        i += finished;
+        *done = i;
+    }
+    return CRBE_OK;
 }
 
 extern "C" int crbe_solver_step(crbe_solver* s, double* u_d, const double* source_d, double dt, crbe_solve_info* info_h) {
@@ -1741,12 +2014,22 @@ extern "C" int crbe_solver_step_ring(crbe_solver* s, double* const* bufs_h, int3
     return step_ring(s, bufs_h, count, cur, source_d, dt, info_h);
 }
 
+extern "C" int crbe_solver_steps_ring(crbe_solver* s, double* const* bufs_h, int32_t count, int32_t cur, int32_t n_steps,
+                                      const double* source_d, double dt, crbe_solve_info* infos_h, int32_t* done_h) {
+    CRBE_REQUIRE(s && bufs_h && infos_h && done_h && n_steps >= 0, "bad argument");
+    int done = 0;
+    const int rc = steps_ring(s, bufs_h, count, cur, n_steps, source_d, dt, infos_h, &done);
+    *done_h = done;
+    return rc;
+}
+
 extern "C" int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d, crbe_solve_info* info_h) {
     CRBE_REQUIRE(s && b_d && x_d && info_h, "null argument");
     CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
     crbe_ctx* ctx = s->ctx;
     memset(info_h, 0, sizeof(*info_h));
     int launches = 1;
+    s->be_u = nullptr;              // b is the stored, scaled copy of the caller's right-hand side
     CRBE_CHECK(halo_exchange(s, x_d, &launches));
     k_init<2><<<s->g_init, CRBE_BLOCK, 0, ctx->stream>>>(s->n, s->ld, s->ell_val, s->ell_col, x_d, b_d, nullptr, 0.0,
                                                                         s->mscale, s->dscale, s->is_bnd, s->b, nullptr, s->rh, s->world == 1 ? nullptr : s->p[0], s->sums, s->dots,
@@ -1897,6 +2180,20 @@ extern "C" int crbe_solver_profile_read(crbe_solver* s, double* ms_h, int64_t* c
         ms_h[k] = (s->prof && k < PK_COUNT) ? s->prof->ms[k] : 0.0;
         count_h[k] = (s->prof && k < PK_COUNT) ? s->prof->count[k] : 0;
     }
+    return CRBE_OK;
+}
+
+// out4_h: update kernels run in their last-iteration form (no r, p stores), chunks of steps enqueued with one host
+// synchronisation, steps that converged inside such chunks, chunks cut short by a step that needed more iterations
+extern "C" int crbe_solver_counters(crbe_solver* s, int64_t* out4_h) {
+    CRBE_REQUIRE(s && out4_h, "null argument");
+    int nlast = 0;
+    CRBE_CUDA(cudaMemcpyAsync(&nlast, s->dstate + D_NLAST, sizeof(int), cudaMemcpyDeviceToHost, s->ctx->stream));
+    CRBE_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    out4_h[0] = nlast;
+    out4_h[1] = s->n_chunks;
+    out4_h[2] = s->n_chunk_steps;
+    out4_h[3] = s->n_chain_breaks;
     return CRBE_OK;
 }
 

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, dou
     grid_sum_last<1>(acc, partials, counter, out, ca);
 }
 
-// ---- t = A s, (t,s), (t,t), (r^,s), (r^,t) -----------------------------------------------------------------
+// ---- t = A s, (t,s), (t,t), (r^,s), (r^,t), (s,s) ----------------------------------------------------------
 template <class IDX>
 __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, double rtol2, const double* __restrict__ eval,
                                                   const IDX* __restrict__ ecol, const int* __restrict__ ecol32, const double* __restrict__ s, double* __restrict__ t,
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, dou
     pipe.vec[1] = rh;
     pipe.start(tile_smem, bars, ntiles);
     halo_wait(2, ca);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     tile_spmv_prefetch(pipe, s, n, [&](int64_t m, int64_t row, int tr, double si, double ti) {
         const double rhi = pipe.svec(m, 1)[tr];
         t[row] = ti;
@@ -237,9 +237,10 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, dou
         acc[1] = fma(ti, ti, acc[1]);
         acc[2] = fma(rhi, si, acc[2]);
         acc[3] = fma(rhi, ti, acc[3]);
+        acc[4] = fma(si, si, acc[4]);      // lets the update kernel predict ||r||^2 = (s,s) - (t,s)^2/(t,t), see k_xrp
     });
-    double* const out[4] = {dots + S_TS, dots + S_TT, dots + S_RS, dots + S_RT};
-    grid_sum_last<4>(acc, partials, counter, out, ca);
+    double* const out[5] = {dots + S_TS, dots + S_TT, dots + S_RS, dots + S_RT, dots + S_SS};
+    grid_sum_last<5>(acc, partials, counter, out, ca);
 }
 
 // ---- Backward-Euler step start: b = mscale*u^n (+ dscale*dt*f), r = r^ = p = b - A x0, (b,b), (r,r) --------
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
                                                        unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
+    if (dstate[D_CHAIN] != 0) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         dstate[D_STATUS] = 0;
         dstate[D_ITERS] = 0;
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
             const double bi = fma(pipe.svec(m, 0)[tr], pipe.svec(m, 1)[tr], extra);
             const double ax = tile_row(pipe, m, tr, xi, [&](int j) { return __ldg(x + j); });
             const double ri = bi - ax;
-            b[row] = bi;
+            if (b) b[row] = bi;   // not stored in the time loop: see crbe_solver::be_u
             rh[row] = ri;
             if (r) r[row] = ri;   // see k_init
             if (p) p[row] = ri;
@@ -295,31 +297,40 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
 }
 
 // ---- true residual b - A x and its norm (guard = 1: verification, norm only; guard = 0: restart, r = r^ = p) ----
-template <class IDX>
+// BE = false: b is a stored vector (one staged stream).  BE = true: b = mscale*u^n (+ dt*dscale*f) rebuilt on the fly from
+// two staged streams, as in t_init_be (the time loop does not store b).
+template <class IDX, bool BE>
 __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntiles, const double* __restrict__ eval, const IDX* __restrict__ ecol, const int* __restrict__ ecol32,
-                                                        const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
+                                                        const double* __restrict__ x, RhsSource rhs, double* __restrict__ r,
                                                         double* __restrict__ rh, double* __restrict__ p, double* sums, double* dots,
                                                         double* partials, unsigned int* counter, const CommArgs* __restrict__ ca,
                                                         const int* dstate, int guard, double rtol2) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
+    if (dstate[D_CHAIN] != 0) return;
     if (guard && (dstate[D_STATUS] != 0 || sums[S_RR] > rtol2 * sums[S_BB])) return;
-    TilePipe<1, TILE_STAGES, IDX> pipe;
+    TilePipe<BE ? 2 : 1, TILE_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
     pipe.ecol32 = ecol32;
-    pipe.vec[0] = b;
+    pipe.vec[0] = BE ? rhs.mscale : rhs.b;
+    if (BE) pipe.vec[BE ? 1 : 0] = rhs.u;
     pipe.start(tile_smem, bars, ntiles);
     halo_wait(0, ca);
     const int tr = threadIdx.x;
     double acc[1] = {0.0};
     for (int64_t m = 0; m < pipe.count; ++m) {
         const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
-        const double xi = row < n ? x[row] : 0.0;
+        double xi = 0.0, extra = 0.0;
+        if (row < n) {
+            xi = x[row];
+            if (BE && rhs.src) extra = rhs.dscale[row] * rhs.dt * rhs.src[row];
+        }
         pipe.wait(m);
         if (row < n) {
             const double ax = tile_row(pipe, m, tr, xi, [&](int j) { return __ldg(x + j); });
-            const double ri = pipe.svec(m, 0)[tr] - ax;
+            const double bi = BE ? fma(pipe.svec(m, 0)[tr], pipe.svec(m, BE ? 1 : 0)[tr], extra) : pipe.svec(m, 0)[tr];
+            const double ri = bi - ax;
             if (!guard) {
                 r[row] = ri;
                 rh[row] = ri;

@@ -63,10 +63,11 @@ def spinup_note(spinup):
 
 def set_index_bits(bits, single_gpu=True):
     """The matrix part of a row is 4 values + 4 indices: 48 B with 32-bit columns, 40 B with 16-bit offsets.
-    The init kernel writes b and r^ only (plus p in the partitioned solver): the first iteration reads r and p
-    through one vector, and the first SpMV of a solve streams one vector instead of two ("pv0")."""
+    The init kernel reads mscale, u^n, x0 and writes r^ only (plus p in the partitioned solver; b is never stored): the
+    first iteration reads r and p through one vector, and the first SpMV of a solve streams one vector instead of two
+    ("pv0").  The update kernel moves 64 B per row, 40 in the last iteration of a solve (no r, p stores, no v)."""
     mat = 32 + 4 * bits // 8
-    ROW_BYTES.update({"init": mat + (5 if single_gpu else 6) * 8, "pv": mat + 3 * 8, "pv0": mat + 2 * 8,
+    ROW_BYTES.update({"init": mat + (4 if single_gpu else 5) * 8, "pv": mat + 3 * 8, "pv0": mat + 2 * 8,
                       "st": mat + 3 * 8, "residual": mat + 2 * 8})
 KINDS = ["init", "pv", "st", "xr", "p", "s", "residual", "extrapolate"]
 
@@ -85,6 +86,8 @@ def parse_args():
     ap.add_argument("--verify-always", action="store_true", help="recompute the true residual after every solve (default: auto)")
     ap.add_argument("--index32", action="store_true", help="stream 32-bit column indices even when 16-bit offsets fit")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")
+    ap.add_argument("--chunk", type=int, default=10, help="steps per library call / host synchronisation in the timed loop (1: step by step)")
+    ap.add_argument("--no-predict", action="store_true", help="always store r and p in the update kernel (CRBE_SOLVER_NO_PREDICT)")
     ap.add_argument("--classic", action="store_true", help="register-load kernels instead of the bulk-copy (TMA) pipeline")
     ap.add_argument("--e2e-steps", type=int, default=120, help="time levels of the e2e BESCRFEM.solve() run (100.7 MB of pinned host memory each)")
     ap.add_argument("--spinup", type=int, default=-1,
@@ -430,20 +433,19 @@ def main():
     assert n == counts["dofs"]
     l0 = C.c_int64()
     spinup = spinup_steps(args, K)
-    for _ in range(spinup + W):
-        loop.step()
+    loop.steps(spinup + W)
     sampler = ClockSampler(local_rank)
     sampler.start()
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l0))
+    cnt_start = (C.c_int64 * 4)()
+    rt.call("crbe_solver_counters", solver._solver, cnt_start)
     torch.cuda.synchronize()
     e0, e1, em = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
     del loop.orders[:]
-    iters = []
-    for k in range(K):
-        iters.append(loop.step())
-        if k + 1 == win["cpu_timed_steps"]:
-            em.record()          # end of the part of the window the host leg can afford (the whole window unless K >= 500)
+    iters = loop.steps(win["cpu_timed_steps"])
+    em.record()                  # end of the part of the window the host leg can afford (the whole window unless K >= 500)
+    iters += loop.steps(K - win["cpu_timed_steps"])
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -457,6 +459,10 @@ def main():
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l1))
     # same region once more with a CUDA event pair around every kernel launch: per-kernel durations for the roofline
     KP = min(K, 40)
+    cnt_timed = (C.c_int64 * 4)()
+    rt.call("crbe_solver_counters", solver._solver, cnt_timed)
+    cnt0 = (C.c_int64 * 4)()
+    rt.call("crbe_solver_counters", solver._solver, cnt0)
     rt.call("crbe_solver_profile", solver._solver, 1)
     torch.cuda.synchronize()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -471,6 +477,11 @@ def main():
     pms = (C.c_double * 8)()
     pcnt = (C.c_int64 * 8)()
     rt.call("crbe_solver_profile_read", solver._solver, pms, pcnt)
+    cnt1 = (C.c_int64 * 4)()
+    rt.call("crbe_solver_counters", solver._solver, cnt1)
+    # update kernels of the profiled pass that ran in their short last-iteration form
+    f_last = min(1.0, (cnt1[0] - cnt0[0]) / pcnt[3]) if pcnt[3] > 0 else 0.0
+    ROW_BYTES["xr"] = f_last * 40 + (1.0 - f_last) * 64
     # pv launches: the first of every solve is the one-stream variant
     f0 = min(1.0, KP / pcnt[1]) if pcnt[1] > 0 else 0.0
     ROW_BYTES["pv"] = f0 * ROW_BYTES["pv0"] + (1.0 - f0) * ROW_BYTES["pv"]
@@ -482,9 +493,9 @@ def main():
     # the roofline is quoted on the kernel that takes the largest share of the step
     dom_k = max(kern, key=lambda k: kern[k]["launches"] * kern[k]["ms_per_launch"])
     achieved = kern[dom_k]["GBps"]
-    label = {"init": "init: b = mscale*u^n, r^ = b - A x0 (ELL SpMV), (b,b), (r,r)",
+    label = {"init": "init: r^ = mscale*u^n - A x0 (ELL SpMV), (b,b), (r,r)",
              "pv": "pv: ELL SpMV v = A p + dot (r^,v)" + (" (mostly its first-iteration form, p = r^)" if f0 > 0.5 else ""),
-             "st": "st: ELL SpMV t = A s + 4 dots", "xr": "xrp: x, r, p updates + (r,r)", "s": "s = r - alpha v",
+             "st": "st: ELL SpMV t = A s + 5 dots", "xr": "xrp: x, r, p updates + (r,r)", "s": "s = r - alpha v",
              "residual": "true residual", "extrapolate": "extrapolated initial guess"}[dom_k]
     ncu_name = {"init": "t_init_be", "pv": "t_pv0" if f0 > 0.5 else "t_pv", "st": "t_st", "xr": "k_xrp", "s": "k_s"}.get(dom_k, dom_k)
     shares = {k: kern[k]["launches"] * kern[k]["ms_per_launch"] for k in kern}
@@ -510,7 +521,10 @@ def main():
                                  + f"; mean order {q_mean:.2f}, orders of the last 16 steps {timed_orders[-16:]})"),
                     "verify": "always" if args.verify_always else "auto (true residual recomputed after solves of > 12 iterations or a restart)",
                     "launch": loop.launch_note,
-                    "index_bits": bits, "iters_per_step": it_mean, "iters_timed_steps": iters if K <= 64 else iters[:32] + ["..."] + iters[-16:],
+                    "index_bits": bits, "iters_per_step": it_mean,
+                    "host_synchronisations": {"chunks": int(cnt_timed[1] - cnt_start[1]), "steps_in_chunks": int(cnt_timed[2] - cnt_start[2]),
+                                              "chunks_cut_short": int(cnt_timed[3] - cnt_start[3]), "timed_steps": K},
+                    "update_kernels_in_last_iteration_form": int(cnt_timed[0] - cnt_start[0]), "iters_timed_steps": iters if K <= 64 else iters[:32] + ["..."] + iters[-16:],
                     "setup_s": loop.setup_s, **spinup_note(spinup)},
         "dof_updates_per_s": steps_per_s * n,
         "steps_per_s_with_kernel_events": KP / (ms_prof * 1e-3),
@@ -592,7 +606,8 @@ def main():
 
 def solver_options(args):
     return dict(tma=not args.classic, extrapolate=False if args.no_extrapolate else (args.extrapolate_order or True),
-                verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False)
+                verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False,
+                predict=not args.no_predict)
 
 
 class SingleGpuLoop:
@@ -629,7 +644,29 @@ class SingleGpuLoop:
         self.info = _lib.SolveInfo()
         self.dt = float(self.solver.dt)
         self.orders = []
-        self.launch_note = "kernel by kernel" if args.no_graph else "one CUDA graph per step (head + first batch of iterations + state download)"
+        self.chunk = max(1, args.chunk)
+        self.launch_note = (("kernel by kernel" if args.no_graph else "one CUDA graph per step (head + first batch of iterations + end-of-step record)")
+                            + (f"; up to {self.chunk} steps per host synchronisation (crbe_solver_steps_ring, convergence enforced per step on the device)"
+                               if self.chunk > 1 else "; one host synchronisation per step"))
+        self._infos = (_lib.SolveInfo * self.chunk)()
+        self._done = C.c_int32()
+
+    def steps(self, count):
+        """`count` steps of the loop, up to `chunk` per library call; returns the iterations of every step."""
+        its = []
+        while count > 0:
+            m = min(count, self.chunk)
+            if m == 1:
+                its.append(self.step())
+            else:
+                self.rt.call("crbe_solver_steps_ring", self.solver._solver, self.ring, self.nring, self.cur, m, self._ptr(None), self.dt,
+                             self._infos, C.byref(self._done))
+                self.cur = (self.cur + m) % self.nring
+                for k in range(m):
+                    self.orders.append(self._infos[k].guess_order)
+                    its.append(self._infos[k].iterations)
+            count -= m
+        return its
 
     def step(self):
         c = self.cur
@@ -667,12 +704,11 @@ def strong_block_single(args, device):
     try:
         wl = workloads.unit_square(args.strong_n, steps=K + W + spin, regime=args.regime)
         loop = SingleGpuLoop(args, wl, device)
-        for _ in range(spin + W):
-            loop.step()
+        loop.steps(spin + W)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        its = [loop.step() for _ in range(K)]
+        its = loop.steps(K)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)

@@ -160,6 +160,10 @@ typedef struct crbe_solve_info {
                                          time against the rounding noise of the earlier solves (higher orders amplify it) */
 #define CRBE_SOLVER_TMA 8u            /* SpMV-type kernels fed by bulk async copies (cp.async.bulk
                                          + mbarrier pipeline through shared memory)               */
+#define CRBE_SOLVER_NO_PREDICT 2048u  /* always store r and p in the update kernel.  Default: the kernel predicts ||r||^2 =
+                                         (s,s) - (t,s)^2/(t,t) from the sums of the preceding kernel and, when that lies clearly
+                                         below the stopping threshold, skips the stores (and the read of v) nobody would use:
+                                         24 bytes per row less in the last iteration of a solve; same x, same (r,r)            */
 
 /* Build the solver for the pattern (indptr/indices, structural, N rows) with
  * Dirichlet rows bnd_seg_d[0..nb) (crbe.py:397-402). */
@@ -194,6 +198,14 @@ int crbe_solver_step_pingpong(crbe_solver* s, double* u_cur_d, double* u_next_d,
  * further steps. */
 int crbe_solver_step_ring(crbe_solver* s, double* const* bufs_h, int32_t count, int32_t cur, const double* source_d, double dt,
                           crbe_solve_info* info_h);
+/* n_steps consecutive steps of the same ring (cur advancing by one per step) with ONE host synchronisation per chunk of steps
+ * instead of one per step: the loop of crbe.py:419-429 for the stretches in which the host has nothing to do between steps
+ * (constant source_d -- NULL for the stock problem --, no row of `solutions` to fetch).  Convergence is enforced per step on
+ * the device; a step that needs more iterations than were enqueued for it stops the chunk there and is finished the ordinary
+ * way.  infos_h: n_steps records.  *done_h: steps completed (= n_steps unless an error is returned).  Results are bit-identical
+ * to n_steps calls of crbe_solver_step_ring. */
+int crbe_solver_steps_ring(crbe_solver* s, double* const* bufs_h, int32_t count, int32_t cur, int32_t n_steps,
+                           const double* source_d, double dt, crbe_solve_info* infos_h, int32_t* done_h);
 /* Solve  A x = b  for the loaded system (Dirichlet rows applied); x_d holds the initial guess. */
 int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d, crbe_solve_info* info_h);
 /* b of crbe.py:384-402 for inspection: b_d (out). */
@@ -257,6 +269,10 @@ int crbe_solver_p2p_error(crbe_solver* s, int* err_h);       /* non-zero: a peer
  * (launches enqueued past convergence, which return at once, are not counted). */
 int crbe_solver_profile(crbe_solver* s, int enable);
 int crbe_solver_profile_read(crbe_solver* s, double* ms_h, int64_t* count_h);
+/* Counters since the solver was created, out4_h: [0] update kernels that ran in their short last-iteration form (see
+ * CRBE_SOLVER_NO_PREDICT), [1] chunks of steps enqueued with one host synchronisation (crbe_solver_steps_ring), [2] steps that
+ * converged inside such chunks, [3] chunks cut short by a step that needed more iterations than were enqueued. */
+int crbe_solver_counters(crbe_solver* s, int64_t* out4_h);
 /* kernels launched through this context so far */
 int crbe_ctx_launch_count(crbe_ctx* ctx, int64_t* count_h);
 

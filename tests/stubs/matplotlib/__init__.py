@@ -28,9 +28,17 @@ class _Anything:
         return False
 
 
+def _any_attribute(attr):
+    """PEP 562 module __getattr__: any public name resolves; dunder probes (__file__, __path__, ... as the import
+    machinery and inspect make them on every entry of sys.modules) fail like on a plain module."""
+    if attr.startswith("__") and attr.endswith("__"):
+        raise AttributeError(attr)
+    return _Anything()
+
+
 def _module(name):
     m = types.ModuleType(name)
-    m.__getattr__ = lambda attr: _Anything()      # PEP 562: any attribute resolves
+    m.__getattr__ = _any_attribute
     return m
 
 
@@ -38,8 +46,7 @@ def use(*a, **k):
     return None
 
 
-def __getattr__(attr):
-    return _Anything()
+__getattr__ = _any_attribute
 
 
 for _sub in ("pyplot", "tri", "colors", "cm"):

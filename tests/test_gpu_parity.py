@@ -701,3 +701,118 @@ def test_moments_match_triangle_integration():
                                    rtol=1e-10, atol=1e-13)
         assert m["peak"] == u.max()
         assert tuple(m["peak_xy"]) == tuple(mid[int(np.argmax(u))])
+
+
+# --------------------------------------------------------------------------
+# round 2: chunks of steps per host synchronisation, last-iteration form of the update kernel, unstored b
+# --------------------------------------------------------------------------
+def _ring_loop(n=96, steps=60, regime="P-ref", **kw):
+    """A BESCRFEM of the benchmark problem at n x n cells, ready for ring stepping: (solver, ring buffers, ctypes ring, N)."""
+    import torch
+    from airpollution_b200 import crbe, workloads
+    wl = workloads.unit_square(n, steps=steps, regime=regime)
+    md = crbe.MeshData(wl.mesh(), wl.domain(), wl.nt)
+    s = crbe.BESCRFEM(wl.domain(), wl.problem(), md, crbe.ElementCR(), 1, history="last", progress=False, **kw)
+    s.set_initial_condition()
+    s.build_global_matrices()
+    rt = s._rt
+    vlen = C.c_int64()
+    rt.call("crbe_solver_vector_length", s._solver, C.byref(vlen), None)
+    bufs = [rt.zeros((vlen.value,), torch.float64) for _ in range(5)]
+    ring = (C.c_void_p * 5)(*[b.data_ptr() for b in bufs])
+    bufs[0][:md.number_of_segments] = rt.upload(np.asarray(s.u_prev, dtype=np.float64))
+    return s, bufs, ring, md.number_of_segments
+
+
+def _run_ring(s, bufs, ring, steps, chunk, perturb_at=None):
+    """`steps` steps, `chunk` per library call (1: crbe_solver_step_ring); returns (final vector, iterations per step)."""
+    import torch
+    from airpollution_b200 import _lib
+    from airpollution_b200.runtime import ptr
+    rt = s._rt
+    infos = (_lib.SolveInfo * max(chunk, 1))()
+    done = C.c_int32()
+    cur, its, k = 0, [], 0
+    while k < steps:
+        if perturb_at is not None and k == perturb_at:      # a jolt the extrapolated guess cannot follow
+            g = torch.Generator(device="cpu").manual_seed(5)
+            noise = torch.randn(bufs[cur].numel(), generator=g, dtype=torch.float64).to(bufs[cur].device)
+            bufs[cur].mul_(1.0 + 1e-3 * noise)
+        m = min(chunk, steps - k)
+        if perturb_at is not None and k < perturb_at:
+            m = min(m, perturb_at - k)
+        if chunk == 1:
+            rt.call("crbe_solver_step_ring", s._solver, ring, 5, cur, ptr(None), float(s.dt), C.byref(infos[0]))
+        else:
+            rt.call("crbe_solver_steps_ring", s._solver, ring, 5, cur, m, ptr(None), float(s.dt), infos, C.byref(done))
+            assert done.value == m
+        its += [infos[j].iterations for j in range(m)]
+        cur = (cur + m) % 5
+        k += m
+    return bufs[cur].cpu().numpy().copy(), its
+
+
+@pytest.mark.parametrize("regime", ["P-ref", "P-T10"])
+def test_chunked_steps_are_bit_identical_to_single_steps(regime):
+    """crbe_solver_steps_ring (several steps per host synchronisation, convergence enforced on the device) against the
+    same steps through crbe_solver_step_ring."""
+    a, ba, ra, n = _ring_loop(regime=regime)
+    ua, ia = _run_ring(a, ba, ra, 60, 1)
+    b, bb, rb, _ = _ring_loop(regime=regime)
+    ub, ib = _run_ring(b, bb, rb, 60, 16)
+    assert np.array_equal(ua, ub)
+    assert ia == ib
+    cnt = (C.c_int64 * 4)()
+    b._rt.call("crbe_solver_counters", b._solver, cnt)
+    if regime == "P-ref":
+        assert cnt[1] > 0 and cnt[2] > cnt[1]          # chunks were used, and held more than one step each on average
+        assert cnt[1] < 45                              # far fewer synchronisations than steps
+
+
+def test_chunk_cut_short_by_a_hard_step_continues_correctly():
+    """A step that needs more iterations than were enqueued stops its chunk on the device; the host finishes it and goes on:
+    same bits as the step-by-step loop."""
+    a, ba, ra, n = _ring_loop()
+    ua, ia = _run_ring(a, ba, ra, 60, 1, perturb_at=40)
+    b, bb, rb, _ = _ring_loop()
+    ub, ib = _run_ring(b, bb, rb, 60, 16, perturb_at=40)
+    assert max(ia[40:44]) > ia[39] + 1                 # the jolt did cost iterations
+    assert np.array_equal(ua, ub) and ia == ib
+    cnt = (C.c_int64 * 4)()
+    b._rt.call("crbe_solver_counters", b._solver, cnt)
+    assert cnt[3] >= 1                                  # at least one chunk was cut short
+
+
+@pytest.mark.parametrize("tma", [True, False], ids=["bulk-copy", "register-loads"])
+def test_last_iteration_form_of_the_update_kernel_is_bit_identical(tma):
+    """predict=True skips the r, p stores of the iteration predicted to be the last of a solve: same x, same norms."""
+    a, ba, ra, n = _ring_loop(predict=True, tma=tma)
+    ua, ia = _run_ring(a, ba, ra, 50, 1)
+    b, bb, rb, _ = _ring_loop(predict=False, tma=tma)
+    ub, ib = _run_ring(b, bb, rb, 50, 1)
+    assert np.array_equal(ua, ub) and ia == ib
+    ca, cb = (C.c_int64 * 4)(), (C.c_int64 * 4)()
+    a._rt.call("crbe_solver_counters", a._solver, ca)
+    b._rt.call("crbe_solver_counters", b._solver, cb)
+    assert cb[0] == 0 and ca[0] >= 40                   # nearly every solve ended in the short form
+
+
+def test_step_residual_check_and_unstored_rhs():
+    """crbe_solver_step_residual recomputes ||b - A u^(n+1)|| / ||b|| from u^n and u^(n+1) alone; the verification kernel that
+    rebuilds b on the fly (verify=True) sees the same system."""
+    from airpollution_b200 import _lib
+    from airpollution_b200.runtime import ptr
+    s, bufs, ring, n = _ring_loop(verify=True)
+    info = _lib.SolveInfo()
+    out, bn = C.c_double(), C.c_double()
+    for k in range(12):
+        s._rt.call("crbe_solver_step_ring", s._solver, ring, 5, k % 5, ptr(None), float(s.dt), C.byref(info))
+        s._rt.call("crbe_solver_step_residual", s._solver, ptr(bufs[k % 5]), ptr(bufs[(k + 1) % 5]), ptr(None), float(s.dt),
+                   C.byref(out), C.byref(bn))
+        assert info.true_relres >= 0.0                                  # verify=True: the solver recomputed it as well
+        assert abs(out.value - info.true_relres) <= 5e-2 * info.true_relres + 1e-17
+        assert abs(bn.value - info.bnorm) <= 1e-12 * info.bnorm
+        assert out.value < 3e-13
+    # a wrong pair of vectors is seen as such
+    s._rt.call("crbe_solver_step_residual", s._solver, ptr(bufs[0]), ptr(bufs[3]), ptr(None), float(s.dt), C.byref(out), None)
+    assert out.value > 1e-9
