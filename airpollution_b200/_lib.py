@@ -104,7 +104,8 @@ _SIGNATURES = {
     "crbe_solver_create_partitioned": [vp, vp, C.c_int64, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, C.c_int32,
                                        c_i32p, c_i64p, vp, c_i64p, C.POINTER(vp)],
     "crbe_solver_vector_length": [vp, c_i64p, c_i64p],
-    "crbe_solver_update_advection": [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp],
+    "crbe_solver_advection_plan": [vp, vp, vp, vp, C.c_int64, vp, vp, vp],
+    "crbe_solver_update_advection": [vp, vp, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, vp, vp],
     "crbe_solver_p2p_export": [vp, vp, c_i64p],
     "crbe_solver_p2p_connect": [vp, C.c_int, vp, c_i64p, c_i64p, c_i64p],
     "crbe_solver_x": [vp, C.POINTER(vp)],

@@ -376,6 +376,11 @@ class BESCRFEM:
                  | (0 if self.predict else _lib.SOLVER_NO_PREDICT))
         rt.call("crbe_solver_set_options", self._solver, float(self.rtol), int(self.max_iterations), flags)
         rt.call("crbe_solver_set_system", self._solver, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
+        if self.velocity_field is not None:
+            # time-varying velocity: everything of the advection matrix that does not depend on v is laid out once
+            m = md._dev
+            rt.call("crbe_solver_advection_plan", self._solver, ptr(m["points"]), ptr(m["tri"]), ptr(m["areas"]),
+                    md.number_of_triangles, ptr(m["edge_slots"]), ptr(d["scatter_pos"]), ptr(d["k_val"]))
 
     @property
     def index_bits(self):
@@ -604,6 +609,8 @@ class BESCRFEM:
                 for k in range(run):
                     i = infos[k]
                     self.step_info.append((i.iterations, i.relres, i.true_relres, i.restarts, i.guess_order, i.initial_relres))
+                if reassemble and self.time_scheme_order == 2:
+                    self._advance_rhs_operator()
                 cur = (cur + run) % nring
                 step += run
                 if bar is not None:
@@ -650,16 +657,22 @@ class BESCRFEM:
 
     def _reassemble_advection(self, t, export=False):
         """Time-varying velocity (config 5): v_T = velocity_field(centroid_T, t) per triangle, A(v) and the solver's
-        system rows rebuilt in one fused pass (``crbe_solver_update_advection``)."""
-        md, rt, d = self.mesh_data, self._rt, self._dev
-        m = md._dev
+        system rows rebuilt in one fused pass (``crbe_solver_update_advection``).  Crank-Nicolson's right-hand-side
+        operator M - dt/2 (K + A) belongs to the old time level: it is rebuilt from the same velocity AFTER the step
+        (``_advance_rhs_operator``)."""
+        rt, d = self._rt, self._dev
         v_elem = self._element_velocity(t)
-        rt.call("crbe_solver_update_advection", self._solver, ptr(m["points"]), ptr(m["tri"]), ptr(m["areas"]),
-                ptr(m["edge_slots"]), ptr(d["scatter_pos"]), ptr(d["m_val"]), ptr(d["k_val"]), ptr(v_elem), 0.0, 0.0,
-                float(self._coef()), ptr(d["a_val"] if export else None), ptr(d["s_val"] if export else None))
-        self._v_elem = v_elem          # keep alive until the kernel has run
+        rt.call("crbe_solver_update_advection", self._solver, ptr(v_elem), 0.0, 0.0, float(self._coef()), 1, 0,
+                ptr(d["a_val"] if export else None), ptr(d["s_val"] if export else None))
+        self._v_elem = v_elem          # keep alive until the kernels have run
         if export:
             self._np.clear()
+
+    def _advance_rhs_operator(self):
+        """Crank-Nicolson with a time-varying velocity: after the step to t_{n+1} the operator of the next right-hand
+        side is M - dt/2 (K + A(t_{n+1}))."""
+        self._rt.call("crbe_solver_update_advection", self._solver, ptr(self._v_elem), 0.0, 0.0, float(self._coef()), 0, 1,
+                      ptr(None), ptr(None))
 
     # ---- errors (crbe.py:435-482) -----------------------------------------
     def compute_errors(self, analytical_sol_fn):

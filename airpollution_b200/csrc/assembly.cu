@@ -115,89 +115,253 @@ extern "C" int crbe_system_values(crbe_ctx* ctx, int64_t nnz, const double* m_va
 }
 
 // --------------------------------------------------------------------------
-// Time-varying velocity (BASELINE config 5): A changes every step, M and K do not.  One thread per ROW gathers the
-// advection contributions of the (<= 2) triangles on its edge, forms  s = m + c (k + a)  entry by entry in the
-// reference's order (crbe.py:358) and writes the solver's rows directly -- Dirichlet identity rows, division by the
-// diagonal, tile-major ELL slots, mass/diagonal scalings -- without materialising A or S and without the element
-// colouring: every output is written once, coalesced, by its own thread.  Values are bit-identical to
-// crbe_assemble + crbe_system_values + crbe_solver_set_system (two-term sums commute).
+// Time-varying velocity (BASELINE config 5): A changes every step, M and K do not, and neither does the geometry.
+// A_loc[a][b] = 2*((area/6)*(grad_phi_b . v)) is linear in v with coefficients that depend on the triangle only, so
+// everything but v is laid out once (crbe_solver_advection_plan):
+//   geom[t]  = { b00, b01, b10, b11, area/6 }   the inverse Jacobian of crbe.py:291-302 and phi_int of :310, evaluated with
+//              the operations of crbe_element_advection, so that the per-step products are the same bits;
+//   meta[i]  = one word per row: entries of the row, position of its diagonal, Dirichlet flag, and for each of the <= 2
+//              triangles of the edge the CSR offsets (0..4) its three local edges add to.
+// The per-step kernel (one thread per row, no colouring, nothing of size nnz materialised) then reads per row: meta (4 B),
+// its two triangle ids (8), the K entries of the row (<= 40) and diag M (8), gathers the two triangle records and
+// velocities (shared with the neighbouring rows through L1/L2: ~38 B per row of DRAM traffic), forms
+// s = m + c (k + a) entry by entry in the reference's order (crbe.py:358), applies the Dirichlet rows and the diagonal
+// scaling, and writes the ELL slots and the two scalings (48 B): ~150 B per row against ~320 for the kernel it replaces,
+// which re-gathered vertex ids, six coordinates, the area and nine scatter positions per triangle and recomputed the
+// Jacobian.  Values are bit-identical to crbe_assemble + crbe_system_values + crbe_solver_set_system.
 // --------------------------------------------------------------------------
-__global__ void __launch_bounds__(CRBE_BLOCK) k_update_system_rows(
-    int64_t n, const int* __restrict__ indptr, const int* __restrict__ indices, const unsigned char* __restrict__ is_bnd,
-    const double* __restrict__ pts, const int* __restrict__ tri, const double* __restrict__ areas, const int* __restrict__ edge_slots,
-    const int* __restrict__ pos, const double* __restrict__ mval, const double* __restrict__ kval, const double* __restrict__ v_elem,
-    double vx0, double vy0, double coef, double* __restrict__ ell_val, double* __restrict__ mdiag, double* __restrict__ mscale,
-    double* __restrict__ dscale, double* __restrict__ rhs_val, double* __restrict__ a_out, double* __restrict__ s_out, int* __restrict__ err) {
+struct AdvectionPlan {
+    double* geom = nullptr;        // nt x 5
+    uint32_t* meta = nullptr;      // n
+    const int32_t* edge_slots = nullptr;   // caller-owned (MeshData), n x 2
+    const double* k_val = nullptr;         // caller-owned, structural pattern
+    int64_t n = 0, nt = 0;
+};
+
+static void advection_plan_free(void* p) {
+    AdvectionPlan* pl = (AdvectionPlan*)p;
+    if (!pl) return;
+    cudaFree(pl->geom);
+    cudaFree(pl->meta);
+    delete pl;
+}
+
+__global__ void __launch_bounds__(CRBE_BLOCK) k_advection_geom(const double* __restrict__ pts, const int* __restrict__ tri,
+                                                               const double* __restrict__ areas, int64_t nt, double* __restrict__ geom) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += (int64_t)gridDim.x * blockDim.x) {
+        const int i0 = tri[3 * t], i1 = tri[3 * t + 1], i2 = tri[3 * t + 2];
+        const double x0 = pts[2 * (int64_t)i0], y0 = pts[2 * (int64_t)i0 + 1], x1 = pts[2 * (int64_t)i1], y1 = pts[2 * (int64_t)i1 + 1],
+                     x2 = pts[2 * (int64_t)i2], y2 = pts[2 * (int64_t)i2 + 1];
+        const double j00 = x1 - x0, j10 = y1 - y0, j01 = x2 - x0, j11 = y2 - y0;       // as crbe_element_advection
+        const double det = fabs(j00 * j11 - j01 * j10);
+        geom[5 * t + 0] = j11 / det;
+        geom[5 * t + 1] = (-j01) / det;
+        geom[5 * t + 2] = (-j10) / det;
+        geom[5 * t + 3] = j00 / det;
+        geom[5 * t + 4] = areas[t] / 6.0;
+    }
+}
+
+// meta word: bits 0-2 entries of the row, 3-5 offset of the diagonal (7: none), 6 Dirichlet row,
+// 7-15 / 16-24: CSR offsets of local edges 0,1,2 of the triangle on side 0 / 1 (3 bits each)
+__global__ void __launch_bounds__(CRBE_BLOCK) k_advection_meta(int64_t n, const int* __restrict__ indptr, const int* __restrict__ indices,
+                                                               const unsigned char* __restrict__ is_bnd, const int* __restrict__ edge_slots,
+                                                               const int* __restrict__ pos, uint32_t* __restrict__ meta, int* __restrict__ err) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int p0 = indptr[i], p1 = indptr[i + 1];
-        double a_loc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
         if (p1 - p0 > 5) {
             atomicOr(err, 2);
+            meta[i] = 0;
             continue;
         }
-#pragma unroll
+        uint32_t w = (uint32_t)(p1 - p0);
+        uint32_t diag = 7;
+        for (int p = p0; p < p1; ++p)
+            if (indices[p] == (int)i) diag = (uint32_t)(p - p0);
+        if (diag == 7) atomicOr(err, 1);
+        w |= diag << 3;
+        w |= (is_bnd[i] ? 1u : 0u) << 6;
         for (int side = 0; side < 2; ++side) {
             const int slot = edge_slots[2 * i + side];
             if (slot < 0) continue;
             const int64_t t = slot / 3;
             const int a = slot - 3 * (int)t;
-            const int i0 = tri[3 * t], i1 = tri[3 * t + 1], i2 = tri[3 * t + 2];
+            for (int b = 0; b < 3; ++b) {
+                const int off = pos[9 * t + 3 * a + b] - p0;
+                if (off < 0 || off > 4) atomicOr(err, 8);
+                w |= ((uint32_t)off & 7u) << (7 + 9 * side + 3 * b);
+            }
+        }
+        meta[i] = w;
+    }
+}
+
+__global__ void __launch_bounds__(CRBE_BLOCK) k_update_system_rows(
+    int64_t n, const int* __restrict__ indptr, const uint32_t* __restrict__ meta, const int2* __restrict__ edge_slots,
+    const double* __restrict__ geom, const double* __restrict__ kval, const double* __restrict__ mdiag, const double* __restrict__ v_elem,
+    double vx0, double vy0, double coef, double* __restrict__ ell_val, double* __restrict__ mscale, double* __restrict__ dscale,
+    double* __restrict__ rhs_val, double* __restrict__ a_out, double* __restrict__ s_out, int* __restrict__ err) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = __ldg(meta + i);
+        const int2 es = __ldg(edge_slots + i);
+        const int p0 = __ldg(indptr + i);
+        const int len = (int)(w & 7u), diag = (int)((w >> 3) & 7u);
+        const bool bd = ((w >> 6) & 1u) != 0;
+        double a_loc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int slot = side == 0 ? es.x : es.y;
+            if (slot < 0) continue;
+            const int64_t t = slot / 3;
+            const double b00 = __ldg(geom + 5 * t), b01 = __ldg(geom + 5 * t + 1), b10 = __ldg(geom + 5 * t + 2),
+                         b11 = __ldg(geom + 5 * t + 3), phi_int = __ldg(geom + 5 * t + 4);
             double vx = vx0, vy = vy0;
             if (v_elem) {
-                vx = v_elem[2 * t];
-                vy = v_elem[2 * t + 1];
+                vx = __ldg(v_elem + 2 * t);
+                vy = __ldg(v_elem + 2 * t + 1);
             }
-            double arow[3];
-            crbe_element_advection(pts[2 * (int64_t)i0], pts[2 * (int64_t)i0 + 1], pts[2 * (int64_t)i1], pts[2 * (int64_t)i1 + 1],
-                                   pts[2 * (int64_t)i2], pts[2 * (int64_t)i2 + 1], areas[t], vx, vy, arow);
 #pragma unroll
-            for (int b = 0; b < 3; ++b) a_loc[pos[9 * t + 3 * a + b] - p0] += arow[b];   // A_loc[a][b] = arow[b] for every a
-        }
-        double sv[5];
-        double d = 0.0, m = 0.0;
-        int diag = -1;
-        for (int p = p0; p < p1; ++p) {
-            const double av = a_loc[p - p0];
-            const double s = mval[p] + coef * (kval[p] + av);        // (K+A) first, times c, plus M     crbe.py:358
-            sv[p - p0] = s;
-            if (a_out) a_out[p] = av;
-            if (s_out) s_out[p] = s;
-            if (rhs_val) rhs_val[p] = mval[p] + (-coef) * (kval[p] + av);   // M - c (K+A)                crbe.py:386
-            if (indices[p] == (int)i) {
-                diag = p - p0;
-                d = s;
-                m = mval[p];
+            for (int b = 0; b < 3; ++b) {
+                const double gx = b00 * CRBE_G(b, 0) + b10 * CRBE_G(b, 1);       // grad_phi[b] = B^T G[b]      crbe.py:305
+                const double gy = b01 * CRBE_G(b, 0) + b11 * CRBE_G(b, 1);
+                const double ar = 2 * (phi_int * (gx * vx + gy * vy));           // :311-313, same for every local row a
+                const int off = (int)((w >> (7 + 9 * side + 3 * b)) & 7u);
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    if (off == q) a_loc[q] += ar;
             }
         }
-        const bool bd = is_bnd[i] != 0;
-        if (diag < 0 || (!bd && !(fabs(d) > 0.0))) atomicOr(err, diag < 0 ? 1 : 4);
+        const double m = __ldg(mdiag + i);
+        double sv[5];
+        double d = 0.0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            sv[q] = 0.0;
+            if (q < len) {
+                const double kq = __ldcs(kval + p0 + q);
+                const double mq = q == diag ? m : 0.0;                   // M carries explicit zeros off the diagonal (crbe.py:282)
+                const double sq = mq + coef * (kq + a_loc[q]);           // (K+A) first, times c, plus M      crbe.py:358
+                sv[q] = sq;
+                if (a_out) a_out[p0 + q] = a_loc[q];
+                if (s_out) s_out[p0 + q] = sq;
+                if (rhs_val) rhs_val[p0 + q] = mq + (-coef) * (kq + a_loc[q]);   // M - c (K+A)              crbe.py:386
+                if (q == diag) d = sq;
+            }
+        }
+        if (diag >= len || (!bd && !(fabs(d) > 0.0))) atomicOr(err, diag >= len ? 1 : 4);
         int k = 0;
-        if (!bd)
-            for (int p = p0; p < p1 && k < 4; ++p) {
-                if (p - p0 == diag) continue;
-                ell_val[ell_at(i, k)] = sv[p - p0] / d;
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            if (!bd && q < len && q != diag && k < 4) {
+                __stcs(ell_val + ell_at(i, k), sv[q] / d);
                 ++k;
             }
-        for (; k < 4; ++k) ell_val[ell_at(i, k)] = 0.0;
-        mdiag[i] = m;
+        for (; k < 4; ++k) __stcs(ell_val + ell_at(i, k), 0.0);
         mscale[i] = bd ? 0.0 : m / d;
         dscale[i] = bd ? 0.0 : 1.0 / d;
     }
 }
 
-extern "C" int crbe_solver_update_advection(crbe_solver* solver, const double* points_d, const int32_t* tri_d, const double* areas_d,
-                                            const int32_t* edge_slots_d, const int32_t* scatter_pos_d, const double* m_val_d,
-                                            const double* k_val_d, const double* v_elem_d, double vx, double vy, double coef,
-                                            double* a_val_out_d, double* s_val_out_d) {
-    CRBE_REQUIRE(solver && points_d && tri_d && areas_d && edge_slots_d && scatter_pos_d && m_val_d && k_val_d, "null argument");
+// Crank-Nicolson only: the right-hand-side operator M - c (K + A(v)) on the structural pattern (crbe.py:386), nothing else
+__global__ void __launch_bounds__(CRBE_BLOCK) k_update_rhs_rows(int64_t n, const int* __restrict__ indptr, const uint32_t* __restrict__ meta,
+                                                                const int2* __restrict__ edge_slots, const double* __restrict__ geom,
+                                                                const double* __restrict__ kval, const double* __restrict__ mdiag,
+                                                                const double* __restrict__ v_elem, double vx0, double vy0, double coef,
+                                                                double* __restrict__ rhs_val) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = __ldg(meta + i);
+        const int2 es = __ldg(edge_slots + i);
+        const int p0 = __ldg(indptr + i);
+        const int len = (int)(w & 7u), diag = (int)((w >> 3) & 7u);
+        double a_loc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int slot = side == 0 ? es.x : es.y;
+            if (slot < 0) continue;
+            const int64_t t = slot / 3;
+            const double b00 = __ldg(geom + 5 * t), b01 = __ldg(geom + 5 * t + 1), b10 = __ldg(geom + 5 * t + 2),
+                         b11 = __ldg(geom + 5 * t + 3), phi_int = __ldg(geom + 5 * t + 4);
+            double vx = vx0, vy = vy0;
+            if (v_elem) {
+                vx = __ldg(v_elem + 2 * t);
+                vy = __ldg(v_elem + 2 * t + 1);
+            }
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const double gx = b00 * CRBE_G(b, 0) + b10 * CRBE_G(b, 1);
+                const double gy = b01 * CRBE_G(b, 0) + b11 * CRBE_G(b, 1);
+                const double ar = 2 * (phi_int * (gx * vx + gy * vy));
+                const int off = (int)((w >> (7 + 9 * side + 3 * b)) & 7u);
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    if (off == q) a_loc[q] += ar;
+            }
+        }
+        const double m = __ldg(mdiag + i);
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            if (q < len) rhs_val[p0 + q] = (q == diag ? m : 0.0) + (-coef) * (__ldcs(kval + p0 + q) + a_loc[q]);
+    }
+}
+
+extern "C" int crbe_solver_advection_plan(crbe_solver* solver, const double* points_d, const int32_t* tri_d, const double* areas_d,
+                                          int64_t nt, const int32_t* edge_slots_d, const int32_t* scatter_pos_d, const double* k_val_d) {
+    CRBE_REQUIRE(solver && points_d && tri_d && areas_d && edge_slots_d && scatter_pos_d && k_val_d && nt > 0, "null argument");
     crbe_solver_arrays ar;
     CRBE_CHECK(crbe_solver_get_arrays(solver, &ar));
     crbe_ctx* ctx = ar.ctx;
-    int* err = (int*)(ctx->dev_scalars + 48);
-    CRBE_CUDA(cudaMemsetAsync(err, 0, sizeof(int), ctx->stream));
-    k_update_system_rows<<<crbe_grid_for(ctx, ar.n), CRBE_BLOCK, 0, ctx->stream>>>(
-        ar.n, ar.indptr, ar.indices, ar.is_bnd, points_d, tri_d, areas_d, edge_slots_d, scatter_pos_d, m_val_d, k_val_d, v_elem_d, vx, vy,
-        coef, ar.ell_val, ar.mdiag, ar.mscale, ar.dscale, ar.rhs_val, a_val_out_d, s_val_out_d, err);
+    if (*ar.plan_slot) {
+        (*ar.plan_free)(*ar.plan_slot);
+        *ar.plan_slot = nullptr;
+    }
+    AdvectionPlan* pl = new AdvectionPlan();
+    *ar.plan_slot = pl;
+    *ar.plan_free = advection_plan_free;
+    pl->n = ar.n;
+    pl->nt = nt;
+    pl->edge_slots = edge_slots_d;
+    pl->k_val = k_val_d;
+    CRBE_CUDA(cudaMalloc(&pl->geom, sizeof(double) * 5 * nt));
+    CRBE_CUDA(cudaMalloc(&pl->meta, sizeof(uint32_t) * ar.n));
+    CRBE_CUDA(cudaMemsetAsync(ar.err, 0, sizeof(int), ctx->stream));
+    k_advection_geom<<<crbe_grid_for(ctx, nt), CRBE_BLOCK, 0, ctx->stream>>>(points_d, tri_d, areas_d, nt, pl->geom);
+    k_advection_meta<<<crbe_grid_for(ctx, ar.n), CRBE_BLOCK, 0, ctx->stream>>>(ar.n, ar.indptr, ar.indices, ar.is_bnd, edge_slots_d,
+                                                                              scatter_pos_d, pl->meta, ar.err);
+    CRBE_KERNEL_CHECK();
+    ctx->launches += 2;
+    int err_h = 0;
+    CRBE_CUDA(cudaMemcpyAsync(&err_h, ar.err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (err_h) {
+        crbe_set_error("advection plan: %s%s%s", (err_h & 1) ? "row without diagonal; " : "", (err_h & 2) ? "row with more than 5 entries; " : "",
+                       (err_h & 8) ? "scatter position outside its row; " : "");
+        return CRBE_ERR_ARG;
+    }
+    return CRBE_OK;
+}
+
+// write_rhs: also rebuild the Crank-Nicolson right-hand-side operator M - c(K+A) from this velocity (it belongs to the OLD time
+// level of a step: call with write_rhs = 0 before the step and once more with write_rhs = 1 after it, see BESCRFEM.solve)
+extern "C" int crbe_solver_update_advection(crbe_solver* solver, const double* v_elem_d, double vx, double vy, double coef, int32_t write_system,
+                                            int32_t write_rhs, double* a_val_out_d, double* s_val_out_d) {
+    CRBE_REQUIRE(solver != nullptr, "null argument");
+    crbe_solver_arrays ar;
+    CRBE_CHECK(crbe_solver_get_arrays(solver, &ar));
+    CRBE_REQUIRE(*ar.plan_slot != nullptr, "crbe_solver_advection_plan has not been called");
+    CRBE_REQUIRE(!write_rhs || ar.rhs_val, "no Crank-Nicolson operator loaded");
+    AdvectionPlan* pl = (AdvectionPlan*)*ar.plan_slot;
+    crbe_ctx* ctx = ar.ctx;
+    // errors (missing / zero diagonal) land in the solver's device state and are reported by the next step's synchronisation
+    if (write_system) {
+        k_update_system_rows<<<crbe_grid_for(ctx, ar.n), CRBE_BLOCK, 0, ctx->stream>>>(
+            ar.n, ar.indptr, pl->meta, (const int2*)pl->edge_slots, pl->geom, pl->k_val, ar.mdiag, v_elem_d, vx, vy, coef, ar.ell_val,
+            ar.mscale, ar.dscale, write_rhs ? ar.rhs_val : nullptr, a_val_out_d, s_val_out_d, ar.err);
+    } else {
+        CRBE_REQUIRE(write_rhs, "nothing to write");
+        k_update_rhs_rows<<<crbe_grid_for(ctx, ar.n), CRBE_BLOCK, 0, ctx->stream>>>(ar.n, ar.indptr, pl->meta, (const int2*)pl->edge_slots,
+                                                                                   pl->geom, pl->k_val, ar.mdiag, v_elem_d, vx, vy, coef,
+                                                                                   ar.rhs_val);
+    }
     CRBE_KERNEL_CHECK();
     ctx->launches += 1;
     return CRBE_OK;

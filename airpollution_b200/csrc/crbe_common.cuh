@@ -88,6 +88,9 @@ struct crbe_solver_arrays {
     const int32_t* indices;
     const unsigned char* is_bnd;
     double *ell_val, *mdiag, *mscale, *dscale, *rhs_val;
+    int* err;                       // device word: unusable rows found by the re-assembly kernels (reported at the next step)
+    void** plan_slot;               // the solver keeps the advection plan of assembly.cu alive ...
+    void (**plan_free)(void*);      // ... and releases it through this
 };
 int crbe_solver_get_arrays(crbe_solver* s, crbe_solver_arrays* out);
 

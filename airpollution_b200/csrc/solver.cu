@@ -151,6 +151,8 @@ struct crbe_solver {
     double* step_log_h = nullptr;        // pinned
     int chunk_len = 1, stable_steps = 0; // how many steps the next chunk may hold (grows while the iteration count is steady)
     int64_t n_chunks = 0, n_chunk_steps = 0, n_chain_breaks = 0;   // statistics (crbe_solver_counters)
+    void* adv_plan = nullptr;                                      // time-varying velocity: see assembly.cu
+    void (*adv_plan_free)(void*) = nullptr;
 };
 
 // ---------------------------------------------------------------- helpers
@@ -564,10 +566,11 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, double
 // p_in: where the old p is read (p itself, or r^ in the first iteration on a single GPU; may alias p: no __restrict__)
 //
 // Last iteration of a solve: ||r||^2 = (s,s) - (t,s)^2/(t,t) is known from the sums of the previous kernel before r exists.
-// When it lies clearly below the stopping threshold (factor 4: the formula cancels, its relative error is ~1e-16 (s,s)/||r||^2)
-// nobody will read this iteration's r and p, and the kernel neither stores them nor reads v: 40 instead of 64 bytes per
-// row.  x and the accumulated (r,r) are the same bits either way.  Should the accumulated norm contradict the prediction
-// the recurrence is gone: status 3, and the host restarts the solve from the true residual.
+// When it lies below the stopping threshold nobody will read this iteration's r and p, and the kernel neither stores them nor
+// reads v: 40 instead of 64 bytes per row.  x and the accumulated (r,r) are the same bits either way.  The formula cancels: its
+// absolute error is a few 1e-15 (s,s), which matters only when the accumulated norm lands within that distance of the threshold
+// (margin 1e-3 of the threshold below); should the accumulated norm then contradict the prediction the recurrence is gone:
+// status 3, and the host restarts the solve from the true residual of the updated x -- correct either way, one extra SpMV.
 __global__ void __launch_bounds__(CRBE_BLOCK) k_xrp(int64_t n, int k, double rtol2, const double* __restrict__ s, const double* __restrict__ t,
                                                     const double* __restrict__ v, double* __restrict__ x, double* __restrict__ r,
                                                     const double* p_in, double* p, double* sums, double* dots, int* dstate, double* partials,
@@ -585,7 +588,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_xrp(int64_t n, int k, double rto
     const double beta = (rho_next / rho) * (alpha / omega);
     const double thr = rtol2 * sums[S_BB];
     const double rr_pred = tt > 0.0 ? sums[S_SS] - sums[S_TS] * sums[S_TS] / tt : sums[S_SS];
-    const bool last = predict && rr_pred <= 0.25 * thr;
+    const bool last = predict && rr_pred <= 0.999 * thr;
     double acc[1] = {0.0};
     if (last) {
         ROW_LOOP(i, n) {
@@ -869,6 +872,7 @@ static void drop_step_graphs(crbe_solver* s) {
 static int solver_release(crbe_solver* s) {
     if (!s) return CRBE_OK;
     drop_step_graphs(s);
+    if (s->adv_plan && s->adv_plan_free) s->adv_plan_free(s->adv_plan);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     cudaFree(s->bc_stage);
     if (s->window) {               // p and s live in the window: free the stand-alone allocations they replaced
@@ -978,7 +982,7 @@ static int solver_init(crbe_solver* s, crbe_ctx* ctx, crbe_comm* comm, int64_t n
     CRBE_CUDA(cudaMemsetAsync(s->dstate, 0, sizeof(int) * D_NSTATE, ctx->stream));
     CRBE_CUDA(cudaMalloc(&s->step_log, sizeof(double) * STEP_LOG_DOUBLES * MAX_CHUNK));
     CRBE_CUDA(cudaMallocHost(&s->step_log_h, sizeof(double) * STEP_LOG_DOUBLES * MAX_CHUNK));
-    CRBE_CUDA(cudaMallocHost(&s->sums_h, sizeof(double) * (CRBE_NSUMS + 2)));
+    CRBE_CUDA(cudaMallocHost(&s->sums_h, sizeof(double) * (CRBE_NSUMS + D_NSTATE / 2)));
     s->dots = s->sums;
     if (s->world > 1) {
         CRBE_CUDA(cudaMalloc(&s->red, sizeof(double) * CRBE_NSUMS));
@@ -1142,6 +1146,7 @@ extern "C" int crbe_solver_p2p_error(crbe_solver* s, int* err_h) {
 
 int crbe_solver_get_arrays(crbe_solver* s, crbe_solver_arrays* out) {
     CRBE_REQUIRE(s && out, "null argument");
+    CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
     out->ctx = s->ctx;
     out->n = s->n;
     out->nnz = s->nnz;
@@ -1153,7 +1158,9 @@ int crbe_solver_get_arrays(crbe_solver* s, crbe_solver_arrays* out) {
     out->mscale = s->mscale;
     out->dscale = s->dscale;
     out->rhs_val = s->rhs_val;
-    s->system_loaded = true;
+    out->err = s->dstate + D_SETUP_ERR;
+    out->plan_slot = &s->adv_plan;
+    out->plan_free = &s->adv_plan_free;
     return CRBE_OK;
 }
 
@@ -1384,7 +1391,7 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
 static int enqueue_fetch(crbe_solver* s) {
     cudaStream_t st = s->ctx->stream;
     CRBE_CUDA(cudaMemcpyAsync(s->sums_h, s->sums, sizeof(double) * CRBE_NSUMS, cudaMemcpyDeviceToHost, st));
-    CRBE_CUDA(cudaMemcpyAsync(s->sums_h + CRBE_NSUMS, s->dstate, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    CRBE_CUDA(cudaMemcpyAsync(s->sums_h + CRBE_NSUMS, s->dstate, sizeof(int) * D_NSTATE, cudaMemcpyDeviceToHost, st));
     return CRBE_OK;
 }
 
@@ -1503,7 +1510,14 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
             if (first == FIRST_FRESH) CRBE_CHECK(enqueue_batch(s, x, k, target, speculate, launches));
             k = target;
             speculated_last = speculate;
-            if (first != FIRST_DONE) CRBE_CUDA(cudaStreamSynchronize(st));
+            if (first != FIRST_DONE) {
+                CRBE_CUDA(cudaStreamSynchronize(st));
+                if (dst_h[D_SETUP_ERR] != 0) {      // rows rebuilt by crbe_solver_update_advection since the last step
+                    crbe_set_error("system matrix unusable after re-assembly: %s%s", (dst_h[D_SETUP_ERR] & 1) ? "row without diagonal; " : "",
+                                   (dst_h[D_SETUP_ERR] & 4) ? "zero diagonal; " : "");
+                    return CRBE_ERR_ARG;
+                }
+            }
             first = FIRST_FRESH;
             const double rr = s->sums_h[S_RR], bb = s->sums_h[S_BB];
             status = dst_h[D_STATUS];
@@ -1967,6 +1981,7 @@ static int steps_ring(crbe_solver* s, double* const* bufs, int count, int cur, i
             const double* rec = s->step_log_h + (size_t)jb * STEP_LOG_DOUBLES;
             memcpy(s->sums_h, rec, sizeof(double) * CRBE_NSUMS);
             int* dst_h = (int*)(s->sums_h + CRBE_NSUMS);
+            dst_h[D_SETUP_ERR] = 0;
             dst_h[D_STATUS] = (int)rec[CRBE_NSUMS] < 0 ? 0 : (int)rec[CRBE_NSUMS];
             dst_h[D_ITERS] = (int)rec[CRBE_NSUMS + 1];
             CRBE_CUDA(cudaMemsetAsync(s->dstate + D_CHAIN, 0, sizeof(int) * 2, st));

@@ -105,16 +105,22 @@ int crbe_assemble(crbe_ctx* ctx, const double* points_d, const int32_t* tri_d, c
 int crbe_system_values(crbe_ctx* ctx, int64_t nnz, const double* m_val_d, const double* k_val_d,
                        const double* a_val_d, double coef, double* s_val_d);
 
-/* Time-varying velocity (BASELINE.json config 5; the reference's v is constant, crbe.py:309, and is the
- * special case v_elem_d == NULL): rebuild A(v) and the rows of the loaded solver system in ONE pass over the
- * rows -- each row gathers the advection terms of its <= 2 triangles, forms m + coef*(k + a) in the reference's
- * order, applies the Dirichlet rows and the diagonal scaling and writes the solver's layout; nothing of size
- * nnz is materialised unless a_val_out_d / s_val_out_d (structural pattern) are given.  Bit-identical to
- * crbe_assemble + crbe_system_values + crbe_solver_set_system.  Requires a previous crbe_solver_set_system. */
-int crbe_solver_update_advection(crbe_solver* s, const double* points_d, const int32_t* tri_d, const double* areas_d,
-                                 const int32_t* edge_slots_d, const int32_t* scatter_pos_d, const double* m_val_d,
-                                 const double* k_val_d, const double* v_elem_d, double vx, double vy, double coef,
-                                 double* a_val_out_d, double* s_val_out_d);
+/* Time-varying velocity (BASELINE.json config 5; the reference's v is constant, crbe.py:309, and is the special case
+ * v_elem_d == NULL).  A_loc (crbe.py:284-313) is linear in v with coefficients that depend on the triangle only:
+ * crbe_solver_advection_plan lays them out once for the loaded solver (per triangle the inverse Jacobian and area/6 of
+ * crbe.py:291-310, per row one word describing where its <= 2 triangles add).  points/tri/areas/scatter_pos are read during
+ * the call only; edge_slots_d and k_val_d must stay alive while the plan is used.  Requires crbe_solver_set_system. */
+int crbe_solver_advection_plan(crbe_solver* s, const double* points_d, const int32_t* tri_d, const double* areas_d, int64_t nt,
+                               const int32_t* edge_slots_d, const int32_t* scatter_pos_d, const double* k_val_d);
+/* Rebuild A(v) and the rows of the loaded solver system in ONE pass over the rows: each row forms m + coef*(k + a) in the
+ * reference's order (crbe.py:358), applies the Dirichlet rows and the diagonal scaling and writes the solver's layout; nothing
+ * of size nnz is materialised unless a_val_out_d / s_val_out_d (structural pattern) are given.  Bit-identical to
+ * crbe_assemble + crbe_system_values + crbe_solver_set_system.  write_system != 0: the system rows; write_rhs != 0: the
+ * Crank-Nicolson operator M - coef*(K + A) (crbe.py:386), which belongs to the old time level of a step -- rebuild the system
+ * before a step (write_rhs = 0) and the operator after it (write_system = 0, write_rhs = 1).  A row that comes out unusable
+ * (zero diagonal) is reported by the next crbe_solver_step*. */
+int crbe_solver_update_advection(crbe_solver* s, const double* v_elem_d, double vx, double vy, double coef, int32_t write_system,
+                                 int32_t write_rhs, double* a_val_out_d, double* s_val_out_d);
 
 /* ---- kernels exposed for unit tests and profiling ----------------------- */
 int crbe_spmv_csr(crbe_ctx* ctx, int64_t n, const int32_t* indptr_d, const int32_t* indices_d,

@@ -335,6 +335,9 @@ class OracleSolver:
         if keep_history:
             self.solutions = np.zeros((nsteps, n))
             self.solutions[0, :] = u_prev                               # :412
+        if self.velocity_fn is not None:        # config-5 extension: the operators of the first step's old time level, A(v(., 0))
+            p, tr = m.points, m.triangles
+            self.v_elem = np.asarray(self.velocity_fn((p[tr[:, 0]] + p[tr[:, 1]] + p[tr[:, 2]]) / 3.0, 0.0), dtype=np.float64)
         self.build_global_matrices()                                    # :415
         if self.linear_solver in ("spsolve", "literal"):
             A = dirichlet_system(self.base_system, m.boundary_segments)
@@ -348,7 +351,11 @@ class OracleSolver:
         start = time.time()
         for step in range(1, nsteps):
             t = step * self.dt                                          # :420
+            b = None
             if self.velocity_fn is not None:
+                # time-varying velocity: the right-hand side belongs to the old time level (Crank-Nicolson:
+                # (M - dt/2 (K + A(t_n))) u^n, crbe.py:386 with the operator of t_n), the system to the new one
+                b = self.rhs(t, u_prev)
                 p, tr = m.points, m.triangles
                 cent = (p[tr[:, 0]] + p[tr[:, 1]] + p[tr[:, 2]]) / 3.0
                 self.v_elem = np.asarray(self.velocity_fn(cent, t), dtype=np.float64)
@@ -357,7 +364,8 @@ class OracleSolver:
                 self.system = A
                 lu = spla.splu(A.tocsc()) if self.linear_solver == "splu" else None
                 dinv = 1.0 / A.diagonal()
-            b = self.rhs(t, u_prev)
+            if b is None:
+                b = self.rhs(t, u_prev)
             if self.linear_solver == "literal":
                 A = dirichlet_system(self.base_system, m.boundary_segments)   # :397-404, every step
             if self.linear_solver in ("spsolve", "literal"):

@@ -816,3 +816,75 @@ def test_step_residual_check_and_unstored_rhs():
     # a wrong pair of vectors is seen as such
     s._rt.call("crbe_solver_step_residual", s._solver, ptr(bufs[0]), ptr(bufs[3]), ptr(None), float(s.dt), C.byref(out), None)
     assert out.value > 1e-9
+
+
+def test_reassembly_at_512_cells_is_bit_identical_to_the_assembly_path():
+    """Config 5 at 512 x 512 cells (786k DOFs): the per-step re-assembly kernel (precomputed triangle records + one word
+    per row) against crbe_assemble + crbe_system_values + crbe_solver_set_system with the same per-element velocity --
+    ELL values, scalings and the exported A, S bit for bit; then three steps against the oracle's re-assembled solve."""
+    import torch
+    from airpollution_b200 import crbe, workloads
+    wl = workloads.unit_square(512, steps=3)
+    mesh = wl.mesh()
+    T = wl.T
+    field = _rotating_field(0.05, T)
+    md = crbe.MeshData(mesh, wl.domain(), wl.nt)
+    s = crbe.BESCRFEM(wl.domain(), wl.problem(), md, crbe.ElementCR(), 1, progress=False, velocity_field=field, history="last")
+    s.build_global_matrices()                       # assembled with v(., 0)
+    rt = s._rt
+
+    def ell_state(solver):
+        ld = C.c_int64()
+        pc, pv, pm, pd = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        rt.call("crbe_solver_debug_ell", solver._solver, C.byref(ld), C.byref(pc), C.byref(pv), C.byref(pm), C.byref(pd))
+
+        def view(p, count):
+            class _W:
+                __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (p.value, True), "version": 3}
+            return torch.as_tensor(_W(), device=rt.device).clone()
+        n = md.number_of_segments
+        return view(pv, 4 * ld.value), view(pm, n), view(pd, n)
+
+    t1 = 0.37 * T
+    # reference path: full assembly with v(., t1), system values, set_system
+    ref = crbe.BESCRFEM(wl.domain(), wl.problem(), md, crbe.ElementCR(), 1, progress=False,
+                        velocity_field=lambda c, t: field(c, t1), history="last")
+    ref.build_global_matrices()
+    ev, em, ed = ell_state(ref)
+    s._reassemble_advection(t1, export=True)
+    rt.synchronize()
+    gv, gm, gd = ell_state(s)
+    assert torch.equal(ev, gv) and torch.equal(em, gm) and torch.equal(ed, gd)
+    assert torch.equal(s._dev["a_val"], ref._dev["a_val"]) and torch.equal(s._dev["s_val"], ref._dev["s_val"])
+    # and the time loop against the oracle (host BiCGStab: a direct factorisation per step is minutes at this size)
+    sol = crbe.BESCRFEM(wl.domain(), wl.problem(), md, crbe.ElementCR(), 1, progress=False, velocity_field=field).solve()
+    o = orc.OracleSolver(T, wl.problem(), orc.OracleMesh(mesh.points, mesh.triangles, T, wl.nt), order=1, velocity_fn=field,
+                         linear_solver="bicgstab")
+    refsol = o.solve()
+    assert max(rel_err(sol[k], refsol[k]) for k in range(1, wl.nt)) <= SOLUTION_RTOL
+
+
+def test_reassembly_reports_an_unusable_row_at_the_next_step():
+    """A velocity that cancels a diagonal exactly cannot happen by accident; a NaN velocity can: the next step must fail
+    loudly instead of iterating on garbage."""
+    import torch
+    from airpollution_b200 import crbe
+    from airpollution_b200.meshgen import structured_mesh
+    mesh = structured_mesh(8, lo=(-1.0, -1.0), hi=(1.0, 1.0))
+    dom, prob = crbe.Domain(1.0, 1.0, 1.0), crbe.Problem(v=[0.1, 0.0], D=0.05, sigma=0.3)
+    md = crbe.MeshData(mesh, dom, 5)
+    bad = lambda c, t: torch.full((c.shape[0], 2), float("nan") if t > 0.3 else 0.1, dtype=torch.float64, device=c.device)  # noqa: E731
+    s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, progress=False, velocity_field=bad)
+    with pytest.raises(RuntimeError, match="unusable after re-assembly|broke down"):
+        s.solve()
+    # before set_system there is no system to rebuild
+    t = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, progress=False)
+    t._assemble_values()
+    h = C.c_void_p()
+    t._rt.call("crbe_solver_create", t._rt.ctx, md.number_of_segments, t._dev["indptr"].data_ptr(), t._dev["indices"].data_ptr(),
+               t._nnz, md._dev["bnd"].data_ptr(), md._dev["bnd"].numel(), C.byref(h))
+    try:
+        with pytest.raises(RuntimeError, match="set_system"):
+            t._rt.call("crbe_solver_update_advection", h, None, 0.0, 0.0, 0.1, 1, 0, None, None)
+    finally:
+        t._rt.call("crbe_solver_destroy", h)
