@@ -109,6 +109,7 @@ _SIGNATURES = {
     "crbe_solver_p2p_export": [vp, vp, c_i64p],
     "crbe_solver_p2p_connect": [vp, C.c_int, vp, c_i64p, c_i64p, c_i64p],
     "crbe_solver_x": [vp, C.POINTER(vp)],
+    "crbe_solver_ring": [vp, C.POINTER(vp), c_i32p],
     "crbe_solver_p2p_error": [vp, c_i32p],
 }
 # test hooks (declared in the header's "test hooks" section)

@@ -98,7 +98,7 @@ int crbe_solver_get_arrays(crbe_solver* s, crbe_solver_arrays* out);
 struct crbe_comm;
 int crbe_comm_rank(const crbe_comm* c);
 int crbe_comm_world(const crbe_comm* c);
-int crbe_comm_allreduce_sum(crbe_comm* c, double* buf_d, int count, cudaStream_t stream);
+int crbe_comm_allreduce_sum(crbe_comm* c, const double* send_d, double* recv_d, int count, cudaStream_t stream);
 int crbe_comm_exchange(crbe_comm* c, int n_neigh, const int* neigh, const double* sendbuf_d, const int64_t* send_off,
                        double* recvbuf_d, const int64_t* recv_off, cudaStream_t stream);
 

@@ -115,9 +115,9 @@ extern "C" int crbe_comm_destroy(crbe_comm* c) {
 int crbe_comm_rank(const crbe_comm* c) { return c ? c->rank : 0; }
 int crbe_comm_world(const crbe_comm* c) { return c ? c->world : 1; }
 
-// in-place sum of `count` doubles over all ranks, enqueued on `stream`
-int crbe_comm_allreduce_sum(crbe_comm* c, double* buf_d, int count, cudaStream_t stream) {
-    CRBE_NCCL(nccl()->AllReduce(buf_d, buf_d, (size_t)count, ncclDouble, ncclSum, c->nccl, stream));
+// sum of `count` doubles over all ranks, send_d -> recv_d (may be the same buffer), enqueued on `stream`
+int crbe_comm_allreduce_sum(crbe_comm* c, const double* send_d, double* recv_d, int count, cudaStream_t stream) {
+    CRBE_NCCL(nccl()->AllReduce(send_d, recv_d, (size_t)count, ncclDouble, ncclSum, c->nccl, stream));
     return CRBE_OK;
 }
 
@@ -138,5 +138,5 @@ int crbe_comm_exchange(crbe_comm* c, int n_neigh, const int* neigh, const double
 // test hooks through the ABI
 extern "C" int crbe_comm_test_allreduce(crbe_comm* c, double* buf_d, int count) {
     CRBE_REQUIRE(c && buf_d && count > 0, "bad argument");
-    return crbe_comm_allreduce_sum(c, buf_d, count, c->ctx->stream);
+    return crbe_comm_allreduce_sum(c, buf_d, buf_d, count, c->ctx->stream);
 }

@@ -27,6 +27,7 @@
 // Kernels launched after convergence return at once, so the host enqueues a
 // predicted number of iterations and synchronises once per batch.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -56,7 +57,10 @@ enum { S_BB = 0, S_RR = 1, S_RHO0 = 2, S_RHO1 = 3, S_RHV = 4, S_TS = 5, S_TT = 6
 // (restart from the true residual), 4 a peer never signalled (peer-memory transport).
 // D_CHAIN: steps enqueued back to back without host synchronisation (crbe_solver_steps_ring): set by the end-of-step
 // kernel when its step has not converged; every later kernel of the chunk then returns at once.
-enum { D_STATUS = 0, D_ITERS = 1, D_SETUP_ERR = 2, D_ESCAPES = 3, D_CHAIN = 4, D_LOGPOS = 5, D_NLAST = 6, D_NSTATE = 8 };
+// D_PRED: the last update kernel ran in its short form (no r, p).  D_NORMSRC: who produced the current (b,b), (r,r) --
+// 0 the init kernel, 1 an update kernel, 2 the host-driven restart (already in the sums); peer-memory transport only.
+enum { D_STATUS = 0, D_ITERS = 1, D_SETUP_ERR = 2, D_ESCAPES = 3, D_CHAIN = 4, D_LOGPOS = 5, D_NLAST = 6, D_PRED = 7, D_NORMSRC = 8,
+       D_NSTATE = 12 };
 constexpr int STEP_LOG_DOUBLES = CRBE_NSUMS + 2;   // one record of the step log: the sums, then status and iterations
 constexpr int MAX_CHUNK = 64;                      // steps enqueued between two host synchronisations
 constexpr int IDX16_ESCAPE = -32768;   // 16-bit column offset that does not fit: read the 32-bit column instead
@@ -131,8 +135,14 @@ struct crbe_solver {
     unsigned char* window = nullptr;
     void* peer_base[8] = {nullptr};
     CommArgs* d_comm = nullptr;                // device copy of the peer table handed to the kernels (nullptr: not connected)
-    double* saved_p0 = nullptr;                // the stand-alone p, s allocations replaced by window storage
+    double* saved_p0 = nullptr;                // the stand-alone p, s, r^ allocations replaced by window storage
     double* saved_s = nullptr;
+    double* saved_rh = nullptr;
+    double* ring[CRBE_MAX_EXTRAP + 1] = {nullptr};   // the ring of solution vectors inside the window (peers write their halo entries)
+    unsigned char* tile_halo = nullptr;        // per tile: references a halo column (partitioned solver)
+    double* red_send = nullptr;                // NCCL transport: where the dot kernels leave this rank's partial sums
+    int64_t rot = 0;                           // tile kernels walk a partitioned strip from its middle (see TilePipe::rot)
+    long long p2p_timeout = 1LL << 35;         // clock64 ticks (~18 s); CRBE_P2P_TIMEOUT_MS overrides
     crbe_profile* prof = nullptr;
     // CUDA graphs of whole steps (CRBE_SOLVER_GRAPH): head kernels + first batch of iterations + state download
     std::vector<StepGraph> graphs;
@@ -149,17 +159,14 @@ struct crbe_solver {
     // steps enqueued back to back (crbe_solver_steps_ring): one record per step, written by the end-of-step kernel
     double* step_log = nullptr;
     double* step_log_h = nullptr;        // pinned
-    int chunk_len = 1, stable_steps = 0; // how many steps the next chunk may hold (grows while the iteration count is steady)
+    int chunk_len = 1, stable_steps = 0; // how many steps the next chunk may hold (doubles while steps fit their enqueued iterations)
     int64_t n_chunks = 0, n_chunk_steps = 0, n_chain_breaks = 0;   // statistics (crbe_solver_counters)
+    bool comm_dead = false;                                        // a peer timed out: every later call fails
     void* adv_plan = nullptr;                                      // time-varying velocity: see assembly.cu
     void (*adv_plan_free)(void*) = nullptr;
 };
 
 // ---------------------------------------------------------------- helpers
-__device__ __forceinline__ bool solver_idle(const double* __restrict__ sums, const int* __restrict__ dstate, double rtol2) {
-    return dstate[D_STATUS] != 0 || dstate[D_CHAIN] != 0 || !(sums[S_RR] > rtol2 * sums[S_BB]);
-}
-
 // y_i = x_i + sum_k val[k][i] * x[col[k][i]]   (unit diagonal implicit)
 template <class F>
 __device__ __forceinline__ double ell_row(const double* __restrict__ val, const int* __restrict__ col, int64_t ld, int64_t i,
@@ -177,21 +184,36 @@ __device__ __forceinline__ double ell_row(const double* __restrict__ val, const 
     return acc;
 }
 
-// grid_sum + "am I thread 0 of the last CTA" for bookkeeping writes
 // ---- peer-memory transport (partitioned solve) ---------------------------------------------------------
+// One CUDA-IPC window per rank holds a mailbox and every vector whose halo entries neighbours write: the ring of solution
+// vectors, p, s and r^.  Two fused exchanges, no separate communication kernels on the iteration path:
+//   halo   the last CTA of the kernel that produced a gathered vector stores this rank's boundary entries straight into the
+//          neighbours' halo segments over NVLink and raises their epoch flag (halo_push_tail).  The consuming SpMV walks its
+//          tiles starting in the MIDDLE of the strip and waits for the flag only when it reaches the first tile that
+//          references a halo column (HaloGate): interior tiles overlap the transfer.
+//   dots   the last CTA of a dot-product kernel deposits the rank's partial sums in every rank's mailbox and returns
+//          (grid_sum_last); the kernels that need the totals add the deposits in rank order at their head, after their
+//          first bulk copies are in flight (head_sums) -- the NVLink latency hides behind the kernel boundary and the
+//          copy prologue, no SM idles in a producer's tail.  Every rank adds the same numbers in the same order: same bits.
+// Epochs are counted on the device and never reset; all ranks take identical control decisions from identical totals, so
+// they stay in lock step through early-exit kernels, graphs and chunks of steps.  Mailbox cells are indexed by reduction
+// kind and epoch parity: a cell is rewritten two epochs later, by when every reader of the old value has finished (a rank
+// cannot deposit epoch e+2 of a kind before all ranks deposited a later kind of epoch e+1, which they do after reading e).
 constexpr int CRBE_MAX_RANKS = 8;
+constexpr int RING_MAX = CRBE_MAX_EXTRAP + 1;
 constexpr size_t P2P_HEADER_BYTES = 8192;
-// Mailbox at the start of every rank's CUDA-IPC window.  Flags carry monotonically increasing epochs (never
-// reset); every rank counts its own epochs on the device, in lock step with the others because all ranks take
-// identical control decisions from identical reduced sums.
+enum { HK_X = 0, HK_P = 1, HK_S = 2, HK_RH = 3 };                                                 // gathered vectors
+enum { DK_INIT = 0, DK_PV = 1, DK_ST = 2, DK_XRP = 3, DK_RES = 4, DK_MISC = 5, DK_COUNT = 6 };    // groups of dot products
+constexpr int DK_MAXV = 5;
+
 struct P2PHeader {
-    unsigned int halo_flag[4][CRBE_MAX_RANKS];                 // [x, p, s][source rank]
-    unsigned int dot_flag[8][CRBE_MAX_RANKS];                  // [reduction kind][source rank]
-    double inbox[2][CRBE_NSUMS][CRBE_MAX_RANKS];               // [epoch parity][slot][source rank]
+    unsigned int halo_flag[4][CRBE_MAX_RANKS];                 // [vector][source rank]
+    unsigned int dot_flag[DK_COUNT][CRBE_MAX_RANKS];           // [reduction kind][source rank]
+    double inbox[DK_COUNT][2][DK_MAXV][CRBE_MAX_RANKS];        // [kind][epoch parity][value][source rank]
     unsigned int my_halo_epoch[4];
-    unsigned int my_dot_epoch[8];
+    unsigned int my_dot_epoch[DK_COUNT];
     unsigned int ticket[4];
-    int error;
+    int error;                                                 // 1: a halo flag, 2: a deposit never arrived
 };
 static_assert(sizeof(P2PHeader) <= P2P_HEADER_BYTES, "mailbox does not fit its header");
 
@@ -202,9 +224,11 @@ struct CommArgs {
     int world, rank, n_neigh;
     int neigh[2 * CRBE_MAX_RANKS];
     long long send_off[2 * CRBE_MAX_RANKS + 1];
-    double* dst[3][2 * CRBE_MAX_RANKS];     // my segment inside neighbour q's halo of x, p, s
+    double* dst[4][2 * CRBE_MAX_RANKS];            // my segment inside neighbour q's halo of p, s, r^ ([HK_X] unused)
+    double* dst_x[RING_MAX][2 * CRBE_MAX_RANKS];   // ... of its ring vector `slot`
     const int* send_idx;
-    double* sums;
+    const unsigned char* tile_halo;                // per 256-row tile: does it reference a halo column
+    long long timeout;                             // clock64 ticks a spin may last before the peer is declared dead
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -215,26 +239,41 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// spin until *flag has reached `epoch` (wrap-safe); gives up after ~20 s so a dead peer cannot wedge the GPU
-__device__ __forceinline__ bool wait_epoch(const unsigned int* flag, unsigned int epoch) {
+// spin until *flag has reached `epoch` (wrap-safe); gives up after `timeout` ticks so a dead peer cannot wedge the GPU
+__device__ __forceinline__ bool wait_epoch(const unsigned int* flag, unsigned int epoch, long long timeout) {
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
-        if (clock64() - t0 > (1LL << 35)) return false;
+        if (clock64() - t0 > timeout) return false;
     }
     return true;
 }
-__device__ __forceinline__ int dot_kind_of(int first_slot) {
-    return first_slot == S_BB ? 0 : (first_slot == S_RHV ? 1 : (first_slot == S_TS ? 2 : (first_slot == S_RR ? 3 : 4)));
+// a peer never signalled: record it, stop the solve (status 4; the host returns CRBE_ERR_COMM) -- see crbe_solver_p2p_error
+__device__ __forceinline__ void comm_dead(const CommArgs* __restrict__ ca, int* dstate, int what) {
+    ca->self->error = what;
+    dstate[D_STATUS] = 4;
 }
 
-// Grid-wide deterministic sum (warp shuffles -> CTA partial -> the last CTA to arrive adds the partials in index
-// order), returning true in thread 0 of that last CTA.  In the partitioned solve (ca != nullptr) the same CTA
-// finishes the job across GPUs before the kernel ends: it deposits the local sums in every peer's mailbox over
-// NVLink, waits for all deposits of this epoch and publishes the totals (added in rank order, so every rank
-// holds the same bits) -- the allreduce is fused into the tail of the kernel that produced the partial sums.
+__device__ __forceinline__ int dk_count(int kind) { return kind == DK_INIT ? 3 : (kind == DK_ST ? 5 : 1); }
+// sums slot of value j of a reduction kind
+__device__ __forceinline__ int dk_slot(int kind, int j) {
+    switch (kind) {
+        case DK_INIT: return j == 0 ? S_BB : (j == 1 ? S_RR : S_RHO0);
+        case DK_PV: return S_RHV;
+        case DK_ST: return S_TS + j;       // S_TS, S_TT, S_RS, S_RT, S_SS are consecutive
+        case DK_XRP: return S_RR;
+        default: return S_RRTRUE;
+    }
+}
+
+// Grid-wide deterministic sum (warp shuffles -> CTA partial -> the last CTA to arrive adds the partials in index order),
+// returning true in thread 0 of that last CTA.  out[k] receives the sums of this GPU.  In the partitioned solve with the
+// peer-memory transport (ca != nullptr) the last CTA instead deposits them in every rank's mailbox, cell (kind, parity of
+// the new epoch, k, this rank), raises the flags and returns: the totals are formed by the consumers (head_sums).
+// DK_MISC (utility reductions with no consuming kernel): the last CTA also waits for all deposits and writes the totals to out.
 template <int NV>
 __device__ __forceinline__ bool grid_sum_last(double (&v)[NV], double* partials, unsigned int* counter, double* const (&out)[NV],
-                                              const CommArgs* __restrict__ ca) {
+                                              const CommArgs* __restrict__ ca, int kind = DK_MISC, int* dstate = nullptr) {
+    static_assert(NV <= DK_MAXV, "mailbox cell count");
     block_sum<NV>(v);
     __shared__ bool last;
     if (threadIdx.x == 0) {
@@ -264,7 +303,6 @@ __device__ __forceinline__ bool grid_sum_last(double (&v)[NV], double* partials,
     }
     __shared__ double loc[NV];
     __shared__ unsigned int ep;
-    const int kind = dot_kind_of((int)(out[0] - ca->sums));
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) loc[k] = acc[k];
@@ -276,18 +314,21 @@ __device__ __forceinline__ bool grid_sum_last(double (&v)[NV], double* partials,
     if ((int)threadIdx.x < ca->world) {
         P2PHeader* d = ca->peers[threadIdx.x];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) d->inbox[par][(int)(out[k] - ca->sums)][ca->rank] = loc[k];
+        for (int k = 0; k < NV; ++k) d->inbox[kind][par][k][ca->rank] = loc[k];
         __threadfence_system();
         st_release_sys(&d->dot_flag[kind][ca->rank], epoch);
-        if (!wait_epoch(&ca->self->dot_flag[kind][threadIdx.x], epoch)) ca->self->error = 2;
+    }
+    if (kind != DK_MISC) return threadIdx.x == 0;
+    if ((int)threadIdx.x < ca->world && !wait_epoch(&ca->self->dot_flag[kind][threadIdx.x], epoch, ca->timeout)) {
+        ca->self->error = 2;
+        if (dstate) dstate[D_STATUS] = 4;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            const int sl = (int)(out[k] - ca->sums);
             double a = 0.0;
-            for (int r = 0; r < ca->world; ++r) a += __ldcv(&ca->self->inbox[par][sl][r]);
+            for (int r = 0; r < ca->world; ++r) a += __ldcv(&ca->self->inbox[kind][par][k][r]);
             *out[k] = a;
         }
         return true;
@@ -295,10 +336,62 @@ __device__ __forceinline__ bool grid_sum_last(double (&v)[NV], double* partials,
     return false;
 }
 
-// Tail of the kernels that produce a gathered vector (p, s) in the partitioned solve: the last CTA to finish
-// stores this rank's boundary entries straight into the neighbours' halo segments over NVLink and raises their
-// epoch flags -- the halo exchange is part of the producing kernel; the consuming kernel waits (halo_wait).
-__device__ __forceinline__ void halo_push_tail(const double* vec, int kind, const CommArgs* __restrict__ ca) {
+// Totals of reduction kind `kind` into S (shared memory copy of the sums): every CTA waits for the deposits of the kind's
+// current epoch (counted by this rank's own producer, which ran before this kernel) and adds them in rank order; CTA 0 also
+// stores them in the device sums, where later kernels, the end-of-step record and the host find them.
+__device__ __forceinline__ void p2p_take(const CommArgs* __restrict__ ca, int kind, double* S, double* sums, int* dstate) {
+    P2PHeader* me = ca->self;
+    const unsigned int epoch = *(volatile unsigned int*)&me->my_dot_epoch[kind];
+    if ((int)threadIdx.x < ca->world && dstate[D_STATUS] != 4 &&
+        !wait_epoch(&me->dot_flag[kind][threadIdx.x], epoch, ca->timeout))
+        comm_dead(ca, dstate, 2);
+    __syncthreads();
+    const int nv = dk_count(kind);
+    if ((int)threadIdx.x < nv) {
+        double a = 0.0;
+        for (int r = 0; r < ca->world; ++r) a += __ldcv(&me->inbox[kind][epoch & 1][threadIdx.x][r]);
+        const int slot = dk_slot(kind, threadIdx.x);
+        S[slot] = a;
+        if (blockIdx.x == 0) sums[slot] = a;
+    }
+}
+
+// What a kernel needs current before it starts: HS_NORMS (b,b), (r,r) -- from the init kernel if no iteration has run yet,
+// else from the last update kernel --, HS_PV (r^,v), HS_ST the five sums of the second SpMV, HS_RES the recomputed residual.
+enum { HS_NONE = 0, HS_NORMS = 1, HS_PV = 2, HS_ST = 4, HS_RES = 8 };
+
+// Head of every solver kernel: returns the sums to read.  Single GPU and NCCL transport: the device sums themselves.
+// Peer-memory transport: a shared-memory copy with the pending totals taken from the mailbox (p2p_take).  *failed: the update
+// kernel skipped its r, p stores predicting the last iteration and the reduced norm says otherwise (status 3).
+template <int WHAT>
+__device__ __forceinline__ const double* head_sums(double* sums, int* dstate, const CommArgs* __restrict__ ca, double* S, double rtol2,
+                                                   bool* failed) {
+    *failed = false;
+    if (ca == nullptr || ca->world <= 1) return sums;
+    if (threadIdx.x < CRBE_NSUMS) S[threadIdx.x] = sums[threadIdx.x];
+    __syncthreads();
+    const int src = dstate[D_NORMSRC];
+    const bool after_update = src == 1;
+    if ((WHAT & HS_NORMS) && src != 2) p2p_take(ca, after_update ? DK_XRP : DK_INIT, S, sums, dstate);
+    if (WHAT & HS_PV) p2p_take(ca, DK_PV, S, sums, dstate);
+    if (WHAT & HS_ST) p2p_take(ca, DK_ST, S, sums, dstate);
+    if (WHAT & HS_RES) p2p_take(ca, DK_RES, S, sums, dstate);
+    __syncthreads();
+    if ((WHAT & HS_NORMS) && after_update && dstate[D_PRED] != 0 && S[S_RR] > rtol2 * S[S_BB]) {
+        *failed = true;
+        if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 3;
+    }
+    return S;
+}
+
+__device__ __forceinline__ bool solver_idle(const double* __restrict__ S, const int* __restrict__ dstate, double rtol2, bool failed = false) {
+    return failed || dstate[D_STATUS] != 0 || dstate[D_CHAIN] != 0 || !(S[S_RR] > rtol2 * S[S_BB]);
+}
+
+// Tail of the kernels that produce a gathered vector in the partitioned solve: the last CTA to finish stores this rank's
+// boundary entries straight into the neighbours' halo segments over NVLink and raises their epoch flags -- the halo
+// exchange is part of the producing kernel; the consuming kernel waits where it first needs a halo entry (HaloGate).
+__device__ __forceinline__ void halo_push_tail(const double* vec, int kind, int slot, const CommArgs* __restrict__ ca) {
     if (ca == nullptr || ca->world <= 1 || ca->n_neigh == 0) return;
     __shared__ bool last_h;
     __shared__ unsigned int ep_h;
@@ -313,7 +406,7 @@ __device__ __forceinline__ void halo_push_tail(const double* vec, int kind, cons
     if (!last_h) return;
     __threadfence();
     for (int q = 0; q < ca->n_neigh; ++q) {
-        double* d = ca->dst[kind][q];
+        double* d = kind == HK_X ? ca->dst_x[slot][q] : ca->dst[kind][q];
         const int* idx = ca->send_idx + ca->send_off[q];
         const long long cnt = ca->send_off[q + 1] - ca->send_off[q];
         const int nt = blockDim.x;
@@ -333,16 +426,36 @@ __device__ __forceinline__ void halo_push_tail(const double* vec, int kind, cons
     if ((int)threadIdx.x < ca->n_neigh) st_release_sys(&ca->peers[ca->neigh[threadIdx.x]]->halo_flag[kind][ca->rank], ep_h);
 }
 
-// Consumer side of the halo exchange: before gathering, wait until every neighbour's push of the current epoch
-// has landed (the epoch is the one this rank's own producer tail just counted; all ranks count in lock step).
-__device__ __forceinline__ void halo_wait(int kind, const CommArgs* __restrict__ ca) {
+// Consumer side of the halo exchange, whole CTA: wait until every neighbour's push of the current epoch has landed (the
+// epoch is the one this rank's own producer tail just counted; all ranks count in lock step).
+__device__ __forceinline__ void halo_wait(int kind, const CommArgs* __restrict__ ca, int* dstate) {
     if (ca == nullptr || ca->world <= 1 || ca->n_neigh == 0) return;
-    if ((int)threadIdx.x < ca->n_neigh) {
+    if ((int)threadIdx.x < ca->n_neigh && dstate[D_STATUS] != 4) {
         const unsigned int epoch = *(volatile unsigned int*)&ca->self->my_halo_epoch[kind];
-        if (!wait_epoch(&ca->self->halo_flag[kind][ca->neigh[threadIdx.x]], epoch)) ca->self->error = 1;
+        if (!wait_epoch(&ca->self->halo_flag[kind][ca->neigh[threadIdx.x]], epoch, ca->timeout)) comm_dead(ca, dstate, 1);
     }
     __syncthreads();
 }
+
+// The same wait, taken by a tile kernel only when (and the first time) it is about to gather a tile that references a halo
+// column.  The tile is the same for all threads of the CTA, so the branch and its barrier are uniform.
+struct HaloGate {
+    const CommArgs* ca;
+    int* dstate;
+    int kind;
+    bool open, off;
+    __device__ __forceinline__ HaloGate(const CommArgs* ca_, int kind_, int* dstate_)
+        : ca(ca_), dstate(dstate_), kind(kind_), open(false), off(ca_ == nullptr || ca_->world <= 1 || ca_->n_neigh == 0) {}
+    // returns whether the tile references halo entries (after having made sure they are there)
+    __device__ __forceinline__ bool before_gather(int64_t tile) {
+        if (off || !ca->tile_halo[tile]) return false;
+        if (!open) {
+            halo_wait(kind, ca, dstate);
+            open = true;
+        }
+        return true;
+    }
+};
 
 #define ROW_LOOP(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
 
@@ -406,6 +519,16 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_pack_col16(int64_t n, int64_t ld
     }
 }
 
+// which tiles reference a halo column (>= ld) of the partitioned matrix: only those wait for the neighbours' pushes
+__global__ void __launch_bounds__(CRBE_BLOCK) k_tile_halo(int64_t n, int64_t ld, const int* __restrict__ ecol, unsigned char* __restrict__ tile_halo) {
+    ROW_LOOP(i, n) {
+        bool h = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h = h || ecol[ell_at(i, k)] >= (int)ld;
+        if (h) tile_halo[i / CRBE_TILE] = 1;
+    }
+}
+
 __global__ void k_zero_rows(double* __restrict__ u, const int* __restrict__ bnd, int64_t nb, const int* __restrict__ dstate) {
     if (dstate[D_CHAIN] != 0) return;
     ROW_LOOP(k, nb) u[bnd[k]] = 0.0;
@@ -425,7 +548,8 @@ struct ExtrapArgs {
 };
 
 template <int Q>
-__global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate(int64_t n, ExtrapArgs a, const int* __restrict__ dstate) {
+__global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate(int64_t n, ExtrapArgs a, const int* __restrict__ dstate,
+                                                            const CommArgs* __restrict__ ca, int xslot) {
     constexpr double C[5][5] = {{1, 0, 0, 0, 0}, {2, -1, 0, 0, 0}, {3, -3, 1, 0, 0}, {4, -6, 4, -1, 0}, {5, -10, 10, -5, 1}};
     if (dstate[D_CHAIN] != 0) return;     // an earlier step of this chunk has not converged: leave every vector as it is
     ROW_LOOP(i, n) {
@@ -439,6 +563,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate(int64_t n, ExtrapArg
         if (a.save) a.save[i] = un;
         a.x0[i] = acc;
     }
+    halo_push_tail(a.x0, HK_X, xslot, ca);      // partitioned solve: the neighbours need the boundary entries of the guess
 }
 
 __global__ void k_lift(const double* __restrict__ bc, const int* __restrict__ bnd, int64_t nb, double* __restrict__ out) {
@@ -477,8 +602,10 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         dstate[D_STATUS] = 0;
         dstate[D_ITERS] = 0;
+        dstate[D_PRED] = 0;
+        dstate[D_NORMSRC] = 0;
     }
-    halo_wait(0, ca);
+    halo_wait(HK_X, ca, dstate);
     double acc[3] = {0.0, 0.0, 0.0};
     ROW_LOOP(i, n) {
         const double xi = x[i];
@@ -498,23 +625,26 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
         if (b) b[i] = bi;   // Backward-Euler steps do not store b (crbe_solver::be_u)
         rh[i] = ri;
         if (r) r[i] = ri;   // r = r^ = p = r0: the first iteration reads them through one vector (launch_iteration), so the
-        if (p) p[i] = ri;   // step kernels pass r = nullptr, and p only where its halo entries are needed (partitioned solver)
+        if (p) p[i] = ri;   // step kernels pass r = nullptr, and p only where its halo travels separately (NCCL transport)
         acc[0] = fma(bi, bi, acc[0]);
         acc[1] = fma(ri, ri, acc[1]);
     }
-    if (p) halo_push_tail(p, 1, ca);
+    halo_push_tail(rh, HK_RH, 0, ca);       // peer-memory transport: the first SpMV gathers r^ (= p), halo included
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
-    grid_sum_last<3>(acc, partials, counter, out, ca);
+    grid_sum_last<3>(acc, partials, counter, out, ca, DK_INIT);
 }
 
 // v = A p, (r^, v)
 __global__ void __launch_bounds__(CRBE_BLOCK) k_pv(int64_t n, int64_t ld, double rtol2, const double* __restrict__ eval,
                                                    const int* __restrict__ ecol, const double* __restrict__ p, double* __restrict__ v,
                                                    const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
-                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
-    if (solver_idle(sums, dstate, rtol2)) return;
-    halo_wait(1, ca);
+                                                   unsigned int* counter, const CommArgs* __restrict__ ca, int hkind) {
+    __shared__ double S_sh[CRBE_NSUMS];
+    bool failed;
+    const double* S = head_sums<HS_NORMS>(sums, dstate, ca, S_sh, rtol2, &failed);
+    if (solver_idle(S, dstate, rtol2, failed)) return;
+    halo_wait(hkind, ca, dstate);
     double acc[1] = {0.0};
     ROW_LOOP(i, n) {
         const double vi = ell_row(eval, ecol, ld, i, p[i], [&](int j) { return __ldg(p + j); });
@@ -522,20 +652,23 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_pv(int64_t n, int64_t ld, double
         acc[0] = fma(rh[i], vi, acc[0]);
     }
     double* const out[1] = {dots + S_RHV};
-    grid_sum_last<1>(acc, partials, counter, out, ca);
+    grid_sum_last<1>(acc, partials, counter, out, ca, DK_PV);
 }
 
 // s = r - alpha v
 __global__ void __launch_bounds__(CRBE_BLOCK) k_s(int64_t n, int k, double rtol2, const double* __restrict__ r, const double* __restrict__ v,
-                                                  double* __restrict__ s, const double* sums, int* dstate, const CommArgs* __restrict__ ca) {
-    if (solver_idle(sums, dstate, rtol2)) return;
-    const double alpha = sums[S_RHO0 + (k & 1)] / sums[S_RHV];
+                                                  double* __restrict__ s, double* sums, int* dstate, const CommArgs* __restrict__ ca) {
+    __shared__ double S_sh[CRBE_NSUMS];
+    bool failed;
+    const double* S = head_sums<HS_PV>(sums, dstate, ca, S_sh, rtol2, &failed);
+    if (solver_idle(S, dstate, rtol2)) return;
+    const double alpha = S[S_RHO0 + (k & 1)] / S[S_RHV];
     if (!isfinite(alpha)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
         return;
     }
     ROW_LOOP(i, n) s[i] = fma(-alpha, v[i], r[i]);
-    halo_push_tail(s, 2, ca);
+    halo_push_tail(s, HK_S, 0, ca);
 }
 
 // t = A s, (t,s), (t,t), (r^,s), (r^,t), (s,s)
@@ -543,8 +676,8 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, double
                                                    const int* __restrict__ ecol, const double* __restrict__ s, double* __restrict__ t,
                                                    const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                    unsigned int* counter, const CommArgs* __restrict__ ca) {
-    if (solver_idle(sums, dstate, rtol2)) return;
-    halo_wait(2, ca);
+    if (solver_idle(sums, dstate, rtol2)) return;     // the sums it reads were brought up to date by the preceding kernels
+    halo_wait(HK_S, ca, dstate);
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     ROW_LOOP(i, n) {
         const double si = s[i];
@@ -558,36 +691,40 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_st(int64_t n, int64_t ld, double
         acc[4] = fma(si, si, acc[4]);
     }
     double* const out[5] = {dots + S_TS, dots + S_TT, dots + S_RS, dots + S_RT, dots + S_SS};
-    grid_sum_last<5>(acc, partials, counter, out, ca);
+    grid_sum_last<5>(acc, partials, counter, out, ca, DK_ST);
 }
 
 // x += alpha p + omega s;  r = s - omega t;  p = r + beta (p - omega v);  (r, r);
 // rho_{k+1} = (r^,s) - omega (r^,t) is published by the last CTA (every rank computes the same value).
-// p_in: where the old p is read (p itself, or r^ in the first iteration on a single GPU; may alias p: no __restrict__)
+// p_in: where the old p is read (p itself, or r^ in the first iteration; may alias p: no __restrict__)
 //
 // Last iteration of a solve: ||r||^2 = (s,s) - (t,s)^2/(t,t) is known from the sums of the previous kernel before r exists.
 // When it lies below the stopping threshold nobody will read this iteration's r and p, and the kernel neither stores them nor
 // reads v: 40 instead of 64 bytes per row.  x and the accumulated (r,r) are the same bits either way.  The formula cancels: its
 // absolute error is a few 1e-15 (s,s), which matters only when the accumulated norm lands within that distance of the threshold
 // (margin 1e-3 of the threshold below); should the accumulated norm then contradict the prediction the recurrence is gone:
-// status 3, and the host restarts the solve from the true residual of the updated x -- correct either way, one extra SpMV.
+// status 3 (set here, or by the next kernel that sees the reduced norm: head_sums), and the host restarts the solve from the
+// true residual of the updated x -- correct either way, one extra SpMV.
 __global__ void __launch_bounds__(CRBE_BLOCK) k_xrp(int64_t n, int k, double rtol2, const double* __restrict__ s, const double* __restrict__ t,
                                                     const double* __restrict__ v, double* __restrict__ x, double* __restrict__ r,
                                                     const double* p_in, double* p, double* sums, double* dots, int* dstate, double* partials,
                                                     unsigned int* counter, const CommArgs* __restrict__ ca, int predict) {
-    if (solver_idle(sums, dstate, rtol2)) return;
-    const double rho = sums[S_RHO0 + (k & 1)];
-    const double alpha = rho / sums[S_RHV];
-    const double tt = sums[S_TT];
-    const double omega = tt > 0.0 ? sums[S_TS] / tt : 0.0;
+    __shared__ double S_sh[CRBE_NSUMS];
+    bool failed;
+    const double* S = head_sums<HS_ST>(sums, dstate, ca, S_sh, rtol2, &failed);
+    if (solver_idle(S, dstate, rtol2)) return;
+    const double rho = S[S_RHO0 + (k & 1)];
+    const double alpha = rho / S[S_RHV];
+    const double tt = S[S_TT];
+    const double omega = tt > 0.0 ? S[S_TS] / tt : 0.0;
     if (!isfinite(alpha) || !isfinite(omega)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
         return;
     }
-    const double rho_next = fma(-omega, sums[S_RT], sums[S_RS]);
+    const double rho_next = fma(-omega, S[S_RT], S[S_RS]);
     const double beta = (rho_next / rho) * (alpha / omega);
-    const double thr = rtol2 * sums[S_BB];
-    const double rr_pred = tt > 0.0 ? sums[S_SS] - sums[S_TS] * sums[S_TS] / tt : sums[S_SS];
+    const double thr = rtol2 * S[S_BB];
+    const double rr_pred = tt > 0.0 ? S[S_SS] - S[S_TS] * S[S_TS] / tt : S[S_SS];
     const bool last = predict && rr_pred <= 0.999 * thr;
     double acc[1] = {0.0};
     if (last) {
@@ -606,17 +743,22 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_xrp(int64_t n, int k, double rto
             p[i] = fma(beta, fma(-omega, v[i], pi), ri);
             acc[0] = fma(ri, ri, acc[0]);
         }
-        halo_push_tail(p, 1, ca);
+        halo_push_tail(p, HK_P, 0, ca);
     }
     double* const out[1] = {dots + S_RR};
-    if (grid_sum_last<1>(acc, partials, counter, out, ca)) {
+    const bool peer = ca != nullptr && ca->world > 1;
+    if (grid_sum_last<1>(acc, partials, counter, out, ca, DK_XRP)) {
         dstate[D_ITERS] += 1;
+        dstate[D_PRED] = last ? 1 : 0;
+        dstate[D_NORMSRC] = 1;
         if (last) dstate[D_NLAST] += 1;     // statistics: update kernels that ran in their short, last-iteration form
         if (k == 0) sums[S_RR0] = rho;      // (r^, r0) = ||r0||^2 of the initial guess, kept for the host (guess-order policy)
         sums[S_RHO0 + ((k + 1) & 1)] = rho_next;
-        const bool own_total = ca == nullptr || ca->world <= 1 || dots == sums;     // *out[0] is the sum over all ranks
-        if (own_total && last && *out[0] > thr) dstate[D_STATUS] = 3;
-        else if (!isfinite(beta) && own_total && *out[0] > thr) dstate[D_STATUS] = 2;
+        // the reduced norm is at hand on a single GPU; with the peer-memory transport the next kernel checks it (head_sums)
+        if (!peer && dots == sums) {
+            if (last && *out[0] > thr) dstate[D_STATUS] = 3;
+            else if (!isfinite(beta) && *out[0] > thr) dstate[D_STATUS] = 2;
+        }
     }
 }
 
@@ -644,10 +786,13 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_residual(int64_t n, int64_t ld, 
                                                          const double* __restrict__ x, RhsSource rhs, double* __restrict__ r,
                                                          double* __restrict__ rh, double* __restrict__ p, double* sums, double* dots,
                                                          double* partials, unsigned int* counter, const CommArgs* __restrict__ ca,
-                                                         const int* dstate, int guard, double rtol2) {
+                                                         int* dstate, int guard, double rtol2) {
+    __shared__ double S_sh[CRBE_NSUMS];
     if (dstate[D_CHAIN] != 0) return;
-    if (guard && (dstate[D_STATUS] != 0 || sums[S_RR] > rtol2 * sums[S_BB])) return;
-    halo_wait(0, ca);
+    bool failed;
+    const double* S = head_sums<HS_NORMS>(sums, dstate, ca, S_sh, rtol2, &failed);
+    if (guard && (failed || dstate[D_STATUS] != 0 || S[S_RR] > rtol2 * S[S_BB])) return;
+    halo_wait(HK_X, ca, dstate);
     double acc[1] = {0.0};
     ROW_LOOP(i, n) {
         const double ax = ell_row(eval, ecol, ld, i, x[i], [&](int j) { return __ldg(x + j); });
@@ -659,16 +804,27 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_residual(int64_t n, int64_t ld, 
         }
         acc[0] = fma(ri, ri, acc[0]);
     }
-    if (!guard) halo_push_tail(p, 1, ca);
+    if (!guard) halo_push_tail(rh, HK_RH, 0, ca);     // the restarted solve begins with the first-iteration kernels (gather r^)
     double* const out[1] = {dots + S_RRTRUE};
-    grid_sum_last<1>(acc, partials, counter, out, ca);
+    grid_sum_last<1>(acc, partials, counter, out, ca, DK_RES);
 }
 
+// host-driven restart from the recomputed residual (the sums are current: the host has just read them)
 __global__ void k_restart(double* sums, int* dstate) {
     sums[S_RR] = sums[S_RRTRUE];
     sums[S_RHO0] = sums[S_RRTRUE];
     dstate[D_STATUS] = 0;
     dstate[D_ITERS] = 0;
+    dstate[D_PRED] = 0;
+    dstate[D_NORMSRC] = 2;
+}
+
+// Peer-memory transport: before the host (or the end-of-step record) reads the sums, form the totals nobody has taken from
+// the mailbox yet -- the norms of the last update kernel when the batch ended with it, the recomputed residual.
+__global__ void k_tail_commit(double* sums, int* dstate, const CommArgs* __restrict__ ca, double rtol2) {
+    __shared__ double S_sh[CRBE_NSUMS];
+    bool failed;
+    head_sums<HS_NORMS | HS_RES>(sums, dstate, ca, S_sh, rtol2, &failed);
 }
 
 #include "solver_tiles.cuh"
@@ -875,10 +1031,13 @@ static int solver_release(crbe_solver* s) {
     if (s->adv_plan && s->adv_plan_free) s->adv_plan_free(s->adv_plan);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     cudaFree(s->bc_stage);
-    if (s->window) {               // p and s live in the window: free the stand-alone allocations they replaced
+    if (s->window) {               // p, s, r^ live in the window: free the stand-alone allocations they replaced
         s->p[0] = s->saved_p0;
         s->s = s->saved_s;
+        s->rh = s->saved_rh;
     }
+    cudaFree(s->tile_halo);
+    cudaFree(s->red_send);
     cudaFree(s->bnd);
     cudaFree(s->is_bnd);
     cudaFree(s->ell_col);
@@ -985,10 +1144,17 @@ static int solver_init(crbe_solver* s, crbe_ctx* ctx, crbe_comm* comm, int64_t n
     CRBE_CUDA(cudaMallocHost(&s->sums_h, sizeof(double) * (CRBE_NSUMS + D_NSTATE / 2)));
     s->dots = s->sums;
     if (s->world > 1) {
+        // NCCL transport: the dot kernels write this rank's partial sums to red_send, the allreduce leaves the totals in red
+        // (out of place: a kernel that returns early past convergence leaves red_send as it is, and reducing it again gives
+        // the same totals), k_commit publishes them in sums
         CRBE_CUDA(cudaMalloc(&s->red, sizeof(double) * CRBE_NSUMS));
         CRBE_CUDA(cudaMemsetAsync(s->red, 0, sizeof(double) * CRBE_NSUMS, ctx->stream));
-        s->dots = s->red;
+        CRBE_CUDA(cudaMalloc(&s->red_send, sizeof(double) * CRBE_NSUMS));
+        CRBE_CUDA(cudaMemsetAsync(s->red_send, 0, sizeof(double) * CRBE_NSUMS, ctx->stream));
+        s->dots = s->red_send;
     }
+    CRBE_CUDA(cudaMalloc(&s->tile_halo, (size_t)(s->ld / CRBE_TILE)));
+    CRBE_CUDA(cudaMemsetAsync(s->tile_halo, 0, (size_t)(s->ld / CRBE_TILE), ctx->stream));
     {   // one resident wave per kernel (a grid-stride sweep must not spill into a second, partial wave)
         s->g_pv = crbe_persistent_grid(ctx, k_pv, n);
         s->g_st = crbe_persistent_grid(ctx, k_st, n);
@@ -1067,15 +1233,19 @@ extern "C" int crbe_solver_p2p_export(crbe_solver* s, void* ipc_handle_out, int6
     CRBE_REQUIRE(s && ipc_handle_out && meta_out && s->world > 1 && s->world <= CRBE_MAX_RANKS, "bad argument");
     crbe_ctx* ctx = s->ctx;
     if (!s->window) {
-        const size_t bytes = P2P_HEADER_BYTES + 3 * sizeof(double) * (size_t)s->veclen;
+        // header | ring of RING_MAX solution vectors | p | s | r^      (every vector veclen doubles: owned rows, padding, halo)
+        const size_t bytes = P2P_HEADER_BYTES + (RING_MAX + 3) * sizeof(double) * (size_t)s->veclen;
         CRBE_CUDA(cudaMalloc(&s->window, bytes));
         CRBE_CUDA(cudaMemsetAsync(s->window, 0, bytes, ctx->stream));
         CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
         double* base = (double*)(s->window + P2P_HEADER_BYTES);
+        for (int k = 0; k < RING_MAX; ++k) s->ring[k] = base + (size_t)k * s->veclen;
         s->saved_p0 = s->p[0];
         s->saved_s = s->s;
-        s->p[0] = base + s->veclen;
-        s->s = base + 2 * s->veclen;
+        s->saved_rh = s->rh;
+        s->p[0] = base + (size_t)(RING_MAX + 0) * s->veclen;
+        s->s = base + (size_t)(RING_MAX + 1) * s->veclen;
+        s->rh = base + (size_t)(RING_MAX + 2) * s->veclen;
     }
     cudaIpcMemHandle_t h;
     CRBE_CUDA(cudaIpcGetMemHandle(&h, s->window));
@@ -1094,6 +1264,10 @@ extern "C" int crbe_solver_p2p_connect(crbe_solver* s, int rank, const void* han
     s->rank = rank;
     const int nn = (int)s->neigh.size();
     CRBE_REQUIRE(nn <= 2 * CRBE_MAX_RANKS && s->world <= CRBE_MAX_RANKS, "too many ranks / neighbours for the peer-memory transport");
+    if (const char* ms = getenv("CRBE_P2P_TIMEOUT_MS")) {
+        const double v = atof(ms);
+        if (v > 0.0) s->p2p_timeout = (long long)(v * 1.9e6);       // SM clock ~1.9 GHz
+    }
     CommArgs ca;
     memset(&ca, 0, sizeof(ca));
     for (int r = 0; r < s->world; ++r) {
@@ -1111,32 +1285,47 @@ extern "C" int crbe_solver_p2p_connect(crbe_solver* s, int rank, const void* han
     ca.rank = rank;
     ca.n_neigh = nn;
     ca.send_idx = s->send_idx;
-    ca.sums = s->sums;
+    ca.tile_halo = s->tile_halo;
+    ca.timeout = s->p2p_timeout;
     for (int q = 0; q <= nn; ++q) ca.send_off[q] = s->send_off[q];
     for (int q = 0; q < nn; ++q) {
         const int r = s->neigh[q];
         CRBE_REQUIRE(halo_seg_off != nullptr, "missing halo offsets");
         ca.neigh[q] = r;
-        for (int kind = 0; kind < 3; ++kind) {
-            double* vbase = (double*)((unsigned char*)s->peer_base[r] + P2P_HEADER_BYTES) + (size_t)kind * veclen_all[r];
-            ca.dst[kind][q] = vbase + ld_all[r] + halo_seg_off[q];
-        }
+        double* vbase = (double*)((unsigned char*)s->peer_base[r] + P2P_HEADER_BYTES);
+        const size_t vl = (size_t)veclen_all[r];
+        const size_t seg = (size_t)ld_all[r] + (size_t)halo_seg_off[q];
+        for (int k = 0; k < RING_MAX; ++k) ca.dst_x[k][q] = vbase + (size_t)k * vl + seg;
+        ca.dst[HK_P][q] = vbase + (size_t)(RING_MAX + 0) * vl + seg;
+        ca.dst[HK_S][q] = vbase + (size_t)(RING_MAX + 1) * vl + seg;
+        ca.dst[HK_RH][q] = vbase + (size_t)(RING_MAX + 2) * vl + seg;
     }
     CRBE_CUDA(cudaMalloc(&s->d_comm, sizeof(CommArgs)));
     CRBE_CUDA(cudaMemcpy(s->d_comm, &ca, sizeof(CommArgs), cudaMemcpyHostToDevice));
     CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
-    s->dots = s->sums;          // the totals are published by the producing kernel itself: no staging buffer
+    s->dots = s->sums;          // single-GPU style: the dot kernels' last CTA deposits in the mailboxes, nothing is staged
     s->p2p = true;
+    s->rot = s->ntiles / 2;     // walk the strip from its middle: the halo tiles come up half a sweep after the start
+    drop_step_graphs(s);
     return CRBE_OK;
 }
 
-// device pointer of the solver-owned solution vector (peer-memory transport: x must live in the window)
+// device pointer of the first vector of the solver-owned ring (peer-memory transport: the solution vectors live in the window)
 extern "C" int crbe_solver_x(crbe_solver* s, void** x_out) {
     CRBE_REQUIRE(s && x_out && s->window, "no window: call crbe_solver_p2p_export first");
-    *x_out = s->window + P2P_HEADER_BYTES;
+    *x_out = s->ring[0];
     return CRBE_OK;
 }
 
+// the ring of solution vectors inside the window, for crbe_solver_step_ring / crbe_solver_steps_ring (count_h receives 5)
+extern "C" int crbe_solver_ring(crbe_solver* s, void** bufs_out5_h, int32_t* count_h) {
+    CRBE_REQUIRE(s && bufs_out5_h && count_h && s->window, "no window: call crbe_solver_p2p_export first");
+    for (int k = 0; k < RING_MAX; ++k) bufs_out5_h[k] = s->ring[k];
+    *count_h = RING_MAX;
+    return CRBE_OK;
+}
+
+// non-zero: a peer never signalled within the time-out (1: halo entries, 2: dot products); the solver is unusable afterwards
 extern "C" int crbe_solver_p2p_error(crbe_solver* s, int* err_h) {
     CRBE_REQUIRE(s && err_h, "null argument");
     *err_h = 0;
@@ -1208,6 +1397,12 @@ extern "C" int crbe_solver_set_system(crbe_solver* s, const double* s_val_d, con
     } else if (s->rhs_val) {
         cudaFree(s->rhs_val);
         s->rhs_val = nullptr;
+    }
+    if (s->world > 1) {
+        CRBE_CUDA(cudaMemsetAsync(s->tile_halo, 0, (size_t)s->ntiles, st));
+        k_tile_halo<<<crbe_grid_for(ctx, s->n), CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_col, s->tile_halo);
+        CRBE_KERNEL_CHECK();
+        ctx->launches += 1;
     }
     int* overflow = s->dstate + D_ESCAPES;
     CRBE_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
@@ -1289,11 +1484,19 @@ __global__ void k_commit(const double* __restrict__ red, double* __restrict__ su
     if (e >= 0) sums[e] = red[e];
 }
 
-__global__ void k_p2p_wait(int kind, const CommArgs* __restrict__ ca) { halo_wait(kind, ca); }
+__global__ void k_p2p_wait(int kind, const CommArgs* __restrict__ ca, int* dstate) { halo_wait(kind, ca, dstate); }
 
-// x halo (step start, verification): a one-CTA kernel running the same push as halo_push_tail
-__global__ void __launch_bounds__(1024) k_p2p_halo(const double* __restrict__ vec, int kind, const CommArgs* __restrict__ ca) {
-    halo_push_tail(vec, kind, ca);
+// halo of a ring vector outside the fused paths (no extrapolation, verification, restart): a one-CTA kernel running the same
+// push as halo_push_tail
+__global__ void __launch_bounds__(1024) k_p2p_halo(const double* __restrict__ vec, int kind, int slot, const CommArgs* __restrict__ ca) {
+    halo_push_tail(vec, kind, slot, ca);
+}
+
+// which vector of the window ring `vec` is (-1: none)
+static int ring_slot_of(const crbe_solver* s, const double* vec) {
+    for (int k = 0; k < RING_MAX; ++k)
+        if (s->ring[k] && s->ring[k] == vec) return k;
+    return -1;
 }
 
 // refresh the halo entries of a gathered vector from their owners (no-op on a single GPU)
@@ -1301,11 +1504,11 @@ static int halo_exchange(crbe_solver* s, double* vec, int* launches) {
     if (s->world <= 1 || s->neigh.empty()) return CRBE_OK;
     crbe_ctx* ctx = s->ctx;
     if (s->p2p) {
-        // p and s are pushed to the neighbours by the tail of the kernel that produced them (halo_push_tail)
-        if (vec == s->p[0] || vec == s->s) return CRBE_OK;
-        CRBE_REQUIRE(vec == (double*)(s->window + P2P_HEADER_BYTES),
-                     "peer-memory transport: the solution vector must be the window vector (crbe_solver_x)");
-        k_p2p_halo<<<1, 1024, 0, ctx->stream>>>(vec, 0, s->d_comm);
+        // p, s and r^ are pushed to the neighbours by the tail of the kernel that produced them (halo_push_tail)
+        if (vec == s->p[0] || vec == s->s || vec == s->rh) return CRBE_OK;
+        const int slot = ring_slot_of(s, vec);
+        CRBE_REQUIRE(slot >= 0, "peer-memory transport: the solution vector must be one of the window ring (crbe_solver_ring)");
+        k_p2p_halo<<<1, 1024, 0, ctx->stream>>>(vec, HK_X, slot, s->d_comm);
         CRBE_KERNEL_CHECK();
         *launches += 1;
         return CRBE_OK;
@@ -1322,8 +1525,8 @@ static int halo_exchange(crbe_solver* s, double* vec, int* launches) {
 
 // sum the freshly written dot products red[first .. first+count) over the ranks, then publish slots a, b, c, d
 static int reduce_dots(crbe_solver* s, int first, int count, int a, int b, int c, int d, int* launches, int e = -1) {
-    if (s->world <= 1 || s->p2p) return CRBE_OK;   // peer-memory transport: done in the tail of the dot kernel (grid_sum_last)
-    CRBE_CHECK(crbe_comm_allreduce_sum(s->comm, s->red + first, count, s->ctx->stream));
+    if (s->world <= 1 || s->p2p) return CRBE_OK;   // peer-memory transport: deposits and totals inside the kernels (grid_sum_last, head_sums)
+    CRBE_CHECK(crbe_comm_allreduce_sum(s->comm, s->red_send + first, s->red + first, count, s->ctx->stream));
     k_commit<<<1, 1, 0, s->ctx->stream>>>(s->red, s->sums, a, b, c, d, e);
     CRBE_KERNEL_CHECK();
     *launches += 1;
@@ -1337,49 +1540,50 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
     const bool tma = (s->flags & CRBE_SOLVER_TMA) != 0;
     double *p = s->p[0], *v = s->v[0];
     // At k = 0 the init / restart kernel has just set r = r^ = p = r0, so the first iteration reads all three through
-    // one vector and its SpMV streams one operand instead of two: r^ on a single GPU (the init kernels then write
-    // neither r nor p: 24 B per row less), p in the partitioned solver (its halo entries live behind p; r is not written).
+    // one vector and its SpMV streams one operand instead of two: r^ (the init kernels then write neither r nor p: 24 B
+    // per row less; with the peer-memory transport r^ carries halo entries for this).  NCCL transport: p, whose halo is
+    // exchanged between the kernels.
     const bool first = k == 0;
-    const double* p_in = first && s->world == 1 ? s->rh : p;
+    const bool via_rh = first && (s->world == 1 || s->p2p);
+    const double* p_in = via_rh ? s->rh : p;
     const double* r_in = first ? p_in : s->r;
+    const int hkind = via_rh ? HK_RH : HK_P;
     // p is up to date (written by the init / restart kernel at k = 0, by k_xrp afterwards), its halo refreshed
-    CRBE_CHECK(halo_exchange(s, p, launches));
+    CRBE_CHECK(halo_exchange(s, via_rh ? s->rh : p, launches));
     const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
+#define CRBE_TPV(IDX, FIRST, GRID, NV, COL, COL32)                                                                                      \
+    PROF_LAUNCH(PK_PV, k, (t_pv<IDX, FIRST><<<GRID, CRBE_TILE, TilePipe<NV, SPMV_STAGES, IDX>::SMEM_BYTES, st>>>(                         \
+                              s->n, s->ntiles, s->rot, rtol2, s->ell_val, COL, COL32, p_in, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials, \
+                              ctx->counter, s->d_comm, hkind)))
     if (tma && i16 && first)
-        PROF_LAUNCH(PK_PV, k, (t_pv<short, true><<<s->gs_pv0, CRBE_TILE, TilePipe<1, SPMV_STAGES, short>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col16, s->ell_col, p_in, v, s->rh, s->sums, s->dots, s->dstate,
-                                  ctx->partials, ctx->counter, s->d_comm)));
+        CRBE_TPV(short, true, s->gs_pv0, 1, s->ell_col16, s->ell_col);
     else if (tma && i16)
-        PROF_LAUNCH(PK_PV, k, (t_pv<short, false><<<s->gs_pv, CRBE_TILE, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col16, s->ell_col, p_in, v, s->rh, s->sums, s->dots, s->dstate,
-                                  ctx->partials, ctx->counter, s->d_comm)));
+        CRBE_TPV(short, false, s->gs_pv, 2, s->ell_col16, s->ell_col);
     else if (tma && first)
-        PROF_LAUNCH(PK_PV, k, (t_pv<int, true><<<s->gt_pv0, CRBE_TILE, TilePipe<1, SPMV_STAGES, int>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, nullptr, p_in, v, s->rh, s->sums, s->dots, s->dstate,
-                                  ctx->partials, ctx->counter, s->d_comm)));
+        CRBE_TPV(int, true, s->gt_pv0, 1, s->ell_col, nullptr);
     else if (tma)
-        PROF_LAUNCH(PK_PV, k, (t_pv<int, false><<<s->gt_pv, CRBE_TILE, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, nullptr, p_in, v, s->rh, s->sums, s->dots, s->dstate,
-                                  ctx->partials, ctx->counter, s->d_comm)));
+        CRBE_TPV(int, false, s->gt_pv, 2, s->ell_col, nullptr);
     else
         PROF_LAUNCH(PK_PV, k, (k_pv<<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, rtol2, s->ell_val, s->ell_col, p_in, v, s->rh, s->sums, s->dots,
-                                                                 s->dstate, ctx->partials, ctx->counter, s->d_comm)));
+                                                                 s->dstate, ctx->partials, ctx->counter, s->d_comm, hkind)));
+#undef CRBE_TPV
     CRBE_CHECK(reduce_dots(s, S_RHV, 1, S_RHV, -1, -1, -1, launches));
     PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, r_in, v, s->s, s->sums, s->dstate, s->d_comm)));
     CRBE_CHECK(halo_exchange(s, s->s, launches));
     if (tma && i16)
         PROF_LAUNCH(PK_ST, k, (t_st<short><<<s->gs_st, CRBE_TILE, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col16, s->ell_col, s->s, s->t, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
-                                  ctx->counter, s->d_comm)));
+                                  s->n, s->ntiles, s->rot, rtol2, s->ell_val, s->ell_col16, s->ell_col, s->s, s->t, s->rh, s->sums, s->dots, s->dstate,
+                                  ctx->partials, ctx->counter, s->d_comm)));
     else if (tma)
         PROF_LAUNCH(PK_ST, k, (t_st<int><<<s->gt_st, CRBE_TILE, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, rtol2, s->ell_val, s->ell_col, nullptr, s->s, s->t, s->rh, s->sums, s->dots, s->dstate, ctx->partials,
-                                  ctx->counter, s->d_comm)));
+                                  s->n, s->ntiles, s->rot, rtol2, s->ell_val, s->ell_col, nullptr, s->s, s->t, s->rh, s->sums, s->dots, s->dstate,
+                                  ctx->partials, ctx->counter, s->d_comm)));
     else
         PROF_LAUNCH(PK_ST, k, (k_st<<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, rtol2, s->ell_val, s->ell_col, s->s, s->t, s->rh, s->sums,
                                                                  s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     CRBE_CHECK(reduce_dots(s, S_TS, 5, S_TS, S_TT, S_RS, S_RT, launches, S_SS));
-    // the last-iteration shortcut needs the reduced (r,r) inside the kernel: single GPU and peer-memory transport
+    // the last-iteration shortcut needs the reduced (r,r) before anybody reads r and p again: at hand on a single GPU, checked
+    // by the next kernel's head with the peer-memory transport; the NCCL transport publishes it one launch too late
     const int predict = (s->world == 1 || s->p2p) && !(s->flags & CRBE_SOLVER_NO_PREDICT) ? 1 : 0;
     PROF_LAUNCH(PK_XR, k, (k_xrp<<<s->g_xr, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, s->s, s->t, v, x, s->r, p_in, p, s->sums, s->dots, s->dstate,
                                                               ctx->partials, ctx->counter, s->d_comm, predict)));
@@ -1390,6 +1594,10 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
 
 static int enqueue_fetch(crbe_solver* s) {
     cudaStream_t st = s->ctx->stream;
+    if (s->p2p) {       // totals nobody has taken from the mailbox yet (the batch may have ended with their producer)
+        k_tail_commit<<<1, 32, 0, st>>>(s->sums, s->dstate, s->d_comm, s->rtol * s->rtol);
+        CRBE_KERNEL_CHECK();
+    }
     CRBE_CUDA(cudaMemcpyAsync(s->sums_h, s->sums, sizeof(double) * CRBE_NSUMS, cudaMemcpyDeviceToHost, st));
     CRBE_CUDA(cudaMemcpyAsync(s->sums_h + CRBE_NSUMS, s->dstate, sizeof(int) * D_NSTATE, cudaMemcpyDeviceToHost, st));
     return CRBE_OK;
@@ -1413,7 +1621,7 @@ static int launch_residual(crbe_solver* s, double* x, int guard, int* launches) 
     const int pk = guard ? -2 : -1;
 #define CRBE_TRES(IDX, BE, GRID, NV, COL, COL32)                                                                                     \
     PROF_LAUNCH(PK_RES, pk, (t_residual<IDX, BE><<<GRID, CRBE_TILE, TilePipe<NV, TILE_STAGES, IDX>::SMEM_BYTES, st>>>(                 \
-                                s->n, s->ntiles, s->ell_val, COL, COL32, x, rhs, s->r, s->rh, s->p[0], s->sums, s->dots, ctx->partials, \
+                                s->n, s->ntiles, s->rot, s->ell_val, COL, COL32, x, rhs, s->r, s->rh, s->p[0], s->sums, s->dots, ctx->partials, \
                                 ctx->counter, s->d_comm, s->dstate, guard, rtol2)))
     if ((s->flags & CRBE_SOLVER_TMA) && i16 && be)
         CRBE_TRES(short, true, s->gs_res_be, 2, s->ell_col16, s->ell_col);
@@ -1453,7 +1661,11 @@ static inline int first_batch_target(const crbe_solver* s, int total_iters) {
 // End of a step enqueued without host synchronisation (crbe_solver_steps_ring): append the state of the solve to the step log
 // and, if the step has not converged, raise D_CHAIN so that every later kernel of the chunk returns at once and the host finds
 // the device exactly where this step stopped.  Steps skipped that way are logged with status -1.
-__global__ void k_step_end(const double* __restrict__ sums, int* dstate, double rtol2, double* __restrict__ log) {
+__global__ void k_step_end(double* sums, int* dstate, double rtol2, double* __restrict__ log, const CommArgs* __restrict__ ca) {
+    __shared__ double S_sh[CRBE_NSUMS];
+    bool failed;
+    if (dstate[D_CHAIN] == 0) head_sums<HS_NORMS>(sums, dstate, ca, S_sh, rtol2, &failed);   // peer-memory transport: totals into the sums
+    __syncthreads();
     const int pos = dstate[D_LOGPOS];
     const bool skipped = dstate[D_CHAIN] != 0;
     const int status = dstate[D_STATUS], iters = dstate[D_ITERS];
@@ -1479,7 +1691,7 @@ static int enqueue_batch(crbe_solver* s, double* x, int k0, int target, bool spe
     if (speculate) CRBE_CHECK(launch_residual(s, x, 1, launches));
     CRBE_KERNEL_CHECK();
     if (chained) {
-        k_step_end<<<1, 32, 0, s->ctx->stream>>>(s->sums, s->dstate, s->rtol * s->rtol, s->step_log);
+        k_step_end<<<1, 32, 0, s->ctx->stream>>>(s->sums, s->dstate, s->rtol * s->rtol, s->step_log, s->d_comm);
         CRBE_KERNEL_CHECK();
         *launches += 1;
         return CRBE_OK;
@@ -1521,6 +1733,12 @@ static int run_bicgstab(crbe_solver* s, double* x, crbe_solve_info* info, int* l
             first = FIRST_FRESH;
             const double rr = s->sums_h[S_RR], bb = s->sums_h[S_BB];
             status = dst_h[D_STATUS];
+            if (status == 4) {      // a peer never signalled (peer-memory transport): nothing on this rank can be trusted any more
+                s->comm_dead = true;
+                crbe_set_error("peer-memory transport: a neighbouring rank did not signal within the time-out (%s never arrived); "
+                               "the partitioned solver is unusable", "halo entries or dot products");
+                return CRBE_ERR_COMM;
+            }
             done = status != 0 || !(rr > rtol2 * bb) || !isfinite(rr);
             prof_collect(s, dst_h[D_ITERS], done && status == 0 && isfinite(rr));
             if (!isfinite(rr)) status = 2;
@@ -1630,11 +1848,16 @@ static int launch_extrapolate(crbe_solver* s, const StepPlan& pl, int* launches)
     a.x0 = pl.x;
     a.save = pl.save;
     for (int j = 0; j < CRBE_MAX_EXTRAP; ++j) a.h[j] = j < pl.q ? pl.h[j] : nullptr;
+    int xslot = 0;
+    if (s->p2p) {       // the kernel's tail pushes the boundary entries of the guess into the neighbours' copy of this ring vector
+        xslot = ring_slot_of(s, pl.x);
+        CRBE_REQUIRE(xslot >= 0, "peer-memory transport: the solution vector must be one of the window ring (crbe_solver_ring)");
+    }
     switch (pl.q) {
-        case 1: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<1><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a, s->dstate))); break;
-        case 2: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<2><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a, s->dstate))); break;
-        case 3: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<3><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a, s->dstate))); break;
-        default: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<4><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a, s->dstate))); break;
+        case 1: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<1><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a, s->dstate, s->d_comm, xslot))); break;
+        case 2: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<2><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a, s->dstate, s->d_comm, xslot))); break;
+        case 3: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<3><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a, s->dstate, s->d_comm, xslot))); break;
+        default: PROF_LAUNCH(PK_EXTRAP, -1, (k_extrapolate<4><<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, a, s->dstate, s->d_comm, xslot))); break;
     }
     *launches += 1;
     CRBE_KERNEL_CHECK();
@@ -1648,7 +1871,7 @@ static int enqueue_step_head(crbe_solver* s, const StepPlan& pl, const double* s
     const bool cn = s->rhs_val != nullptr;
     if (cn) {   // Crank-Nicolson: (M - c(K+A)) u_prev with u_prev as given, boundary values included (crbe.py:386)
         CRBE_CHECK(halo_exchange(s, pl.u0, launches));
-        if (s->p2p) k_p2p_wait<<<1, 32, 0, st>>>(0, s->d_comm);
+        if (s->p2p) k_p2p_wait<<<1, 32, 0, st>>>(HK_X, s->d_comm, s->dstate);
         k_spmv_csr<<<s->g_spmv, CRBE_BLOCK, 0, st>>>(s->n, s->indptr, s->indices, s->rhs_val, pl.u0, s->tmp);
         *launches += 1;
     }
@@ -1665,10 +1888,10 @@ static int enqueue_step_head(crbe_solver* s, const StepPlan& pl, const double* s
         if (pl.save) CRBE_CUDA(cudaMemcpyAsync(pl.save, pl.u0, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
         if (x != pl.u0) CRBE_CUDA(cudaMemcpyAsync(x, pl.u0, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
     }
-    CRBE_CHECK(halo_exchange(s, x, launches));
+    if (!(s->p2p && pl.q > 0)) CRBE_CHECK(halo_exchange(s, x, launches));   // (peer-memory transport: pushed by k_extrapolate's tail)
     const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
     double* const r_w = nullptr;                          // see launch_iteration: the first iteration does not read r,
-    double* const p_w = s->world == 1 ? nullptr : s->p[0];   // and p only in the partitioned solver
+    double* const p_w = (s->world > 1 && !s->p2p) ? s->p[0] : nullptr;   // and p only with the NCCL transport
     // Backward Euler: b is not stored, the verification / restart kernels rebuild it from u^n (bind_rhs, crbe_solver::be_u)
     double* const b_w = cn ? s->b : nullptr;
     if (cn)
@@ -1677,11 +1900,11 @@ static int enqueue_step_head(crbe_solver* s, const StepPlan& pl, const double* s
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if ((s->flags & CRBE_SOLVER_TMA) && i16)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<short><<<s->gs_init, CRBE_TILE, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->ell_val, s->ell_col16, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, b_w, r_w,
+                                     s->n, s->ntiles, s->rot, s->ell_val, s->ell_col16, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, b_w, r_w,
                                      s->rh, p_w, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else if (s->flags & CRBE_SOLVER_TMA)
         PROF_LAUNCH(PK_INIT, -1, (t_init_be<int><<<s->gt_init, CRBE_TILE, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->ell_val, s->ell_col, nullptr, x, xb, source_d, dt, s->mscale, s->dscale, b_w, r_w,
+                                     s->n, s->ntiles, s->rot, s->ell_val, s->ell_col, nullptr, x, xb, source_d, dt, s->mscale, s->dscale, b_w, r_w,
                                      s->rh, p_w, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     else
         PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, xb, source_d, dt,
@@ -1759,7 +1982,7 @@ static int enqueue_step(crbe_solver* s, const StepPlan& pl, const double* source
                         int* launches) {
     crbe_ctx* ctx = s->ctx;
     bind_rhs(s, pl, source_d, dt);
-    const bool graphs_on = (s->flags & CRBE_SOLVER_GRAPH) && s->world == 1 && !(s->prof && s->prof->on);
+    const bool graphs_on = (s->flags & CRBE_SOLVER_GRAPH) && (s->world == 1 || s->p2p) && !(s->prof && s->prof->on);
     if (graphs_on) {
         StepGraph key = {pl.u0, pl.x, pl.save, {pl.h[0], pl.h[1], pl.h[2], pl.h[3]}, source_d, dt, pl.q, target, speculate ? 1 : 0,
                          chained ? 1 : 0, nullptr, 0, 0};
@@ -1802,6 +2025,7 @@ static int step_impl(crbe_solver* s, const StepPlan& pl, const double* source_d,
 // and the extrapolated initial guess.
 static int step_in_place(crbe_solver* s, double* u_d, const double* source_d, double dt, crbe_solve_info* info_h) {
     CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
+    CRBE_REQUIRE(!s->comm_dead, "a peer timed out earlier: the partitioned solver is unusable");
     StepPlan pl;
     memset(&pl, 0, sizeof(pl));
     pl.u0 = u_d;
@@ -1835,8 +2059,11 @@ static int step_in_place(crbe_solver* s, double* u_d, const double* source_d, do
 // plan_ring_step does the bookkeeping of one such step (which buffers hold consecutive solutions, the order of the guess).
 static int plan_ring_step(crbe_solver* s, double* const* bufs, int count, int cur, StepPlan* out) {
     CRBE_REQUIRE(s->system_loaded, "crbe_solver_set_system has not been called");
-    CRBE_REQUIRE(s->world == 1, "ring stepping is for the single-GPU solver");
+    CRBE_REQUIRE(!s->comm_dead, "a peer timed out earlier: the partitioned solver is unusable");
+    CRBE_REQUIRE(s->world == 1 || s->p2p, "ring stepping needs the peer-memory transport in the partitioned solver");
     CRBE_REQUIRE(count >= 2 && count <= CRBE_MAX_EXTRAP + 1 && cur >= 0 && cur < count, "bad ring");
+    if (s->world > 1)
+        for (int k = 0; k < count; ++k) CRBE_REQUIRE(bufs[k] == s->ring[k], "partitioned solver: the ring must be the window ring (crbe_solver_ring)");
     bool same = s->ring_n == count && s->ring_expect == cur;
     for (int k = 0; k < count; ++k) {
         CRBE_REQUIRE(bufs[k] != nullptr, "null ring buffer");
@@ -1879,9 +2106,9 @@ static int step_ring(crbe_solver* s, double* const* bufs, int count, int cur, co
 // the previous steps needed plus one, and synchronises once.  Convergence is still enforced step by step, on the device:
 // the end-of-step kernel (k_step_end) logs the norms of every step and raises D_CHAIN when a step has not met the
 // stopping rule, which turns the rest of the chunk into no-ops; the host then finds the device exactly where that step
-// stopped, finishes it with the ordinary iteration loop and goes on.  Chunks grow (2, 4, ... MAX_CHUNK/2) while the
-// iteration count is steady, and end at a step whose guess order is a probe of the policy (its result must be recorded
-// before the next order is chosen).  Same kernels, same arguments, same order as step-by-step calls: identical bits.
+// stopped, finishes it with the ordinary iteration loop and goes on.  Chunks grow (2, 4, ... MAX_CHUNK/2) while every step
+// fits the iterations enqueued for it, start again at one step after a cut, and end at a step whose guess order is a probe of
+// the policy (its result must be recorded before the next order is chosen).  Same kernels, same arguments, same order as step-by-step calls: identical bits.
 struct RingSnapshot {
     GuessPolicy guess;
     int ring_valid, ring_expect;
@@ -1899,21 +2126,14 @@ static void fill_info_from_log(crbe_solver* s, const double* rec, crbe_solve_inf
 
 static bool chunking_allowed(const crbe_solver* s, const double* source_d) {
     (void)source_d;
-    if (s->world != 1 || s->rhs_val || (s->prof && s->prof->on)) return false;
+    if ((s->world != 1 && !s->p2p) || s->rhs_val || (s->prof && s->prof->on)) return false;
     if (s->flags & CRBE_SOLVER_VERIFY) return false;                    // every solve is followed by a host decision
     return first_batch_target(s, 0) <= VERIFY_AUTO_ITERS;              // beyond that the verification policy wants a look
 }
 
-static void chunk_feedback(crbe_solver* s, int iterations, int iterations_before) {
-    if (iterations == iterations_before) {
-        if (++s->stable_steps >= 3) {
-            s->chunk_len = s->chunk_len < 2 ? 2 : (2 * s->chunk_len > MAX_CHUNK / 2 ? MAX_CHUNK / 2 : 2 * s->chunk_len);
-            s->stable_steps = 2;
-        }
-    } else {
-        s->stable_steps = 0;
-        s->chunk_len = 1;
-    }
+// a chunk (or a single step) went through within the iterations enqueued for it: the next chunk may be twice as long
+static void chunk_grow(crbe_solver* s) {
+    s->chunk_len = s->chunk_len < 1 ? 1 : (2 * s->chunk_len > MAX_CHUNK / 2 ? MAX_CHUNK / 2 : 2 * s->chunk_len);
 }
 
 static int steps_ring(crbe_solver* s, double* const* bufs, int count, int cur, int n_steps, const double* source_d, double dt,
@@ -1929,7 +2149,8 @@ static int steps_ring(crbe_solver* s, double* const* bufs, int count, int cur, i
         const int before = s->last_iters;
         if (m <= 1 || !chunking_allowed(s, source_d)) {
             CRBE_CHECK(step_ring(s, bufs, count, (cur + i) % count, source_d, dt, &infos[i]));
-            chunk_feedback(s, infos[i].iterations, before);
+            if (infos[i].iterations <= before + 1 && infos[i].restarts == 0) chunk_grow(s);   // it would have fitted a chunk
+            else s->chunk_len = 1;
             ++i;
             *done = i;
             continue;
@@ -1976,6 +2197,12 @@ static int steps_ring(crbe_solver* s, double* const* bufs, int count, int cur, i
             record_guess(s, plans[j].q, &infos[i + j]);
             ++finished;
         }
+        if (jb < enq && (int)s->step_log_h[(size_t)jb * STEP_LOG_DOUBLES + CRBE_NSUMS] == 4) {
+            s->comm_dead = true;
+            *done = i + finished;
+            crbe_set_error("peer-memory transport: a neighbouring rank did not signal within the time-out; the partitioned solver is unusable");
+            return CRBE_ERR_COMM;
+        }
         if (jb < enq) {
             // this step needs more iterations (or a restart): continue it from the state the device stopped in
             const double* rec = s->step_log_h + (size_t)jb * STEP_LOG_DOUBLES;
@@ -2000,8 +2227,7 @@ static int steps_ring(crbe_solver* s, double* const* bufs, int count, int cur, i
             s->chunk_len = 1;
             s->stable_steps = 0;
         } else {
-            // the chunk went through: the iteration counts of its steps decide how long the next one may be
-            for (int j = 0; j < enq; ++j) chunk_feedback(s, infos[i + j].iterations, j == 0 ? before : infos[i + j - 1].iterations);
+            chunk_grow(s);
         }
         i += finished;
         *done = i;
@@ -2047,7 +2273,7 @@ extern "C" int crbe_solver_solve(crbe_solver* s, const double* b_d, double* x_d,
     s->be_u = nullptr;              // b is the stored, scaled copy of the caller's right-hand side
     CRBE_CHECK(halo_exchange(s, x_d, &launches));
     k_init<2><<<s->g_init, CRBE_BLOCK, 0, ctx->stream>>>(s->n, s->ld, s->ell_val, s->ell_col, x_d, b_d, nullptr, 0.0,
-                                                                        s->mscale, s->dscale, s->is_bnd, s->b, nullptr, s->rh, s->world == 1 ? nullptr : s->p[0], s->sums, s->dots,
+                                                                        s->mscale, s->dscale, s->is_bnd, s->b, nullptr, s->rh, (s->world > 1 && !s->p2p) ? s->p[0] : nullptr, s->sums, s->dots,
                                                                         s->dstate, ctx->partials, ctx->counter, s->d_comm);
     CRBE_KERNEL_CHECK();
     CRBE_CHECK(reduce_dots(s, S_BB, 3, S_BB, S_RR, S_RHO0, -1, &launches));

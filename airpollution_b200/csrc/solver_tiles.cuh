@@ -77,9 +77,14 @@ struct TilePipe {
     const IDX* ecol;
     const int* ecol32;              // IDX = short: absolute columns of the escaped entries
     const double* vec[NVEC > 0 ? NVEC : 1];
-    int64_t first, stride, count;   // tiles first, first+stride, ... (count of them) belong to this CTA
+    int64_t first, stride, count;   // positions first, first+stride, ... (count of them) of the walk belong to this CTA
+    int64_t rot = 0, ntiles_ = 0;   // position g of the walk is tile (g + rot) mod ntiles: a partitioned strip is walked from
+                                    // its middle, so the tiles that reference halo entries come up half a sweep after the start
 
-    __device__ __forceinline__ int64_t tile_of(int64_t m) const { return first + m * stride; }
+    __device__ __forceinline__ int64_t tile_of(int64_t m) const {
+        const int64_t t = first + m * stride + rot;
+        return t >= ntiles_ ? t - ntiles_ : t;
+    }
 
     __device__ __forceinline__ void issue(int64_t m) {
         const int st = (int)(m % STAGES);
@@ -93,11 +98,13 @@ struct TilePipe {
     }
 
     // all threads of the CTA; returns with the first STAGES tiles in flight
-    __device__ __forceinline__ void start(unsigned char* smem_, uint64_t* bars_, int64_t ntiles) {
+    __device__ __forceinline__ void start(unsigned char* smem_, uint64_t* bars_, int64_t ntiles, int64_t rot_ = 0) {
         smem = smem_;
         bars = bars_;
         first = blockIdx.x;
         stride = gridDim.x;
+        ntiles_ = ntiles;
+        rot = rot_;
         count = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
         if (threadIdx.x == 0) {
 #pragma unroll
@@ -110,6 +117,11 @@ struct TilePipe {
     }
 
     __device__ __forceinline__ void wait(int64_t m) const { mbar_wait(&bars[m % STAGES], (uint32_t)((m / STAGES) & 1)); }
+
+    // leave early (the solve turned out to be over): the copies in flight target this CTA's shared memory and must land first
+    __device__ __forceinline__ void drain() const {
+        for (int64_t m = 0; m < STAGES && m < count; ++m) wait(m);
+    }
 
     // every thread has finished reading stage m: refill it with tile m + STAGES
     __device__ __forceinline__ void release(int64_t m) {
@@ -154,12 +166,19 @@ __device__ __forceinline__ double tile_row(const Pipe& pipe, int64_t m, int r, d
 // are issued before tile m is finished, so gather latency overlaps arithmetic, stores and the barrier.
 // body(m, row, tr, own, y) consumes the row result y = own + sum a_k x[col_k]; own = staged vector 0.
 template <int NV, int ST, class IDX, class Body>
-__device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, const double* __restrict__ x, int64_t n, Body body) {
+__device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, const double* __restrict__ x, int64_t n, HaloGate& gate,
+                                                   Body body) {
     const int tr = threadIdx.x;
     double g[4], gn[4];
     auto gather = [&](int64_t m, double (&dst)[4]) {
+        // halo entries are written by the neighbours while this kernel runs: tiles that reference them wait for the flag
+        // first and read through L2 (no read-only path); all other tiles gather through L1 as on a single GPU
+        const bool halo_tile = gate.before_gather(pipe.tile_of(m));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dst[k] = __ldg(x + pipe.column(m, k, tr));
+        for (int k = 0; k < 4; ++k) {
+            const double* q = x + pipe.column(m, k, tr);
+            dst[k] = halo_tile ? __ldcg(q) : __ldg(q);
+        }
     };
     if (pipe.count > 0) {
         pipe.wait(0);
@@ -187,50 +206,61 @@ __device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, 
 
 // ---- v = A p, (r^, v) ------------------------------------------------------------------------------------
 // FIRST: the first iteration after an init / restart, where p = r^ = r0: one vector stream instead of two.
+// hkind: which gathered vector p is (HK_P, or HK_RH in the first iteration: its halo flag).
 template <class IDX, bool FIRST>
-__global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, double rtol2, const double* __restrict__ eval,
+__global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int64_t rot, double rtol2, const double* __restrict__ eval,
                                                   const IDX* __restrict__ ecol, const int* __restrict__ ecol32, const double* __restrict__ p, double* __restrict__ v,
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
-                                                  unsigned int* counter, const CommArgs* __restrict__ ca) {
+                                                  unsigned int* counter, const CommArgs* __restrict__ ca, int hkind) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[SPMV_STAGES];
-    if (solver_idle(sums, dstate, rtol2)) return;
+    __shared__ double S_sh[CRBE_NSUMS];
+    const bool peer = ca != nullptr && ca->world > 1;
+    if (!peer && solver_idle(sums, dstate, rtol2)) return;
     TilePipe<FIRST ? 1 : 2, SPMV_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
     pipe.ecol32 = ecol32;
     pipe.vec[0] = p;
     if (!FIRST) pipe.vec[FIRST ? 0 : 1] = rh;
-    pipe.start(tile_smem, bars, ntiles);
-    halo_wait(1, ca);   // the bulk copies are already in flight
+    pipe.start(tile_smem, bars, ntiles, rot);
+    if (peer) {     // the norms of the kernel before this one are still travelling: take them with the bulk copies in flight
+        bool failed;
+        const double* S = head_sums<HS_NORMS>(sums, dstate, ca, S_sh, rtol2, &failed);
+        if (solver_idle(S, dstate, rtol2, failed)) {
+            pipe.drain();
+            return;
+        }
+    }
+    HaloGate gate(ca, hkind, dstate);
     double acc[1] = {0.0};
-    tile_spmv_prefetch(pipe, p, n, [&](int64_t m, int64_t row, int tr, double, double vi) {
+    tile_spmv_prefetch(pipe, p, n, gate, [&](int64_t m, int64_t row, int tr, double, double vi) {
         v[row] = vi;
         acc[0] = fma(pipe.svec(m, FIRST ? 0 : 1)[tr], vi, acc[0]);
     });
     double* const out[1] = {dots + S_RHV};
-    grid_sum_last<1>(acc, partials, counter, out, ca);
+    grid_sum_last<1>(acc, partials, counter, out, ca, DK_PV);
 }
 
 // ---- t = A s, (t,s), (t,t), (r^,s), (r^,t), (s,s) ----------------------------------------------------------
 template <class IDX>
-__global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, double rtol2, const double* __restrict__ eval,
+__global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int64_t rot, double rtol2, const double* __restrict__ eval,
                                                   const IDX* __restrict__ ecol, const int* __restrict__ ecol32, const double* __restrict__ s, double* __restrict__ t,
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter, const CommArgs* __restrict__ ca) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[SPMV_STAGES];
-    if (solver_idle(sums, dstate, rtol2)) return;
+    if (solver_idle(sums, dstate, rtol2)) return;     // the sums it reads were brought up to date by the preceding kernels
     TilePipe<2, SPMV_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
     pipe.ecol32 = ecol32;
     pipe.vec[0] = s;
     pipe.vec[1] = rh;
-    pipe.start(tile_smem, bars, ntiles);
-    halo_wait(2, ca);
+    pipe.start(tile_smem, bars, ntiles, rot);
+    HaloGate gate(ca, HK_S, dstate);
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    tile_spmv_prefetch(pipe, s, n, [&](int64_t m, int64_t row, int tr, double si, double ti) {
+    tile_spmv_prefetch(pipe, s, n, gate, [&](int64_t m, int64_t row, int tr, double si, double ti) {
         const double rhi = pipe.svec(m, 1)[tr];
         t[row] = ti;
         acc[0] = fma(ti, si, acc[0]);
@@ -240,12 +270,13 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, dou
         acc[4] = fma(si, si, acc[4]);      // lets the update kernel predict ||r||^2 = (s,s) - (t,s)^2/(t,t), see k_xrp
     });
     double* const out[5] = {dots + S_TS, dots + S_TT, dots + S_RS, dots + S_RT, dots + S_SS};
-    grid_sum_last<5>(acc, partials, counter, out, ca);
+    grid_sum_last<5>(acc, partials, counter, out, ca, DK_ST);
 }
 
-// ---- Backward-Euler step start: b = mscale*u^n (+ dscale*dt*f), r = r^ = p = b - A x0, (b,b), (r,r) --------
+// ---- Backward-Euler step start: b = mscale*u^n (+ dscale*dt*f), r^ = b - A x0 (= r = p), (b,b), (r,r) --------
+// b is not stored unless asked for (see crbe_solver::be_u); xslot: which ring vector x is (peer-memory transport).
 template <class IDX>
-__global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles, const double* __restrict__ eval, const IDX* __restrict__ ecol, const int* __restrict__ ecol32,
+__global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles, int64_t rot, const double* __restrict__ eval, const IDX* __restrict__ ecol, const int* __restrict__ ecol32,
                                                        const double* __restrict__ x, const double* __restrict__ xb,
                                                        const double* __restrict__ src, double dt,
                                                        const double* __restrict__ mscale, const double* __restrict__ dscale,
@@ -258,6 +289,8 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         dstate[D_STATUS] = 0;
         dstate[D_ITERS] = 0;
+        dstate[D_PRED] = 0;
+        dstate[D_NORMSRC] = 0;
     }
     TilePipe<2, TILE_STAGES, IDX> pipe;
     pipe.eval = eval;
@@ -265,23 +298,25 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
     pipe.ecol32 = ecol32;
     pipe.vec[0] = mscale;
     pipe.vec[1] = xb;     // previous solution u^n (right-hand side); x is the initial guess, possibly extrapolated
-    pipe.start(tile_smem, bars, ntiles);
-    halo_wait(0, ca);
+    pipe.start(tile_smem, bars, ntiles, rot);
+    HaloGate gate(ca, HK_X, dstate);
     const int tr = threadIdx.x;
     double acc[3] = {0.0, 0.0, 0.0};
     for (int64_t m = 0; m < pipe.count; ++m) {
-        const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
+        const int64_t tile = pipe.tile_of(m);
+        const int64_t row = tile * CRBE_TILE + tr;
         double xi = 0.0, extra = 0.0;
         if (row < n) {                      // the caller-owned vectors are not padded: plain loads, issued before the wait
             xi = x[row];
             if (src) extra = dscale[row] * dt * src[row];
         }
+        const bool halo_tile = gate.before_gather(tile);
         pipe.wait(m);
         if (row < n) {
             const double bi = fma(pipe.svec(m, 0)[tr], pipe.svec(m, 1)[tr], extra);
-            const double ax = tile_row(pipe, m, tr, xi, [&](int j) { return __ldg(x + j); });
+            const double ax = tile_row(pipe, m, tr, xi, [&](int j) { return halo_tile ? __ldcg(x + j) : __ldg(x + j); });
             const double ri = bi - ax;
-            if (b) b[row] = bi;   // not stored in the time loop: see crbe_solver::be_u
+            if (b) b[row] = bi;
             rh[row] = ri;
             if (r) r[row] = ri;   // see k_init
             if (p) p[row] = ri;
@@ -290,45 +325,50 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
         }
         pipe.release(m);
     }
-    if (p) halo_push_tail(p, 1, ca);
+    halo_push_tail(rh, HK_RH, 0, ca);       // peer-memory transport: the first SpMV gathers r^ (= p), halo included
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
-    grid_sum_last<3>(acc, partials, counter, out, ca);
+    grid_sum_last<3>(acc, partials, counter, out, ca, DK_INIT);
 }
 
 // ---- true residual b - A x and its norm (guard = 1: verification, norm only; guard = 0: restart, r = r^ = p) ----
 // BE = false: b is a stored vector (one staged stream).  BE = true: b = mscale*u^n (+ dt*dscale*f) rebuilt on the fly from
 // two staged streams, as in t_init_be (the time loop does not store b).
 template <class IDX, bool BE>
-__global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntiles, const double* __restrict__ eval, const IDX* __restrict__ ecol, const int* __restrict__ ecol32,
+__global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntiles, int64_t rot, const double* __restrict__ eval, const IDX* __restrict__ ecol, const int* __restrict__ ecol32,
                                                         const double* __restrict__ x, RhsSource rhs, double* __restrict__ r,
                                                         double* __restrict__ rh, double* __restrict__ p, double* sums, double* dots,
                                                         double* partials, unsigned int* counter, const CommArgs* __restrict__ ca,
-                                                        const int* dstate, int guard, double rtol2) {
+                                                        int* dstate, int guard, double rtol2) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[TILE_STAGES];
+    __shared__ double S_sh[CRBE_NSUMS];
     if (dstate[D_CHAIN] != 0) return;
-    if (guard && (dstate[D_STATUS] != 0 || sums[S_RR] > rtol2 * sums[S_BB])) return;
+    bool failed;
+    const double* S = head_sums<HS_NORMS>(sums, dstate, ca, S_sh, rtol2, &failed);
+    if (guard && (failed || dstate[D_STATUS] != 0 || S[S_RR] > rtol2 * S[S_BB])) return;
     TilePipe<BE ? 2 : 1, TILE_STAGES, IDX> pipe;
     pipe.eval = eval;
     pipe.ecol = ecol;
     pipe.ecol32 = ecol32;
     pipe.vec[0] = BE ? rhs.mscale : rhs.b;
     if (BE) pipe.vec[BE ? 1 : 0] = rhs.u;
-    pipe.start(tile_smem, bars, ntiles);
-    halo_wait(0, ca);
+    pipe.start(tile_smem, bars, ntiles, rot);
+    HaloGate gate(ca, HK_X, dstate);
     const int tr = threadIdx.x;
     double acc[1] = {0.0};
     for (int64_t m = 0; m < pipe.count; ++m) {
-        const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
+        const int64_t tile = pipe.tile_of(m);
+        const int64_t row = tile * CRBE_TILE + tr;
         double xi = 0.0, extra = 0.0;
         if (row < n) {
             xi = x[row];
             if (BE && rhs.src) extra = rhs.dscale[row] * rhs.dt * rhs.src[row];
         }
+        const bool halo_tile = gate.before_gather(tile);
         pipe.wait(m);
         if (row < n) {
-            const double ax = tile_row(pipe, m, tr, xi, [&](int j) { return __ldg(x + j); });
+            const double ax = tile_row(pipe, m, tr, xi, [&](int j) { return halo_tile ? __ldcg(x + j) : __ldg(x + j); });
             const double bi = BE ? fma(pipe.svec(m, 0)[tr], pipe.svec(m, BE ? 1 : 0)[tr], extra) : pipe.svec(m, 0)[tr];
             const double ri = bi - ax;
             if (!guard) {
@@ -340,7 +380,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntile
         }
         pipe.release(m);
     }
-    if (!guard) halo_push_tail(p, 1, ca);
+    if (!guard) halo_push_tail(rh, HK_RH, 0, ca);     // the restarted solve begins with the first-iteration kernels (gather r^)
     double* const out[1] = {dots + S_RRTRUE};
-    grid_sum_last<1>(acc, partials, counter, out, ca);
+    grid_sum_last<1>(acc, partials, counter, out, ca, DK_RES);
 }

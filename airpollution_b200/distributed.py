@@ -208,7 +208,7 @@ class PartitionedCRBE:
 
     def __init__(self, workload=None, *, mesh=None, domain=None, problem=None, nt=None, order=1, rank=None, world=None,
                  device=None, comm=None, rtol=1e-13, max_iterations=10000, tma=True, verify="auto", p2p=None,
-                 extrapolate=True):
+                 extrapolate=True, graph=True, predict=True):
         from . import _lib, crbe
         from .runtime import Runtime, ptr
         import os
@@ -295,22 +295,27 @@ class PartitionedCRBE:
                 (C.c_int64 * max(nn, 1))(*recv_counts), C.byref(h))
         self._solver = h
         flags = (_lib.SOLVER_VERIFY_AUTO if verify == "auto" else (_lib.SOLVER_VERIFY if verify else 0)) | \
-                (_lib.SOLVER_TMA if tma else 0) | \
-                _lib.extrapolation_flags(extrapolate)
+                (_lib.SOLVER_TMA if tma else 0) | (_lib.SOLVER_GRAPH if graph else 0) | \
+                (0 if predict else _lib.SOLVER_NO_PREDICT) | _lib.extrapolation_flags(extrapolate)
         rt.call("crbe_solver_set_options", h, float(rtol), int(max_iterations), flags)
         rt.call("crbe_solver_set_system", h, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
         vlen = C.c_int64()
         rt.call("crbe_solver_vector_length", h, C.byref(vlen), None)
         self.transport = "nccl"
+        self.ring = None               # peer-memory transport: the solver-owned ring of solution vectors (ring stepping)
+        self.cur = 0
         if self.world > 1 and p2p:
-            self.u = self._connect_peers(rt, h, neigh, recv_counts, vlen.value)
+            self.ring = self._connect_peers(rt, h, neigh, recv_counts, vlen.value)
+            self._ring_c = (C.c_void_p * len(self.ring))(*[b.data_ptr() for b in self.ring])
             self.transport = "peer-memory (CUDA IPC over NVLink)"
         else:
-            self.u = rt.zeros((vlen.value,), torch.float64)
+            self._u = rt.zeros((vlen.value,), torch.float64)
         # initial condition at the owned midpoints (crbe.py:364-365), evaluated on the host like the reference
         u0 = problem.initial_condition_fn(self.midpoints.cpu().numpy())
         self.u[:self.n_own] = rt.upload(np.asarray(u0, dtype=np.float64))
         self.info = _lib.SolveInfo()
+        self._infos = (_lib.SolveInfo * 64)()
+        self._done = C.c_int32()
         self.step_index = 0
         self.step_info = []
         del loc, md
@@ -335,21 +340,57 @@ class PartitionedCRBE:
         rt.call("crbe_solver_p2p_connect", h, self.rank, C.create_string_buffer(handles, len(handles)),
                 (C.c_int64 * self.world)(*[m["ld"] for m in allm]), (C.c_int64 * self.world)(*[m["veclen"] for m in allm]),
                 (C.c_int64 * nn)(*(seg or [0])))
-        xp = C.c_void_p()
-        rt.call("crbe_solver_x", h, C.byref(xp))
+        bufs = (C.c_void_p * 8)()
+        count = C.c_int32()
+        rt.call("crbe_solver_ring", h, bufs, C.byref(count))
         dist.barrier()            # every window is mapped before anybody starts pushing into it
 
-        class _Window:
-            __cuda_array_interface__ = {"shape": (veclen,), "typestr": "<f8", "data": (xp.value, False), "version": 3}
-        return torch.as_tensor(_Window(), device=rt.device)
+        def view(address):
+            class _Window:
+                __cuda_array_interface__ = {"shape": (veclen,), "typestr": "<f8", "data": (address, False), "version": 3}
+            return torch.as_tensor(_Window(), device=rt.device)
+        return [view(bufs[k]) for k in range(count.value)]
+
+    @property
+    def u(self):
+        """The current solution vector (owned rows, padding, halo entries)."""
+        return self.ring[self.cur] if self.ring is not None else self._u
+
+    def _record(self, info):
+        self.step_info.append((info.iterations, info.relres, info.true_relres, info.restarts, info.guess_order, info.initial_relres))
 
     def step(self, source=None):
         from .runtime import ptr
         self.step_index += 1
-        self.rt.call("crbe_solver_step", self._solver, ptr(self.u), ptr(source), float(self.dt), C.byref(self.info))
-        self.step_info.append((self.info.iterations, self.info.relres, self.info.true_relres, self.info.restarts,
-                               self.info.guess_order, self.info.initial_relres))
+        if self.ring is not None:     # ring stepping: u^(n+1) is built in the vector that held the oldest solution
+            self.rt.call("crbe_solver_step_ring", self._solver, self._ring_c, len(self.ring), self.cur, ptr(source), float(self.dt),
+                         C.byref(self.info))
+            self.cur = (self.cur + 1) % len(self.ring)
+        else:
+            self.rt.call("crbe_solver_step", self._solver, ptr(self._u), ptr(source), float(self.dt), C.byref(self.info))
+        self._record(self.info)
         return self.info.iterations
+
+    def steps(self, count, source=None, chunk=16):
+        """`count` steps with a constant source, up to `chunk` per library call (one host synchronisation per chunk of steps
+        with the peer-memory transport); returns the iterations of every step."""
+        from .runtime import ptr
+        its = []
+        while count > 0:
+            m = min(count, chunk, 64)
+            if self.ring is None or m == 1:
+                its.append(self.step(source))
+                m = 1
+            else:
+                self.rt.call("crbe_solver_steps_ring", self._solver, self._ring_c, len(self.ring), self.cur, m, ptr(source),
+                             float(self.dt), self._infos, C.byref(self._done))
+                self.cur = (self.cur + m) % len(self.ring)
+                self.step_index += m
+                for k in range(m):
+                    self._record(self._infos[k])
+                    its.append(self._infos[k].iterations)
+            count -= m
+        return its
 
     def owned_solution(self, lifted=True):
         """Owned block of the current solution (global rows d0..d1), lifted by the boundary data (crbe.py:429)."""
@@ -378,7 +419,8 @@ class PartitionedCRBE:
 
     def close(self):
         from . import _lib
-        self.u = None             # aliases library memory
+        self.ring = None          # aliases library memory
+        self._u = None
         if self.world > 1:
             torch.cuda.synchronize()
             dist.barrier()        # nobody unmaps a window a neighbour may still write to
@@ -392,16 +434,15 @@ class PartitionedCRBE:
 # --------------------------------------------------------------------------
 # bench.py --gpus N
 # --------------------------------------------------------------------------
-def _timed_partitioned_steps(part, lead, K, device):
+def _timed_partitioned_steps(part, lead, K, device, chunk=10):
     """lead untimed steps, then K timed ones: CUDA events on the launching stream between barrier + synchronize, max over
     ranks.  Returns (ms, iterations per timed step)."""
-    for _ in range(lead):
-        part.step()
+    part.steps(lead, chunk=chunk)
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    iters = [part.step() for _ in range(K)]
+    iters = part.steps(K, chunk=chunk)
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -420,7 +461,7 @@ def partition_parity_check(args, device, n=256, steps=30):
     rank = dist.get_rank()
     wl = workloads.unit_square(n, steps=steps, regime=args.regime)
     part = PartitionedCRBE(wl, device=device, tma=not args.classic, extrapolate=not args.no_extrapolate)
-    its_p = [part.step() for _ in range(steps)]
+    its_p = part.steps(steps, chunk=args.chunk)
     full = part.gather_solution(lifted=False)
     part.close()
     out = [None]
@@ -455,7 +496,7 @@ def strong_block(args, device):
         t0 = time.time()
         part = PartitionedCRBE(wl, device=device, tma=not args.classic, extrapolate=not args.no_extrapolate)
         setup_s = time.time() - t0
-        ms, iters = _timed_partitioned_steps(part, spin + W, K, device)
+        ms, iters = _timed_partitioned_steps(part, spin + W, K, device, args.chunk)
         n_own = part.n_own
         part.close()
         sps = K / (ms * 1e-3)
@@ -487,13 +528,12 @@ def bench_partitioned(args, K, W, device):
     part = PartitionedCRBE(wl, device=device, tma=not args.classic, extrapolate=not args.no_extrapolate)
     setup_s = time.time() - t0
     spinup = B.spinup_steps(args, K)
-    for _ in range(spinup + W):
-        part.step()
+    part.steps(spinup + W, chunk=args.chunk)
     sampler = B.ClockSampler(device.index)
     sampler.start()
     l0, l1 = C.c_int64(), C.c_int64()
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l0))
-    ms, iters = _timed_partitioned_steps(part, 0, K, device)
+    ms, iters = _timed_partitioned_steps(part, 0, K, device, args.chunk)
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l1))
     # the same steps once more with a CUDA event pair around every kernel launch (per-kernel durations)
     rt.call("crbe_solver_profile", part._solver, 1)
@@ -507,12 +547,12 @@ def bench_partitioned(args, K, W, device):
     n_own = part.n_own
     bits = C.c_int32()
     rt.call("crbe_solver_index_bits", part._solver, C.byref(bits))
-    B.set_index_bits(bits.value, single_gpu=False)
+    B.set_index_bits(bits.value, single_gpu=part.ring is not None)   # peer-memory transport: the init kernel writes r^ only
     q_mean = float(np.mean([i[4] for i in part.step_info[-K:]])) if part.step_info else 0.0
     rb = dict(B.ROW_BYTES)
     f0 = min(1.0, min(K, 30) / pcnt[1]) if pcnt[1] > 0 else 0.0     # share of first-iteration (one-stream) SpMV launches
     rb["pv"] = f0 * rb["pv0"] + (1.0 - f0) * rb["pv"]
-    rb["extrapolate"] = (q_mean + 3) * 8      # in-place form: reads u^n ... u^(n-q), writes the guess and the copy of u^n
+    rb["extrapolate"] = (q_mean + (2 if part.ring is not None else 3)) * 8   # ring: reads u^n ... u^(n-q), writes the guess over the oldest
     kern = {B.KINDS[k]: {"launches": int(pcnt[k]), "ms_per_launch": pms[k] / pcnt[k],
                          "GBps": rb[B.KINDS[k]] * n_own / (pms[k] / pcnt[k] * 1e-3) / 1e9} for k in range(8) if pcnt[k] > 0}
     kernel_ms_per_step = sum(pms[k] for k in range(8)) / max(1, min(K, 30))

@@ -255,18 +255,24 @@ int crbe_solver_create_partitioned(crbe_ctx* ctx, crbe_comm* comm, int64_t n_own
                                    const int32_t* neigh_ranks_h, const int64_t* send_counts_h,
                                    const int32_t* send_idx_d, const int64_t* recv_counts_h, crbe_solver** out);
 int crbe_solver_vector_length(crbe_solver* s, int64_t* len_h, int64_t* halo_offset_h);
-/* Peer-memory transport (optional, replaces the NCCL calls of the partitioned solver): the gathered
- * vectors x, p, s and a mailbox live in one CUDA-IPC window per rank; neighbours store halo values
- * straight into it over NVLink and raise epoch flags, dot products are all-reduced through the mailboxes
- * by one-CTA kernels.  Step 1, every rank: export (64-byte IPC handle; meta_h[2] = {ld, veclen}).
- * The host gathers handles and metas of all ranks.  Step 2: connect (handles_h = world x 64 bytes in rank
- * order; halo_seg_off_h[q] = offset of this rank's segment inside neighbour q's halo region).
- * Afterwards crbe_solver_step must be given the window vector returned by crbe_solver_x. */
+/* Peer-memory transport (default on one NVLink node; replaces the NCCL calls of the partitioned solver): a ring of five
+ * solution vectors, the gathered work vectors p, s, r^ and a mailbox live in one CUDA-IPC window per rank.  The halo exchange
+ * is fused into the kernels that produce a gathered vector (their last CTA stores the boundary entries straight into the
+ * neighbours' halo segments over NVLink and raises an epoch flag; the consuming SpMV walks its strip from the middle and waits
+ * only when it reaches a tile that references a halo column), and so is the allreduce of the dot products (the producer's last
+ * CTA deposits the partial sums in every rank's mailbox, the kernels that need the totals add the deposits in rank order at
+ * their head).  Step 1, every rank: export (64-byte IPC handle; meta_h[2] = {ld, veclen}).  The host gathers handles and metas
+ * of all ranks.  Step 2: connect (handles_h = world x 64 bytes in rank order; halo_seg_off_h[q] = offset of this rank's segment
+ * inside neighbour q's halo region).  Afterwards the solution vectors handed to crbe_solver_step* must be those of the window
+ * ring: crbe_solver_ring (all five, for crbe_solver_step_ring / crbe_solver_steps_ring) or crbe_solver_x (the first, for the
+ * in-place crbe_solver_step).  CRBE_P2P_TIMEOUT_MS (environment, default ~18000): how long a kernel spins on a peer's flag
+ * before it declares the peer dead; the running step then returns CRBE_ERR_COMM and the solver refuses further steps. */
 int crbe_solver_p2p_export(crbe_solver* s, void* ipc_handle_out_h, int64_t* meta_h);
 int crbe_solver_p2p_connect(crbe_solver* s, int rank, const void* handles_h, const int64_t* ld_all_h,
                             const int64_t* veclen_all_h, const int64_t* halo_seg_off_h);
 int crbe_solver_x(crbe_solver* s, void** x_d_out);
-int crbe_solver_p2p_error(crbe_solver* s, int* err_h);       /* non-zero: a peer never signalled (timeout) */
+int crbe_solver_ring(crbe_solver* s, void** bufs_out5_h, int32_t* count_h);
+int crbe_solver_p2p_error(crbe_solver* s, int* err_h);       /* non-zero: a peer never signalled (1 halo entries, 2 dot products) */
 
 /* ---- measurement -------------------------------------------------------- */
 /* Per-kernel device time of the solver kernels, CUDA events on the context stream.

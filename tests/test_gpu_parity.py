@@ -840,7 +840,7 @@ def test_reassembly_at_512_cells_is_bit_identical_to_the_assembly_path():
 
         def view(p, count):
             class _W:
-                __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (p.value, True), "version": 3}
+                __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (p.value, False), "version": 3}
             return torch.as_tensor(_W(), device=rt.device).clone()
         n = md.number_of_segments
         return view(pv, 4 * ld.value), view(pm, n), view(pd, n)
