@@ -11,6 +11,7 @@
 // pattern of ``base_system`` (crbe.py:358).
 #include "crbe_common.cuh"
 #include "crbe_element.cuh"
+#include "bulk_copy.cuh"
 
 __device__ __forceinline__ void load_element(const double* __restrict__ pts, const int* __restrict__ tri,
                                              const double* __restrict__ areas, int64_t t, double D, double vx, double vy,
@@ -132,10 +133,11 @@ extern "C" int crbe_system_values(crbe_ctx* ctx, int64_t nnz, const double* m_va
 // --------------------------------------------------------------------------
 struct AdvectionPlan {
     double* geom = nullptr;        // nt x 5
-    uint32_t* meta = nullptr;      // n
-    const int32_t* edge_slots = nullptr;   // caller-owned (MeshData), n x 2
-    const double* k_val = nullptr;         // caller-owned, structural pattern
-    int64_t n = 0, nt = 0;
+    uint32_t* meta = nullptr;      // ld (rows padded to whole tiles: padding rows have no entries)
+    int2* slots = nullptr;         // ld: the two slots 3t+a of every edge (copy of MeshData's edge_slots, padded with -1)
+    double* k5 = nullptr;          // K in tile-major order: entry q (CSR offset 0..4) of row i at (i/256)*1280 + q*256 + i%256
+    const double* k_val = nullptr;         // caller-owned, structural pattern (general kernel: exports, Crank-Nicolson operator)
+    int64_t n = 0, ld = 0, nt = 0;
 };
 
 static void advection_plan_free(void* p) {
@@ -143,6 +145,8 @@ static void advection_plan_free(void* p) {
     if (!pl) return;
     cudaFree(pl->geom);
     cudaFree(pl->meta);
+    cudaFree(pl->slots);
+    cudaFree(pl->k5);
     delete pl;
 }
 
@@ -196,6 +200,136 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_advection_meta(int64_t n, const 
     }
 }
 
+// sum over the (<= 2) triangles of an edge of the advection terms its row receives, by CSR offset: the arithmetic of
+// crbe_element_advection (crbe.py:305-313) on the stored inverse Jacobian, accumulated side 0 then side 1 like crbe_assemble
+__device__ __forceinline__ void advection_row_terms(uint32_t w, int2 es, const double* __restrict__ geom, const double* __restrict__ v_elem,
+                                                    double vx0, double vy0, double (&a_loc)[5]) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) a_loc[q] = 0.0;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const int slot = side == 0 ? es.x : es.y;
+        if (slot < 0) continue;
+        const int64_t t = slot / 3;
+        const double b00 = __ldg(geom + 5 * t), b01 = __ldg(geom + 5 * t + 1), b10 = __ldg(geom + 5 * t + 2),
+                     b11 = __ldg(geom + 5 * t + 3), phi_int = __ldg(geom + 5 * t + 4);
+        double vx = vx0, vy = vy0;
+        if (v_elem) {
+            vx = __ldg(v_elem + 2 * t);
+            vy = __ldg(v_elem + 2 * t + 1);
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const double gx = b00 * CRBE_G(b, 0) + b10 * CRBE_G(b, 1);       // grad_phi[b] = B^T G[b]      crbe.py:305
+            const double gy = b01 * CRBE_G(b, 0) + b11 * CRBE_G(b, 1);
+            const double ar = 2 * (phi_int * (gx * vx + gy * vy));           // :311-313, same for every local row a
+            const int off = (int)((w >> (7 + 9 * side + 3 * b)) & 7u);
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+                if (off == q) a_loc[q] += ar;
+        }
+    }
+}
+
+// The per-step kernel: a bulk-copy pipeline like the solver's SpMV kernels (solver_tiles.cuh).  One elected thread streams
+// the row-aligned inputs of a 256-row tile -- K in tile-major order, diag M, the row words and the triangle slots, 15 KB --
+// into a ring of shared-memory stages STAGES tiles ahead; the 256 threads gather the two triangle records and velocities of
+// their row (L1/L2 hits: neighbouring rows share triangles), do the arithmetic and store the ELL slots and scalings
+// coalesced.  Nothing waits on a dependent chain of global loads (the register-load form of this kernel ran at 46 % of the
+// DRAM peak, 92 % of its stalls on the scoreboard).
+constexpr int ADV_STAGES = 3;
+constexpr int ADV_K_BYTES = 5 * CRBE_TILE * 8, ADV_M_BYTES = CRBE_TILE * 8, ADV_S_BYTES = CRBE_TILE * 8, ADV_W_BYTES = CRBE_TILE * 4;
+constexpr int ADV_STAGE_BYTES = ADV_K_BYTES + ADV_M_BYTES + ADV_S_BYTES + ADV_W_BYTES;
+
+__global__ void __launch_bounds__(CRBE_TILE) t_update_system_rows(int64_t n, int64_t ntiles, const double* __restrict__ k5,
+                                                                  const double* __restrict__ mdiag, const int2* __restrict__ slots,
+                                                                  const uint32_t* __restrict__ meta, const double* __restrict__ geom,
+                                                                  const double* __restrict__ v_elem, double vx0, double vy0, double coef,
+                                                                  double* __restrict__ ell_val, double* __restrict__ mscale,
+                                                                  double* __restrict__ dscale, int* __restrict__ err) {
+    extern __shared__ __align__(128) unsigned char adv_smem[];
+    __shared__ uint64_t bars[ADV_STAGES];
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    const int64_t count = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+    auto issue = [&](int64_t m) {
+        const int st = (int)(m % ADV_STAGES);
+        unsigned char* base = adv_smem + st * ADV_STAGE_BYTES;
+        const int64_t tile = first + m * stride;
+        mbar_expect_tx(&bars[st], ADV_STAGE_BYTES);
+        bulk_g2s(base, k5 + tile * (5 * CRBE_TILE), ADV_K_BYTES, &bars[st]);
+        bulk_g2s(base + ADV_K_BYTES, mdiag + tile * CRBE_TILE, ADV_M_BYTES, &bars[st]);
+        bulk_g2s(base + ADV_K_BYTES + ADV_M_BYTES, slots + tile * CRBE_TILE, ADV_S_BYTES, &bars[st]);
+        bulk_g2s(base + ADV_K_BYTES + ADV_M_BYTES + ADV_S_BYTES, meta + tile * CRBE_TILE, ADV_W_BYTES, &bars[st]);
+    };
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int st = 0; st < ADV_STAGES; ++st) mbar_init(&bars[st], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int64_t m = 0; m < ADV_STAGES && m < count; ++m) issue(m);
+    const int tr = threadIdx.x;
+    for (int64_t m = 0; m < count; ++m) {
+        const int64_t tile = first + m * stride;
+        const int64_t i = tile * CRBE_TILE + tr;
+        mbar_wait(&bars[m % ADV_STAGES], (uint32_t)((m / ADV_STAGES) & 1));
+        const unsigned char* base = adv_smem + (m % ADV_STAGES) * ADV_STAGE_BYTES;
+        const double* sk = (const double*)base;
+        const double m_i = ((const double*)(base + ADV_K_BYTES))[tr];
+        const int2 es = ((const int2*)(base + ADV_K_BYTES + ADV_M_BYTES))[tr];
+        const uint32_t w = ((const uint32_t*)(base + ADV_K_BYTES + ADV_M_BYTES + ADV_S_BYTES))[tr];
+        double kq[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) kq[q] = sk[q * CRBE_TILE + tr];
+        __syncthreads();                                  // every thread has read its stage: refill it
+        if (threadIdx.x == 0 && m + ADV_STAGES < count) issue(m + ADV_STAGES);
+        if (i >= n) continue;
+        const int len = (int)(w & 7u), diag = (int)((w >> 3) & 7u);
+        const bool bd = ((w >> 6) & 1u) != 0;
+        double a_loc[5];
+        advection_row_terms(w, es, geom, v_elem, vx0, vy0, a_loc);
+        double sv[5];
+        double d = 0.0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            sv[q] = 0.0;
+            if (q < len) {
+                const double mq = q == diag ? m_i : 0.0;                 // M carries explicit zeros off the diagonal (crbe.py:282)
+                sv[q] = mq + coef * (kq[q] + a_loc[q]);                  // (K+A) first, times c, plus M      crbe.py:358
+                if (q == diag) d = sv[q];
+            }
+        }
+        if (diag >= len || (!bd && !(fabs(d) > 0.0))) atomicOr(err, diag >= len ? 1 : 4);
+        double* ev = ell_val + tile * (4 * CRBE_TILE) + tr;
+        int k = 0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            if (!bd && q < len && q != diag && k < 4) {
+                __stcs(ev + k * CRBE_TILE, sv[q] / d);
+                ++k;
+            }
+        for (; k < 4; ++k) __stcs(ev + k * CRBE_TILE, 0.0);
+        mscale[i] = bd ? 0.0 : m_i / d;
+        dscale[i] = bd ? 0.0 : 1.0 / d;
+    }
+}
+
+// K (structural CSR values) into the tile-major order the pipeline streams; padding entries are zero
+__global__ void __launch_bounds__(CRBE_BLOCK) k_advection_k5(int64_t n, int64_t ld, const int* __restrict__ indptr, const double* __restrict__ kval,
+                                                             double* __restrict__ k5) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ld; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p0 = i < n ? indptr[i] : 0, len = i < n ? indptr[i + 1] - p0 : 0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) k5[(i / CRBE_TILE) * (5 * CRBE_TILE) + q * CRBE_TILE + (i % CRBE_TILE)] = q < len ? kval[p0 + q] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(CRBE_BLOCK) k_advection_slots(int64_t n, int64_t ld, const int* __restrict__ edge_slots, int2* __restrict__ slots) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ld; i += (int64_t)gridDim.x * blockDim.x)
+        slots[i] = i < n ? make_int2(edge_slots[2 * i], edge_slots[2 * i + 1]) : make_int2(-1, -1);
+}
+
 __global__ void __launch_bounds__(CRBE_BLOCK) k_update_system_rows(
     int64_t n, const int* __restrict__ indptr, const uint32_t* __restrict__ meta, const int2* __restrict__ edge_slots,
     const double* __restrict__ geom, const double* __restrict__ kval, const double* __restrict__ mdiag, const double* __restrict__ v_elem,
@@ -207,30 +341,8 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_update_system_rows(
         const int p0 = __ldg(indptr + i);
         const int len = (int)(w & 7u), diag = (int)((w >> 3) & 7u);
         const bool bd = ((w >> 6) & 1u) != 0;
-        double a_loc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const int slot = side == 0 ? es.x : es.y;
-            if (slot < 0) continue;
-            const int64_t t = slot / 3;
-            const double b00 = __ldg(geom + 5 * t), b01 = __ldg(geom + 5 * t + 1), b10 = __ldg(geom + 5 * t + 2),
-                         b11 = __ldg(geom + 5 * t + 3), phi_int = __ldg(geom + 5 * t + 4);
-            double vx = vx0, vy = vy0;
-            if (v_elem) {
-                vx = __ldg(v_elem + 2 * t);
-                vy = __ldg(v_elem + 2 * t + 1);
-            }
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                const double gx = b00 * CRBE_G(b, 0) + b10 * CRBE_G(b, 1);       // grad_phi[b] = B^T G[b]      crbe.py:305
-                const double gy = b01 * CRBE_G(b, 0) + b11 * CRBE_G(b, 1);
-                const double ar = 2 * (phi_int * (gx * vx + gy * vy));           // :311-313, same for every local row a
-                const int off = (int)((w >> (7 + 9 * side + 3 * b)) & 7u);
-#pragma unroll
-                for (int q = 0; q < 5; ++q)
-                    if (off == q) a_loc[q] += ar;
-            }
-        }
+        double a_loc[5];
+        advection_row_terms(w, es, geom, v_elem, vx0, vy0, a_loc);
         const double m = __ldg(mdiag + i);
         double sv[5];
         double d = 0.0;
@@ -273,30 +385,8 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_update_rhs_rows(int64_t n, const
         const int2 es = __ldg(edge_slots + i);
         const int p0 = __ldg(indptr + i);
         const int len = (int)(w & 7u), diag = (int)((w >> 3) & 7u);
-        double a_loc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const int slot = side == 0 ? es.x : es.y;
-            if (slot < 0) continue;
-            const int64_t t = slot / 3;
-            const double b00 = __ldg(geom + 5 * t), b01 = __ldg(geom + 5 * t + 1), b10 = __ldg(geom + 5 * t + 2),
-                         b11 = __ldg(geom + 5 * t + 3), phi_int = __ldg(geom + 5 * t + 4);
-            double vx = vx0, vy = vy0;
-            if (v_elem) {
-                vx = __ldg(v_elem + 2 * t);
-                vy = __ldg(v_elem + 2 * t + 1);
-            }
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                const double gx = b00 * CRBE_G(b, 0) + b10 * CRBE_G(b, 1);
-                const double gy = b01 * CRBE_G(b, 0) + b11 * CRBE_G(b, 1);
-                const double ar = 2 * (phi_int * (gx * vx + gy * vy));
-                const int off = (int)((w >> (7 + 9 * side + 3 * b)) & 7u);
-#pragma unroll
-                for (int q = 0; q < 5; ++q)
-                    if (off == q) a_loc[q] += ar;
-            }
-        }
+        double a_loc[5];
+        advection_row_terms(w, es, geom, v_elem, vx0, vy0, a_loc);
         const double m = __ldg(mdiag + i);
 #pragma unroll
         for (int q = 0; q < 5; ++q)
@@ -318,17 +408,22 @@ extern "C" int crbe_solver_advection_plan(crbe_solver* solver, const double* poi
     *ar.plan_slot = pl;
     *ar.plan_free = advection_plan_free;
     pl->n = ar.n;
+    pl->ld = (ar.n + CRBE_TILE - 1) / CRBE_TILE * CRBE_TILE;
     pl->nt = nt;
-    pl->edge_slots = edge_slots_d;
     pl->k_val = k_val_d;
     CRBE_CUDA(cudaMalloc(&pl->geom, sizeof(double) * 5 * nt));
-    CRBE_CUDA(cudaMalloc(&pl->meta, sizeof(uint32_t) * ar.n));
+    CRBE_CUDA(cudaMalloc(&pl->meta, sizeof(uint32_t) * pl->ld));
+    CRBE_CUDA(cudaMalloc(&pl->slots, sizeof(int2) * pl->ld));
+    CRBE_CUDA(cudaMalloc(&pl->k5, sizeof(double) * 5 * pl->ld));
+    CRBE_CUDA(cudaMemsetAsync(pl->meta, 0, sizeof(uint32_t) * pl->ld, ctx->stream));
     CRBE_CUDA(cudaMemsetAsync(ar.err, 0, sizeof(int), ctx->stream));
     k_advection_geom<<<crbe_grid_for(ctx, nt), CRBE_BLOCK, 0, ctx->stream>>>(points_d, tri_d, areas_d, nt, pl->geom);
     k_advection_meta<<<crbe_grid_for(ctx, ar.n), CRBE_BLOCK, 0, ctx->stream>>>(ar.n, ar.indptr, ar.indices, ar.is_bnd, edge_slots_d,
                                                                               scatter_pos_d, pl->meta, ar.err);
+    k_advection_slots<<<crbe_grid_for(ctx, pl->ld), CRBE_BLOCK, 0, ctx->stream>>>(ar.n, pl->ld, edge_slots_d, pl->slots);
+    k_advection_k5<<<crbe_grid_for(ctx, pl->ld), CRBE_BLOCK, 0, ctx->stream>>>(ar.n, pl->ld, ar.indptr, k_val_d, pl->k5);
     CRBE_KERNEL_CHECK();
-    ctx->launches += 2;
+    ctx->launches += 4;
     int err_h = 0;
     CRBE_CUDA(cudaMemcpyAsync(&err_h, ar.err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -337,6 +432,7 @@ extern "C" int crbe_solver_advection_plan(crbe_solver* solver, const double* poi
                        (err_h & 8) ? "scatter position outside its row; " : "");
         return CRBE_ERR_ARG;
     }
+    CRBE_CUDA(cudaFuncSetAttribute(t_update_system_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, ADV_STAGES * ADV_STAGE_BYTES));
     return CRBE_OK;
 }
 
@@ -352,15 +448,23 @@ extern "C" int crbe_solver_update_advection(crbe_solver* solver, const double* v
     AdvectionPlan* pl = (AdvectionPlan*)*ar.plan_slot;
     crbe_ctx* ctx = ar.ctx;
     // errors (missing / zero diagonal) land in the solver's device state and are reported by the next step's synchronisation
-    if (write_system) {
+    if (write_system && !write_rhs && !a_val_out_d && !s_val_out_d) {
+        // the per-step path: bulk-copy pipeline, one resident wave of CTAs walking the tiles grid-stride
+        const int64_t ntiles = pl->ld / CRBE_TILE;
+        int per_sm = 0;
+        CRBE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t_update_system_rows, CRBE_TILE, ADV_STAGES * ADV_STAGE_BYTES));
+        int64_t grid = (int64_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
+        if (grid > ntiles) grid = ntiles;
+        t_update_system_rows<<<(int)grid, CRBE_TILE, ADV_STAGES * ADV_STAGE_BYTES, ctx->stream>>>(
+            ar.n, ntiles, pl->k5, ar.mdiag, pl->slots, pl->meta, pl->geom, v_elem_d, vx, vy, coef, ar.ell_val, ar.mscale, ar.dscale, ar.err);
+    } else if (write_system) {
         k_update_system_rows<<<crbe_grid_for(ctx, ar.n), CRBE_BLOCK, 0, ctx->stream>>>(
-            ar.n, ar.indptr, pl->meta, (const int2*)pl->edge_slots, pl->geom, pl->k_val, ar.mdiag, v_elem_d, vx, vy, coef, ar.ell_val,
+            ar.n, ar.indptr, pl->meta, pl->slots, pl->geom, pl->k_val, ar.mdiag, v_elem_d, vx, vy, coef, ar.ell_val,
             ar.mscale, ar.dscale, write_rhs ? ar.rhs_val : nullptr, a_val_out_d, s_val_out_d, ar.err);
     } else {
         CRBE_REQUIRE(write_rhs, "nothing to write");
-        k_update_rhs_rows<<<crbe_grid_for(ctx, ar.n), CRBE_BLOCK, 0, ctx->stream>>>(ar.n, ar.indptr, pl->meta, (const int2*)pl->edge_slots,
-                                                                                   pl->geom, pl->k_val, ar.mdiag, v_elem_d, vx, vy, coef,
-                                                                                   ar.rhs_val);
+        k_update_rhs_rows<<<crbe_grid_for(ctx, ar.n), CRBE_BLOCK, 0, ctx->stream>>>(ar.n, ar.indptr, pl->meta, pl->slots, pl->geom, pl->k_val,
+                                                                                   ar.mdiag, v_elem_d, vx, vy, coef, ar.rhs_val);
     }
     CRBE_KERNEL_CHECK();
     ctx->launches += 1;

@@ -241,11 +241,15 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 }
 // spin until *flag has reached `epoch` (wrap-safe); gives up after `timeout` ticks so a dead peer cannot wedge the GPU
 __device__ __forceinline__ bool wait_epoch(const unsigned int* flag, unsigned int epoch, long long timeout) {
+    if ((int)(ld_acquire_sys(flag) - epoch) >= 0) return true;
     const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+    // hundreds of CTAs may poll the same word while the peer's store is on its way: relaxed loads with a short back-off,
+    // one acquire once the epoch is there
+    while ((int)(*(volatile const unsigned int*)flag - epoch) < 0) {
+        __nanosleep(64);
         if (clock64() - t0 > timeout) return false;
     }
-    return true;
+    return (int)(ld_acquire_sys(flag) - epoch) >= 0;
 }
 // a peer never signalled: record it, stop the solve (status 4; the host returns CRBE_ERR_COMM) -- see crbe_solver_p2p_error
 __device__ __forceinline__ void comm_dead(const CommArgs* __restrict__ ca, int* dstate, int what) {
@@ -439,21 +443,40 @@ __device__ __forceinline__ void halo_wait(int kind, const CommArgs* __restrict__
 
 // The same wait, taken by a tile kernel only when (and the first time) it is about to gather a tile that references a halo
 // column.  The tile is the same for all threads of the CTA, so the branch and its barrier are uniform.
+constexpr int HALO_FLAG_CAP = 2048;     // tiles per CTA whose flags are staged in shared memory (more: looked up in global memory)
+
 struct HaloGate {
     const CommArgs* ca;
+    const unsigned char* flags;     // per tile: references a halo column
+    unsigned char* staged;          // the flags of this CTA's tiles, in walk order (shared memory)
     int* dstate;
     int kind;
     bool open, off;
-    __device__ __forceinline__ HaloGate(const CommArgs* ca_, int kind_, int* dstate_)
-        : ca(ca_), dstate(dstate_), kind(kind_), open(false), off(ca_ == nullptr || ca_->world <= 1 || ca_->n_neigh == 0) {}
-    // returns whether the tile references halo entries (after having made sure they are there)
-    __device__ __forceinline__ bool before_gather(int64_t tile) {
-        if (off || !ca->tile_halo[tile]) return false;
-        if (!open) {
+    __device__ __forceinline__ HaloGate(const CommArgs* ca_, int kind_, int* dstate_, unsigned char* staged_)
+        : ca(ca_), flags(nullptr), staged(staged_), dstate(dstate_), kind(kind_), open(false),
+          off(ca_ == nullptr || ca_->world <= 1 || ca_->n_neigh == 0) {
+        if (!off) flags = ca_->tile_halo;
+    }
+    // Stage the flags of the tiles this CTA will walk (position m -> tile_of(m)) once, while the first bulk copies are in
+    // flight: the per-tile lookup then costs a shared-memory read instead of a dependent global load in front of the gathers.
+    template <class Pipe>
+    __device__ __forceinline__ void stage(const Pipe& pipe) {
+        if (off) return;
+        const int64_t cnt = pipe.count < HALO_FLAG_CAP ? pipe.count : HALO_FLAG_CAP;
+        for (int64_t m = threadIdx.x; m < cnt; m += blockDim.x) staged[m] = __ldg(flags + pipe.tile_of(m));
+        __syncthreads();
+    }
+    // does the tile at walk position m reference halo entries?
+    __device__ __forceinline__ bool needs(int64_t m, int64_t tile) const {
+        if (off) return false;
+        return m < HALO_FLAG_CAP ? staged[m] != 0 : __ldg(flags + tile) != 0;
+    }
+    // ... then make sure they are there (first such tile of this CTA only)
+    __device__ __forceinline__ void pass(bool need) {
+        if (need && !open) {
             halo_wait(kind, ca, dstate);
             open = true;
         }
-        return true;
     }
 };
 

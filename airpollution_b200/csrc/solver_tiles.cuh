@@ -28,35 +28,7 @@ constexpr int TILE_STAGES = CRBE_TILE_STAGES;     // init / residual kernels
 // smaller shared-memory footprint lets more CTAs share an SM (measured best of {2,3,4} stages x {prefetch on, off}).
 constexpr int SPMV_STAGES = CRBE_SPMV_STAGES;
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_addr(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completion counted on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
+#include "bulk_copy.cuh"
 
 // One stage holds, for the 256 rows of a tile:  val[4][256] f64 | vec[NVEC][256] f64 | col[4][256] IDX
 // IDX = int: absolute column indices.  IDX = short: column - row, 8 bytes per row less to stream (the neighbours of a CR
@@ -170,24 +142,29 @@ __device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, 
                                                    Body body) {
     const int tr = threadIdx.x;
     double g[4], gn[4];
-    auto gather = [&](int64_t m, double (&dst)[4]) {
-        // halo entries are written by the neighbours while this kernel runs: tiles that reference them wait for the flag
-        // first and read through L2 (no read-only path); all other tiles gather through L1 as on a single GPU
-        const bool halo_tile = gate.before_gather(pipe.tile_of(m));
+    // halo entries are written by the neighbours while this kernel runs: tiles that reference them wait for the flag
+    // first and read through L2 (no read-only path); all other tiles gather through L1 as on a single GPU.  Whether a
+    // tile is such a tile is looked up before waiting for its bulk copies, off the critical path of the gathers.
+    auto gather = [&](int64_t m, bool halo_tile, double (&dst)[4]) {
+        gate.pass(halo_tile);
+        if (halo_tile) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double* q = x + pipe.column(m, k, tr);
-            dst[k] = halo_tile ? __ldcg(q) : __ldg(q);
+            for (int k = 0; k < 4; ++k) dst[k] = __ldcg(x + pipe.column(m, k, tr));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = __ldg(x + pipe.column(m, k, tr));
         }
     };
     if (pipe.count > 0) {
+        const bool h0 = gate.needs(0, pipe.tile_of(0));
         pipe.wait(0);
-        gather(0, g);
+        gather(0, h0, g);
     }
     for (int64_t m = 0; m < pipe.count; ++m) {
         if (m + 1 < pipe.count) {
+            const bool h1 = gate.needs(m + 1, pipe.tile_of(m + 1));
             pipe.wait(m + 1);
-            gather(m + 1, gn);
+            gather(m + 1, h1, gn);
         }
         const int64_t row = pipe.tile_of(m) * CRBE_TILE + tr;
         if (row < n) {
@@ -232,7 +209,9 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int
             return;
         }
     }
-    HaloGate gate(ca, hkind, dstate);
+    __shared__ unsigned char hflags[HALO_FLAG_CAP];
+    HaloGate gate(ca, hkind, dstate, hflags);
+    gate.stage(pipe);
     double acc[1] = {0.0};
     tile_spmv_prefetch(pipe, p, n, gate, [&](int64_t m, int64_t row, int tr, double, double vi) {
         v[row] = vi;
@@ -258,7 +237,9 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int
     pipe.vec[0] = s;
     pipe.vec[1] = rh;
     pipe.start(tile_smem, bars, ntiles, rot);
-    HaloGate gate(ca, HK_S, dstate);
+    __shared__ unsigned char hflags[HALO_FLAG_CAP];
+    HaloGate gate(ca, HK_S, dstate, hflags);
+    gate.stage(pipe);
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     tile_spmv_prefetch(pipe, s, n, gate, [&](int64_t m, int64_t row, int tr, double si, double ti) {
         const double rhi = pipe.svec(m, 1)[tr];
@@ -299,7 +280,9 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
     pipe.vec[0] = mscale;
     pipe.vec[1] = xb;     // previous solution u^n (right-hand side); x is the initial guess, possibly extrapolated
     pipe.start(tile_smem, bars, ntiles, rot);
-    HaloGate gate(ca, HK_X, dstate);
+    __shared__ unsigned char hflags[HALO_FLAG_CAP];
+    HaloGate gate(ca, HK_X, dstate, hflags);
+    gate.stage(pipe);
     const int tr = threadIdx.x;
     double acc[3] = {0.0, 0.0, 0.0};
     for (int64_t m = 0; m < pipe.count; ++m) {
@@ -310,7 +293,8 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
             xi = x[row];
             if (src) extra = dscale[row] * dt * src[row];
         }
-        const bool halo_tile = gate.before_gather(tile);
+        const bool halo_tile = gate.needs(m, tile);
+        gate.pass(halo_tile);
         pipe.wait(m);
         if (row < n) {
             const double bi = fma(pipe.svec(m, 0)[tr], pipe.svec(m, 1)[tr], extra);
@@ -354,7 +338,9 @@ __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntile
     pipe.vec[0] = BE ? rhs.mscale : rhs.b;
     if (BE) pipe.vec[BE ? 1 : 0] = rhs.u;
     pipe.start(tile_smem, bars, ntiles, rot);
-    HaloGate gate(ca, HK_X, dstate);
+    __shared__ unsigned char hflags[HALO_FLAG_CAP];
+    HaloGate gate(ca, HK_X, dstate, hflags);
+    gate.stage(pipe);
     const int tr = threadIdx.x;
     double acc[1] = {0.0};
     for (int64_t m = 0; m < pipe.count; ++m) {
@@ -365,7 +351,8 @@ __global__ void __launch_bounds__(CRBE_TILE) t_residual(int64_t n, int64_t ntile
             xi = x[row];
             if (BE && rhs.src) extra = rhs.dscale[row] * rhs.dt * rhs.src[row];
         }
-        const bool halo_tile = gate.before_gather(tile);
+        const bool halo_tile = gate.needs(m, tile);
+        gate.pass(halo_tile);
         pipe.wait(m);
         if (row < n) {
             const double ax = tile_row(pipe, m, tr, xi, [&](int j) { return halo_tile ? __ldcg(x + j) : __ldg(x + j); });
