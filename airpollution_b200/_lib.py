@@ -76,6 +76,7 @@ _SIGNATURES = {
     "crbe_spmv_csr": [vp, C.c_int64, vp, vp, vp, vp, vp],
     "crbe_dot": [vp, C.c_int64, vp, vp, c_f64p],
     "crbe_errors": [vp, C.c_int64, vp, vp, c_f64p],
+    "crbe_error_sums": [vp, C.c_int64, vp, vp, c_f64p],
     "crbe_moments": [vp, C.c_int64, vp, vp, vp, c_f64p],
     "crbe_solver_mass_diagonal": [vp, C.POINTER(vp)],
     "crbe_solver_create": [vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, C.POINTER(vp)],

@@ -213,6 +213,13 @@ class BESCRFEM:
                         then no longer travel over PCIe one by one while a solution row is being downloaded).
     ``predict``         let the update kernel skip the stores of r and p in the iteration it predicts to be the last of a
                         solve (default; same solution bits, 24 bytes per row less).
+    ``n_gpus``          ``None`` / 1: this GPU.  N > 1 or ``"auto"``: the row-block partitioned solve over the N GPUs of the
+                        running ``torch.distributed`` job (one process per GPU, e.g. under torchrun; every rank constructs
+                        the same ``MeshData`` and ``BESCRFEM`` and calls ``solve()``).  The DOFs are split geometrically,
+                        each rank assembles and solves its rows (halo exchange and dot products over NVLink peer memory),
+                        keeps its columns of the history in its own pinned memory (``solutions_local``,
+                        ``local_dofs``) and ``compute_errors`` reduces over the ranks.  ``solutions`` / ``u_prev`` are
+                        gathered to the reference's full nt x N layout on first access (every rank gets a copy).
     ``progress``        tqdm bar like the reference (default: only for nt*N < 2e7).
     ``velocity_field``  ``f(centroids[Nt,2], t) -> v[Nt,2]`` (torch tensors on the device): a velocity that varies in
                         space and time, one value per triangle, re-assembled every step (BASELINE config 5).  The
@@ -221,7 +228,7 @@ class BESCRFEM:
 
     def __init__(self, domain, problem, mesh_data, element, time_scheme_order=1, *, rtol=1e-13,
                  max_iterations=10000, history="all", tma=True, verify="auto", extrapolate=True,
-                 graph=True, index16=True, progress=None, velocity_field=None, predict=True):
+                 graph=True, index16=True, progress=None, velocity_field=None, predict=True, n_gpus=None):
         self.domain = domain
         self.problem = problem
         self.mesh_data = mesh_data
@@ -240,6 +247,8 @@ class BESCRFEM:
         self.predict = predict
         self.progress = progress
         self.velocity_field = velocity_field
+        self.n_gpus = n_gpus
+        self._part = None
         self._rt = mesh_data._rt
         self._dev = {}
         self._solver = None
@@ -501,7 +510,69 @@ class BESCRFEM:
             rows.append(n_steps - 1)
         return rows
 
+    # ---- the partitioned solve behind the same API ---------------------------------
+    def _world(self):
+        """Number of ranks the solve is split over (1: this GPU only)."""
+        if self.n_gpus in (None, 1):
+            return 1
+        import torch.distributed as dist
+        if not dist.is_available() or not dist.is_initialized():
+            raise RuntimeError("n_gpus > 1 needs one process per GPU with torch.distributed initialised (e.g. torchrun)")
+        world = dist.get_world_size()
+        if self.n_gpus != "auto" and int(self.n_gpus) != world:
+            raise ValueError(f"n_gpus={self.n_gpus} but the torch.distributed job has {world} ranks")
+        return world
+
+    def __getattr__(self, name):
+        # partitioned solve: the reference's full-size attributes are assembled from the ranks' blocks on first access
+        if name in ("solutions", "u_prev") and self.__dict__.get("_part_done"):
+            self._gather_partitioned()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    def _gather_partitioned(self):
+        import torch.distributed as dist
+        order = self._part_order                               # partition id -> reference DOF id
+        blocks = [None] * dist.get_world_size()
+        dist.all_gather_object(blocks, (self.solutions_local, self._u_local))
+        full = np.empty((self.solutions_local.shape[0], len(order)))
+        full[:, order] = np.concatenate([b[0] for b in blocks], axis=1)
+        u = np.empty(len(order))
+        u[order] = np.concatenate([b[1] for b in blocks])
+        self.__dict__["solutions"] = full
+        self.__dict__["u_prev"] = u
+
+    def _solve_partitioned(self):
+        """``solve()`` over the GPUs of the torch.distributed job: the same loop (crbe.py:406-433) on this rank's rows."""
+        from .distributed import PartitionedCRBE
+        md, rt = self.mesh_data, self._rt
+        rt.bind_stream()
+        self._coef()                                           # ValueError for an unsupported order, like crbe.py:362
+        if self.velocity_field is not None:
+            raise NotImplementedError("velocity_field is a single-GPU extension")
+        n_steps = md.nt
+        part = self._part = PartitionedCRBE(mesh=md.mesh, mesh_data=md, domain=self.domain, problem=self.problem, nt=md.nt,
+                                            order=self.time_scheme_order, device=rt.device, rtol=self.rtol,
+                                            max_iterations=self.max_iterations, tma=self.tma, verify=self.verify,
+                                            extrapolate=self.extrapolate, graph=self.graph, predict=self.predict,
+                                            index16=self.index16)
+        self.local_dofs = part.partition_order[part.d0:part.d1]        # reference DOF ids of this rank's columns
+        self._part_order = part.partition_order
+        self.solutions_local = part.solve(history=self.history, history_rows=self._history_rows(n_steps))
+        self.solve_time = part.solve_time
+        self.step_info = list(part.step_info)
+        self._u_local = part.u[:part.n_own].cpu().numpy().copy()
+        self._dev["u"] = part.u[:part.n_own]
+        self.__dict__.pop("solutions", None)
+        self.__dict__.pop("u_prev", None)
+        self._part_done = True
+        if part.rank == 0:
+            print(f"Solve completed in {self.solve_time:.2f}s")
+        return self.solutions_local
+
     def solve(self):
+        if self._world() > 1:
+            return self._solve_partitioned()
         md, rt = self.mesh_data, self._rt
         rt.bind_stream()
         # 1. initial condition and storage (crbe.py:408-412)
@@ -681,6 +752,21 @@ class BESCRFEM:
         (unweighted discrete norms, crbe.py:447-453), reduced on the device."""
         md, rt = self.mesh_data, self._rt
         rt.bind_stream()
+        if self.__dict__.get("_part_done"):
+            # partitioned solve: this rank's block, sums added / maximum taken over the ranks (torch.distributed allreduce)
+            import torch.distributed as dist
+            part = self._part
+            mid = part.midpoints.cpu().numpy()
+            u_exact = rt.upload(np.asarray(analytical_sol_fn(np.hstack([mid, np.full((len(mid), 1), self.domain.T)])), dtype=np.float64))
+            u_num = rt.upload(np.ascontiguousarray(self.solutions_local[-1, :]))
+            out = (C.c_double * 3)()
+            rt.call("crbe_error_sums", rt.ctx, part.n_own, ptr(u_exact), ptr(u_num), out)
+            sums = torch.tensor([out[0], out[1]], dtype=torch.float64, device=rt.device)
+            emax = torch.tensor([out[2]], dtype=torch.float64, device=rt.device)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+            l2 = float(torch.sqrt(sums[0]))
+            return np.float64(l2 / float(torch.sqrt(sums[1]))), np.float64(l2), np.float64(float(emax[0]))
         midpoints = md.midpoints
         xyt = np.hstack([midpoints, np.full((midpoints.shape[0], 1), self.domain.T)])
         u_exact = rt.upload(np.asarray(analytical_sol_fn(xyt), dtype=np.float64))

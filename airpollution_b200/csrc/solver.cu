@@ -116,6 +116,8 @@ struct crbe_solver {
     int gt_pv = 1, gt_st = 1, gt_init = 1, gt_res = 1, gt_res_be = 1;   // tile (bulk-copy) kernels
     int gs_pv = 1, gs_st = 1, gs_init = 1, gs_res = 1, gs_res_be = 1;
     int gt_pv0 = 1, gs_pv0 = 1;                          // first-iteration SpMV (one vector stream)   // ... their 16-bit-offset variants (smaller stages, maybe more CTAs per SM)
+    // the same for the instantiations of the partitioned solver with the peer-memory transport (halo gate, totals at the head)
+    int pt_pv = 1, pt_pv0 = 1, pt_st = 1, pt_init = 1, ps_pv = 1, ps_pv0 = 1, ps_st = 1, ps_init = 1;
     int64_t ntiles = 0;
     // row-block partition (world > 1): this solver holds the rows [0, n) of its rank; gathered vectors carry the
     // halo entries (values owned by other ranks) behind the padded owned part, at [ld, ld + n_halo)
@@ -479,6 +481,22 @@ struct HaloGate {
         }
     }
 };
+
+// single-GPU instantiations of the tile kernels carry none of this: a gate that is never there
+struct NoGate {
+    template <class... A>
+    __device__ __forceinline__ NoGate(A...) {}
+    template <class Pipe>
+    __device__ __forceinline__ void stage(const Pipe&) {}
+    __device__ __forceinline__ bool needs(int64_t, int64_t) const { return false; }
+    __device__ __forceinline__ void pass(bool) {}
+};
+template <bool PEER>
+struct GateSelect { typedef NoGate type; };
+template <>
+struct GateSelect<true> { typedef HaloGate type; };
+template <bool PEER>
+using GateFor = typename GateSelect<PEER>::type;
 
 #define ROW_LOOP(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
 
@@ -954,6 +972,23 @@ extern "C" int crbe_errors(crbe_ctx* ctx, int64_t n, const double* u_exact_d, co
     return CRBE_OK;
 }
 
+// the raw sums behind crbe_errors, for callers that combine them over several GPUs: out3_h = sum error^2, sum u_exact^2, max error
+extern "C" int crbe_error_sums(crbe_ctx* ctx, int64_t n, const double* u_exact_d, const double* u_num_d, double* out3_h) {
+    CRBE_REQUIRE(ctx && out3_h && n >= 0 && (n == 0 || (u_exact_d && u_num_d)), "bad argument");
+    out3_h[0] = out3_h[1] = out3_h[2] = 0.0;
+    if (n == 0) return CRBE_OK;
+    unsigned long long* max_bits = (unsigned long long*)(ctx->dev_scalars + 2);
+    CRBE_CUDA(cudaMemsetAsync(max_bits, 0, sizeof(unsigned long long), ctx->stream));
+    k_errors<<<crbe_grid_for(ctx, n), CRBE_BLOCK, 0, ctx->stream>>>(n, u_exact_d, u_num_d, ctx->dev_scalars, max_bits, ctx->partials,
+                                                                   ctx->counter, nullptr);
+    CRBE_KERNEL_CHECK();
+    ctx->launches += 1;
+    CRBE_CUDA(cudaMemcpyAsync(ctx->host_scalars, ctx->dev_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 3; ++k) out3_h[k] = ctx->host_scalars[k];
+    return CRBE_OK;
+}
+
 // ---------------------------------------------------------------- plume diagnostics
 // The analysis scripts of the reference integrate the solution triangle by triangle with the CR quadrature
 // (area/3 per edge midpoint): mass, first and second moments, peak (scripts/problem3_comprehensive_analysis2.py:60-302).
@@ -1190,18 +1225,28 @@ static int solver_init(crbe_solver* s, crbe_ctx* ctx, crbe_comm* comm, int64_t n
         s->g_spmv = crbe_persistent_grid(ctx, k_spmv_csr, n);
         // bulk-copy kernels: opt in to their dynamic shared memory, then size one resident wave over the tiles
         s->ntiles = s->ld / CRBE_TILE;
-        CRBE_CHECK(tile_grid(ctx, t_pv<int, false>, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_pv));
-        CRBE_CHECK(tile_grid(ctx, t_pv<int, true>, TilePipe<1, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_pv0));
-        CRBE_CHECK(tile_grid(ctx, t_st<int>, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_st));
-        CRBE_CHECK(tile_grid(ctx, t_init_be<int>, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_init));
+        CRBE_CHECK(tile_grid(ctx, t_pv<int, false, false>, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_pv));
+        CRBE_CHECK(tile_grid(ctx, t_pv<int, true, false>, TilePipe<1, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_pv0));
+        CRBE_CHECK(tile_grid(ctx, t_st<int, false>, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_st));
+        CRBE_CHECK(tile_grid(ctx, t_init_be<int, false>, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_init));
         CRBE_CHECK(tile_grid(ctx, t_residual<int, false>, TilePipe<1, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_res));
         CRBE_CHECK(tile_grid(ctx, t_residual<int, true>, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->gt_res_be));
-        CRBE_CHECK(tile_grid(ctx, t_pv<short, false>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_pv));
-        CRBE_CHECK(tile_grid(ctx, t_pv<short, true>, TilePipe<1, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_pv0));
-        CRBE_CHECK(tile_grid(ctx, t_st<short>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_st));
-        CRBE_CHECK(tile_grid(ctx, t_init_be<short>, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_init));
+        CRBE_CHECK(tile_grid(ctx, t_pv<short, false, false>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_pv));
+        CRBE_CHECK(tile_grid(ctx, t_pv<short, true, false>, TilePipe<1, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_pv0));
+        CRBE_CHECK(tile_grid(ctx, t_st<short, false>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_st));
+        CRBE_CHECK(tile_grid(ctx, t_init_be<short, false>, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_init));
         CRBE_CHECK(tile_grid(ctx, t_residual<short, false>, TilePipe<1, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_res));
         CRBE_CHECK(tile_grid(ctx, t_residual<short, true>, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->gs_res_be));
+        if (s->world > 1) {
+            CRBE_CHECK(tile_grid(ctx, t_pv<int, false, true>, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->pt_pv));
+            CRBE_CHECK(tile_grid(ctx, t_pv<int, true, true>, TilePipe<1, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->pt_pv0));
+            CRBE_CHECK(tile_grid(ctx, t_st<int, true>, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, s->ntiles, &s->pt_st));
+            CRBE_CHECK(tile_grid(ctx, t_init_be<int, true>, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, s->ntiles, &s->pt_init));
+            CRBE_CHECK(tile_grid(ctx, t_pv<short, false, true>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->ps_pv));
+            CRBE_CHECK(tile_grid(ctx, t_pv<short, true, true>, TilePipe<1, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->ps_pv0));
+            CRBE_CHECK(tile_grid(ctx, t_st<short, true>, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, s->ntiles, &s->ps_st));
+            CRBE_CHECK(tile_grid(ctx, t_init_be<short, true>, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, s->ntiles, &s->ps_init));
+        }
     }
     CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
     return CRBE_OK;
@@ -1574,18 +1619,27 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
     // p is up to date (written by the init / restart kernel at k = 0, by k_xrp afterwards), its halo refreshed
     CRBE_CHECK(halo_exchange(s, via_rh ? s->rh : p, launches));
     const bool i16 = s->idx16 && !(s->flags & CRBE_SOLVER_INDEX32);
-#define CRBE_TPV(IDX, FIRST, GRID, NV, COL, COL32)                                                                                      \
-    PROF_LAUNCH(PK_PV, k, (t_pv<IDX, FIRST><<<GRID, CRBE_TILE, TilePipe<NV, SPMV_STAGES, IDX>::SMEM_BYTES, st>>>(                         \
+#define CRBE_TPV(IDX, FIRST, PEER, GRID, NV, COL, COL32)                                                                                \
+    PROF_LAUNCH(PK_PV, k, (t_pv<IDX, FIRST, PEER><<<GRID, CRBE_TILE, TilePipe<NV, SPMV_STAGES, IDX>::SMEM_BYTES, st>>>(                   \
                               s->n, s->ntiles, s->rot, rtol2, s->ell_val, COL, COL32, p_in, v, s->rh, s->sums, s->dots, s->dstate, ctx->partials, \
                               ctx->counter, s->d_comm, hkind)))
-    if (tma && i16 && first)
-        CRBE_TPV(short, true, s->gs_pv0, 1, s->ell_col16, s->ell_col);
+    const bool peer = s->p2p;     // instantiations with the halo gate and the totals taken at the kernel head
+    if (tma && i16 && first && peer)
+        CRBE_TPV(short, true, true, s->ps_pv0, 1, s->ell_col16, s->ell_col);
+    else if (tma && i16 && first)
+        CRBE_TPV(short, true, false, s->gs_pv0, 1, s->ell_col16, s->ell_col);
+    else if (tma && i16 && peer)
+        CRBE_TPV(short, false, true, s->ps_pv, 2, s->ell_col16, s->ell_col);
     else if (tma && i16)
-        CRBE_TPV(short, false, s->gs_pv, 2, s->ell_col16, s->ell_col);
+        CRBE_TPV(short, false, false, s->gs_pv, 2, s->ell_col16, s->ell_col);
+    else if (tma && first && peer)
+        CRBE_TPV(int, true, true, s->pt_pv0, 1, s->ell_col, nullptr);
     else if (tma && first)
-        CRBE_TPV(int, true, s->gt_pv0, 1, s->ell_col, nullptr);
+        CRBE_TPV(int, true, false, s->gt_pv0, 1, s->ell_col, nullptr);
+    else if (tma && peer)
+        CRBE_TPV(int, false, true, s->pt_pv, 2, s->ell_col, nullptr);
     else if (tma)
-        CRBE_TPV(int, false, s->gt_pv, 2, s->ell_col, nullptr);
+        CRBE_TPV(int, false, false, s->gt_pv, 2, s->ell_col, nullptr);
     else
         PROF_LAUNCH(PK_PV, k, (k_pv<<<s->g_pv, CRBE_BLOCK, 0, st>>>(s->n, s->ld, rtol2, s->ell_val, s->ell_col, p_in, v, s->rh, s->sums, s->dots,
                                                                  s->dstate, ctx->partials, ctx->counter, s->d_comm, hkind)));
@@ -1593,15 +1647,20 @@ static inline int launch_iteration(crbe_solver* s, int k, double* x, int* launch
     CRBE_CHECK(reduce_dots(s, S_RHV, 1, S_RHV, -1, -1, -1, launches));
     PROF_LAUNCH(PK_S, k, (k_s<<<s->g_vec, CRBE_BLOCK, 0, st>>>(s->n, k, rtol2, r_in, v, s->s, s->sums, s->dstate, s->d_comm)));
     CRBE_CHECK(halo_exchange(s, s->s, launches));
-    if (tma && i16)
-        PROF_LAUNCH(PK_ST, k, (t_st<short><<<s->gs_st, CRBE_TILE, TilePipe<2, SPMV_STAGES, short>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, s->rot, rtol2, s->ell_val, s->ell_col16, s->ell_col, s->s, s->t, s->rh, s->sums, s->dots, s->dstate,
-                                  ctx->partials, ctx->counter, s->d_comm)));
+#define CRBE_TST(IDX, PEER, GRID, COL, COL32)                                                                                            \
+    PROF_LAUNCH(PK_ST, k, (t_st<IDX, PEER><<<GRID, CRBE_TILE, TilePipe<2, SPMV_STAGES, IDX>::SMEM_BYTES, st>>>(                              \
+                              s->n, s->ntiles, s->rot, rtol2, s->ell_val, COL, COL32, s->s, s->t, s->rh, s->sums, s->dots, s->dstate, ctx->partials, \
+                              ctx->counter, s->d_comm)))
+    if (tma && i16 && peer)
+        CRBE_TST(short, true, s->ps_st, s->ell_col16, s->ell_col);
+    else if (tma && i16)
+        CRBE_TST(short, false, s->gs_st, s->ell_col16, s->ell_col);
+    else if (tma && peer)
+        CRBE_TST(int, true, s->pt_st, s->ell_col, nullptr);
     else if (tma)
-        PROF_LAUNCH(PK_ST, k, (t_st<int><<<s->gt_st, CRBE_TILE, TilePipe<2, SPMV_STAGES, int>::SMEM_BYTES, st>>>(
-                                  s->n, s->ntiles, s->rot, rtol2, s->ell_val, s->ell_col, nullptr, s->s, s->t, s->rh, s->sums, s->dots, s->dstate,
-                                  ctx->partials, ctx->counter, s->d_comm)));
+        CRBE_TST(int, false, s->gt_st, s->ell_col, nullptr);
     else
+#undef CRBE_TST
         PROF_LAUNCH(PK_ST, k, (k_st<<<s->g_st, CRBE_BLOCK, 0, st>>>(s->n, s->ld, rtol2, s->ell_val, s->ell_col, s->s, s->t, s->rh, s->sums,
                                                                  s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
     CRBE_CHECK(reduce_dots(s, S_TS, 5, S_TS, S_TT, S_RS, S_RT, launches, S_SS));
@@ -1921,15 +1980,20 @@ static int enqueue_step_head(crbe_solver* s, const StepPlan& pl, const double* s
         PROF_LAUNCH(PK_INIT, -1, (k_init<1><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, s->tmp, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, s->b, r_w, s->rh, p_w, s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));
+#define CRBE_TINIT(IDX, PEER, GRID, COL, COL32)                                                                                          \
+    PROF_LAUNCH(PK_INIT, -1, (t_init_be<IDX, PEER><<<GRID, CRBE_TILE, TilePipe<2, TILE_STAGES, IDX>::SMEM_BYTES, st>>>(                      \
+                                 s->n, s->ntiles, s->rot, s->ell_val, COL, COL32, x, xb, source_d, dt, s->mscale, s->dscale, b_w, r_w, s->rh, p_w, \
+                                 s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)))
+    else if ((s->flags & CRBE_SOLVER_TMA) && i16 && s->p2p)
+        CRBE_TINIT(short, true, s->ps_init, s->ell_col16, s->ell_col);
     else if ((s->flags & CRBE_SOLVER_TMA) && i16)
-        PROF_LAUNCH(PK_INIT, -1, (t_init_be<short><<<s->gs_init, CRBE_TILE, TilePipe<2, TILE_STAGES, short>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->rot, s->ell_val, s->ell_col16, s->ell_col, x, xb, source_d, dt, s->mscale, s->dscale, b_w, r_w,
-                                     s->rh, p_w, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
+        CRBE_TINIT(short, false, s->gs_init, s->ell_col16, s->ell_col);
+    else if ((s->flags & CRBE_SOLVER_TMA) && s->p2p)
+        CRBE_TINIT(int, true, s->pt_init, s->ell_col, nullptr);
     else if (s->flags & CRBE_SOLVER_TMA)
-        PROF_LAUNCH(PK_INIT, -1, (t_init_be<int><<<s->gt_init, CRBE_TILE, TilePipe<2, TILE_STAGES, int>::SMEM_BYTES, st>>>(
-                                     s->n, s->ntiles, s->rot, s->ell_val, s->ell_col, nullptr, x, xb, source_d, dt, s->mscale, s->dscale, b_w, r_w,
-                                     s->rh, p_w, s->sums, s->dots, s->dstate, ctx->partials, ctx->counter, s->d_comm)));
+        CRBE_TINIT(int, false, s->gt_init, s->ell_col, nullptr);
     else
+#undef CRBE_TINIT
         PROF_LAUNCH(PK_INIT, -1, (k_init<0><<<s->g_init, CRBE_BLOCK, 0, st>>>(s->n, s->ld, s->ell_val, s->ell_col, x, xb, source_d, dt,
                                                                              s->mscale, s->dscale, s->is_bnd, b_w, r_w, s->rh, p_w, s->sums, s->dots,
                                                                              s->dstate, ctx->partials, ctx->counter, s->d_comm)));

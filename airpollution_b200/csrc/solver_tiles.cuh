@@ -137,8 +137,8 @@ __device__ __forceinline__ double tile_row(const Pipe& pipe, int64_t m, int r, d
 // SpMV over the tiles of this CTA with the gathers software-pipelined one tile ahead: the x[col] loads of tile m+1
 // are issued before tile m is finished, so gather latency overlaps arithmetic, stores and the barrier.
 // body(m, row, tr, own, y) consumes the row result y = own + sum a_k x[col_k]; own = staged vector 0.
-template <int NV, int ST, class IDX, class Body>
-__device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, const double* __restrict__ x, int64_t n, HaloGate& gate,
+template <int NV, int ST, class IDX, class Gate, class Body>
+__device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, const double* __restrict__ x, int64_t n, Gate& gate,
                                                    Body body) {
     const int tr = threadIdx.x;
     double g[4], gn[4];
@@ -184,15 +184,15 @@ __device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, 
 // ---- v = A p, (r^, v) ------------------------------------------------------------------------------------
 // FIRST: the first iteration after an init / restart, where p = r^ = r0: one vector stream instead of two.
 // hkind: which gathered vector p is (HK_P, or HK_RH in the first iteration: its halo flag).
-template <class IDX, bool FIRST>
+template <class IDX, bool FIRST, bool PEER>
 __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int64_t rot, double rtol2, const double* __restrict__ eval,
                                                   const IDX* __restrict__ ecol, const int* __restrict__ ecol32, const double* __restrict__ p, double* __restrict__ v,
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter, const CommArgs* __restrict__ ca, int hkind) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ uint64_t bars[SPMV_STAGES];
-    __shared__ double S_sh[CRBE_NSUMS];
-    const bool peer = ca != nullptr && ca->world > 1;
+    __shared__ double S_sh[PEER ? CRBE_NSUMS : 1];
+    constexpr bool peer = PEER;       // PEER: partitioned solve with the peer-memory transport (ca != nullptr, world > 1)
     if (!peer && solver_idle(sums, dstate, rtol2)) return;
     TilePipe<FIRST ? 1 : 2, SPMV_STAGES, IDX> pipe;
     pipe.eval = eval;
@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int
             return;
         }
     }
-    __shared__ unsigned char hflags[HALO_FLAG_CAP];
-    HaloGate gate(ca, hkind, dstate, hflags);
+    __shared__ unsigned char hflags[PEER ? HALO_FLAG_CAP : 1];
+    GateFor<PEER> gate(ca, hkind, dstate, hflags);
     gate.stage(pipe);
     double acc[1] = {0.0};
     tile_spmv_prefetch(pipe, p, n, gate, [&](int64_t m, int64_t row, int tr, double, double vi) {
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int
 }
 
 // ---- t = A s, (t,s), (t,t), (r^,s), (r^,t), (s,s) ----------------------------------------------------------
-template <class IDX>
+template <class IDX, bool PEER>
 __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int64_t rot, double rtol2, const double* __restrict__ eval,
                                                   const IDX* __restrict__ ecol, const int* __restrict__ ecol32, const double* __restrict__ s, double* __restrict__ t,
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int
     pipe.vec[0] = s;
     pipe.vec[1] = rh;
     pipe.start(tile_smem, bars, ntiles, rot);
-    __shared__ unsigned char hflags[HALO_FLAG_CAP];
-    HaloGate gate(ca, HK_S, dstate, hflags);
+    __shared__ unsigned char hflags[PEER ? HALO_FLAG_CAP : 1];
+    GateFor<PEER> gate(ca, HK_S, dstate, hflags);
     gate.stage(pipe);
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     tile_spmv_prefetch(pipe, s, n, gate, [&](int64_t m, int64_t row, int tr, double si, double ti) {
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_st(int64_t n, int64_t ntiles, int
 
 // ---- Backward-Euler step start: b = mscale*u^n (+ dscale*dt*f), r^ = b - A x0 (= r = p), (b,b), (r,r) --------
 // b is not stored unless asked for (see crbe_solver::be_u); xslot: which ring vector x is (peer-memory transport).
-template <class IDX>
+template <class IDX, bool PEER>
 __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles, int64_t rot, const double* __restrict__ eval, const IDX* __restrict__ ecol, const int* __restrict__ ecol32,
                                                        const double* __restrict__ x, const double* __restrict__ xb,
                                                        const double* __restrict__ src, double dt,
@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
     pipe.vec[0] = mscale;
     pipe.vec[1] = xb;     // previous solution u^n (right-hand side); x is the initial guess, possibly extrapolated
     pipe.start(tile_smem, bars, ntiles, rot);
-    __shared__ unsigned char hflags[HALO_FLAG_CAP];
-    HaloGate gate(ca, HK_X, dstate, hflags);
+    __shared__ unsigned char hflags[PEER ? HALO_FLAG_CAP : 1];
+    GateFor<PEER> gate(ca, HK_X, dstate, hflags);
     gate.stage(pipe);
     const int tr = threadIdx.x;
     double acc[3] = {0.0, 0.0, 0.0};
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
         }
         pipe.release(m);
     }
-    halo_push_tail(rh, HK_RH, 0, ca);       // peer-memory transport: the first SpMV gathers r^ (= p), halo included
+    if (PEER) halo_push_tail(rh, HK_RH, 0, ca);       // peer-memory transport: the first SpMV gathers r^ (= p), halo included
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
     grid_sum_last<3>(acc, partials, counter, out, ca, DK_INIT);

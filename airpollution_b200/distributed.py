@@ -123,6 +123,42 @@ def rcb_partition(midpoints, world):
 
 
 # --------------------------------------------------------------------------
+# the part of an arbitrary mesh one rank assembles: its rows plus one ghost layer of triangles
+# --------------------------------------------------------------------------
+def submesh_of_rows(points, triangles, t2s, owned):
+    """Every triangle that touches an owned edge (``owned``: bool per global edge), as a stand-alone mesh.
+
+    Returns ``(local_points, local_triangles, tri_ids)``: the selected triangles in their global order with vertices
+    renumbered compactly (ascending global id), and their global indices.  The rows of the owned edges assembled on this
+    mesh are complete (an edge's <= 2 triangles are both in); rows of the other edges are not and are never used.
+    Works on numpy arrays or torch tensors (any device)."""
+    import numpy as _np
+    if isinstance(t2s, torch.Tensor):
+        sel = owned[t2s.long()].any(dim=1)
+        tri_ids = torch.nonzero(sel).squeeze(1)
+        tri_g = triangles[tri_ids].long()
+        verts, inv = torch.unique(tri_g.reshape(-1), return_inverse=True)     # sorted ascending
+        return points[verts], inv.reshape(-1, 3), tri_ids
+    sel = owned[t2s].any(axis=1)
+    tri_ids = _np.nonzero(sel)[0]
+    tri_g = triangles[tri_ids]
+    verts, inv = _np.unique(tri_g.reshape(-1), return_inverse=True)
+    return points[verts], inv.reshape(-1, 3), tri_ids
+
+
+def local_to_global_edges(t2s_local, t2s_global_rows, n_local):
+    """Global edge id of every edge of a sub-mesh: triangle k of the sub-mesh is global triangle tri_ids[k] with the same
+    vertex order, so its local edge a (opposite vertex a, crbe.py:117) is the same edge as the global triangle's."""
+    if isinstance(t2s_local, torch.Tensor):
+        out = torch.empty(n_local, dtype=torch.int64, device=t2s_local.device)
+        out[t2s_local.long().reshape(-1)] = t2s_global_rows.long().reshape(-1)
+        return out
+    out = np.empty(n_local, dtype=np.int64)
+    out[t2s_local.reshape(-1)] = t2s_global_rows.reshape(-1)
+    return out
+
+
+# --------------------------------------------------------------------------
 # localisation of the owned rows: global column ids -> [owned | halo]
 # --------------------------------------------------------------------------
 def localize_columns(cols_global, d0, d1):
@@ -203,12 +239,14 @@ class PartitionedCRBE:
     """Backward-Euler / Crank-Nicolson stepping of a structured ``Workload``
     (``airpollution_b200.workloads``) split into strips of cell rows, or of an
     arbitrary mesh (``mesh=``) partitioned geometrically by recursive coordinate
-    bisection of the edge midpoints (the global system is assembled redundantly
-    on every rank in that case; each rank keeps the rows of its part)."""
+    bisection of the edge midpoints.  Either way a rank meshes and assembles only
+    its own rows plus one ghost layer of triangles (the global ``MeshData`` --
+    numbering and midpoints, no matrices -- is still computed on every rank for an
+    arbitrary mesh; pass ``mesh_data=`` to reuse one that exists)."""
 
-    def __init__(self, workload=None, *, mesh=None, domain=None, problem=None, nt=None, order=1, rank=None, world=None,
-                 device=None, comm=None, rtol=1e-13, max_iterations=10000, tma=True, verify="auto", p2p=None,
-                 extrapolate=True, graph=True, predict=True):
+    def __init__(self, workload=None, *, mesh=None, mesh_data=None, domain=None, problem=None, nt=None, order=1, rank=None,
+                 world=None, device=None, comm=None, rtol=1e-13, max_iterations=10000, tma=True, verify="auto", p2p=None,
+                 extrapolate=True, graph=True, predict=True, index16=True):
         from . import _lib, crbe
         from .runtime import Runtime, ptr
         import os
@@ -232,23 +270,36 @@ class PartitionedCRBE:
             md = crbe.MeshData(local_mesh, domain, nt, device=rt.device)
             gid = structured_global_dof(nx, md._dev["segments"], j0)
             self.n_global = structured_total_dofs(nx, ny)
+            self.partition_order = None                        # strips: the partition's numbering is the reference's
         else:
             # arbitrary mesh: geometric partition (recursive coordinate bisection of the edge midpoints); the solver
             # works in the partition's numbering (part after part), results are mapped back to the reference's
-            md = crbe.MeshData(mesh, domain, nt, device=rt.device)
-            n = md.number_of_segments
-            part_order, self.offsets = rcb_partition(md.midpoints, self.world)
+            mdg = mesh_data if mesh_data is not None else crbe.MeshData(mesh, domain, nt, device=rt.device)
+            n = mdg.number_of_segments
+            part_order, self.offsets = rcb_partition(mdg.midpoints, self.world)
             self.partition_order = part_order                  # partition id -> reference DOF id
             gid_np = np.empty(n, dtype=np.int64)
             gid_np[part_order] = np.arange(n, dtype=np.int64)  # reference DOF id -> partition id
-            gid = torch.from_numpy(gid_np).to(rt.device)
+            gid_of_ref = torch.from_numpy(gid_np).to(rt.device)
             self.n_global = n
+            # this rank's sub-mesh: the triangles touching its rows (= its rows + one ghost layer), meshed and assembled alone
+            d0_, d1_ = self.offsets[self.rank], self.offsets[self.rank + 1]
+            owned_ref = (gid_of_ref >= d0_) & (gid_of_ref < d1_)
+            g = mdg._dev
+            pts_l, tri_l, tri_ids = submesh_of_rows(g["points"], g["tri"], g["t2s"], owned_ref)
+            from .meshgen import TriMesh
+            md = crbe.MeshData(TriMesh(pts_l.cpu().numpy(), tri_l.cpu().numpy()), domain, nt, device=rt.device)
+            ref_of_local = local_to_global_edges(md._dev["t2s"], g["t2s"][tri_ids], md.number_of_segments)
+            gid = gid_of_ref[ref_of_local]                      # partition id of every edge of the sub-mesh
+            self.assembled_triangles = int(tri_ids.numel())
+            del mdg, g
         self.domain, self.problem, self.nt, self.order = domain, problem, nt, order
         self.dt = domain.T / (nt - 1)
         d0, d1 = self.offsets[self.rank], self.offsets[self.rank + 1]
         self.d0, self.d1, self.n_own = d0, d1, d1 - d0
 
         # local assembly with the single-GPU kernels (set-up, not timed)
+        self.assembled_triangles = getattr(self, "assembled_triangles", md.number_of_triangles)
         loc = crbe.BESCRFEM(domain, problem, md, crbe.ElementCR(), order, rtol=rtol, progress=False)
         loc._coef()
         loc._build_pattern()
@@ -296,7 +347,8 @@ class PartitionedCRBE:
         self._solver = h
         flags = (_lib.SOLVER_VERIFY_AUTO if verify == "auto" else (_lib.SOLVER_VERIFY if verify else 0)) | \
                 (_lib.SOLVER_TMA if tma else 0) | (_lib.SOLVER_GRAPH if graph else 0) | \
-                (0 if predict else _lib.SOLVER_NO_PREDICT) | _lib.extrapolation_flags(extrapolate)
+                (0 if predict else _lib.SOLVER_NO_PREDICT) | (0 if index16 else _lib.SOLVER_INDEX32) | \
+                _lib.extrapolation_flags(extrapolate)
         rt.call("crbe_solver_set_options", h, float(rtol), int(max_iterations), flags)
         rt.call("crbe_solver_set_system", h, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
         vlen = C.c_int64()
@@ -391,6 +443,108 @@ class PartitionedCRBE:
                     its.append(self._infos[k].iterations)
             count -= m
         return its
+
+    def solve(self, history="all", history_rows=None):
+        """The time loop of ``BESCRFEM.solve()`` (crbe.py:406-433) on this rank's rows, from the initial condition already in
+        ``self.u``: per stored step the boundary values of the owned boundary rows go up and the lifted block of the solution
+        comes down into this rank's own pinned history (``solutions_local``, rows x n_own) on a copy stream, straight from the
+        ring vector while the next steps are being solved.  Stretches between stored rows go down as chunks of steps
+        (one host synchronisation per chunk).  ``history``: ``"all"``, ``"last"`` or an int stride (as in ``BESCRFEM``)."""
+        from . import crbe
+        from .runtime import ptr
+        rt, n, n_steps = self.rt, self.n_own, self.nt
+        if history_rows is None:
+            if history == "all":
+                history_rows = list(range(n_steps))
+            elif history == "last":
+                history_rows = [0, n_steps - 1] if n_steps > 1 else [0]
+            else:
+                history_rows = list(range(0, n_steps, int(history)))
+                if history_rows[-1] != n_steps - 1:
+                    history_rows.append(n_steps - 1)
+        row_of = {s: k for k, s in enumerate(history_rows)}
+        try:
+            sol_t = torch.zeros((len(history_rows), n), dtype=torch.float64, pin_memory=True)
+            pinned = True
+        except RuntimeError:
+            sol_t = torch.zeros((len(history_rows), n), dtype=torch.float64)
+            pinned = False
+        self.solutions_local = sol_t.numpy()
+        mid = self.midpoints.cpu().numpy()
+        self.solutions_local[0, :] = self.u[:n].cpu().numpy()            # the initial condition as given (crbe.py:412)
+        bnd = self._dev["bnd"].cpu().numpy().astype(np.int64)            # owned boundary rows (local ids)
+        nb = len(bnd)
+        mid_b = mid[bnd] if nb else np.zeros((0, 2))
+        problem = self.problem
+        static_source = getattr(type(problem), "source_term", None) is crbe.Problem.source_term
+        xyt_dev = None
+        if not static_source:
+            xyt_dev = rt.empty((3, n), torch.float64)
+            xyt_dev[:2] = self.midpoints.t()
+
+        def source_at(t):
+            if static_source:
+                return None
+            xyt_dev[2].fill_(t)
+            try:
+                f = problem.source_term(xyt_dev.t())
+                if isinstance(f, torch.Tensor):
+                    return f.to(torch.float64).contiguous()
+            except (TypeError, AttributeError, NotImplementedError):
+                pass
+            return rt.upload(np.asarray(problem.source_term(np.hstack((mid, t * np.ones((n, 1))))), dtype=np.float64))
+
+        def boundary_values(t_out):
+            return np.asarray(problem.boundary_fn(np.hstack((mid_b, t_out * np.ones((nb, 1))))), dtype=np.float64)
+
+        overlap = self.ring is not None and pinned             # ring vectors stay intact while their download runs
+        copy_stream = torch.cuda.Stream(device=rt.device)
+        main = torch.cuda.current_stream(rt.device)
+        nring = len(self.ring) if self.ring is not None else 1
+        copied = [None] * nring
+        bc_pin = torch.zeros((4, max(nb, 1)), dtype=torch.float64, pin_memory=True) if pinned else None
+        bc_ev = [None] * 4
+        n_stored = 0
+        max_run = 64 if (static_source and self.ring is not None) else 1
+        self.h2d_bytes_per_stored_row = 8 * nb
+        start = time.time()
+        step = 1
+        while step < n_steps:
+            run = 1
+            while run < max_run and step + run - 1 < n_steps - 1 and (step + run - 1) not in row_of:
+                run += 1
+            src = source_at(step * self.dt)
+            for k in range(1, min(run, nring) + 1):             # vectors the run overwrites must have finished their download
+                slot = (self.cur + k) % nring
+                if copied[slot] is not None:
+                    main.wait_event(copied[slot])
+                    copied[slot] = None
+            self.steps(run, source=src, chunk=run)
+            step += run
+            last = step - 1
+            if last in row_of:
+                row = sol_t[row_of[last]]
+                if overlap:
+                    ev = torch.cuda.Event()
+                    slot = n_stored % 4
+                    if bc_ev[slot] is not None:
+                        bc_ev[slot].synchronize()
+                    if nb:
+                        bc_pin[slot, :nb] = torch.from_numpy(boundary_values(last * self.dt))
+                    rt.call("crbe_solver_store_lifted_async", self._solver, ptr(self.u), bc_pin[slot].data_ptr(), row.data_ptr(),
+                            copy_stream.cuda_stream)
+                    ev.record(copy_stream)
+                    bc_ev[slot] = ev
+                    copied[self.cur] = ev
+                else:                                             # NCCL transport / pageable history: plain download, lift on the host
+                    row.copy_(self.u[:n])
+                    if nb:
+                        self.solutions_local[row_of[last], bnd] += boundary_values(last * self.dt)
+                n_stored += 1
+        copy_stream.synchronize()
+        rt.synchronize()
+        self.solve_time = time.time() - start
+        return self.solutions_local
 
     def owned_solution(self, lifted=True):
         """Owned block of the current solution (global rows d0..d1), lifted by the boundary data (crbe.py:429)."""
@@ -559,28 +713,35 @@ def bench_partitioned(args, K, W, device):
     steps_per_s = K / (ms * 1e-3)
     counts = wl.counts()
     units = world if scaling == "weak" else 1
-    # e2e: every step the owned block of the solution is downloaded into pinned host memory
-    e2e = None
-    if not args.no_e2e:
-        E = max(2, min(args.e2e_steps, 120))
-        host = torch.zeros((2, n_own), dtype=torch.float64, pin_memory=True)
-        dist.barrier()
-        torch.cuda.synchronize()
-        t1 = time.time()
-        for k in range(E):
-            part.step()
-            host[k & 1].copy_(part.u[:n_own], non_blocking=True)
-        torch.cuda.synchronize()
-        dist.barrier()
-        el = torch.tensor([time.time() - t1], device=device, dtype=torch.float64)
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        e2e = {"value": units * E / float(el.item()), "unit": B.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * n_own,
-               "steps": E, "api": "PartitionedCRBE.step() + download of the owned solution block per rank"}
     transport = part.transport
     n_halo = part.n_halo
     part.close()
     del part
     torch.cuda.empty_cache()
+    # e2e: the public API with host buffers -- the time loop of BESCRFEM.solve() on every rank's rows (PartitionedCRBE.solve, the
+    # code BESCRFEM(..., n_gpus=N).solve() runs): per step the boundary values of the owned boundary rows go up and the lifted
+    # block of the solution comes down into the rank's own pinned history, on a copy stream.  From the initial condition.
+    e2e = None
+    if not args.no_e2e:
+        E = max(2, min(args.e2e_steps, 60))           # 60 x 100.7 MB of pinned host memory per rank
+        wl_e = workloads.unit_square(args.n, steps=E, regime=args.regime, ny=wl.ny)
+        pe = PartitionedCRBE(wl_e, device=device, tma=not args.classic, extrapolate=not args.no_extrapolate)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        pe.solve(history="all")
+        torch.cuda.synchronize()
+        dist.barrier()
+        el = torch.tensor([time.time() - t1], device=device, dtype=torch.float64)
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e = {"value": units * E / float(el.item()), "unit": B.UNIT, "h2d_bytes_per_step": pe.h2d_bytes_per_stored_row,
+               "d2h_bytes_per_step": 8 * pe.n_own, "steps": E,
+               "api": "PartitionedCRBE.solve(history='all') on every rank (the loop behind BESCRFEM(..., n_gpus=N).solve()): "
+                      "per-rank pinned history, lift on the device, copy stream",
+               "iters_per_step": float(np.mean([i[0] for i in pe.step_info]))}
+        pe.close()
+        del pe
+        torch.cuda.empty_cache()
     cfg = B.shared_config(wl, win)
     cfg["workload"] = wl.name + f", {world} strips of cell rows"
     result = {

@@ -128,6 +128,9 @@ int crbe_spmv_csr(crbe_ctx* ctx, int64_t n, const int32_t* indptr_d, const int32
 int crbe_dot(crbe_ctx* ctx, int64_t n, const double* x_d, const double* y_d, double* out_h);
 /* (rel_l2, l2, max) of crbe.py:447-453 */
 int crbe_errors(crbe_ctx* ctx, int64_t n, const double* u_exact_d, const double* u_num_d, double* out3_h);
+/* The raw sums behind crbe_errors for a block of DOFs: out3_h = sum error^2, sum u_exact^2, max error.  A partitioned solve adds
+ * the first two and takes the maximum of the third over the ranks before forming the triple of crbe.py:447-453. */
+int crbe_error_sums(crbe_ctx* ctx, int64_t n, const double* u_exact_d, const double* u_num_d, double* out3_h);
 
 /* Plume diagnostics of the reference's analysis scripts (scripts/problem3_comprehensive_analysis2.py:60-302:
  * mass, centre of mass, spread, peak) in one pass over the DOFs: with the CR quadrature they are weighted sums

@@ -206,3 +206,64 @@ def test_dead_peer_is_reported_not_ignored():
     assert first[0] == "comm" and "time-out" in first[1], first
     assert "unusable" in second
     assert err in (1, 2)
+
+
+def _worker_api(rank, world, port, out_q):
+    """BESCRFEM(..., n_gpus="auto") under one process per GPU: the reference's API on a partitioned solve."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from conftest import golden_mesh, golden_problem, load_golden
+        from airpollution_b200 import crbe
+        from airpollution_b200.meshgen import delaunay_mesh
+        out = {}
+        # (1) the reference's own fixtures (time-dependent boundary data, non-zero source; BE and CN): full history
+        for name in ("source_delaunay80", "source_delaunay80_o2"):
+            g = load_golden(name)
+            dom = crbe.Domain(Lx=1.0, Ly=1.0, T=float(g["T"]))
+            prob = golden_problem(name, g)
+            md = crbe.MeshData(golden_mesh(g), dom, int(g["nt"]), device=dev)
+            s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), progress=False, n_gpus="auto")
+            local = s.solve()
+            assert local.shape == (int(g["nt"]), len(s.local_dofs))
+            ref = g["solutions"]
+            out[name] = (float(np.abs(local - ref[:, s.local_dofs]).max() / np.abs(ref).max()),          # this rank's columns
+                         float(np.linalg.norm(s.solutions - ref) / np.linalg.norm(ref)),                  # gathered nt x N
+                         float(np.linalg.norm(s.u_prev - g["u_prev_final"]) / np.linalg.norm(g["u_prev_final"])))
+        # (2) a larger unstructured mesh against the single-GPU solve: history stride, errors reduced over the ranks
+        mesh = delaunay_mesh(3000, seed=11, lo=(-2.0, -2.0), hi=(2.0, 2.0))
+        dom, prob, nt = crbe.Domain(2.0, 2.0, T=0.4), crbe.Problem(v=[1.0, 0.5], D=0.1, sigma=0.5), 25
+        md = crbe.MeshData(mesh, dom, nt, device=dev)
+        s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, progress=False, n_gpus=world, history=6)
+        s.solve()
+        errs = s.compute_errors(prob.analytical_solution)
+        full = s.solutions
+        assembled = s._part.assembled_triangles
+        res = None
+        if rank == 0:
+            one = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), 1, progress=False, history=6)
+            ref = one.solve()
+            e1 = one.compute_errors(prob.analytical_solution)
+            res = (float(np.linalg.norm(full - ref) / np.linalg.norm(ref)), [abs(a - b) / abs(b) for a, b in zip(errs, e1)], full.shape,
+                   ref.shape)
+        out_q.put((rank, out, res, assembled, md.number_of_triangles))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bescrfem_n_gpus_behind_the_reference_api():
+    world, results = _run_ranks(_worker_api, ())
+    for rank, out, res, assembled, n_tri in results:
+        for name, (loc, full, up) in out.items():
+            assert loc <= 1e-10 and full <= 1e-10 and up <= 1e-10, (name, loc, full, up)      # vs the UNMODIFIED reference's fixture
+        assert assembled < 0.75 * n_tri            # a rank assembles its rows + one ghost layer, not the global system
+    rel, err_rel, shape, ref_shape = results[0][2]
+    assert shape == ref_shape and rel <= 1e-11
+    assert max(err_rel) <= 1e-10

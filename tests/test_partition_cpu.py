@@ -145,3 +145,37 @@ def test_rcb_partition_is_balanced_and_local(world):
     blocks = (np.arange(n) * world) // n
     cut_blocks = np.count_nonzero(blocks[coo.row] != blocks[coo.col])
     assert cut_rcb < 0.25 * cut_blocks
+
+
+def test_submesh_of_rows_assembles_complete_owned_rows():
+    """Per-rank assembly of an arbitrary mesh: the triangles touching a rank's edges, renumbered; every owned edge keeps all
+    its triangles and every local edge maps to the right global edge."""
+    from airpollution_b200.distributed import local_to_global_edges, rcb_partition, submesh_of_rows
+    from airpollution_b200.meshgen import delaunay_mesh
+    from oracle import crbe_oracle as orc
+    m = delaunay_mesh(500, seed=3)
+    segs, t2s = orc.enumerate_segments(m.triangles)
+    n = len(segs)
+    mid = 0.5 * (m.points[segs[:, 0], :2] + m.points[segs[:, 1], :2])
+    order, off = rcb_partition(mid, 3)
+    total = 0
+    for r in range(3):
+        owned = np.zeros(n, bool)
+        owned[order[off[r]:off[r + 1]]] = True
+        pts_l, tri_l, ids = submesh_of_rows(m.points, m.triangles, t2s, owned)
+        segs_l, t2s_l = orc.enumerate_segments(tri_l)
+        ref = local_to_global_edges(t2s_l, t2s[ids], len(segs_l))
+        verts = np.unique(m.triangles[ids].reshape(-1))
+        assert (np.sort(verts[segs_l], axis=1) == segs[ref]).all()          # same edges, by their global vertex pairs
+        assert np.array_equal(pts_l, m.points[verts])
+        cnt_g = np.bincount(t2s.reshape(-1), minlength=n)
+        cnt_l = np.bincount(ref[t2s_l.reshape(-1)], minlength=n)
+        assert (cnt_l[owned] == cnt_g[owned]).all()                          # owned rows see all their triangles
+        assert len(ids) < 0.6 * len(m.triangles)
+        total += len(ids)
+        # the torch path gives the same selection
+        import torch
+        pts_t, tri_t, ids_t = submesh_of_rows(torch.from_numpy(m.points), torch.from_numpy(m.triangles), torch.from_numpy(t2s),
+                                              torch.from_numpy(owned))
+        assert np.array_equal(ids_t.numpy(), ids) and np.array_equal(tri_t.numpy(), tri_l)
+    assert total < 1.5 * len(m.triangles)                                    # ghost layers only
