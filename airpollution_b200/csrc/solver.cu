@@ -143,6 +143,8 @@ struct crbe_solver {
     double* ring[CRBE_MAX_EXTRAP + 1] = {nullptr};   // the ring of solution vectors inside the window (peers write their halo entries)
     unsigned char* tile_halo = nullptr;        // per tile: references a halo column (partitioned solver)
     double* red_send = nullptr;                // NCCL transport: where the dot kernels leave this rank's partial sums
+    int *tile_push = nullptr, *push_map = nullptr, *push_map2 = nullptr;   // direct halo pushes (CommArgs)
+    std::vector<int32_t> send_idx_h;
     int64_t rot = 0;                           // tile kernels walk a partitioned strip from its middle (see TilePipe::rot)
     long long p2p_timeout = 1LL << 35;         // clock64 ticks (~18 s); CRBE_P2P_TIMEOUT_MS overrides
     crbe_profile* prof = nullptr;
@@ -231,6 +233,10 @@ struct CommArgs {
     const int* send_idx;
     const unsigned char* tile_halo;                // per 256-row tile: does it reference a halo column
     long long timeout;                             // clock64 ticks a spin may last before the peer is declared dead
+    // direct pushes: the thread that produces an entry a neighbour needs stores it into the neighbour's halo itself
+    const int* tile_push;                          // per tile: index of its block in push_map, -1 if no row of it is sent
+    const int* push_map;                           // [blocks][256]: entry e of the send list | neighbour q << 26, or -1
+    const int* push_map2;                          // a second destination of the same row (partition corners), or -1
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -432,6 +438,48 @@ __device__ __forceinline__ void halo_push_tail(const double* vec, int kind, int 
     if ((int)threadIdx.x < ca->n_neigh) st_release_sys(&ca->peers[ca->neigh[threadIdx.x]]->halo_flag[kind][ca->rank], ep_h);
 }
 
+// Direct form of the push for the kernels of the iteration: the thread that has just produced entry `row` of a gathered
+// vector stores it into the halo segments of the neighbours that need it (most rows: one byte-sized lookup per tile says
+// nobody does).  Returns whether it stored anything.  halo_signal_tail then only has to raise the flags.
+__device__ __forceinline__ bool halo_push_row(double value, int64_t row, int kind, int slot, const CommArgs* __restrict__ ca) {
+    const int blk = __ldg(ca->tile_push + (row >> 8));
+    if (blk < 0) return false;
+    const int e1 = __ldg(ca->push_map + (int64_t)blk * CRBE_TILE + (row & 255));
+    if (e1 < 0) return false;
+    {
+        const int q = e1 >> 26, e = e1 & ((1 << 26) - 1);
+        double* d = kind == HK_X ? ca->dst_x[slot][q] : ca->dst[kind][q];
+        d[e - ca->send_off[q]] = value;
+    }
+    const int e2 = __ldg(ca->push_map2 + (int64_t)blk * CRBE_TILE + (row & 255));
+    if (e2 >= 0) {
+        const int q = e2 >> 26, e = e2 & ((1 << 26) - 1);
+        double* d = kind == HK_X ? ca->dst_x[slot][q] : ca->dst[kind][q];
+        d[e - ca->send_off[q]] = value;
+    }
+    return true;
+}
+
+// ... and once every CTA is through (ticket), the last one raises the neighbours' epoch flags.  pushed: this thread stored
+// into a peer (its stores must be visible system-wide before its CTA takes a ticket).
+__device__ __forceinline__ void halo_signal_tail(bool pushed, int kind, const CommArgs* __restrict__ ca) {
+    if (ca == nullptr || ca->world <= 1 || ca->n_neigh == 0) return;
+    __shared__ bool last_s;
+    __shared__ unsigned int ep_s;
+    if (pushed) __threadfence_system();
+    else __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tk = atomicInc(&ca->self->ticket[kind], gridDim.x - 1);
+        last_s = (tk == gridDim.x - 1);
+        if (last_s) ep_s = ++ca->self->my_halo_epoch[kind];
+    }
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence();
+    if ((int)threadIdx.x < ca->n_neigh) st_release_sys(&ca->peers[ca->neigh[threadIdx.x]]->halo_flag[kind][ca->rank], ep_s);
+}
+
 // Consumer side of the halo exchange, whole CTA: wait until every neighbour's push of the current epoch has landed (the
 // epoch is the one this rank's own producer tail just counted; all ranks count in lock step).
 __device__ __forceinline__ void halo_wait(int kind, const CommArgs* __restrict__ ca, int* dstate) {
@@ -593,6 +641,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate(int64_t n, ExtrapArg
                                                             const CommArgs* __restrict__ ca, int xslot) {
     constexpr double C[5][5] = {{1, 0, 0, 0, 0}, {2, -1, 0, 0, 0}, {3, -3, 1, 0, 0}, {4, -6, 4, -1, 0}, {5, -10, 10, -5, 1}};
     if (dstate[D_CHAIN] != 0) return;     // an earlier step of this chunk has not converged: leave every vector as it is
+    bool pushed = false;
     ROW_LOOP(i, n) {
         const double un = a.u0[i];
         double hv[Q > 0 ? Q : 1];
@@ -603,8 +652,9 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_extrapolate(int64_t n, ExtrapArg
         for (int j = 0; j < Q; ++j) acc = fma(C[Q][j + 1], hv[j], acc);
         if (a.save) a.save[i] = un;
         a.x0[i] = acc;
+        if (ca) pushed |= halo_push_row(acc, i, HK_X, xslot, ca);    // partitioned solve: the neighbours need the boundary entries
     }
-    halo_push_tail(a.x0, HK_X, xslot, ca);      // partitioned solve: the neighbours need the boundary entries of the guess
+    halo_signal_tail(pushed, HK_X, ca);
 }
 
 __global__ void k_lift(const double* __restrict__ bc, const int* __restrict__ bnd, int64_t nb, double* __restrict__ out) {
@@ -648,6 +698,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
     }
     halo_wait(HK_X, ca, dstate);
     double acc[3] = {0.0, 0.0, 0.0};
+    bool pushed = false;
     ROW_LOOP(i, n) {
         const double xi = x[i];
         double bi;
@@ -667,10 +718,11 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_init(int64_t n, int64_t ld, cons
         rh[i] = ri;
         if (r) r[i] = ri;   // r = r^ = p = r0: the first iteration reads them through one vector (launch_iteration), so the
         if (p) p[i] = ri;   // step kernels pass r = nullptr, and p only where its halo travels separately (NCCL transport)
+        if (ca) pushed |= halo_push_row(ri, i, HK_RH, 0, ca);   // peer-memory transport: the first SpMV gathers r^ (= p), halo included
         acc[0] = fma(bi, bi, acc[0]);
         acc[1] = fma(ri, ri, acc[1]);
     }
-    halo_push_tail(rh, HK_RH, 0, ca);       // peer-memory transport: the first SpMV gathers r^ (= p), halo included
+    halo_signal_tail(pushed, HK_RH, ca);
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
     grid_sum_last<3>(acc, partials, counter, out, ca, DK_INIT);
@@ -708,8 +760,13 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_s(int64_t n, int k, double rtol2
         if (blockIdx.x == 0 && threadIdx.x == 0) dstate[D_STATUS] = 2;
         return;
     }
-    ROW_LOOP(i, n) s[i] = fma(-alpha, v[i], r[i]);
-    halo_push_tail(s, HK_S, 0, ca);
+    bool pushed = false;
+    ROW_LOOP(i, n) {
+        const double si = fma(-alpha, v[i], r[i]);
+        s[i] = si;
+        if (ca) pushed |= halo_push_row(si, i, HK_S, 0, ca);
+    }
+    halo_signal_tail(pushed, HK_S, ca);
 }
 
 // t = A s, (t,s), (t,t), (r^,s), (r^,t), (s,s)
@@ -768,6 +825,7 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_xrp(int64_t n, int k, double rto
     const double rr_pred = tt > 0.0 ? S[S_SS] - S[S_TS] * S[S_TS] / tt : S[S_SS];
     const bool last = predict && rr_pred <= 0.999 * thr;
     double acc[1] = {0.0};
+    bool pushed = false;
     if (last) {
         ROW_LOOP(i, n) {
             const double si = s[i];
@@ -781,10 +839,12 @@ __global__ void __launch_bounds__(CRBE_BLOCK) k_xrp(int64_t n, int k, double rto
             x[i] = fma(alpha, pi, fma(omega, si, x[i]));
             const double ri = fma(-omega, t[i], si);
             r[i] = ri;
-            p[i] = fma(beta, fma(-omega, v[i], pi), ri);
+            const double pn = fma(beta, fma(-omega, v[i], pi), ri);
+            p[i] = pn;
+            if (ca) pushed |= halo_push_row(pn, i, HK_P, 0, ca);
             acc[0] = fma(ri, ri, acc[0]);
         }
-        halo_push_tail(p, HK_P, 0, ca);
+        halo_signal_tail(pushed, HK_P, ca);
     }
     double* const out[1] = {dots + S_RR};
     const bool peer = ca != nullptr && ca->world > 1;
@@ -1096,6 +1156,9 @@ static int solver_release(crbe_solver* s) {
     }
     cudaFree(s->tile_halo);
     cudaFree(s->red_send);
+    cudaFree(s->tile_push);
+    cudaFree(s->push_map);
+    cudaFree(s->push_map2);
     cudaFree(s->bnd);
     cudaFree(s->is_bnd);
     cudaFree(s->ell_col);
@@ -1282,6 +1345,8 @@ extern "C" int crbe_solver_create_partitioned(crbe_ctx* ctx, crbe_comm* comm, in
         CRBE_CUDA(cudaMalloc(&s->send_idx, sizeof(int32_t) * ns));
         CRBE_CUDA(cudaMemcpyAsync(s->send_idx, send_idx_d, sizeof(int32_t) * ns, cudaMemcpyDeviceToDevice, ctx->stream));
         CRBE_CUDA(cudaMalloc(&s->sendbuf, sizeof(double) * ns));
+        s->send_idx_h.resize((size_t)ns);
+        CRBE_CUDA(cudaMemcpyAsync(s->send_idx_h.data(), send_idx_d, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CRBE_CUDA(cudaStreamSynchronize(ctx->stream));
     return CRBE_OK;
@@ -1355,6 +1420,43 @@ extern "C" int crbe_solver_p2p_connect(crbe_solver* s, int rank, const void* han
     ca.send_idx = s->send_idx;
     ca.tile_halo = s->tile_halo;
     ca.timeout = s->p2p_timeout;
+    {   // direct pushes: for every tile that holds a row some neighbour needs, a 256-entry block saying where the row goes
+        const int64_t ntiles = s->ntiles;
+        std::vector<int> tile_push((size_t)ntiles, -1), map1, map2;
+        int blocks = 0;
+        for (int q = 0; q < nn; ++q)
+            for (int64_t e = s->send_off[q]; e < s->send_off[q + 1]; ++e) {
+                const int64_t row = s->send_idx_h[(size_t)e];
+                CRBE_REQUIRE(row >= 0 && row < s->n && e < (1 << 26), "bad send list");
+                const int64_t tile = row / CRBE_TILE;
+                if (tile_push[(size_t)tile] < 0) {
+                    tile_push[(size_t)tile] = blocks++;
+                    map1.resize((size_t)blocks * CRBE_TILE, -1);
+                    map2.resize((size_t)blocks * CRBE_TILE, -1);
+                }
+                const size_t at = (size_t)tile_push[(size_t)tile] * CRBE_TILE + (size_t)(row % CRBE_TILE);
+                const int code = (int)e | (q << 26);
+                if (map1[at] < 0) map1[at] = code;
+                else if (map2[at] < 0) map2[at] = code;
+                else {
+                    crbe_set_error("peer-memory transport: a row is needed by more than two neighbours (unsupported partition shape)");
+                    return CRBE_ERR_ARG;
+                }
+            }
+        if (map1.empty()) {
+            map1.assign(CRBE_TILE, -1);
+            map2.assign(CRBE_TILE, -1);
+        }
+        CRBE_CUDA(cudaMalloc(&s->tile_push, sizeof(int) * (size_t)ntiles));
+        CRBE_CUDA(cudaMalloc(&s->push_map, sizeof(int) * map1.size()));
+        CRBE_CUDA(cudaMalloc(&s->push_map2, sizeof(int) * map2.size()));
+        CRBE_CUDA(cudaMemcpy(s->tile_push, tile_push.data(), sizeof(int) * (size_t)ntiles, cudaMemcpyHostToDevice));
+        CRBE_CUDA(cudaMemcpy(s->push_map, map1.data(), sizeof(int) * map1.size(), cudaMemcpyHostToDevice));
+        CRBE_CUDA(cudaMemcpy(s->push_map2, map2.data(), sizeof(int) * map2.size(), cudaMemcpyHostToDevice));
+        ca.tile_push = s->tile_push;
+        ca.push_map = s->push_map;
+        ca.push_map2 = s->push_map2;
+    }
     for (int q = 0; q <= nn; ++q) ca.send_off[q] = s->send_off[q];
     for (int q = 0; q < nn; ++q) {
         const int r = s->neigh[q];
