@@ -37,6 +37,7 @@ SOLVER_VERIFY_AUTO = 32
 SOLVER_INDEX32 = 64
 SOLVER_EXTRAP_ADAPT = 128
 SOLVER_NO_PREDICT = 2048
+SOLVER_ILU0 = 4096
 MAX_EXTRAP_ORDER = 4
 
 

@@ -23,7 +23,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # Translation units whose arithmetic must follow the reference's unfused
 # evaluation order (element matrices, geometry): no FMA contraction.
 NO_FMAD = {"assembly.cu", "mesh.cu"}
-SOURCES = ["core.cu", "mesh.cu", "assembly.cu", "solver.cu", "dist.cu"]
+SOURCES = ["core.cu", "mesh.cu", "assembly.cu", "solver.cu", "precond.cu", "dist.cu"]
 
 
 def _nvcc():

@@ -213,6 +213,9 @@ class BESCRFEM:
                         then no longer travel over PCIe one by one while a solution row is being downloaded).
     ``predict``         let the update kernel skip the stores of r and p in the iteration it predicts to be the last of a
                         solve (default; same solution bits, 24 bytes per row less).
+    ``preconditioner``  ``"jacobi"`` (default: the diagonally scaled iteration, about one iteration per step in the reference's
+                        regime) or ``"ilu0"``: BiCGStab preconditioned with a multicolour ILU(0) factorisation, for steps
+                        with ``dt D / h^2 >> 1`` where Jacobi needs tens to hundreds of iterations (single GPU).
     ``n_gpus``          ``None`` / 1: this GPU.  N > 1 or ``"auto"``: the row-block partitioned solve over the N GPUs of the
                         running ``torch.distributed`` job (one process per GPU, e.g. under torchrun; every rank constructs
                         the same ``MeshData`` and ``BESCRFEM`` and calls ``solve()``).  The DOFs are split geometrically,
@@ -228,7 +231,8 @@ class BESCRFEM:
 
     def __init__(self, domain, problem, mesh_data, element, time_scheme_order=1, *, rtol=1e-13,
                  max_iterations=10000, history="all", tma=True, verify="auto", extrapolate=True,
-                 graph=True, index16=True, progress=None, velocity_field=None, predict=True, n_gpus=None):
+                 graph=True, index16=True, progress=None, velocity_field=None, predict=True, n_gpus=None,
+                 preconditioner="jacobi"):
         self.domain = domain
         self.problem = problem
         self.mesh_data = mesh_data
@@ -248,6 +252,9 @@ class BESCRFEM:
         self.progress = progress
         self.velocity_field = velocity_field
         self.n_gpus = n_gpus
+        if preconditioner not in ("jacobi", "ilu0"):
+            raise ValueError("preconditioner must be 'jacobi' or 'ilu0'")
+        self.preconditioner = preconditioner
         self._part = None
         self._rt = mesh_data._rt
         self._dev = {}
@@ -382,7 +389,8 @@ class BESCRFEM:
         flags = ((_lib.SOLVER_VERIFY_AUTO if self.verify == "auto" else (_lib.SOLVER_VERIFY if self.verify else 0))
                  | (_lib.SOLVER_TMA if self.tma else 0) | _lib.extrapolation_flags(self.extrapolate)
                  | (_lib.SOLVER_GRAPH if self.graph else 0) | (0 if self.index16 else _lib.SOLVER_INDEX32)
-                 | (0 if self.predict else _lib.SOLVER_NO_PREDICT))
+                 | (0 if self.predict else _lib.SOLVER_NO_PREDICT)
+                 | (_lib.SOLVER_ILU0 if self.preconditioner == "ilu0" else 0))
         rt.call("crbe_solver_set_options", self._solver, float(self.rtol), int(self.max_iterations), flags)
         rt.call("crbe_solver_set_system", self._solver, ptr(d["s_val"]), ptr(d["m_val"]), ptr(d.get("r_val")))
         if self.velocity_field is not None:

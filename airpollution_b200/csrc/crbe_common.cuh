@@ -102,6 +102,13 @@ int crbe_comm_allreduce_sum(crbe_comm* c, const double* send_d, double* recv_d, 
 int crbe_comm_exchange(crbe_comm* c, int n_neigh, const int* neigh, const double* sendbuf_d, const int64_t* send_off,
                        double* recvbuf_d, const int64_t* recv_off, cudaStream_t stream);
 
+// precond.cu: multicolour ILU(0)-preconditioned BiCGStab on the solver's row-scaled ELL system (single GPU)
+struct crbe_ilu;
+int crbe_ilu_create(crbe_ctx* ctx, int64_t n, const int32_t* ell_col_d, const double* ell_val_d, crbe_ilu** out);
+void crbe_ilu_destroy(crbe_ilu* f);
+int crbe_ilu_colours(const crbe_ilu* f);
+int crbe_ilu_solve(crbe_ilu* f, const double* b_scaled_d, double* x_d, double rtol, int maxit, crbe_solve_info* info);
+
 // core.cu
 int crbe_exclusive_scan_i32(crbe_ctx* ctx, const int32_t* in_d, int32_t* out_d, int64_t n, int64_t* total_h);
 

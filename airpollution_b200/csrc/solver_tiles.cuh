@@ -285,7 +285,6 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
     gate.stage(pipe);
     const int tr = threadIdx.x;
     double acc[3] = {0.0, 0.0, 0.0};
-    bool pushed = false;
     for (int64_t m = 0; m < pipe.count; ++m) {
         const int64_t tile = pipe.tile_of(m);
         const int64_t row = tile * CRBE_TILE + tr;
@@ -305,13 +304,12 @@ __global__ void __launch_bounds__(CRBE_TILE) t_init_be(int64_t n, int64_t ntiles
             rh[row] = ri;
             if (r) r[row] = ri;   // see k_init
             if (p) p[row] = ri;
-            if (PEER) pushed |= halo_push_row(ri, row, HK_RH, 0, ca);   // the first SpMV gathers r^ (= p), halo included
             acc[0] = fma(bi, bi, acc[0]);
             acc[1] = fma(ri, ri, acc[1]);
         }
         pipe.release(m);
     }
-    if (PEER) halo_signal_tail(pushed, HK_RH, ca);
+    if (PEER) halo_push_tail(rh, HK_RH, 0, ca);       // peer-memory transport: the first SpMV gathers r^ (= p), halo included
     acc[2] = acc[1];
     double* const out[3] = {dots + S_BB, dots + S_RR, dots + S_RHO0};
     grid_sum_last<3>(acc, partials, counter, out, ca, DK_INIT);

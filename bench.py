@@ -87,6 +87,7 @@ def parse_args():
     ap.add_argument("--index32", action="store_true", help="stream 32-bit column indices even when 16-bit offsets fit")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels of a step one by one instead of replaying a CUDA graph")
     ap.add_argument("--chunk", type=int, default=10, help="steps per library call / host synchronisation in the timed loop (1: step by step)")
+    ap.add_argument("--preconditioner", default="jacobi", choices=["jacobi", "ilu0"], help="ilu0: multicolour ILU(0)-preconditioned BiCGStab")
     ap.add_argument("--no-predict", action="store_true", help="always store r and p in the update kernel (CRBE_SOLVER_NO_PREDICT)")
     ap.add_argument("--classic", action="store_true", help="register-load kernels instead of the bulk-copy (TMA) pipeline")
     ap.add_argument("--e2e-steps", type=int, default=120, help="time levels of the e2e BESCRFEM.solve() run (100.7 MB of pinned host memory each)")
@@ -556,7 +557,8 @@ def main():
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": shared_config(wl, win),
-        "details": {"solver": "Jacobi-BiCGStab, merged-reduction 4-kernel iteration" + (", register loads" if args.classic else ", bulk-copy pipeline")
+        "details": {"solver": ("multicolour ILU(0)-BiCGStab (precond.cu)" if args.preconditioner == "ilu0" else
+                               "Jacobi-BiCGStab, merged-reduction 4-kernel iteration" + (", register loads" if args.classic else ", bulk-copy pipeline"))
                               + ("" if args.no_extrapolate else ", initial guess extrapolated from the last solutions ("
                                  + (f"order {args.extrapolate_order}" if args.extrapolate_order else "order 1..4 chosen per step from the measured initial residuals")
                                  + f"; mean order {q_mean:.2f}, orders of the last 16 steps {timed_orders[-16:]})"),
@@ -648,7 +650,7 @@ def main():
 def solver_options(args):
     return dict(tma=not args.classic, extrapolate=False if args.no_extrapolate else (args.extrapolate_order or True),
                 verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False,
-                predict=not args.no_predict)
+                predict=not args.no_predict, preconditioner=args.preconditioner)
 
 
 class SingleGpuLoop:

@@ -169,6 +169,10 @@ typedef struct crbe_solve_info {
                                          time against the rounding noise of the earlier solves (higher orders amplify it) */
 #define CRBE_SOLVER_TMA 8u            /* SpMV-type kernels fed by bulk async copies (cp.async.bulk
                                          + mbarrier pipeline through shared memory)               */
+#define CRBE_SOLVER_ILU0 4096u        /* precondition BiCGStab with a multicolour ILU(0) factorisation instead of the diagonal: rows are
+                                         coloured and renumbered so that the triangular solves are one data-parallel pass per colour.
+                                         For the regimes where the diagonally scaled iteration needs tens to hundreds of iterations
+                                         per step (dt D / h^2 >> 1); single GPU; starts every step from u^n or the extrapolated guess */
 #define CRBE_SOLVER_NO_PREDICT 2048u  /* always store r and p in the update kernel.  Default: the kernel predicts ||r||^2 =
                                          (s,s) - (t,s)^2/(t,t) from the sums of the preceding kernel and, when that lies clearly
                                          below the stopping threshold, skips the stores (and the read of v) nobody would use:

@@ -888,3 +888,43 @@ def test_reassembly_reports_an_unusable_row_at_the_next_step():
             t._rt.call("crbe_solver_update_advection", h, None, 0.0, 0.0, 0.1, 1, 0, None, None)
     finally:
         t._rt.call("crbe_solver_destroy", h)
+
+
+# --------------------------------------------------------------------------
+# the ILU(0) preconditioner (north_star: "Jacobi/ILU0-preconditioned BiCGStab")
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["struct_n16_D10", "struct_n32_o1", "delaunay150_o2", "source_delaunay80"])
+def test_ilu0_solve_matches_reference_fixture(name):
+    """preconditioner="ilu0" against the UNMODIFIED reference's solutions (SuperLU): same bar as the Jacobi path."""
+    g = load_golden(name)
+    crbe, dom, md = _product(g)
+    prob = golden_problem(name, g)
+    s = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), progress=False, preconditioner="ilu0")
+    sol = s.solve()
+    assert rel_err(sol[-1], g["final"]) <= SOLUTION_RTOL
+    if "solutions" in g:
+        assert max(rel_err(sol[k], g["solutions"][k]) for k in range(1, sol.shape[0])) <= SOLUTION_RTOL
+    j = crbe.BESCRFEM(dom, prob, md, crbe.ElementCR(), int(g["order"]), progress=False)
+    j.solve()
+    if name == "struct_n16_D10":        # the stiff fixture (dt D / h^2 ~ 0.5 per cell at h = 2.5... D = 10): ILU needs fewer iterations
+        assert sum(i[0] for i in s.step_info) < sum(i[0] for i in j.step_info)
+
+
+def test_ilu0_on_a_stiff_mesh_vs_oracle_direct():
+    """P-stiff (dt D / h^2 = 26) at 96 x 96 cells: ILU(0)-BiCGStab against the oracle's direct solve, and far fewer iterations
+    than the diagonally scaled iteration."""
+    from airpollution_b200 import crbe, workloads
+    wl = workloads.unit_square(96, steps=6, regime="P-stiff")
+    mesh = wl.mesh()
+    md = crbe.MeshData(mesh, wl.domain(), wl.nt)
+    a = crbe.BESCRFEM(wl.domain(), wl.problem(), md, crbe.ElementCR(), 1, progress=False, preconditioner="ilu0")
+    sa = a.solve()
+    o = orc.OracleSolver(wl.T, wl.problem(), orc.OracleMesh(mesh.points, mesh.triangles, wl.T, wl.nt), order=1, linear_solver="splu")
+    ref = o.solve()
+    assert max(rel_err(sa[k], ref[k]) for k in range(1, wl.nt)) <= SOLUTION_RTOL
+    b = crbe.BESCRFEM(wl.domain(), wl.problem(), md, crbe.ElementCR(), 1, progress=False)
+    b.solve()
+    its_ilu, its_jac = sum(i[0] for i in a.step_info), sum(i[0] for i in b.step_info)
+    assert its_ilu < 0.6 * its_jac, (its_ilu, its_jac)
+    assert np.array_equal(sa, crbe.BESCRFEM(wl.domain(), wl.problem(), md, crbe.ElementCR(), 1, progress=False,
+                                            preconditioner="ilu0").solve())      # deterministic
