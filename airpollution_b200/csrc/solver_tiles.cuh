@@ -185,7 +185,7 @@ __device__ __forceinline__ void tile_spmv_prefetch(TilePipe<NV, ST, IDX>& pipe, 
 // FIRST: the first iteration after an init / restart, where p = r^ = r0: one vector stream instead of two.
 // hkind: which gathered vector p is (HK_P, or HK_RH in the first iteration: its halo flag).
 template <class IDX, bool FIRST, bool PEER>
-__global__ void __launch_bounds__(CRBE_TILE) t_pv(int64_t n, int64_t ntiles, int64_t rot, double rtol2, const double* __restrict__ eval,
+__global__ void __launch_bounds__(CRBE_TILE, PEER ? 6 : 1) t_pv(int64_t n, int64_t ntiles, int64_t rot, double rtol2, const double* __restrict__ eval,
                                                   const IDX* __restrict__ ecol, const int* __restrict__ ecol32, const double* __restrict__ p, double* __restrict__ v,
                                                   const double* __restrict__ rh, double* sums, double* dots, int* dstate, double* partials,
                                                   unsigned int* counter, const CommArgs* __restrict__ ca, int hkind) {

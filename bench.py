@@ -98,6 +98,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--strong", action="store_true", help="fixed n x n mesh split over the ranks as the main measurement (config 4 style)")
+    ap.add_argument("--no-whole-job", action="store_true", help="skip the 1000-step job block a short run (--steps < 500) also reports")
     ap.add_argument("--no-strong", action="store_true", help="skip the config-4 block (8192 x 8192 cells split over the ranks) every line carries")
     ap.add_argument("--strong-n", type=int, default=STRONG_N, help="cells per axis of the strong-scaling block")
     ap.add_argument("--strong-steps", type=int, default=40, help="timed steps of the strong-scaling block")
@@ -532,6 +533,16 @@ def main():
             for k in range(8) if pcnt[k] > 0}
     steps_per_s = K / (ms * 1e-3)
     it_mean = float(np.mean(iters))
+    if not kern:        # the ILU(0) path is not instrumented kernel by kernel: report the step, no per-kernel roofline
+        emit({"metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K,
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+              "config": shared_config(wl, win), "clocks": clocks, "gpu_launches": int(l1.value - l0.value),
+              "details": {"solver": "multicolour ILU(0)-BiCGStab (precond.cu)", "iters_per_step": it_mean, "iters_timed_steps": iters,
+                          "setup_s": loop.setup_s, **spinup_note(spinup)},
+              "check": {"true_relres_last_timed_step": last_true_relres},
+              "roofline": {"bound": "hbm", "kernel": "not instrumented per kernel on this path", "achieved": None, "peak": peak, "unit": "GB/s",
+                           "frac": None, "traffic": None}})
+        return
     # the roofline is quoted on the kernel that takes the largest share of the step
     dom_k = max(kern, key=lambda k: kern[k]["launches"] * kern[k]["ms_per_launch"])
     achieved = kern[dom_k]["GBps"]
@@ -641,6 +652,22 @@ def main():
                       "rel_diff_note": f"||u_gpu - u_cpu|| / ||u_cpu|| after the same {S} steps from the initial condition at {n} DOFs; "
                                        "both sides iterate to 1e-13 (the host port is the oracle's C leg, the only CPU form of the "
                                        "step that reaches this size; the direct solve is compared at <= 45k DOFs in tests/)"})
+    # ---- config 3 as BASELINE.json names it: the whole 1000-step job from the initial condition, transient included -------
+    if K < 500 and not args.no_whole_job:
+        wj = SingleGpuLoop(args, workloads.unit_square(args.n, steps=1000, regime=args.regime), device)
+        torch.cuda.synchronize()
+        j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        j0.record()
+        its_j = wj.steps(1000)
+        j1.record()
+        torch.cuda.synchronize()
+        ms_j = j0.elapsed_time(j1)
+        line["whole_job"] = {"steps": 1000, "from": "initial condition, no lead-in", "steps_per_s": 1000 / (ms_j * 1e-3), "ms_per_step": ms_j / 1000,
+                             "iters_per_step": float(np.mean(its_j)), "iters_first_30_steps": its_j[:30],
+                             "true_relres_last_step": wj.last_step_true_relres(),
+                             "note": "BASELINE config 3 (1000 BE steps at 12.6 M DOFs on one B200); `value` times the --steps window the driver asks for"}
+        wj.close()
+        del wj
     # ---- config 4 (strong scaling, 8192 x 8192 cells): the single-GPU figure ----------------------------
     if not args.no_strong:
         line["strong"] = strong_block_single(args, device)

@@ -35,7 +35,7 @@ def test_reference_arm_line():
 
 @pytest.mark.gpu
 def test_product_arm_line(cuda_device):
-    d = run_bench("--cells", "256", "--steps", "12", "--warmup", "3", "--e2e-steps", "6", "--strong-n", "320", "--strong-steps", "5")
+    d = run_bench("--cells", "256", "--steps", "12", "--warmup", "3", "--e2e-steps", "6", "--strong-n", "320", "--strong-steps", "5", "--no-whole-job")
     assert BASE_KEYS | {"roofline", "clocks", "gpu_launches", "kernels", "check", "strong", "details"} <= set(d)
     ref = run_bench("--impl", "reference", "--cells", "256", "--steps", "12", "--warmup", "3")
     assert ref["config"] == d["config"] and ref["steps"] == d["steps"] and ref["warmup"] == d["warmup"]   # like for like
