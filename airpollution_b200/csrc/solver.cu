@@ -218,6 +218,8 @@ struct P2PHeader {
     unsigned int my_dot_epoch[DK_COUNT];
     unsigned int ticket[4];
     int error;                                                 // 1: a halo flag, 2: a deposit never arrived
+    unsigned int pad[16];
+    unsigned int taken[DK_COUNT];                              // local: epoch of each kind whose totals CTA 0 has put into the sums
 };
 static_assert(sizeof(P2PHeader) <= P2P_HEADER_BYTES, "mailbox does not fit its header");
 
@@ -344,23 +346,51 @@ __device__ __forceinline__ bool grid_sum_last(double (&v)[NV], double* partials,
     return false;
 }
 
-// Totals of reduction kind `kind` into S (shared memory copy of the sums): every CTA waits for the deposits of the kind's
-// current epoch (counted by this rank's own producer, which ran before this kernel) and adds them in rank order; CTA 0 also
-// stores them in the device sums, where later kernels, the end-of-step record and the host find them.
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Totals of reduction kind `kind` into S (shared memory copy of the sums).  CTA 0 waits for the deposits of the kind's current
+// epoch (counted by this rank's own producer, which ran before this kernel), adds them in rank order, stores the totals in the
+// device sums -- where later kernels, the end-of-step record and the host find them -- and publishes the epoch in a word of
+// its own; the other CTAs wait for that word.  Only one CTA per GPU polls memory the peers write to: hundreds of pollers on
+// the flag words delay the very stores they are waiting for (measured at 8 GPUs).  All CTAs of a solver kernel are resident
+// (persistent grids), so CTA 0 is always running.
 __device__ __forceinline__ void p2p_take(const CommArgs* __restrict__ ca, int kind, double* S, double* sums, int* dstate) {
     P2PHeader* me = ca->self;
     const unsigned int epoch = *(volatile unsigned int*)&me->my_dot_epoch[kind];
-    if ((int)threadIdx.x < ca->world && dstate[D_STATUS] != 4 &&
-        !wait_epoch(&me->dot_flag[kind][threadIdx.x], epoch, ca->timeout))
-        comm_dead(ca, dstate, 2);
-    __syncthreads();
     const int nv = dk_count(kind);
+    if (blockIdx.x == 0) {
+        if ((int)(*(volatile unsigned int*)&me->taken[kind] - epoch) < 0) {
+            if ((int)threadIdx.x < ca->world && dstate[D_STATUS] != 4 &&
+                !wait_epoch(&me->dot_flag[kind][threadIdx.x], epoch, ca->timeout))
+                comm_dead(ca, dstate, 2);
+            __syncthreads();
+            if ((int)threadIdx.x < nv) {
+                double a = 0.0;
+                for (int r = 0; r < ca->world; ++r) a += __ldcv(&me->inbox[kind][epoch & 1][threadIdx.x][r]);
+                sums[dk_slot(kind, threadIdx.x)] = a;
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release_gpu(&me->taken[kind], epoch);
+        }
+    } else if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_gpu(&me->taken[kind]) - epoch) < 0) {
+            __nanosleep(100);
+            if (clock64() - t0 > 2 * ca->timeout) break;       // CTA 0 gives up first and still publishes
+        }
+    }
+    __syncthreads();
     if ((int)threadIdx.x < nv) {
-        double a = 0.0;
-        for (int r = 0; r < ca->world; ++r) a += __ldcv(&me->inbox[kind][epoch & 1][threadIdx.x][r]);
         const int slot = dk_slot(kind, threadIdx.x);
-        S[slot] = a;
-        if (blockIdx.x == 0) sums[slot] = a;
+        S[slot] = __ldcg(sums + slot);
     }
 }
 
@@ -2011,7 +2041,7 @@ static int enqueue_step_head(crbe_solver* s, const StepPlan& pl, const double* s
 // A step is ~10-25 short launches; their descriptors are fetched by the GPU front end from host memory, which costs
 // several microseconds per launch while a solution row is travelling over the same PCIe link (measured: +6 % per
 // step during BESCRFEM.solve(history="all")).  An instantiated graph keeps the whole step on the device side.
-constexpr size_t STEP_GRAPH_SLOTS = 32;
+constexpr size_t STEP_GRAPH_SLOTS = 96;
 
 static StepGraph* find_step_graph(crbe_solver* s, const StepGraph& key) {
     for (StepGraph& g : s->graphs)
@@ -2067,6 +2097,48 @@ static void bind_rhs(crbe_solver* s, const StepPlan& pl, const double* source_d,
     s->be_dt = dt;
 }
 
+static void add_step_graph_key(crbe_solver* s, StepGraph& key) {
+    if (s->graphs.size() >= STEP_GRAPH_SLOTS) {
+        size_t oldest = 0;
+        for (size_t i = 1; i < s->graphs.size(); ++i)
+            if (s->graphs[i].stamp < s->graphs[oldest].stamp) oldest = i;
+        if (s->graphs[oldest].exec) cudaGraphExecDestroy(s->graphs[oldest].exec);
+        s->graphs.erase(s->graphs.begin() + oldest);
+    }
+    key.stamp = ++s->graph_clock;
+    s->graphs.push_back(key);
+}
+
+// the step shape of `key` (guess order, iterations, verification, chained) at the other positions of the ring the plan
+// belongs to: plans differ only by a rotation of the buffers
+static int capture_ring_rotations(crbe_solver* s, const StepPlan& pl, const double* source_d, double dt, const StepGraph& key) {
+    const int n = s->ring_n;
+    if (n < 2 || pl.save != nullptr) return CRBE_OK;          // in-place stepping: one position only
+    int c = -1;
+    for (int k = 0; k < n; ++k)
+        if (s->ring_sig[k] == pl.u0) c = k;
+    if (c < 0 || s->ring_sig[(c + 1) % n] != pl.x) return CRBE_OK;
+    for (int rot = 1; rot < n; ++rot) {
+        StepPlan pr;
+        memset(&pr, 0, sizeof(pr));
+        const int cr = (c + rot) % n;
+        pr.u0 = const_cast<double*>(s->ring_sig[cr]);
+        pr.x = const_cast<double*>(s->ring_sig[(cr + 1) % n]);
+        pr.q = pl.q;
+        for (int j = 0; j < pl.q; ++j) pr.h[j] = s->ring_sig[((cr - 1 - j) % n + n) % n];
+        StepGraph kr = {pr.u0, pr.x, pr.save, {pr.h[0], pr.h[1], pr.h[2], pr.h[3]}, source_d, dt, pr.q, key.target, key.speculate,
+                        key.chained, nullptr, 0, 0};
+        StepGraph* g = find_step_graph(s, kr);
+        if (g && g->exec) continue;
+        if (!g) {
+            add_step_graph_key(s, kr);
+            g = &s->graphs.back();
+        }
+        CRBE_CHECK(capture_step(s, pr, source_d, dt, g));
+    }
+    return CRBE_OK;
+}
+
 // Enqueue one planned step without synchronising: head kernels + `target` iterations (+ the speculative verification) + the
 // state download, or, chained, the end-of-step record.  Steady state on one GPU: replayed as one graph (captured the second
 // time the same step shape is asked for).
@@ -2080,18 +2152,17 @@ static int enqueue_step(crbe_solver* s, const StepPlan& pl, const double* source
                          chained ? 1 : 0, nullptr, 0, 0};
         StepGraph* g = find_step_graph(s, key);
         if (!g) {                       // first sighting: remember the shape, launch directly
-            if (s->graphs.size() >= STEP_GRAPH_SLOTS) {
-                size_t oldest = 0;
-                for (size_t i = 1; i < s->graphs.size(); ++i)
-                    if (s->graphs[i].stamp < s->graphs[oldest].stamp) oldest = i;
-                if (s->graphs[oldest].exec) cudaGraphExecDestroy(s->graphs[oldest].exec);
-                s->graphs.erase(s->graphs.begin() + oldest);
-            }
-            key.stamp = ++s->graph_clock;
-            s->graphs.push_back(key);
+            add_step_graph_key(s, key);
         } else {
             g->stamp = ++s->graph_clock;
-            if (!g->exec) CRBE_CHECK(capture_step(s, pl, source_d, dt, g));
+            if (!g->exec) {
+                CRBE_CHECK(capture_step(s, pl, source_d, dt, g));
+                // A ring walks through count positions and each of them is a graph of its own (the pointers are baked in).
+                // Capture the same step shape for the other positions now instead of one by one over the next steps: on
+                // several GPUs a capture on any rank stalls all of them, and a short time loop would pay for it in the middle.
+                CRBE_CHECK(capture_ring_rotations(s, pl, source_d, dt, key));
+                g = find_step_graph(s, key);
+            }
             CRBE_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
             *launches += g->launches;
             return CRBE_OK;
@@ -2310,7 +2381,8 @@ static int steps_ring(crbe_solver* s, double* const* bufs, int count, int cur, i
         int m = n_steps - i < s->chunk_len ? n_steps - i : s->chunk_len;
         if (m > MAX_CHUNK) m = MAX_CHUNK;
         const int before = s->last_iters;
-        if (m <= 1 || !chunking_allowed(s, source_d)) {
+        if (m < 1) m = 1;
+        if (!chunking_allowed(s, source_d)) {
             CRBE_CHECK(step_ring(s, bufs, count, (cur + i) % count, source_d, dt, &infos[i]));
             if (infos[i].iterations <= before + 1 && infos[i].restarts == 0) chunk_grow(s);   // it would have fitted a chunk
             else s->chunk_len = 1;

@@ -687,8 +687,11 @@ def bench_partitioned(args, K, W, device):
     sampler.start()
     l0, l1 = C.c_int64(), C.c_int64()
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l0))
+    cnt0, cnt1 = (C.c_int64 * 4)(), (C.c_int64 * 4)()
+    rt.call("crbe_solver_counters", part._solver, cnt0)
     ms, iters = _timed_partitioned_steps(part, 0, K, device, args.chunk)
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l1))
+    rt.call("crbe_solver_counters", part._solver, cnt1)
     # the same steps once more with a CUDA event pair around every kernel launch (per-kernel durations)
     rt.call("crbe_solver_profile", part._solver, 1)
     for _ in range(min(K, 30)):
@@ -753,7 +756,11 @@ def bench_partitioned(args, K, W, device):
                                          if scaling == "weak" else "steps/s of the fixed mesh"),
                     "solver": "Jacobi-BiCGStab, merged-reduction 4-kernel iteration, halo exchange + allreduce over " + transport,
                     "index_bits": bits.value, "guess_order_mean": q_mean,
-                    "iters_per_step": float(np.mean(iters)), "setup_s": setup_s, **B.spinup_note(spinup)},
+                    "host_synchronisations": {"chunks": int(cnt1[1] - cnt0[1]), "steps_in_chunks": int(cnt1[2] - cnt0[2]),
+                                              "chunks_cut_short": int(cnt1[3] - cnt0[3]), "timed_steps": K},
+                    "update_kernels_in_last_iteration_form": int(cnt1[0] - cnt0[0]),
+                    "iters_per_step": float(np.mean(iters)), "iters_timed_steps": iters if K <= 64 else iters[:32],
+                    "setup_s": setup_s, **B.spinup_note(spinup)},
         "dof_updates_per_s": steps_per_s * counts["dofs"],
         "clocks": clocks, "gpu_launches": int(l1.value - l0.value), "kernels": kern, "kernel_ms_per_step": kernel_ms_per_step,
         "roofline": {"bound": "hbm", "kernel": "pv: ELL SpMV v = A p + dot (r^,v), rank 0", "achieved": kern["pv"]["GBps"],
