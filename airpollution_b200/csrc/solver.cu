@@ -2041,7 +2041,7 @@ static int enqueue_step_head(crbe_solver* s, const StepPlan& pl, const double* s
 // A step is ~10-25 short launches; their descriptors are fetched by the GPU front end from host memory, which costs
 // several microseconds per launch while a solution row is travelling over the same PCIe link (measured: +6 % per
 // step during BESCRFEM.solve(history="all")).  An instantiated graph keeps the whole step on the device side.
-constexpr size_t STEP_GRAPH_SLOTS = 96;
+constexpr size_t STEP_GRAPH_SLOTS = 32;
 
 static StepGraph* find_step_graph(crbe_solver* s, const StepGraph& key) {
     for (StepGraph& g : s->graphs)
@@ -2109,36 +2109,6 @@ static void add_step_graph_key(crbe_solver* s, StepGraph& key) {
     s->graphs.push_back(key);
 }
 
-// the step shape of `key` (guess order, iterations, verification, chained) at the other positions of the ring the plan
-// belongs to: plans differ only by a rotation of the buffers
-static int capture_ring_rotations(crbe_solver* s, const StepPlan& pl, const double* source_d, double dt, const StepGraph& key) {
-    const int n = s->ring_n;
-    if (n < 2 || pl.save != nullptr) return CRBE_OK;          // in-place stepping: one position only
-    int c = -1;
-    for (int k = 0; k < n; ++k)
-        if (s->ring_sig[k] == pl.u0) c = k;
-    if (c < 0 || s->ring_sig[(c + 1) % n] != pl.x) return CRBE_OK;
-    for (int rot = 1; rot < n; ++rot) {
-        StepPlan pr;
-        memset(&pr, 0, sizeof(pr));
-        const int cr = (c + rot) % n;
-        pr.u0 = const_cast<double*>(s->ring_sig[cr]);
-        pr.x = const_cast<double*>(s->ring_sig[(cr + 1) % n]);
-        pr.q = pl.q;
-        for (int j = 0; j < pl.q; ++j) pr.h[j] = s->ring_sig[((cr - 1 - j) % n + n) % n];
-        StepGraph kr = {pr.u0, pr.x, pr.save, {pr.h[0], pr.h[1], pr.h[2], pr.h[3]}, source_d, dt, pr.q, key.target, key.speculate,
-                        key.chained, nullptr, 0, 0};
-        StepGraph* g = find_step_graph(s, kr);
-        if (g && g->exec) continue;
-        if (!g) {
-            add_step_graph_key(s, kr);
-            g = &s->graphs.back();
-        }
-        CRBE_CHECK(capture_step(s, pr, source_d, dt, g));
-    }
-    return CRBE_OK;
-}
-
 // Enqueue one planned step without synchronising: head kernels + `target` iterations (+ the speculative verification) + the
 // state download, or, chained, the end-of-step record.  Steady state on one GPU: replayed as one graph (captured the second
 // time the same step shape is asked for).
@@ -2146,7 +2116,12 @@ static int enqueue_step(crbe_solver* s, const StepPlan& pl, const double* source
                         int* launches) {
     crbe_ctx* ctx = s->ctx;
     bind_rhs(s, pl, source_d, dt);
-    const bool graphs_on = (s->flags & CRBE_SOLVER_GRAPH) && (s->world == 1 || s->p2p) && !(s->prof && s->prof->on);
+    // Graphs pay where the host synchronises after every step (launch latency is exposed, and during BESCRFEM.solve(history=
+    // "all") the launches share the PCIe link with the row downloads).  Inside a chunk of steps the host runs several steps
+    // ahead of the device with plain launches, and a capture -- ~0.2 ms on one GPU, > 1 ms on each of 8 ranks, stalling all of
+    // them -- never pays for itself: chained steps are launched directly (measured at 8 GPUs: 0.74 ms per step either way in
+    // steady state, but a 20-step window that contained the captures ran at 1.1 ms per step).
+    const bool graphs_on = (s->flags & CRBE_SOLVER_GRAPH) && (s->world == 1 || s->p2p) && !(s->prof && s->prof->on) && !chained;
     if (graphs_on) {
         StepGraph key = {pl.u0, pl.x, pl.save, {pl.h[0], pl.h[1], pl.h[2], pl.h[3]}, source_d, dt, pl.q, target, speculate ? 1 : 0,
                          chained ? 1 : 0, nullptr, 0, 0};
@@ -2155,14 +2130,7 @@ static int enqueue_step(crbe_solver* s, const StepPlan& pl, const double* source
             add_step_graph_key(s, key);
         } else {
             g->stamp = ++s->graph_clock;
-            if (!g->exec) {
-                CRBE_CHECK(capture_step(s, pl, source_d, dt, g));
-                // A ring walks through count positions and each of them is a graph of its own (the pointers are baked in).
-                // Capture the same step shape for the other positions now instead of one by one over the next steps: on
-                // several GPUs a capture on any rank stalls all of them, and a short time loop would pay for it in the middle.
-                CRBE_CHECK(capture_ring_rotations(s, pl, source_d, dt, key));
-                g = find_step_graph(s, key);
-            }
+            if (!g->exec) CRBE_CHECK(capture_step(s, pl, source_d, dt, g));
             CRBE_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
             *launches += g->launches;
             return CRBE_OK;
@@ -2381,8 +2349,7 @@ static int steps_ring(crbe_solver* s, double* const* bufs, int count, int cur, i
         int m = n_steps - i < s->chunk_len ? n_steps - i : s->chunk_len;
         if (m > MAX_CHUNK) m = MAX_CHUNK;
         const int before = s->last_iters;
-        if (m < 1) m = 1;
-        if (!chunking_allowed(s, source_d)) {
+        if (m <= 1 || !chunking_allowed(s, source_d)) {     // a single step: the step-by-step path (replayed as a graph)
             CRBE_CHECK(step_ring(s, bufs, count, (cur + i) % count, source_d, dt, &infos[i]));
             if (infos[i].iterations <= before + 1 && infos[i].restarts == 0) chunk_grow(s);   // it would have fitted a chunk
             else s->chunk_len = 1;
