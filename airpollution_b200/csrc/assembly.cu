@@ -237,11 +237,17 @@ __device__ __forceinline__ void advection_row_terms(uint32_t w, int2 es, const d
 // their row (L1/L2 hits: neighbouring rows share triangles), do the arithmetic and store the ELL slots and scalings
 // coalesced.  Nothing waits on a dependent chain of global loads (the register-load form of this kernel ran at 46 % of the
 // DRAM peak, 92 % of its stalls on the scoreboard).
-constexpr int ADV_STAGES = 3;
+#ifndef CRBE_ADV_STAGES
+#define CRBE_ADV_STAGES 2        // measured at 4096^2 cells: 2 stages 1.59 ms, 3 stages 1.64 ms, 4 stages 1.77 ms per launch
+#endif
+#ifndef CRBE_ADV_MIN_CTAS
+#define CRBE_ADV_MIN_CTAS 5      // caps the registers so that five CTAs share an SM
+#endif
+constexpr int ADV_STAGES = CRBE_ADV_STAGES;
 constexpr int ADV_K_BYTES = 5 * CRBE_TILE * 8, ADV_M_BYTES = CRBE_TILE * 8, ADV_S_BYTES = CRBE_TILE * 8, ADV_W_BYTES = CRBE_TILE * 4;
 constexpr int ADV_STAGE_BYTES = ADV_K_BYTES + ADV_M_BYTES + ADV_S_BYTES + ADV_W_BYTES;
 
-__global__ void __launch_bounds__(CRBE_TILE) t_update_system_rows(int64_t n, int64_t ntiles, const double* __restrict__ k5,
+__global__ void __launch_bounds__(CRBE_TILE, CRBE_ADV_MIN_CTAS) t_update_system_rows(int64_t n, int64_t ntiles, const double* __restrict__ k5,
                                                                   const double* __restrict__ mdiag, const int2* __restrict__ slots,
                                                                   const uint32_t* __restrict__ meta, const double* __restrict__ geom,
                                                                   const double* __restrict__ v_elem, double vx0, double vy0, double coef,

@@ -2116,12 +2116,14 @@ static int enqueue_step(crbe_solver* s, const StepPlan& pl, const double* source
                         int* launches) {
     crbe_ctx* ctx = s->ctx;
     bind_rhs(s, pl, source_d, dt);
-    // Graphs pay where the host synchronises after every step (launch latency is exposed, and during BESCRFEM.solve(history=
-    // "all") the launches share the PCIe link with the row downloads).  Inside a chunk of steps the host runs several steps
-    // ahead of the device with plain launches, and a capture -- ~0.2 ms on one GPU, > 1 ms on each of 8 ranks, stalling all of
-    // them -- never pays for itself: chained steps are launched directly (measured at 8 GPUs: 0.74 ms per step either way in
-    // steady state, but a 20-step window that contained the captures ran at 1.1 ms per step).
-    const bool graphs_on = (s->flags & CRBE_SOLVER_GRAPH) && (s->world == 1 || s->p2p) && !(s->prof && s->prof->on) && !chained;
+    // A graph replays a step with ~1.5 us between its 13 kernels instead of ~3 us for stream launches (3 % of a step), and
+    // keeps the launches off the PCIe link while rows of `solutions` are being downloaded.  A capture costs ~0.2 ms on one
+    // GPU, soon repaid -- but over 1 ms on each of 8 ranks, with all of them stalled by whichever rank is capturing: on
+    // several GPUs the steps of a chunk are therefore launched directly (the host runs several steps ahead anyway; measured
+    // at 8 GPUs: 0.74 ms per step either way in steady state, but a 20-step window that contained the captures of a new
+    // step shape at its five ring positions ran at 1.1 ms per step).
+    const bool graphs_on = (s->flags & CRBE_SOLVER_GRAPH) && (s->world == 1 || s->p2p) && !(s->prof && s->prof->on) &&
+                           (!chained || s->world == 1);
     if (graphs_on) {
         StepGraph key = {pl.u0, pl.x, pl.save, {pl.h[0], pl.h[1], pl.h[2], pl.h[3]}, source_d, dt, pl.q, target, speculate ? 1 : 0,
                          chained ? 1 : 0, nullptr, 0, 0};

@@ -119,12 +119,23 @@ def load_peaks():
 
 def ncu_traffic(kernel, args, n, bits=32):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r01_traffic.json); only valid for the configuration it was taken on."""
-    if args.classic or args.n != 2048:
+    `ncu --set full` capture of the developed time loop (profiles/r02_traffic.json, summary in r02_ncu_step_kernels.txt);
+    only valid for the configuration it was taken on (2048 x 2048 cells, bulk-copy kernels, 16-bit offsets)."""
+    if args.classic or args.n != 2048 or bits != 16:
         return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return json.load(f).get(kernel if bits == 32 else f"{kernel}_idx{bits}")
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f).get(f"{kernel}_idx{bits}")
+    except Exception:
+        return None
+
+
+def ncu_traffic_config5(n):
+    if n != 4096:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f).get("t_update_system_rows")
     except Exception:
         return None
 
@@ -407,7 +418,8 @@ def run_config5(args):
                                  "outside the product's kernels)",
             "roofline": {"bound": "hbm", "kernel": "t_update_system_rows: A(v) + system rows rebuilt per row from precomputed triangle records (bulk-copy pipeline)",
                          "achieved": asm_bytes / asm_s / 1e9, "peak": peak, "unit": "GB/s", "frac": asm_bytes / asm_s / 1e9 / peak,
-                         "peak_source": peak_src, "bytes_per_launch": asm_bytes, "bytes_per_row": asm_bytes / ndof, "traffic": None}}
+                         "peak_source": peak_src, "bytes_per_launch": asm_bytes, "bytes_per_row": asm_bytes / ndof,
+                         "traffic": ncu_traffic_config5(n)}}
     if not args.no_cpu_baseline:
         # the oracle's re-assembly (vectorised numpy, crbe.py:284-313 + :336-358 restated) + Dirichlet rows on a bounded mesh
         from oracle import crbe_oracle as orc
@@ -550,7 +562,8 @@ def main():
              "pv": "pv: ELL SpMV v = A p + dot (r^,v)" + (" (mostly its first-iteration form, p = r^)" if f0 > 0.5 else ""),
              "st": "st: ELL SpMV t = A s + 5 dots", "xr": "xrp: x, r, p updates + (r,r)", "s": "s = r - alpha v",
              "residual": "true residual", "extrapolate": "extrapolated initial guess"}[dom_k]
-    ncu_name = {"init": "t_init_be", "pv": "t_pv0" if f0 > 0.5 else "t_pv", "st": "t_st", "xr": "k_xrp", "s": "k_s"}.get(dom_k, dom_k)
+    ncu_name = {"init": "t_init_be", "pv": "t_pv0" if f0 > 0.5 else "t_pv", "st": "t_st", "xr": "k_xrp", "s": "k_s",
+                "extrapolate": "k_extrapolate"}.get(dom_k, dom_k)
     shares = {k: kern[k]["launches"] * kern[k]["ms_per_launch"] for k in kern}
     tot_share = sum(shares.values())
     kernel_ms_per_step = tot_share / KP
