@@ -241,7 +241,7 @@ __device__ __forceinline__ void advection_row_terms(uint32_t w, int2 es, const d
 #define CRBE_ADV_STAGES 2        // measured at 4096^2 cells: 2 stages 1.59 ms, 3 stages 1.64 ms, 4 stages 1.77 ms per launch
 #endif
 #ifndef CRBE_ADV_MIN_CTAS
-#define CRBE_ADV_MIN_CTAS 5      // caps the registers so that five CTAs share an SM
+#define CRBE_ADV_MIN_CTAS 1      // no register cap: forcing 5 or 6 CTAs per SM spills and is slower (1.73 / 1.88 ms against 1.56 ms)
 #endif
 constexpr int ADV_STAGES = CRBE_ADV_STAGES;
 constexpr int ADV_K_BYTES = 5 * CRBE_TILE * 8, ADV_M_BYTES = CRBE_TILE * 8, ADV_S_BYTES = CRBE_TILE * 8, ADV_W_BYTES = CRBE_TILE * 4;
