@@ -79,6 +79,14 @@ struct StepGraph {
     uint64_t stamp;
 };
 
+// how often a step shape (everything of a StepGraph key but the buffers) has been asked for lately, inside chunks
+struct ShapeStat {
+    const double* source;
+    double dt;
+    int q, target;
+    uint32_t recent;        // bit k: the shape was used k chained steps ago
+};
+
 struct crbe_solver {
     crbe_ctx* ctx = nullptr;
     int64_t n = 0, ld = 0, nnz = 0, nb = 0;
@@ -148,6 +156,7 @@ struct crbe_solver {
     crbe_profile* prof = nullptr;
     // CUDA graphs of whole steps (CRBE_SOLVER_GRAPH): head kernels + first batch of iterations + state download
     std::vector<StepGraph> graphs;
+    std::vector<ShapeStat> shapes;
     cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the context's may be the legacy default stream)
     uint64_t graph_clock = 0;
     double* bc_stage = nullptr;          // crbe_solver_store_lifted_async: boundary values on the device
@@ -161,7 +170,7 @@ struct crbe_solver {
     // steps enqueued back to back (crbe_solver_steps_ring): one record per step, written by the end-of-step kernel
     double* step_log = nullptr;
     double* step_log_h = nullptr;        // pinned
-    int chunk_len = 1, stable_steps = 0; // how many steps the next chunk may hold (doubles while steps fit their enqueued iterations)
+    int chunk_len = 1;                   // how many steps the next chunk may hold (doubles while steps fit their enqueued iterations)
     int64_t n_chunks = 0, n_chunk_steps = 0, n_chain_breaks = 0;   // statistics (crbe_solver_counters)
     bool comm_dead = false;                                        // a peer timed out: every later call fails
     crbe_ilu* ilu = nullptr;                                       // CRBE_SOLVER_ILU0: factors of the loaded system (precond.cu)
@@ -1113,6 +1122,7 @@ static void drop_step_graphs(crbe_solver* s) {
     for (StepGraph& g : s->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     s->graphs.clear();
+    s->shapes.clear();
 }
 
 static int solver_release(crbe_solver* s) {
@@ -2041,7 +2051,7 @@ static int enqueue_step_head(crbe_solver* s, const StepPlan& pl, const double* s
 // A step is ~10-25 short launches; their descriptors are fetched by the GPU front end from host memory, which costs
 // several microseconds per launch while a solution row is travelling over the same PCIe link (measured: +6 % per
 // step during BESCRFEM.solve(history="all")).  An instantiated graph keeps the whole step on the device side.
-constexpr size_t STEP_GRAPH_SLOTS = 32;
+constexpr size_t STEP_GRAPH_SLOTS = 64;
 
 static StepGraph* find_step_graph(crbe_solver* s, const StepGraph& key) {
     for (StepGraph& g : s->graphs)
@@ -2109,6 +2119,51 @@ static void add_step_graph_key(crbe_solver* s, StepGraph& key) {
     s->graphs.push_back(key);
 }
 
+// a chained step of this shape is being enqueued: how many of the last 32 chained steps had it
+static int note_shape(crbe_solver* s, const double* source_d, double dt, int q, int target) {
+    ShapeStat* mine = nullptr;
+    for (ShapeStat& st : s->shapes) {
+        st.recent <<= 1;
+        if (st.source == source_d && st.dt == dt && st.q == q && st.target == target) mine = &st;
+    }
+    if (!mine) {
+        if (s->shapes.size() >= 32) s->shapes.erase(s->shapes.begin());
+        s->shapes.push_back({source_d, dt, q, target, 0u});
+        mine = &s->shapes.back();
+    }
+    mine->recent |= 1u;
+    return __builtin_popcount(mine->recent);
+}
+
+// the step shape of `key` at the other positions of the ring the plan belongs to: the plans differ by a rotation of the buffers
+static int capture_ring_rotations(crbe_solver* s, const StepPlan& pl, const double* source_d, double dt, const StepGraph& key) {
+    const int n = s->ring_n;
+    if (n < 2 || pl.save != nullptr) return CRBE_OK;          // in-place stepping: one position only
+    int c = -1;
+    for (int k = 0; k < n; ++k)
+        if (s->ring_sig[k] == pl.u0) c = k;
+    if (c < 0 || s->ring_sig[(c + 1) % n] != pl.x) return CRBE_OK;
+    for (int rot = 1; rot < n; ++rot) {
+        StepPlan pr;
+        memset(&pr, 0, sizeof(pr));
+        const int cr = (c + rot) % n;
+        pr.u0 = const_cast<double*>(s->ring_sig[cr]);
+        pr.x = const_cast<double*>(s->ring_sig[(cr + 1) % n]);
+        pr.q = pl.q;
+        for (int j = 0; j < pl.q; ++j) pr.h[j] = s->ring_sig[((cr - 1 - j) % n + n) % n];
+        StepGraph kr = {pr.u0, pr.x, pr.save, {pr.h[0], pr.h[1], pr.h[2], pr.h[3]}, source_d, dt, pr.q, key.target, key.speculate,
+                        key.chained, nullptr, 0, 0};
+        StepGraph* g = find_step_graph(s, kr);
+        if (g && g->exec) continue;
+        if (!g) {
+            add_step_graph_key(s, kr);
+            g = &s->graphs.back();
+        }
+        CRBE_CHECK(capture_step(s, pr, source_d, dt, g));
+    }
+    return CRBE_OK;
+}
+
 // Enqueue one planned step without synchronising: head kernels + `target` iterations (+ the speculative verification) + the
 // state download, or, chained, the end-of-step record.  Steady state on one GPU: replayed as one graph (captured the second
 // time the same step shape is asked for).
@@ -2118,17 +2173,40 @@ static int enqueue_step(crbe_solver* s, const StepPlan& pl, const double* source
     bind_rhs(s, pl, source_d, dt);
     // A graph replays a step with ~1.5 us between its 13 kernels instead of ~3 us for stream launches (3 % of a step), and
     // keeps the launches off the PCIe link while rows of `solutions` are being downloaded.  A capture costs ~0.2 ms on one
-    // GPU, soon repaid -- but over 1 ms on each of 8 ranks, with all of them stalled by whichever rank is capturing: on
-    // several GPUs the steps of a chunk are therefore launched directly (the host runs several steps ahead anyway; measured
-    // at 8 GPUs: 0.74 ms per step either way in steady state, but a 20-step window that contained the captures of a new
-    // step shape at its five ring positions ran at 1.1 ms per step).
+    // GPU -- but over 1 ms on each of 8 ranks, with all of them stalled by whichever rank is capturing.  Step by step: a
+    // shape is captured the second time it is asked for.  Inside a chunk on one GPU: only shapes in steady use, for all ring
+    // positions at once (below).  Inside a chunk on several GPUs: never -- the host runs several steps ahead anyway, and a
+    // 200-step window that met the captures of every rare shape ran at 1.05 ms per step on 8 GPUs instead of 0.74.
     const bool graphs_on = (s->flags & CRBE_SOLVER_GRAPH) && (s->world == 1 || s->p2p) && !(s->prof && s->prof->on) &&
                            (!chained || s->world == 1);
     if (graphs_on) {
         StepGraph key = {pl.u0, pl.x, pl.save, {pl.h[0], pl.h[1], pl.h[2], pl.h[3]}, source_d, dt, pl.q, target, speculate ? 1 : 0,
                          chained ? 1 : 0, nullptr, 0, 0};
         StepGraph* g = find_step_graph(s, key);
-        if (!g) {                       // first sighting: remember the shape, launch directly
+        if (chained) {
+            // Inside a chunk: a step shape is captured once it is in steady use (4 of the last 32 chained steps) -- then for
+            // all positions of the ring at once, so that a short time loop does not meet the captures one by one -- and the
+            // rare shapes (a probe of the guess order, the step after a two-iteration solve) are launched directly.
+            const bool hot = note_shape(s, source_d, dt, pl.q, target) >= 4;
+            if (!(g && g->exec)) {
+                if (!hot) g = nullptr;
+                else {
+                    if (!g) {
+                        add_step_graph_key(s, key);
+                        g = &s->graphs.back();
+                    }
+                    CRBE_CHECK(capture_step(s, pl, source_d, dt, g));
+                    CRBE_CHECK(capture_ring_rotations(s, pl, source_d, dt, key));
+                    g = find_step_graph(s, key);
+                }
+            }
+            if (g && g->exec) {
+                g->stamp = ++s->graph_clock;
+                CRBE_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+                *launches += g->launches;
+                return CRBE_OK;
+            }
+        } else if (!g) {                // step by step: first sighting, remember the shape and launch directly
             add_step_graph_key(s, key);
         } else {
             g->stamp = ++s->graph_clock;
@@ -2429,7 +2507,6 @@ static int steps_ring(crbe_solver* s, double* const* bufs, int count, int cur, i
             record_guess(s, plans[jb].q, &infos[i + jb]);
             ++finished;
             s->chunk_len = 1;
-            s->stable_steps = 0;
         } else {
             chunk_grow(s);
         }
