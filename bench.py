@@ -592,7 +592,8 @@ def main():
                     "host_synchronisations": {"chunks": int(cnt_timed[1] - cnt_start[1]), "steps_in_chunks": int(cnt_timed[2] - cnt_start[2]),
                                               "chunks_cut_short": int(cnt_timed[3] - cnt_start[3]), "timed_steps": K},
                     "update_kernels_in_last_iteration_form": int(cnt_timed[0] - cnt_start[0]), "iters_timed_steps": iters if K <= 64 else iters[:32] + ["..."] + iters[-16:],
-                    "setup_s": loop.setup_s, **spinup_note(spinup)},
+                    "setup_s": loop.setup_s, "device_warmup": "0.4 s of the library's CSR SpMV before the lead-in (clocks out of idle)",
+                    **spinup_note(spinup)},
         "dof_updates_per_s": steps_per_s * n,
         "steps_per_s_with_kernel_events": KP / (ms_prof * 1e-3),
         "kernel_ms_per_step": kernel_ms_per_step,
@@ -687,6 +688,21 @@ def main():
     emit(line)
 
 
+def warm_device(rt, dev, x, n, seconds=0.4):
+    """Bring the GPU out of its idle power state before anything is timed: a fresh box runs its first process at reduced clocks
+    for seconds (seen as 0.78 instead of 0.64 ms of kernels per step in the first bench of a lease).  Repeats the library's own
+    CSR SpMV on the assembled system (no solver state is touched) for about `seconds`; not part of any timed region or of the
+    time loop's lead-in."""
+    import torch
+    from airpollution_b200.runtime import ptr
+    y = torch.empty_like(x)
+    t0 = time.time()
+    while time.time() - t0 < seconds:
+        for _ in range(50):
+            rt.call("crbe_spmv_csr", rt.ctx, n, ptr(dev["indptr"]), ptr(dev["indices"]), ptr(dev["s_val"]), ptr(x), ptr(y))
+        rt.synchronize()
+
+
 def solver_options(args):
     return dict(tma=not args.classic, extrapolate=False if args.no_extrapolate else (args.extrapolate_order or True),
                 verify=True if args.verify_always else "auto", graph=not args.no_graph, index16=not args.index32, progress=False,
@@ -723,6 +739,7 @@ class SingleGpuLoop:
         self.ubuf = [rt.zeros((vlen.value,), torch.float64) for _ in range(self.nring)]
         self.ring = (C.c_void_p * self.nring)(*[b.data_ptr() for b in self.ubuf])
         self.ubuf[0][:n] = rt.upload(np.asarray(self.solver.u_prev, dtype=np.float64))
+        warm_device(rt, self.solver._dev, self.ubuf[0], n)
         self.cur = 0
         self.info = _lib.SolveInfo()
         self.dt = float(self.solver.dt)
