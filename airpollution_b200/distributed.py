@@ -682,10 +682,10 @@ def bench_partitioned(args, K, W, device):
     part = PartitionedCRBE(wl, device=device, tma=not args.classic, extrapolate=not args.no_extrapolate)
     setup_s = time.time() - t0
     spinup = B.spinup_steps(args, K)
-    B.warm_device(rt, part._dev, part.u, part.n_own)       # clocks up before anything is timed (see bench.warm_device)
-    part.steps(spinup + W, chunk=args.chunk)
-    sampler = B.ClockSampler(device.index)
+    sampler = B.ClockSampler(device.index)                  # sampled from the warm-up on: the timed steps alone take milliseconds
     sampler.start()
+    warmup_s = B.warm_device(rt, part._dev, part.u, part.n_own)       # clocks up before anything is timed (see bench.warm_device)
+    part.steps(spinup + W, chunk=args.chunk)
     l0, l1 = C.c_int64(), C.c_int64()
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l0))
     cnt0, cnt1 = (C.c_int64 * 4)(), (C.c_int64 * 4)()
@@ -761,7 +761,8 @@ def bench_partitioned(args, K, W, device):
                                               "chunks_cut_short": int(cnt1[3] - cnt0[3]), "timed_steps": K},
                     "update_kernels_in_last_iteration_form": int(cnt1[0] - cnt0[0]),
                     "iters_per_step": float(np.mean(iters)), "iters_timed_steps": iters if K <= 64 else iters[:32],
-                    "setup_s": setup_s, "device_warmup": "0.4 s of the library's CSR SpMV before the lead-in (clocks out of idle)",
+                    "setup_s": setup_s, "device_warmup_s": warmup_s,
+                    "clocks_sampled_over": "device warm-up, lead-in, timed steps, per-kernel pass",
                     **B.spinup_note(spinup)},
         "dof_updates_per_s": steps_per_s * counts["dofs"],
         "clocks": clocks, "gpu_launches": int(l1.value - l0.value), "kernels": kern, "kernel_ms_per_step": kernel_ms_per_step,

@@ -482,15 +482,18 @@ def main():
     wl = workloads.unit_square(args.n, steps=K + W, regime=args.regime)
     counts = wl.counts()
     win = time_window(args, K, W)
-    loop = SingleGpuLoop(args, wl, device)
+    loop = SingleGpuLoop(args, wl, device, warm=False)
     solver, rt, n, bits = loop.solver, loop.rt, loop.n, loop.bits
     set_index_bits(bits)
     assert n == counts["dofs"]
     l0 = C.c_int64()
     spinup = spinup_steps(args, K)
-    loop.steps(spinup + W)
+    # clocks are sampled from the device warm-up on, through the lead-in, the timed steps and the per-kernel pass (the timed
+    # region alone is a few milliseconds: shorter than nvidia-smi's sampling period)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    loop.warmup_s = warm_device(rt, solver._dev, loop.ubuf[0], n)
+    loop.steps(spinup + W)
     rt.call("crbe_ctx_launch_count", rt.ctx, C.byref(l0))
     cnt_start = (C.c_int64 * 4)()
     rt.call("crbe_solver_counters", solver._solver, cnt_start)
@@ -592,7 +595,9 @@ def main():
                     "host_synchronisations": {"chunks": int(cnt_timed[1] - cnt_start[1]), "steps_in_chunks": int(cnt_timed[2] - cnt_start[2]),
                                               "chunks_cut_short": int(cnt_timed[3] - cnt_start[3]), "timed_steps": K},
                     "update_kernels_in_last_iteration_form": int(cnt_timed[0] - cnt_start[0]), "iters_timed_steps": iters if K <= 64 else iters[:32] + ["..."] + iters[-16:],
-                    "setup_s": loop.setup_s, "device_warmup": "0.4 s of the library's CSR SpMV before the lead-in (clocks out of idle)",
+                    "setup_s": loop.setup_s, "device_warmup_s": loop.warmup_s,
+                    "device_warmup": "the library's CSR SpMV repeated before the lead-in until its time settles (clocks out of idle)",
+                    "clocks_sampled_over": "device warm-up, lead-in, timed steps, per-kernel pass",
                     **spinup_note(spinup)},
         "dof_updates_per_s": steps_per_s * n,
         "steps_per_s_with_kernel_events": KP / (ms_prof * 1e-3),
@@ -688,19 +693,29 @@ def main():
     emit(line)
 
 
-def warm_device(rt, dev, x, n, seconds=0.4):
-    """Bring the GPU out of its idle power state before anything is timed: a fresh box runs its first process at reduced clocks
-    for seconds (seen as 0.78 instead of 0.64 ms of kernels per step in the first bench of a lease).  Repeats the library's own
-    CSR SpMV on the assembled system (no solver state is touched) for about `seconds`; not part of any timed region or of the
-    time loop's lead-in."""
+def warm_device(rt, dev, x, n, min_s=0.5, max_s=4.0):
+    """Bring the GPU out of its idle power state before anything is timed: after a fresh lease, or after the host-only legs of
+    this script, the first kernels run at reduced clocks for a while (seen as 0.78 instead of 0.64 ms of kernels per step).
+    Repeats the library's own CSR SpMV on the assembled system (no solver state is touched) in batches until a batch is no
+    faster than the best one before it (clocks have settled), for at least `min_s` and at most `max_s` seconds; not part of
+    any timed region or of the time loop's lead-in.  Returns the seconds spent."""
     import torch
     from airpollution_b200.runtime import ptr
     y = torch.empty_like(x)
-    t0 = time.time()
-    while time.time() - t0 < seconds:
-        for _ in range(50):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0, best, settled = time.time(), None, 0
+    while True:
+        e0.record()
+        for _ in range(40):
             rt.call("crbe_spmv_csr", rt.ctx, n, ptr(dev["indptr"]), ptr(dev["indices"]), ptr(dev["s_val"]), ptr(x), ptr(y))
-        rt.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        settled = settled + 1 if (best is not None and ms > 0.99 * best) else 0
+        best = ms if best is None else min(best, ms)
+        el = time.time() - t0
+        if (el >= min_s and settled >= 3) or el >= max_s:
+            return el
 
 
 def solver_options(args):
@@ -713,7 +728,7 @@ class SingleGpuLoop:
     """The time loop of one GPU as BESCRFEM.solve() drives it (a ring of solution vectors through crbe_solver_step_ring),
     from the initial condition."""
 
-    def __init__(self, args, wl, device, mesh=None):
+    def __init__(self, args, wl, device, mesh=None, warm=True):
         import numpy as np
         import torch
         from airpollution_b200 import _lib, crbe
@@ -739,7 +754,7 @@ class SingleGpuLoop:
         self.ubuf = [rt.zeros((vlen.value,), torch.float64) for _ in range(self.nring)]
         self.ring = (C.c_void_p * self.nring)(*[b.data_ptr() for b in self.ubuf])
         self.ubuf[0][:n] = rt.upload(np.asarray(self.solver.u_prev, dtype=np.float64))
-        warm_device(rt, self.solver._dev, self.ubuf[0], n)
+        self.warmup_s = warm_device(rt, self.solver._dev, self.ubuf[0], n) if warm else 0.0
         self.cur = 0
         self.info = _lib.SolveInfo()
         self.dt = float(self.solver.dt)
