@@ -302,13 +302,25 @@ def run_reference_arm(args):
     r = cpu_port_run(wl, win["lead_in_steps"], timed, 0 if args.no_extrapolate else (args.extrapolate_order or 3))
     v = r["value"]
     import numpy as np
+    cfg = shared_config(wl, win)
+    weak_note = None
+    if args.gpus > 1 and not args.strong:
+        # The repo arm at N GPUs advances a mesh of N strips (weak scaling) and counts strip-steps/s.  The host has the same cores
+        # whatever N is: N strips take N times as long per step, so its rate in strip-steps/s is that of one strip -- which is
+        # what is measured here (the N-strip mesh would only lengthen the run).  `config` names the N-strip workload like the
+        # repo arm's line does.
+        wl_n = workloads.unit_square(args.n, steps=K + W, regime=args.regime, ny=args.n * args.gpus)
+        cfg = shared_config(wl_n, win)
+        cfg["workload"] = wl_n.name + f", {args.gpus} strips of cell rows"
+        weak_note = (f"strip-steps/s of the host measured on ONE of the {args.gpus} strips ({wl.name}): the host's rate in strip-steps/s "
+                     "does not depend on the number of strips (N strips take N times as long per step on the same cores)")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": W, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": shared_config(wl, win),
+        "config": cfg,
         "details": {"iters_per_step": float(np.mean(r["its"])), "iters_timed_steps": r["its"], "iters_lead_in": r["its_lead"],
-                    "timed_steps_run": timed,
+                    "timed_steps_run": timed, "weak_scaling_note": weak_note,
                     "note": None if timed == K else f"the host times the first {timed} of the {K} steps of the window (bounded sample)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": f"{timed} BE steps of the full {wl.name} problem after {win['lead_in_steps']} untimed steps from the "

@@ -54,3 +54,12 @@ def test_product_arm_line(cuda_device):
     assert c["reference_literal_n128"]["value"] > 0 and c["reference_splu_once_n512"]["value"] > 0
     assert d["value"] > c["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_names_the_weak_scaling_workload():
+    """At N > 1 the repo arm advances N strips; the reference arm's `config` must name the same workload (its rate in
+    strip-steps/s is measured on one strip and says so)."""
+    d = run_bench("--impl", "reference", "--gpus", "2", "--cells", "64", "--steps", "5", "--warmup", "3", "--spinup", "2")
+    assert d["n_gpus"] == 2 and d["config"]["workload"] == "unit-square 64x128 cells, P-ref, 2 strips of cell rows"
+    assert d["config"]["dofs"] == 3 * 64 * 128 + 64 + 128
+    assert "ONE of the 2 strips" in d["details"]["weak_scaling_note"]
