@@ -179,3 +179,77 @@ def test_submesh_of_rows_assembles_complete_owned_rows():
                                               torch.from_numpy(owned))
         assert np.array_equal(ids_t.numpy(), ids) and np.array_equal(tri_t.numpy(), tri_l)
     assert total < 1.5 * len(m.triangles)                                    # ghost layers only
+
+
+def _worker_submesh(rank, world, port, out_q):
+    """The unstructured path of PartitionedCRBE on CPU: RCB, this rank's sub-mesh (its rows + one ghost layer of triangles),
+    assembly of that sub-mesh alone (oracle assembly), owned rows in the partition's numbering, halo plan and exchange over
+    gloo -- the local SpMV must equal the global one."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from airpollution_b200.meshgen import delaunay_mesh
+        mesh = delaunay_mesh(700, seed=5, shuffle=True, flip_fraction=0.2)
+        gm = orc.OracleMesh(mesh.points, mesh.triangles, 1.0, 3)
+        n = gm.number_of_segments
+        order, offsets = D.rcb_partition(gm.midpoints, world)
+        gid_of_ref = np.empty(n, dtype=np.int64)
+        gid_of_ref[order] = np.arange(n)                       # reference id -> partition id
+        d0, d1 = offsets[rank], offsets[rank + 1]
+        owned_ref = (gid_of_ref >= d0) & (gid_of_ref < d1)
+        pts_l, tri_l, tri_ids = D.submesh_of_rows(mesh.points, mesh.triangles, gm.triangle_to_segments, owned_ref)
+        lm = orc.OracleMesh(pts_l, tri_l, 1.0, 3)
+        ref_of_local = D.local_to_global_edges(lm.triangle_to_segments, gm.triangle_to_segments[tri_ids], lm.number_of_segments)
+        gid = gid_of_ref[ref_of_local]                          # partition id of every edge of the sub-mesh
+        Ml, Kl, Al = orc.assemble_global(lm.points, lm.triangles, lm.triangle_to_segments, lm.triangle_areas, 0.1, (1.0, 0.5),
+                                         lm.number_of_segments)
+        Sl = (Ml + 0.01 * (Kl + Al)).tocsr()
+        # owned rows in ascending partition id
+        own_local = np.nonzero((gid >= d0) & (gid < d1))[0]
+        lrow = own_local[np.argsort(gid[own_local])]
+        assert np.array_equal(gid[lrow], np.arange(d0, d1))
+        rows = Sl[lrow]
+        cols_g = torch.from_numpy(gid[rows.indices])
+        local_cols, halo_ids, ld = D.localize_columns(cols_g, d0, d1)
+        neigh, send_ids, recv_counts = D.exchange_plan(halo_ids, offsets, rank, world)
+        x_loc = np.zeros(ld + len(halo_ids))
+        x_loc[:d1 - d0] = np.sin(np.arange(d0, d1) + 0.5)
+        reqs, bufs, pos = [], [], 0
+        for q, sids, nr in zip(neigh, send_ids, recv_counts):
+            send = torch.from_numpy(x_loc[sids - d0].copy())
+            recv = torch.zeros(nr, dtype=torch.float64)
+            reqs += [dist.isend(send, q), dist.irecv(recv, q)]
+            bufs.append((pos, recv, send))
+            pos += nr
+        for r in reqs:
+            r.wait()
+        for p, recv, _ in bufs:
+            x_loc[ld + p: ld + p + len(recv)] = recv.numpy()
+        y_loc = np.add.reduceat(rows.data * x_loc[local_cols.numpy()], rows.indptr[:-1])
+        # the global system in the partition's numbering
+        M, K, A = orc.assemble_global(gm.points, gm.triangles, gm.triangle_to_segments, gm.triangle_areas, 0.1, (1.0, 0.5), n)
+        S = (M + 0.01 * (K + A)).tocsr()
+        x_ref = np.empty(n)
+        x_ref[order] = np.sin(np.arange(n) + 0.5)               # reference numbering
+        y_ref = (S @ x_ref)[order][d0:d1]
+        out_q.put((rank, float(np.abs(y_loc - y_ref).max() / np.abs(y_ref).max()), len(tri_ids), len(mesh.triangles), len(neigh)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_submesh_assembly_and_halo_exchange_between_gloo_ranks(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_submesh, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, n_sub, n_tri, n_neigh in results:
+        assert err < 1e-13, (rank, err)            # owned rows assembled on the sub-mesh alone are the global rows
+        assert n_sub < 0.8 * n_tri and n_neigh >= 1
