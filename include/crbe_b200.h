@@ -143,7 +143,7 @@ int crbe_moments(crbe_ctx* ctx, int64_t n, const double* u_d, const double* weig
 typedef struct crbe_solve_info {
     int32_t iterations;      /* BiCGStab iterations of this solve                     */
     int32_t restarts;        /* restarts from the true residual                       */
-    int32_t status;          /* 0 converged; 1 iteration limit; 2 breakdown           */
+    int32_t status;          /* 0 converged; 1 iteration limit; 2 breakdown (3, 4: see CRBE_SOLVER_NO_PREDICT, CRBE_ERR_COMM) */
     int32_t launches;        /* kernels launched by this call                         */
     double relres;           /* recurrence residual  ||r|| / ||b||  (Jacobi-scaled)   */
     double true_relres;      /* ||b - A x|| / ||b|| recomputed after convergence      */
@@ -159,8 +159,11 @@ typedef struct crbe_solve_info {
                                          of the matrix fits 16 bits (default: the 16-bit form, 8 bytes per row and SpMV less) */
 #define CRBE_SOLVER_VERIFY_AUTO 32u   /* ... only after solves of more than 12 iterations or a restart (the gap between
                                          recurrence and true residual grows with the length of the recurrence) */
-#define CRBE_SOLVER_GRAPH 4u          /* single GPU: replay a step (head kernels, first batch of iterations, state download)
-                                         as one CUDA graph once the same step shape has been seen twice            */
+#define CRBE_SOLVER_GRAPH 4u          /* replay a step (head kernels, first batch of iterations, state download or end-of-step
+                                         record) as one CUDA graph.  Step by step: once the same step shape has been seen twice
+                                         (single GPU and peer-memory transport).  Inside the chunks of crbe_solver_steps_ring: on one
+                                         GPU, for shapes in steady use, all ring positions at once; on several GPUs never (a capture
+                                         on any rank stalls all of them)                                                        */
 #define CRBE_SOLVER_EXTRAPOLATE 16u   /* start each step from the polynomial extrapolation of the last q+1 solutions instead of
                                          u^n (q = 1: 2 u^n - u^(n-1)), as far as the history of the time loop reaches    */
 #define CRBE_SOLVER_EXTRAP_ORDER(q) (((q) & 7u) << 8)   /* q = 1..4 with CRBE_SOLVER_EXTRAPOLATE; 0 means 1 */
