@@ -15,7 +15,6 @@ too; large ones are downloaded from the device the first time they are read.
 from __future__ import annotations
 
 import ctypes as C
-import os
 import time
 
 import numpy as np
