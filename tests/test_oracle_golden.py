@@ -227,3 +227,31 @@ def test_openmp_leg_extrapolated_guess(order):
     ub, ib = omp.be_steps(A, so.global_mass.diagonal(), om.boundary_segments, u0, 40, order=order)
     assert rel_err(ub, ua) <= 1e-11
     assert sum(ib[-10:]) < sum(ia[-10:])
+
+
+@pytest.mark.parametrize("name", ["struct_n8_o1", "source_delaunay80", "struct_n8_o2"])
+def test_literal_mode_is_the_reference_loop(name):
+    """linear_solver="literal" (LIL Dirichlet rows + a fresh SuperLU factorisation every step: crbe.py:397-404,426, what
+    bench.py times as the reference's own algorithm) gives the fixture's solutions to the last bit of "spsolve" mode."""
+    g = load_golden(name)
+    m = _mesh(g)
+    prob = golden_problem(name, g)
+    a = orc.OracleSolver(float(g["T"]), prob, m, order=int(g["order"]), linear_solver="literal").solve()
+    b = orc.OracleSolver(float(g["T"]), prob, m, order=int(g["order"]), linear_solver="spsolve").solve()
+    np.testing.assert_array_equal(a, b)
+    assert rel_err(a[-1], g["final"]) <= 1e-12
+
+
+def test_openmp_leg_reports_per_step_times():
+    """bench.py times a window of the host loop (lead-in steps excluded) from the per-step times of the C leg."""
+    from oracle import omp
+    g = load_golden("struct_n16_o1")
+    m = _mesh(g)
+    prob = golden_problem("struct_n16_o1", g)
+    s = orc.OracleSolver(float(g["T"]), prob, m, order=1, linear_solver="bicgstab")
+    s.build_global_matrices()
+    A = orc.dirichlet_system_fast(s.base_system, m.boundary_segments)
+    u0 = prob.initial_condition_fn(m.midpoints)
+    u, its, secs = omp.be_steps(A, s.global_mass.diagonal(), m.boundary_segments, u0, 12, order=3, timings=True)
+    u2, its2 = omp.be_steps(A, s.global_mass.diagonal(), m.boundary_segments, u0, 12, order=3)
+    assert len(secs) == 12 and (secs > 0).all() and its == its2 and np.array_equal(u, u2)
