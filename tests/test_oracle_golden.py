@@ -254,4 +254,5 @@ def test_openmp_leg_reports_per_step_times():
     u0 = prob.initial_condition_fn(m.midpoints)
     u, its, secs = omp.be_steps(A, s.global_mass.diagonal(), m.boundary_segments, u0, 12, order=3, timings=True)
     u2, its2 = omp.be_steps(A, s.global_mass.diagonal(), m.boundary_segments, u0, 12, order=3)
-    assert len(secs) == 12 and (secs > 0).all() and its == its2 and np.array_equal(u, u2)
+    assert len(secs) == 12 and (secs > 0).all() and its == its2
+    assert rel_err(u, u2) <= 1e-12          # OpenMP reductions are not ordered: last bits may differ between runs
